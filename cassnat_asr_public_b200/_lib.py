@@ -1,0 +1,85 @@
+"""ctypes binding of libcassnat_b200.so (the C ABI declared in include/cassnat_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or a call returns a
+non-zero cn_status, a RuntimeError is raised.  PyTorch only supplies device memory and the
+current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcassnat_b200.so")
+
+_i64, _i32, _f32, _vp, _int = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p, ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/cassnat_b200.h one to one
+SIGNATURES = {
+    "cn_version": (_int, []),
+    "cn_status_string": (ctypes.c_char_p, [_int]),
+    "cn_device_check": (_int, []),
+    "cn_row_stats": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cn_bestpath_collapse": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp]),
+    "cn_bestpath_workspace_bytes": (_i64, [_i64, _i64]),
+    "cn_bestpath_from_logp": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _int,
+                                     _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cn_viterbi_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "cn_viterbi_align": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64,
+                                _vp, _vp, _i64, _vp]),
+    "cn_align_to_mask": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "cn_expand_trigger_mask": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "cn_tgt_length_mask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "cn_gemm_f32": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "cn_layernorm": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _f32, _vp, _vp, _i64, _vp]),
+    "cn_attention_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
+                                _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "cn_segment_attention_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int,
+                                        _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library, raising (never falling back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m cassnat_asr_public_b200.build` "
+            "(nvcc, sm_100a). cassnat_asr_public_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def status_string(rc):
+    return load().cn_status_string(rc).decode()
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {status_string(rc)} (cn_status {rc})")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cassnat_asr_public_b200 ops need CUDA tensors (no CPU fallback)")

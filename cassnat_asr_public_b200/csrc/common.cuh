@@ -1,0 +1,53 @@
+// Shared device/host helpers for the cassnat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <float.h>
+
+#include "../../include/cassnat_b200.h"
+
+#define CN_LOGZERO (-1e10f)          // reference: src/utils/ctc_prefix.py:12
+#define CN_F32_MIN (-FLT_MAX)        // reference: np.finfo(float32).min, modules/attention.py:19
+
+#define CN_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return CN_ERR_LAUNCH;           \
+  } while (0)
+
+static inline int cn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float cn_ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 cn_ld_stream_f32x4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float cn_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float cn_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int cn_warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// (value, index) pair ordered like torch.argmax / a stable descending sort:
+// larger value first, equal values -> lower index first.
+__device__ __forceinline__ bool cn_better(float va, int ia, float vb, int ib) {
+  return (va > vb) || (va == vb && ia < ib);
+}

@@ -1,0 +1,236 @@
+"""Tensor-level operators of the CASS-NAT alignment-conditioned path, each a thin wrapper that
+allocates outputs with torch and calls one entry point of the C ABI (include/cassnat_b200.h).
+Signatures and return conventions follow the reference methods they stand in for
+(src/models/cassnat.py:259-418); every operator raises if its input is not on a CUDA device.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, require_cuda, stream
+
+ACT = {None: 0, "none": 0, "relu": 1, "swish": 2}
+
+
+def _u8(mask, B, T):
+    """[B,1,T] / [B,T] mask of any integer/bool dtype -> contiguous uint8 [B,T]."""
+    m = mask.reshape(B, T)
+    if m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    return m.contiguous()
+
+
+def _i64(x):
+    return x.to(torch.int64).contiguous()
+
+
+# ----------------------------------------------------------------------------- K1/K2/K9
+def row_stats(x, top2=False, peak=False, lse=False, logp_out=None):
+    """argmax (+runner-up, max, log-sum-exp, log-softmax) of every row of a [...,V] f32 tensor.
+    Returns dict with int32 'top1' (+ 'top2', 'peak', 'lse'); logp_out (same shape) is filled
+    with x - lse when given."""
+    require_cuda(x)
+    V = x.shape[-1]
+    x2 = x.reshape(-1, V)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    dev = x.device
+    out = {"top1": torch.empty(rows, dtype=torch.int32, device=dev)}
+    if top2:
+        out["top2"] = torch.empty(rows, dtype=torch.int32, device=dev)
+    if peak:
+        out["peak"] = torch.empty(rows, dtype=torch.float32, device=dev)
+    if lse or logp_out is not None:
+        out["lse"] = torch.empty(rows, dtype=torch.float32, device=dev)
+    lp = logp_out.reshape(-1, V) if logp_out is not None else None
+    call("cn_row_stats", ptr(x2), rows, V, x2.stride(0), ptr(out["top1"]), ptr(out.get("top2")),
+         ptr(out.get("peak")), ptr(out.get("lse")), ptr(lp), lp.stride(0) if lp is not None else 0, stream())
+    lead = x.shape[:-1]
+    return {k: v.reshape(lead) for k, v in out.items()}
+
+
+def best_path_align(ctc_out, src_mask, src_size, blank, sample_num=0, threshold=0.9, include_best=True):
+    """CassNAT.best_path_align (cassnat.py:367-389) -> (aligned_seq_shift i64 [B,T], ylen i64 [B], ymax int).
+    With sample_num > 1 the per-frame coin flips are drawn here with torch.randint on the CPU
+    default generator, the call the reference makes at cassnat.py:373."""
+    require_cuda(ctc_out)
+    B, T, V = ctc_out.shape
+    lp = ctc_out if ctc_out.stride(-1) == 1 and ctc_out.stride(0) == T * ctc_out.stride(1) else ctc_out.contiguous()
+    dev = ctc_out.device
+    select = None
+    if sample_num > 1:
+        select = torch.randint(0, 2, (B, T, 1)).to(torch.uint8).reshape(B, T).to(dev, non_blocking=True)
+    mask = _u8(src_mask, B, T)
+    aligned = torch.empty(B, T, dtype=torch.int64, device=dev)
+    ylen = torch.empty(B, dtype=torch.int64, device=dev)
+    ymax = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = _lib.load().cn_bestpath_workspace_bytes(B, T)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("cn_bestpath_from_logp", ptr(lp), B, T, V, lp.stride(0), lp.stride(1), ptr(mask), ptr(select),
+         int(blank), int(sample_num), float(threshold), int(bool(include_best)),
+         ptr(aligned), ptr(ylen), ptr(ymax), ptr(ws), ws_bytes, stream())
+    return aligned, ylen, int(ymax.item())      # .item(): the reference's host sync at cassnat.py:387
+
+
+def viterbi_align(ctc_out, src_mask, src_size, ys, ylens, blank, sample_topk=0):
+    """CassNAT.viterbi_align (cassnat.py:272-353) -> (aligned_seq_shift i64 [B,T], ylens, ymax=ys.size(1))."""
+    require_cuda(ctc_out)
+    B, T, V = ctc_out.shape
+    U = ys.size(1)
+    dev = ctc_out.device
+    lp = ctc_out if ctc_out.stride(-1) == 1 else ctc_out.contiguous()
+    t_sample = None
+    n_sample = 0
+    if sample_topk > 1:
+        # same draw as cassnat.py:312 (CPU default generator)
+        t_sample = torch.randint(1, T, (1, sample_topk)).to(torch.int32).reshape(-1).to(dev)
+        n_sample = int(sample_topk)
+    mask = _u8(src_mask, B, T)
+    ys64, yl64, sz64 = _i64(ys), _i64(ylens), _i64(src_size)
+    aligned = torch.empty(B, T, dtype=torch.int64, device=dev)
+    ws_bytes = _lib.load().cn_viterbi_workspace_bytes(B, T, U)
+    if ws_bytes < 0:
+        raise RuntimeError(f"viterbi_align: unsupported label length U={U} (1..511)")
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    call("cn_viterbi_align", ptr(lp), B, T, V, lp.stride(0), lp.stride(1), ptr(mask), ptr(sz64), ptr(ys64), U,
+         ys64.stride(0), ptr(yl64), int(blank), ptr(t_sample), n_sample, ptr(aligned), ptr(ws), ws_bytes, stream())
+    return aligned, ylens, U
+
+
+def align_to_mask(aligned_seq_shift, ylens, ymax, src_mask, src_size, blank, left=0, right=0, and_src_mask=False,
+                  want_mask=True, want_seg=False):
+    """CassNAT.align_to_mask (cassnat.py:355-365) -> (bool [B,ymax+1,T], ylens+1, ymax+1).
+    left/right/and_src_mask fold expand_trigger_mask and the `& src_mask` of cassnat.py:467-468 into
+    the same kernel; want_seg additionally returns the int32 segment ids the fused extractor uses."""
+    require_cuda(aligned_seq_shift)
+    B, T = aligned_seq_shift.shape
+    dev = aligned_seq_shift.device
+    al, yl, sz = _i64(aligned_seq_shift), _i64(ylens), _i64(src_size)
+    mask_in = _u8(src_mask, B, T)
+    out = torch.empty(B, ymax + 1, T, dtype=torch.uint8, device=dev) if want_mask else None
+    ylen_out = torch.empty(B, dtype=torch.int64, device=dev)
+    seg = torch.empty(B, T, dtype=torch.int32, device=dev) if want_seg else None
+    call("cn_align_to_mask", ptr(al), ptr(yl), ptr(mask_in), ptr(sz), B, T, int(ymax), int(blank),
+         int(left > 0), int(right > 0), int(bool(and_src_mask)), ptr(out), ptr(ylen_out), ptr(seg), stream())
+    res = (out.view(torch.bool) if out is not None else None, ylen_out, ymax + 1)
+    return res + (seg,) if want_seg else res
+
+
+def expand_trigger_mask(trigger_mask, left_trigger, right_trigger):
+    """CassNAT.expand_trigger_mask (cassnat.py:259-270)."""
+    require_cuda(trigger_mask)
+    if left_trigger <= 0 and right_trigger <= 0:
+        return trigger_mask
+    B, U, T = trigger_mask.shape
+    m = trigger_mask.contiguous()
+    m8 = m.view(torch.uint8) if m.dtype == torch.bool else (m != 0).to(torch.uint8)
+    out = torch.empty_like(m8)
+    call("cn_expand_trigger_mask", ptr(m8), B, U, T, int(left_trigger), int(right_trigger), ptr(out), stream())
+    return out.view(torch.bool)
+
+
+def tgt_length_mask(ylen, ymax, as_u8=False):
+    """The scatter/cumprod/scatter of cassnat.py:476-478 -> int64 [B,1,ymax] (1 where u < ylen[b])."""
+    require_cuda(ylen)
+    B = ylen.numel()
+    yl = _i64(ylen)
+    o64 = None if as_u8 else torch.empty(B, 1, ymax, dtype=torch.int64, device=ylen.device)
+    o8 = torch.empty(B, ymax, dtype=torch.uint8, device=ylen.device) if as_u8 else None
+    call("cn_tgt_length_mask", ptr(yl), B, int(ymax), ptr(o64), ptr(o8), stream())
+    return o8 if as_u8 else o64
+
+
+# ----------------------------------------------------------------------------- fp32 blocks
+def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None):
+    """residual + alpha * act(x @ weight.T + bias) over the last dim of x (f32)."""
+    require_cuda(x, weight)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, dtype=torch.float32, device=x.device)
+    o2 = out.reshape(-1, N)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    w = weight if weight.stride(-1) == 1 else weight.contiguous()
+    call("cn_gemm_f32", ptr(x2), x2.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(r2),
+         r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ACT[act], ptr(o2), o2.stride(0),
+         M, N, K, stream())
+    return out
+
+
+def layer_norm(x, a_2, b_2, eps=1e-6, bf16=False):
+    """LayerNorm of modules/norm.py:15-18 (unbiased std, eps added to std)."""
+    require_cuda(x)
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
+    o2 = out.reshape(-1, d)
+    call("cn_layernorm", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps),
+         None if bf16 else ptr(o2), ptr(o2) if bf16 else None, o2.stride(0), stream())
+    return out
+
+
+def _mask_strides(mask, B, Tq, Tk):
+    if mask is None:
+        return None, 0, 0
+    m = mask
+    if m.dtype != torch.uint8:
+        m = m.view(torch.uint8) if m.dtype == torch.bool else (m != 0).to(torch.uint8)
+    if m.dim() == 2:
+        m = m.unsqueeze(1)
+    assert m.shape[0] == B and m.shape[-1] == Tk and m.shape[1] in (1, Tq), tuple(m.shape)
+    m = m.contiguous()
+    return m, m.stride(0), (0 if m.shape[1] == 1 else m.stride(1))
+
+
+def attention(q, k, v, mask, n_head, rel=None, out=None):
+    """Masked multi-head attention on projected q [B,Tq,d], k/v [B,Tk,d] (views with a row stride
+    are fine, e.g. slices of a fused QKV buffer).  mask: [B,1,Tk] or [B,Tq,Tk], 0 = masked.
+    rel = (rel_pos [2m+1,d], pos_bias_u [h,dk], pos_bias_v [h,dk], m) selects the relative-position
+    variant (modules/attention.py:104-143)."""
+    require_cuda(q, k, v)
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    dk = d // n_head
+    for t in (q, k, v):
+        assert t.stride(-1) == 1
+    if out is None:
+        out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
+    m, mb, mi = _mask_strides(mask, B, Tq, Tk)
+    rp = ru = rv = None
+    mr = 0
+    if rel is not None:
+        rp, ru, rv, mr = rel
+        rp, ru, rv = rp.contiguous(), ru.contiguous(), rv.contiguous()
+    call("cn_attention_f32", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
+         ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp), ptr(ru), ptr(rv), int(mr),
+         B, n_head, Tq, Tk, dk, ptr(out), out.stride(1), out.stride(0), stream())
+    return out
+
+
+def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, out=None):
+    """Extractor attention with the trigger mask evaluated on the fly from segment ids
+    (cassnat.py:465-468 + modules/attention.py:13-24).  q_rows [U,d] is batch independent."""
+    require_cuda(q_rows, k, v, seg)
+    U, d = q_rows.shape
+    B, T, _ = k.shape
+    if out is None:
+        out = torch.empty(B, U, d, dtype=torch.float32, device=k.device)
+    vmean = torch.empty(B, d, dtype=torch.float32, device=k.device)
+    mask = _u8(src_mask, B, T)
+    call("cn_segment_attention_f32", ptr(q_rows), q_rows.stride(0), ptr(k), k.stride(1), k.stride(0),
+         ptr(v), v.stride(1), v.stride(0), ptr(seg), ptr(_i64(ylens)), ptr(mask), ptr(_i64(src_size)),
+         int(left > 0), int(right > 0), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
+         ptr(vmean), stream())
+    return out

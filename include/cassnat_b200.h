@@ -1,0 +1,185 @@
+/* cassnat_b200 — C ABI of the B200-native CASS-NAT alignment-conditioned decoding path.
+ *
+ * The reference (balaji1312/cassnat_asr_public) has no FFI layer: its boundary for this
+ * path is the Python object protocol of `CassNAT` (src/models/cassnat.py) and the FaNAT
+ * blocks (src/models/blocks/fanat_blocks.py, fanat_conformer_blocks.py).  This header is
+ * what a ctypes binding of that path binds instead; every entry point cites the reference
+ * code (file:line, relative to the reference root) whose torch-op sequence it replaces.
+ * The Python mirror in cassnat_asr_public_b200/ is the only in-tree caller.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (tensor.data_ptr()) unless it says "host";
+ *   - sizes/strides are in ELEMENTS, int64_t; innermost dimension contiguous unless a
+ *     stride is given for it;
+ *   - the caller allocates outputs and workspaces (no cudaMalloc inside);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronises the host;
+ *   - return value: CN_OK (0) or a negative cn_status; nothing is thrown;
+ *   - sm_100a only.  There is no CPU fallback: without a Blackwell GPU every compute call
+ *     returns CN_ERR_DEVICE / CN_ERR_LAUNCH.
+ *   - masks are uint8 (0 = masked), integer tensors the reference returns as int64 stay int64.
+ */
+#ifndef CASSNAT_B200_H_
+#define CASSNAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cn_stream_t;
+
+enum cn_status {
+  CN_OK = 0,
+  CN_ERR_BAD_ARG = -1,      /* null pointer, negative size, inconsistent shapes            */
+  CN_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement (says which in doc) */
+  CN_ERR_LAUNCH = -3,       /* cudaGetLastError() after a launch                            */
+  CN_ERR_WORKSPACE = -4,    /* workspace too small                                          */
+  CN_ERR_DEVICE = -5        /* no sm_100 device / driver entry point missing                */
+};
+
+enum cn_act { CN_ACT_NONE = 0, CN_ACT_RELU = 1, CN_ACT_SWISH = 2 };
+
+int cn_version(void);
+const char* cn_status_string(int status);
+/* 0 when the current device is compute capability 10.x, CN_ERR_DEVICE otherwise. */
+int cn_device_check(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1/K2/K9 row statistics over a [rows, V] f32 matrix (V contiguous, row_stride elements
+ * between rows): first-index argmax, runner-up index, max value, log-sum-exp and an
+ * optional log-softmax write.
+ *   replaces: ctc_out.argmax(-1) / .max(-1) / .topk(2,-1)   src/models/cassnat.py:371-378
+ *             F.log_softmax in Generator.forward             src/models/cassnat.py:110-113
+ *             att_out.argmax / topk(beam_width=1)            src/models/cassnat.py:501,611
+ * Ties: lower index first (torch.argmax order; torch.topk's order among equal values is
+ * implementation-defined).  top2/peak/lse/logp_out may be NULL.
+ * logp_out[r, v] = x[r, v] - lse[r]  (out_stride elements between rows; may alias x).
+ */
+int cn_row_stats(const float* x, int64_t rows, int64_t V, int64_t row_stride,
+                 int32_t* top1, int32_t* top2, float* peak, float* lse,
+                 float* logp_out, int64_t out_stride, cn_stream_t stream);
+
+/* K2  greedy / sampled CTC best path -> aligned_seq_shift, ylen, ymax.
+ *   replaces: CassNAT.best_path_align                        src/models/cassnat.py:367-389
+ * top1/top2/peak [B*T] come from cn_row_stats on the [B,T,V] log-posteriors.
+ * src_mask u8 [B,T].  select u8 [B,T] = the host-drawn torch.randint(0,2,(B,T,1)) of
+ * cassnat.py:373 (NULL when sample_num <= 1; the draw stays on the host so the CPU default
+ * generator is consumed exactly like the reference).  Outputs: aligned i64 [B,T],
+ * ylen i64 [B], ymax i32 [1] (device; max over b of ylen). */
+int cn_bestpath_collapse(const int32_t* top1, const int32_t* top2, const float* peak,
+                         const uint8_t* select, const uint8_t* src_mask,
+                         int64_t B, int64_t T, int64_t blank, int64_t sample_num,
+                         float threshold, int include_best,
+                         int64_t* aligned, int64_t* ylen, int32_t* ymax, cn_stream_t stream);
+
+/* K2 convenience: cn_row_stats + cn_bestpath_collapse on log-posteriors logp [B,T,V]
+ * (strides sb, st in elements).  workspace: cn_bestpath_workspace_bytes(B,T). */
+int64_t cn_bestpath_workspace_bytes(int64_t B, int64_t T);
+int cn_bestpath_from_logp(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                          const uint8_t* src_mask, const uint8_t* select, int64_t blank,
+                          int64_t sample_num, float threshold, int include_best,
+                          int64_t* aligned, int64_t* ylen, int32_t* ymax,
+                          void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* K3  CTC forced alignment (max-plus DP over the (2U+1) x T lattice + back-trace +
+ * collapse + shift), one CTA per utterance: one DP warp, three emission-gather warps,
+ * lattice staged through shared memory, 2-bit back-pointers in the workspace.
+ *   replaces: CassNAT.viterbi_align                          src/models/cassnat.py:272-353
+ * logp f32 [B,T,V] (strides sb, st); src_mask u8 [B,T]; src_size i64 [B] (frames);
+ * ys i64 [B,U] (row stride ys_stride); ylens i64 [B]; t_sample i32 [n_sample] = frames
+ * where the 2nd-best predecessor is taken (cassnat.py:311-326; host-drawn), may be NULL.
+ * Output aligned i64 [B,T].  Supported: 1 <= U <= 511 (2U+1 <= 1024 lattice states).
+ * Tie-breaks as the reference: stay > s-1 > s-2; end state needs strict '>'. */
+int64_t cn_viterbi_workspace_bytes(int64_t B, int64_t T, int64_t U);
+int cn_viterbi_align(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                     const uint8_t* src_mask, const int64_t* src_size,
+                     const int64_t* ys, int64_t U, int64_t ys_stride, const int64_t* ylens,
+                     int64_t blank, const int32_t* t_sample, int64_t n_sample,
+                     int64_t* aligned, void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* K4/K5  alignment -> per-token trigger mask (+ optional +-1 frame dilation and src_mask AND).
+ *   replaces: CassNAT.align_to_mask                          src/models/cassnat.py:355-365
+ *             CassNAT.expand_trigger_mask + "& src_mask"     src/models/cassnat.py:259-270,:175,:468
+ * aligned i64 [B,T]; ylens i64 [B]; src_mask u8 [B,T]; src_size i64 [B].
+ * mask_out u8 [B, ymax+1, T]; ylen_out i64 [B] = ylens + 1 (may be NULL).
+ * left/right: 0 or 1 (the reference only tests > 0).  and_src_mask != 0 applies the final
+ * "& src_mask" of cassnat.py:468.  With left=right=0 and and_src_mask=0 the result is
+ * exactly align_to_mask's.  seg_out i32 [B,T] (may be NULL) receives cumsum(aligned != blank),
+ * the compact form the fused extractor consumes. */
+int cn_align_to_mask(const int64_t* aligned, const int64_t* ylens, const uint8_t* src_mask,
+                     const int64_t* src_size, int64_t B, int64_t T, int64_t ymax, int64_t blank,
+                     int left, int right, int and_src_mask,
+                     uint8_t* mask_out, int64_t* ylen_out, int32_t* seg_out, cn_stream_t stream);
+
+/*   replaces: CassNAT.expand_trigger_mask on an arbitrary mask   src/models/cassnat.py:259-270
+ * mask u8 [B,U,T] -> out u8 [B,U,T] (out must not alias mask). */
+int cn_expand_trigger_mask(const uint8_t* mask, int64_t B, int64_t U, int64_t T,
+                           int left, int right, uint8_t* out, cn_stream_t stream);
+
+/*   replaces: tgt_mask scatter/cumprod/scatter                 src/models/cassnat.py:185-187,476-478
+ * out_i64 i64 [B,1,ymax] and/or out_u8 u8 [B,ymax] (either may be NULL): 1 where u < ylen[b]. */
+int cn_tgt_length_mask(const int64_t* ylen, int64_t B, int64_t ymax,
+                       int64_t* out_i64, uint8_t* out_u8, cn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * fp32 building blocks of the extractor / SAD / MAD / heads (parity mode: plain FFMA,
+ * one rounding per multiply-add, no tensor cores).
+ */
+
+/* C[M,N] = residual + alpha * act(A[M,K] * W[N,K]^T + bias)   (bias, residual may be NULL);
+ * residual row for output row m is (res_rows > 0 ? m % res_rows : m), which lets the
+ * batch-independent sinusoid rows of cassnat.py:481 act as the residual without a repeat.
+ *   replaces: nn.Linear / PositionwiseFeedForward / SublayerConnection residual
+ *             src/models/modules/positionff.py:6-16, modules/utils.py:25-32,
+ *             modules/attention.py:55-66 (projections), cassnat.py:105,113 (Generator.proj) */
+int cn_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, cn_stream_t stream);
+
+/* y = a * (x - mean) / (std_unbiased + eps) + b over the last dim (d <= 2048)
+ *   replaces: LayerNorm.forward                               src/models/modules/norm.py:15-18
+ * out_f32 and/or out_bf16 (uint16 storage) may be NULL. */
+int cn_layernorm(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
+                 float eps, float* out_f32, void* out_bf16, int64_t ldo, cn_stream_t stream);
+
+/* Masked multi-head attention, exact reference semantics: scores/sqrt(dk), masked entries
+ * set to finfo(f32).min (fully masked rows -> uniform over ALL Tk keys), softmax, P*V.
+ *   replaces: attention() + head split/merge                  src/models/modules/attention.py:13-24,55-65
+ * Q [B,Tq,h*dk] row stride ldq; K,V [B,Tk,h*dk] row strides ldk, ldv; batch strides sbq/sbk/sbv.
+ * mask u8, element (b,i,j) at mask[b*mb + i*mi + j] (mi = 0 broadcasts a [B,1,Tk] mask;
+ * mask may be NULL).  rel_* (all or none NULL) add Transformer-XL relative-position scores:
+ *   replaces: RelMultiHeadedAttention.forward                 src/models/modules/attention.py:104-143
+ *   score(i,j) = ((q_i+u_h).k_j + (q_i+v_h).P[clamp(j-i,-m,m)+m, h]) / sqrt(dk),
+ *   rel_pos f32 [2m+1, h*dk] = linear_pos(embedding rows), and masked probabilities are
+ *   re-zeroed after the softmax (attention.py:138) so fully masked rows give 0.
+ * out [B,Tq,h*dk] row stride ldo.  dk must be 64. */
+int cn_attention_f32(const float* Q, int64_t ldq, int64_t sbq, const float* K, int64_t ldk, int64_t sbk,
+                     const float* V, int64_t ldv, int64_t sbv,
+                     const uint8_t* mask, int64_t mb, int64_t mi,
+                     const float* rel_pos, const float* rel_bias_u, const float* rel_bias_v, int64_t max_rel,
+                     int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                     float* out, int64_t ldo, int64_t sbo, cn_stream_t stream);
+
+/* K6  token acoustic extractor attention with the trigger mask evaluated on the fly from
+ * the alignment (never materialised): each token row u pools only the frames of its CTC
+ * segment (+-1 dilation), rows whose mask is empty reproduce the reference's uniform
+ * attention over all T frames.
+ *   replaces: align_to_mask + expand_trigger_mask + MultiHeadedAttention on the trigger mask
+ *             src/models/cassnat.py:465-468,482; modules/attention.py:13-24
+ * Q f32 [U, h*dk] (batch-independent: projected sinusoid rows) row stride ldq;
+ * K,V [B,T,h*dk]; seg i32 [B,T] from cn_align_to_mask; ylens i64 [B] (token counts BEFORE
+ * the +1 of align_to_mask); src_mask u8 [B,T]; src_size i64 [B]; out [B,U,h*dk]. dk == 64. */
+int cn_segment_attention_f32(const float* Q, int64_t ldq, const float* K, int64_t ldk, int64_t sbk,
+                             const float* V, int64_t ldv, int64_t sbv,
+                             const int32_t* seg, const int64_t* ylens, const uint8_t* src_mask,
+                             const int64_t* src_size, int left, int right,
+                             int64_t B, int64_t h, int64_t U, int64_t T, int64_t dk,
+                             float* out, int64_t ldo, int64_t sbo,
+                             float* vmean_ws /* f32 [B, h*dk] scratch */, cn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASSNAT_B200_H_ */

@@ -1,0 +1,92 @@
+"""CPU: the oracle (oracle/*.py) against the golden vectors generated from the unmodified
+reference (tests/golden/make_golden*.py).  Bit-exact for integer outputs."""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+import oracle.align_np as A
+import oracle.nat_torch as O
+
+
+def test_known_answer_vector(align_golden):
+    g = align_golden
+    a, yl, ym = A.best_path_align(g["kat_lp"], g["kat_mask"], 0)
+    assert a.tolist() == [[0, 0, 3, 0, 0, 2, 0, 0], [0, 1, 0, 0, 1, 0, 2, 0]]
+    assert np.array_equal(a, g["kat_bp_aligned"]) and yl.tolist() == [2, 3] and ym == 3
+    tm, yl2, ym2 = A.align_to_mask(a, yl, ym, g["kat_mask"], g["kat_src_size"], 0)
+    assert np.array_equal(tm, g["kat_trigger"]) and yl2.tolist() == [3, 4] and ym2 == 4
+    ex = A.expand_trigger_mask(tm, 1, 1) & (g["kat_mask"] != 0)
+    assert np.array_equal(ex, g["kat_expanded"])
+    va, _, _ = A.viterbi_align(g["kat_lp"], g["kat_mask"], g["kat_src_size"], g["kat_ys"], np.array([3, 3]), 0)
+    assert np.array_equal(va, g["kat_vit_aligned"])
+
+
+def test_alignment_cases(align_golden):
+    g = align_golden
+    for c in range(int(g["n_case"])):
+        p = f"c{c}_"
+        lp, mask, xl, ys, yls = g[p + "ctc_out"], g[p + "mask"], g[p + "src_size"], g[p + "ys"], g[p + "ylens"]
+        T = lp.shape[1]
+        a, yl, ym = A.best_path_align(lp, mask, 0)
+        assert np.array_equal(a, g[p + "bp_aligned"]) and np.array_equal(yl, g[p + "bp_ylen"]) and ym == int(g[p + "bp_ymax"])
+        if p + "bps_select" in g:
+            S = 3
+            rep = lambda x: np.repeat(x, S, axis=0)
+            sa, syl, sym = A.best_path_align(rep(lp), rep(mask), 0, S, 0.9, True, g[p + "bps_select"])
+            assert np.array_equal(sa, g[p + "bps_aligned"]) and np.array_equal(syl, g[p + "bps_ylen"])
+        va, _, vym = A.viterbi_align(lp, mask, xl, ys, yls, 0)
+        assert np.array_equal(va, g[p + "vit_aligned"])
+        vs, _, _ = A.viterbi_align(lp, mask, xl, ys, yls, 0, g[p + "vits_t_sample"].tolist())
+        assert np.array_equal(vs, g[p + "vits_aligned"])
+        for tag, (al, yin, ymx) in {"bp": (a, yl, ym), "vit": (va, yls, vym)}.items():
+            tm, tyl, tym = A.align_to_mask(al, yin, ymx, mask, xl, 0)
+            assert np.array_equal(tm, np.unpackbits(g[p + tag + "_trigger"], axis=-1)[..., :T].astype(bool))
+            assert np.array_equal(tyl, g[p + tag + "_trigger_ylen"])
+            for (l, r) in [(0, 1), (1, 0), (1, 1)]:
+                ex = A.expand_trigger_mask(tm, l, r) & (mask != 0)
+                assert np.array_equal(ex, np.unpackbits(g[p + tag + f"_trigger_l{l}r{r}"], axis=-1)[..., :T].astype(bool))
+            assert np.array_equal(A.target_length_mask(tyl, tym)[:, 0], g[p + tag + "_tgt_mask"][:, 0])
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-6)).item()
+
+
+def _hyps(z, tag):
+    flat, lens = z[tag + "::hyp_flat"], z[tag + "::hyp_len"]
+    out, o = [], 0
+    for n in lens:
+        out.append(flat[o:o + n].tolist())
+        o += n
+    return out
+
+
+def test_decode_port(blocks_golden):
+    name, z, sd, cfg = blocks_golden
+    src, mask, size = (torch.from_numpy(z[k]) for k in ("src", "src_mask", "src_size"))
+    for tag, (l, r) in {"greedy": (0, 0), "greedy_l1r1": (1, 1)}.items():
+        c = SimpleNamespace(**{**vars(cfg), "left_trigger": l, "right_trigger": r})
+        with torch.no_grad():
+            o = O.beam_decode(src, mask, size, sd, c)
+        for key in ("enc_h", "ctc_out", "ac_embed", "pred_embed", "dec_h", "att_out"):
+            assert _rel(o[key], z[f"{tag}::{key}"]) < 2e-5, (name, tag, key)
+        assert np.array_equal(o["aligned"], z[tag + "::aligned"])
+        T = o["trigger"].shape[-1]
+        assert np.array_equal(o["trigger"], np.unpackbits(z[tag + "::trigger"], axis=-1)[..., :T].astype(bool))
+        assert o["hyps"] == _hyps(z, tag)
+        assert np.allclose(o["scores"], z[tag + "::score"], rtol=1e-5)
+
+
+def test_train_port(blocks_golden):
+    name, z, sd, cfg = blocks_golden
+    enc_h = torch.from_numpy(z["train::enc_h"])
+    x_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2]
+    o = O.train_forward_from_encoder(enc_h, x_mask, torch.from_numpy(z["train::frames"]),
+                                     torch.from_numpy(z["train::labels"]), torch.from_numpy(z["train::label_sizes"]),
+                                     sd, cfg)
+    assert np.array_equal(o["aligned"], z["train::aligned"])
+    assert _rel(o["ctc_out"], z["train::ctc_out"]) < 2e-5 and _rel(o["att_out"], z["train::att_out"]) < 2e-5
+    for k in ("loss", "ctc_loss", "att_loss"):
+        assert abs(float(o[k]) - float(z["train::" + k])) < 1e-4 * max(1.0, abs(float(z["train::" + k])))

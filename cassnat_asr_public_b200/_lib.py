@@ -36,6 +36,9 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "cn_segment_attention_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int,
                                         _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "cn_conv_module_workspace_bytes": (_i64, [_i64, _i64]),
+    "cn_glu_dwconv_groupnorm_act": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _int, _i64, _i64, _i64, _i64,
+                                           _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,305 @@
+"""`CassNAT` and `make_model` with the reference's surface (src/models/cassnat.py:21-89, 115-637):
+same sub-module attribute names (src_embed, encoder, acembed_extractor, embed_mapper, decoder,
+ctc_generator, att_generator, pe), same state_dict keys, same helper-method signatures and the same
+`beam_decode(...) -> (batch_top_seqs, args)` contract — executing the alignment-conditioned path
+(everything after `enc_h`) on the sm_100a kernels of libcassnat_b200.so.
+
+What is different in HOW: the CTC posteriors are never materialised in decoding (the head GEMM is
+followed by one row-statistics pass), the trigger mask is never materialised (segment ids drive
+the extractor), the MAD memory K/V projections of all layers are one GEMM, and the B x U Python
+`.item()` pick loop (cassnat.py:574-637) is one device pass + one device->host copy.
+"""
+import copy
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import blocks as BK
+from . import modules as MD
+from . import ops
+
+
+def create_pe(d_model, max_len=5000):
+    """cassnat.py:91-99"""
+    pe = torch.zeros(max_len, d_model, requires_grad=False)
+    position = torch.arange(0., max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0., d_model, 2) * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+class Generator(nn.Module):
+    """cassnat.py:101-113: linear + log-softmax (full log-probabilities on request only)."""
+
+    def __init__(self, d_model, vocab, add_norm=False):
+        super().__init__()
+        self.proj = nn.Linear(d_model, vocab)
+        self.add_norm = add_norm
+        if add_norm:
+            self.norm = MD.LayerNorm(d_model)
+
+    def logits(self, x, T=1.0):
+        if self.add_norm:
+            x = self.norm(x)
+        return ops.linear(x, self.proj.weight, self.proj.bias, alpha=1.0 / T)
+
+    def forward(self, x, T=1.0):
+        z = self.logits(x, T)
+        ops.row_stats(z, lse=True, logp_out=z)      # in-place log-softmax
+        return z
+
+    def greedy(self, x, want_top2=False):
+        """argmax id, its log-probability (and runner-up id) per row without writing log-probs."""
+        st = ops.row_stats(self.logits(x), top2=want_top2, peak=True, lse=True)
+        st["logp"] = st["peak"] - st["lse"]
+        return st
+
+
+def make_model(input_size, args):
+    """cassnat.py:21-89 (same args attributes read, same args mutations, same initialisation)."""
+    c = copy.deepcopy
+    if args.use_conv_enc:
+        assert args.pos_type == "relative", "conformer must use relative positional encoding"
+        enc_position = MD.RelativePositionalEncoding(args.d_model, args.dropout, args.enc_max_relative_len)
+        enc_attn = MD.RelMultiHeadedAttention(args.n_head, args.d_model, args.dropout)
+        enc_conv = MD.ConvModule(args.d_model, args.enc_kernel_size, activation=MD.Swish())
+        enc_ff = MD.PositionwiseFeedForward(args.d_model, args.d_encff, args.dropout, activation=MD.Swish())
+        encoder = BK.ConEncoder(args.d_model, c(enc_ff), enc_attn, enc_conv, c(enc_ff), args.dropout, args.N_enc,
+                                args.pos_type, args.share_ff)
+    else:
+        assert args.model_type == "transformer"
+        attn = MD.MultiHeadedAttention(args.n_head, args.d_model)
+        ff = MD.PositionwiseFeedForward(args.d_model, args.d_encff, args.dropout)
+        enc_position = MD.PositionalEncoding(args.d_model, args.dropout)
+        encoder = BK.TrfEncoder(args.d_model, c(attn), c(ff), args.dropout, args.N_enc)
+
+    if args.use_conv_dec:
+        self_attn = MD.RelMultiHeadedAttention(args.n_head, args.d_model, args.dropout)
+        src_attn = MD.MultiHeadedAttention(args.n_head, args.d_model, args.dropout)
+        conv = MD.ConvModule(args.d_model, args.dec_kernel_size, activation=MD.Swish())
+        position = MD.RelativePositionalEncoding(args.d_model, args.dropout, args.dec_max_relative_len)
+        ff = MD.PositionwiseFeedForward(args.d_model, args.d_decff, args.dropout, activation=MD.Swish())
+        ff_extra = MD.PositionwiseFeedForward(args.d_model, args.d_ff, args.dropout, activation=MD.Swish())
+        extra = BK.ConAcExtra(args.d_model, c(src_attn), ff_extra, position, args.pos_type, args.dropout, args.N_extra)
+        sad = BK.ConSAD(args.d_model, c(ff), c(self_attn), c(conv), c(ff), args.dropout, args.N_self_dec,
+                        args.pos_type, args.share_ff)
+        mad = BK.ConMAD(args.d_model, c(ff), c(self_attn), c(conv), c(src_attn), c(ff), args.dropout, args.N_mix_dec,
+                        args.pos_type, args.share_ff)
+    else:
+        ff = MD.PositionwiseFeedForward(args.d_model, args.d_decff, args.dropout)
+        attn = MD.MultiHeadedAttention(args.n_head, args.d_model, args.dropout)
+        extra = BK.TrfAcExtra(args.d_model, c(attn), c(ff), args.dropout, args.N_extra)
+        sad = BK.TrfSAD(args.d_model, c(attn), c(ff), args.dropout, args.N_self_dec)
+        mad = BK.TrfMAD(args.d_model, c(attn), c(attn), c(ff), args.dropout, args.N_mix_dec)
+
+    gen = Generator(args.d_model, args.vocab_size)
+    interctc_gen = Generator(args.d_model, args.vocab_size, add_norm=True) if args.interctc_alpha > 0 else None
+    interce_gen = Generator(args.d_model, args.vocab_size, add_norm=True) if args.interce_alpha > 0 else None
+    model = CassNAT(MD.ConvEmbedding(input_size, args.d_model, args.dropout, enc_position), encoder, extra, sad, mad,
+                    c(gen), c(gen), create_pe(args.d_model), interctc_gen, interce_gen, args)
+
+    if args.interce_alpha > 0:
+        if args.interce_layer <= args.N_self_dec:
+            args.selfce_alpha, args.mixce_alpha = args.interce_alpha, 0
+        else:
+            args.selfce_alpha, args.mixce_alpha = 0, args.interce_alpha
+            args.interce_layer = args.interce_layer - args.N_self_dec
+    else:
+        args.selfce_alpha = args.mixce_alpha = 0
+    for p in model.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_uniform_(p)
+    return model
+
+
+class CassNAT(nn.Module):
+    def __init__(self, src_embed, encoder, acembed_extractor, embed_mapper, decoder, ctc_gen, att_gen, pe,
+                 interctc_gen, interce_gen, args):
+        super().__init__()
+        self.src_embed = src_embed
+        self.encoder = encoder
+        self.acembed_extractor = acembed_extractor
+        self.embed_mapper = embed_mapper
+        self.decoder = decoder
+        self.ctc_generator = ctc_gen
+        self.att_generator = att_gen
+        self.pe = pe                       # plain tensor attribute like the reference (not in state_dict)
+        if interctc_gen is not None:
+            self.interctc_generator = interctc_gen
+        if interce_gen is not None:
+            self.interce_generator = interce_gen
+        self._conformer_dec = isinstance(acembed_extractor, BK.ConAcEmbedExtractor)
+
+    # ------------------------------------------------------------------ helper methods (public API)
+    def expand_trigger_mask(self, trigger_mask, left_trigger, right_trigger):
+        return ops.expand_trigger_mask(trigger_mask, left_trigger, right_trigger)
+
+    def viterbi_align(self, ctc_out, src_mask, src_size, ys, ylens, blank, sample_topk):
+        return ops.viterbi_align(ctc_out, src_mask, src_size, ys, ylens, blank, sample_topk)
+
+    def align_to_mask(self, aligned_seq_shift, ylens, ymax, src_mask, src_size, blank):
+        return ops.align_to_mask(aligned_seq_shift, ylens, ymax, src_mask, src_size, blank)
+
+    def best_path_align(self, ctc_out, src_mask, src_size, blank, sample_num=0, threshold=0.9, include_best=True):
+        return ops.best_path_align(ctc_out, src_mask, src_size, blank, sample_num, threshold, include_best)
+
+    def subsequent_mask(self, size):
+        ret = torch.ones(size, size, dtype=torch.uint8)
+        return torch.tril(ret, out=ret).unsqueeze(0)
+
+    def _pe_rows(self, like, n):
+        if self.pe.device != like.device or self.pe.dtype != like.dtype:
+            self.pe = self.pe.to(device=like.device, dtype=like.dtype)
+        return self.pe[:n]
+
+    # ------------------------------------------------------------------ the accelerated path
+    def encode(self, src, x_mask):
+        """src_embed + encoder (cassnat.py:431-432) -> enc_h [B,T,d], src_mask [B,1,T]."""
+        x, src_mask = self.src_embed(src, x_mask)
+        return self.encoder(x, src_mask), src_mask
+
+    def decode_from_encoder(self, enc_h, src_mask, src_size, vocab, args, lm_model=None, labels=None,
+                            label_sizes=None, return_intermediates=False):
+        """Everything CassNAT.beam_decode does after the encoder (cassnat.py:433-637).
+        src_size is the length RATIO tensor the reference takes (frames = (ratio*T).long(), :436)."""
+        if args.lm_weight > 0 or args.beam_width != 1:
+            raise NotImplementedError("token-level LM fusion / beam_width > 1 (cassnat.py:600-636) is outside the "
+                                      "single-step path this package accelerates")
+        if getattr(args, "test_hitrate", False):
+            raise NotImplementedError("test_hitrate diagnostic (cassnat.py:438-462) is not provided")
+        sos, blank = vocab.word2index["sos"], vocab.word2index["blank"]
+        B, T, d = enc_h.shape
+        dev = enc_h.device
+        S = args.sample_num if (args.use_trigger and args.sample_num > 1) else 1
+        mask2 = src_mask.reshape(B, T)
+        frames = (src_size.to(dev) * T).long()                                       # :436 / :471
+        keep = {}
+
+        # ---- K1 + K2: CTC head -> per-frame argmax/top-2 -> collapsed, shifted alignment
+        if args.use_trigger and args.decode_type == "oracle_att":
+            ctc_out = self.ctc_generator(enc_h)
+            aligned, ylen, ymax = ops.viterbi_align(ctc_out, src_mask, frames, labels[:, 1:-1].to(dev),
+                                                    label_sizes.to(dev), blank, 0)
+        elif args.use_trigger and args.decode_type == "ctc_att":
+            raise NotImplementedError("decode_type='ctc_att' raises TypeError in the reference (cassnat.py:413)")
+        else:
+            st = self.ctc_generator.greedy(enc_h, want_top2=S > 1)
+            aligned, ylen, ymax = self._collapse(st, mask2, B, T, S, blank, args.threshold if S > 1 else 0.9)
+        if S > 1:                                                                      # :441-445
+            rep = lambda x: x.repeat_interleave(S, 0)
+            enc_h, src_mask, mask2, frames = rep(enc_h), rep(src_mask), rep(mask2), rep(frames)
+        BS = B * S
+
+        # ---- K4/K5: segment ids (trigger mask stays implicit), ylen+1, target-length mask
+        if args.use_trigger:
+            _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
+                                                   want_seg=True)
+            seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
+            dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
+                                                      args.left_trigger, args.right_trigger, True)[0]
+        else:                                                                          # :470-473
+            seg_ctx = None
+        tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)            # [BS,1,U]
+
+        # ---- K6: token acoustic extractor
+        pe_rows = self._pe_rows(enc_h, ymax)
+        if seg_ctx is not None:
+            ac_embed = self.acembed_extractor.forward_segments(pe_rows, enc_h, seg_ctx, dense_trigger)
+        else:
+            ac_embed = self.acembed_extractor(pe_rows.unsqueeze(0).repeat(BS, 1, 1), enc_h, src_mask)
+        # ---- K7: SAD
+        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
+        if getattr(args, "save_embedding", False) and S == 1:
+            first = lambda x: x[0] if isinstance(x, tuple) else x
+            args.ac_embed, args.pred_embed = first(ac_embed)[0].cpu(), first(pred_embed)[0].cpu()
+        # ---- K8: MAD
+        if args.use_unimask:                                                           # :486-489
+            pos = None
+            if isinstance(pred_embed, tuple):
+                pred_embed, pos = pred_embed
+            pred_embed = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
+            causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=dev)).unsqueeze(0)
+            dec_mask = tgt_mask & causal
+            if pos is not None:
+                pred_embed = (pred_embed, pos)
+        else:
+            dec_mask = tgt_mask
+        mem_mask = dense_trigger() if (args.src_trigger and seg_ctx is not None) else src_mask
+        dec_h = self.decoder(pred_embed, enc_h, mem_mask, dec_mask)
+        # ---- K9: output head + greedy pick
+        st = self.att_generator.greedy(dec_h)
+        ids, logp = st["top1"], st["logp"]                                             # [BS,U]
+        if return_intermediates:
+            first = lambda x: x[0] if isinstance(x, tuple) else x
+            keep.update(aligned=aligned, seg=seg_ctx[0] if seg_ctx else None, ylen=ylen, ymax=ymax,
+                        ac_embed=first(ac_embed), pred_embed=first(pred_embed), dec_h=dec_h, ids=ids, logp=logp)
+        if S > 1:
+            ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
+            keep["best_sample"] = best
+        # ---- hypothesis assembly (cassnat.py:574-637 for beam_width 1): one D2H copy
+        ids_h, logp_h, ylen_h = ids.cpu(), logp.double().cpu(), ylen.cpu()
+        ys0 = torch.ones(1, 1).fill_(sos).long()
+        if getattr(args, "use_gpu", False):
+            ys0 = ys0.to(dev)
+        out = []
+        for b in range(B):
+            n = min(int(ylen_h[b]) + 1, ymax)          # the reference keeps i <= ylen[b] (one past eos)
+            score = 0.0
+            for s_ in logp_h[b, :n].tolist():
+                score = score + s_
+            out.append([{"ys": ys0, "score": score if n else 0.0, "hyp": [sos] + ids_h[b, :n].tolist()}])
+        if return_intermediates:
+            return out, args, keep
+        return out, args
+
+    def _collapse(self, st, mask2, B, T, S, blank, threshold):
+        dev = mask2.device
+        top1, top2, peak, select = st["top1"], st.get("top2"), None, None
+        if S > 1:
+            # same CPU-generator draw as cassnat.py:373, on the [B*S, T] replicated batch
+            select = torch.randint(0, 2, (B * S, T, 1)).to(torch.uint8).reshape(B * S, T).to(dev, non_blocking=True)
+            rep = lambda x: x.reshape(B, T).repeat_interleave(S, 0).contiguous()
+            top1, top2, peak = rep(top1), rep(top2), rep(st["logp"])
+            mask2 = mask2.repeat_interleave(S, 0)
+        mask8 = (mask2 != 0).to(torch.uint8).contiguous()
+        BS = B * S
+        aligned = torch.empty(BS, T, dtype=torch.int64, device=dev)
+        ylen = torch.empty(BS, dtype=torch.int64, device=dev)
+        ymax = torch.empty(1, dtype=torch.int32, device=dev)
+        from ._lib import call, ptr, stream
+        call("cn_bestpath_collapse", ptr(top1.contiguous()), ptr(top2), ptr(peak), ptr(select), ptr(mask8), BS, T,
+             int(blank), int(S if S > 1 else 0), float(threshold), 1, ptr(aligned), ptr(ylen), ptr(ymax), stream())
+        return aligned, ylen, int(ymax.item())          # the one host sync the API needs (cassnat.py:387)
+
+    def _rescore(self, ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax):
+        """cassnat.py:499-561 with rank_model in {'lm','at_baseline'-style callable}: the ranker is a
+        stock PyTorch module supplied by the caller; K11 = gather/mean/argmax."""
+        if args.rank_model != "lm":
+            raise NotImplementedError(f"rank_model={args.rank_model!r}")
+        ids64 = ids.long()
+        lm_in = torch.cat([torch.full((B * S, 1), sos, dtype=torch.long, device=ids.device), ids64[:, :-1]], 1)
+        causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=ids.device)).unsqueeze(0)
+        lm_out = lm_model(lm_in, (tgt_mask & causal).long())
+        valid = tgt_mask.reshape(B, S, ymax) != 0
+        sc = torch.gather(lm_out, -1, ids64.unsqueeze(-1)).squeeze(-1).reshape(B, S, ymax).masked_fill(~valid, 0)
+        mean = sc.sum(-1) / (sc != 0).sum(-1).float()
+        best = mean.max(-1, keepdim=True)[1]                                            # [B,1]
+        pick = lambda x: x.reshape(B, S, -1).gather(1, best.unsqueeze(-1).expand(B, 1, x.shape[-1])).squeeze(1)
+        # the reference zeroes att_out beyond ylen before picking (:536) -> id 0 / score 0 there
+        ids = pick(ids.masked_fill(tgt_mask.squeeze(1) == 0, 0))
+        logp = pick(logp.masked_fill(tgt_mask.squeeze(1) == 0, 0.0))
+        ylen = ylen.reshape(B, S).gather(1, best).squeeze(1)
+        return ids, logp, ylen, int(ylen.max().item()), best.squeeze(1)
+
+    def beam_decode(self, src, x_mask, src_size, vocab, args, lm_model=None, ctc_top_seqs=None, labels=None,
+                    label_sizes=None):
+        """cassnat.py:420-637 -> (batch_top_seqs, args)."""
+        with torch.no_grad():
+            enc_h, src_mask = self.encode(src, x_mask)
+            return self.decode_from_encoder(enc_h, src_mask, src_size, vocab, args, lm_model, labels, label_sizes)
+
+    def forward(self, src, src_mask, src_size, tgt_label, label_sizes, args):
+        raise NotImplementedError("training forward (cassnat.py:136-257) lands with the CTC-loss / backward kernels")

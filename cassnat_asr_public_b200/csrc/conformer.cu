@@ -1,0 +1,114 @@
+// Conformer convolution module core (modules/conformer_related.py:29-41), between the two
+// pointwise convolutions (which are GEMMs): GLU over channels -> depthwise conv along the token
+// axis -> GroupNorm(1, C) over the whole [C, L] slab of each utterance -> activation.
+// Note the reference normalises over the PADDED length L of the batch (it passes no mask), so the
+// statistics include padding rows; this kernel reproduces that.
+#include "common.cuh"
+
+namespace {
+constexpr int TL = 32;     // token rows per CTA
+constexpr int CC = 256;    // channels per pass (one per thread)
+
+// pass 1: z = dwconv(glu(y)) + per-CTA partial (sum, sum of squares) in double
+__global__ void __launch_bounds__(CC) glu_dwconv_kernel(const float* __restrict__ y, int64_t ldy, int64_t sby,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int L, int C, int ksz, float* __restrict__ z,
+                                                        double* __restrict__ partial) {
+  extern __shared__ float g[];                      // [(TL + ksz - 1)][CC]
+  const int b = blockIdx.y, l0 = blockIdx.x * TL, pad = (ksz - 1) / 2;
+  const int rows = TL + ksz - 1;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    const int c = c0 + threadIdx.x;
+    for (int r = 0; r < rows; ++r) {
+      const int l = l0 - pad + r;
+      float v = 0.f;
+      if (c < C && l >= 0 && l < L) {
+        const float* row = y + (int64_t)b * sby + (int64_t)l * ldy;
+        const float a = row[c], gate = row[C + c];
+        v = a * (1.f / (1.f + expf(-gate)));        // F.glu: first half * sigmoid(second half)
+      }
+      g[r * CC + threadIdx.x] = v;
+    }
+    // each thread only reads back its own column -> no barrier needed
+    if (c < C) {
+      const float bc = bias ? bias[c] : 0.f;
+      for (int i = 0; i < TL && l0 + i < L; ++i) {
+        float acc = bc;
+        for (int k = 0; k < ksz; ++k) acc = fmaf(w[c * ksz + k], g[(i + k) * CC + threadIdx.x], acc);
+        z[((int64_t)b * L + (l0 + i)) * C + c] = acc;
+        s1 += acc;
+        s2 = fmaf(acc, acc, s2);
+      }
+    }
+  }
+  __shared__ double red[2][CC / 32];
+  double d1 = s1, d2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d1; red[1][threadIdx.x >> 5] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < CC / 32; ++i) { t1 += red[0][i]; t2 += red[1][i]; }
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 0] = t1;
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = t2;
+  }
+}
+
+// pass 2: GroupNorm(1,C) affine + activation, in place
+__global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ z, const double* __restrict__ partial,
+                                                            int nblk, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, int act, int L,
+                                                            int C) {
+  const int b = blockIdx.y;
+  double t1 = 0, t2 = 0;
+  for (int i = 0; i < nblk; ++i) { t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1]; }
+  const double n = (double)L * C;
+  const double mean = t1 / n;
+  double var = t2 / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
+  const int64_t total = (int64_t)L * C;
+  float* zb = z + (int64_t)b * total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = (zb[i] - mu) * rstd * gamma[c] + beta[c];
+    if (act == CN_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == CN_ACT_SWISH) v = v / (1.f + expf(-v));
+    zb[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L) {
+  return B * ((L + TL - 1) / TL) * 2 * (int64_t)sizeof(double);
+}
+
+extern "C" int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t sby, const float* dw_weight,
+                                           const float* dw_bias, const float* gamma, const float* beta, float eps,
+                                           int act, int64_t B, int64_t L, int64_t C, int64_t ksz, float* out,
+                                           void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
+  if (!y || !dw_weight || !gamma || !beta || !out || !workspace || B < 0 || L <= 0 || C <= 0) return CN_ERR_BAD_ARG;
+  if (ksz < 1 || (ksz & 1) == 0 || ksz > 63 || ldy < 2 * C || B > 65535) return CN_ERR_UNSUPPORTED;
+  if (workspace_bytes < cn_conv_module_workspace_bytes(B, L)) return CN_ERR_WORKSPACE;
+  if (B == 0) return CN_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nblk = (int)((L + TL - 1) / TL);
+  const size_t smem = (size_t)(TL + ksz - 1) * CC * sizeof(float);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(glu_dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  glu_dwconv_kernel<<<dim3(nblk, (unsigned)B), CC, smem, stream>>>(y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C,
+                                                                   (int)ksz, out, (double*)workspace);
+  CN_CHECK_LAUNCH();
+  int gx = (int)((L * C + 255) / 256);
+  if (gx > 148 * 4) gx = 148 * 4;
+  groupnorm_act_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(out, (const double*)workspace, nblk, gamma, beta, eps,
+                                                                  act, (int)L, (int)C);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}

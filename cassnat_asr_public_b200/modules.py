@@ -1,0 +1,272 @@
+"""Leaf modules of the CASS-NAT decoder side, mirroring the names, constructor arguments and
+parameter names of the reference's `src/models/modules/*` so that a reference `state_dict` loads
+unchanged, with every forward running on the sm_100a kernels behind include/cassnat_b200.h.
+
+Reference interfaces mirrored (paths relative to /root/reference/src/models/modules):
+  LayerNorm                     norm.py:6-18
+  MultiHeadedAttention          attention.py:26-66
+  RelMultiHeadedAttention       attention.py:68-147
+  PositionwiseFeedForward       positionff.py:6-16
+  SublayerConnection            utils.py:13-32
+  ConvModule, Swish             conformer_related.py:10-44
+  PositionalEncoding, RelativePositionalEncoding, ConvEmbedding   embedding.py:10-124
+
+Inference only for now: modules raise in training mode with dropout > 0 (the kernels have no
+dropout), and tensors must live on a CUDA device (no CPU fallback).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _cat_cached(owner, key, tensors, dim=0):
+    """Concatenation of parameters, rebuilt only when one of them changed (fused QKV weights)."""
+    stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+    cache = owner.__dict__.setdefault("_cn_cache", {})
+    hit = cache.get(key)
+    if hit is None or hit[0] != stamp:
+        with torch.no_grad():
+            hit = (stamp, torch.cat([t.detach() for t in tensors], dim).contiguous())
+        cache[key] = hit
+    return hit[1]
+
+
+def _no_dropout(mod, p):
+    if mod.training and p > 0:
+        raise NotImplementedError("cassnat_asr_public_b200 kernels implement no dropout: call .eval() or use dropout=0")
+
+
+class Swish(nn.Module):
+    act_name = "swish"
+
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+def _act_name(activation):
+    if isinstance(activation, str) or activation is None:
+        return activation
+    if isinstance(activation, nn.ReLU):
+        return "relu"
+    if getattr(activation, "act_name", None) == "swish" or type(activation).__name__ == "Swish":
+        return "swish"
+    raise NotImplementedError(f"activation {activation!r}")
+
+
+class LayerNorm(nn.Module):
+    def __init__(self, features, eps=1e-6):
+        super().__init__()
+        self.a_2 = nn.Parameter(torch.ones(features))
+        self.b_2 = nn.Parameter(torch.zeros(features))
+        self.eps = eps
+
+    def forward(self, x):
+        return ops.layer_norm(x, self.a_2, self.b_2, self.eps)
+
+
+class PositionwiseFeedForward(nn.Module):
+    def __init__(self, d_model, d_ff, dropout=0.1, activation=nn.ReLU()):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, d_ff)
+        self.w_2 = nn.Linear(d_ff, d_model)
+        self.p_drop = dropout
+        self.activation = activation
+
+    def forward(self, x, residual=None, scale=1.0):
+        """w_2(act(w_1 x)); with `residual` the pre-norm residual add (and the conformer's 1/2
+        scale) is fused into the second GEMM's epilogue."""
+        _no_dropout(self, self.p_drop)
+        hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation))
+        return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale)
+
+
+class SublayerConnection(nn.Module):
+    def __init__(self, size, dropout):
+        super().__init__()
+        self.norm = LayerNorm(size)
+        self.p_drop = dropout
+
+    def forward(self, x, sublayer, scale=1.0, has_cache=False):
+        _no_dropout(self, self.p_drop)
+        residual = x[:, -1:, :] if has_cache else x
+        y = sublayer(self.norm(x))
+        return residual + scale * y
+
+
+class MultiHeadedAttention(nn.Module):
+    def __init__(self, h, d_model, dropout=0.1):
+        super().__init__()
+        assert d_model % h == 0
+        self.d_k = d_model // h
+        self.h = h
+        self.linears = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(4)])
+        self.attn = None
+        self.p_drop = dropout
+
+    # -- pieces the fused decode plan reuses --------------------------------------------
+    def project_q(self, x):
+        return ops.linear(x, self.linears[0].weight, self.linears[0].bias)
+
+    def project_kv(self, memory):
+        """One GEMM for K and V: [B,T,2d]; returns the two strided views."""
+        w = _cat_cached(self, "kv_w", [self.linears[1].weight, self.linears[2].weight])
+        b = _cat_cached(self, "kv_b", [self.linears[1].bias, self.linears[2].bias])
+        kv = ops.linear(memory, w, b)
+        d = self.h * self.d_k
+        return kv[..., :d], kv[..., d:]
+
+    def project_qkv(self, x):
+        w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
+        b = _cat_cached(self, "qkv_b", [l.bias for l in self.linears[:3]])
+        qkv = ops.linear(x, w, b)
+        d = self.h * self.d_k
+        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+
+    def output(self, ctx, residual=None, scale=1.0, res_rows=0):
+        return ops.linear(ctx, self.linears[3].weight, self.linears[3].bias, residual=residual, alpha=scale,
+                          res_rows=res_rows)
+
+    def forward(self, query, key, value, mask=None, pos_embed=None):
+        _no_dropout(self, self.p_drop)
+        if query is key and key is value:
+            q, k, v = self.project_qkv(query)
+        elif key is value:
+            q = self.project_q(query)
+            k, v = self.project_kv(key)
+        else:
+            q = self.project_q(query)
+            k = ops.linear(key, self.linears[1].weight, self.linears[1].bias)
+            v = ops.linear(value, self.linears[2].weight, self.linears[2].bias)
+        return self.output(ops.attention(q, k, v, mask, self.h))
+
+
+class RelMultiHeadedAttention(nn.Module):
+    def __init__(self, h, d_model, dropout=0.1):
+        super().__init__()
+        assert d_model % h == 0
+        self.d_k = d_model // h
+        self.h = h
+        self.linears = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(4)])
+        self.linear_pos = nn.Linear(d_model, d_model, bias=False)
+        self.pos_bias_u = nn.Parameter(torch.empty(h, self.d_k))
+        self.pos_bias_v = nn.Parameter(torch.empty(h, self.d_k))
+        nn.init.xavier_uniform_(self.pos_bias_u)
+        nn.init.xavier_uniform_(self.pos_bias_v)
+        self.attn = None
+        self.p_drop = dropout
+
+    project_qkv = MultiHeadedAttention.project_qkv
+    output = MultiHeadedAttention.output
+
+    def forward(self, query, key, value, mask=None, pos_embed=None):
+        """pos_embed: [2L-1, d] rows of the clamped relative-position table (what
+        RelativePositionalEncoding returns).  Only 2m+1 of them are distinct; the kernel works on
+        those, recovered from the first, middle-run and last rows."""
+        _no_dropout(self, self.p_drop)
+        assert query is key and key is value, "relative attention is self-attention in CASS-NAT"
+        L = query.size(1)
+        assert pos_embed.size(0) == 2 * L - 1
+        table, m = distinct_rel_rows(pos_embed, L)
+        rel_pos = ops.linear(table, self.linear_pos.weight)
+        q, k, v = self.project_qkv(query)
+        ctx = ops.attention(q, k, v, mask, self.h, (rel_pos, self.pos_bias_u, self.pos_bias_v, m))
+        return self.output(ctx)
+
+
+def distinct_rel_rows(pos_embed, L):
+    """pos_embed[i] = E[clamp(i-(L-1), -m, m) + m] (embedding.py:52-60).  Returns a [2m'+1, d]
+    table with table[clamp(r,-m',m')+m'] == pos_embed[r+L-1] for all |r| <= L-1, m' = min(m, L-1).
+    A `_cn_table` attribute set by RelativePositionalEncoding short-cuts the reconstruction."""
+    tagged = getattr(pos_embed, "_cn_table", None)
+    if tagged is not None:
+        return tagged
+    # generic path: any window of 2(L-1)+1 consecutive offsets is itself a valid clamped table
+    return pos_embed.contiguous(), L - 1
+
+
+class RelativePositionalEncoding(nn.Module):
+    def __init__(self, d_model, dropout, max_relative_len=10):
+        super().__init__()
+        self.max_relative_len = max_relative_len
+        n = 2 * max_relative_len + 1
+        pe = torch.zeros(n, d_model)
+        pos = torch.arange(0., n).unsqueeze(1)
+        div = torch.exp(torch.arange(0., d_model, 2) * -(math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.embedding = nn.Embedding.from_pretrained(pe, freeze=True)
+        self.p_drop = dropout
+        self.d_model = d_model
+
+    def forward(self, x):
+        _no_dropout(self, self.p_drop)
+        L, m = x.size(1), self.max_relative_len
+        idx = torch.arange(-(L - 1), L, device=x.device).clamp(-m, m) + m
+        pos = self.embedding.weight.detach()[idx]
+        mm = min(m, L - 1)
+        pos._cn_table = (self.embedding.weight.detach()[m - mm:m + mm + 1].contiguous(), mm)
+        return (x, pos)
+
+
+class PositionalEncoding(nn.Module):
+    def __init__(self, d_model, dropout, max_len=5000):
+        super().__init__()
+        self.d_model = d_model
+        self.p_drop = dropout
+        pe = torch.zeros(max_len, d_model)
+        pos = torch.arange(0., max_len).unsqueeze(1)
+        div = torch.exp(torch.arange(0., d_model, 2) * -(math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):
+        _no_dropout(self, self.p_drop)
+        return x + self.pe[:, :x.size(1)]
+
+
+class ConvModule(nn.Module):
+    def __init__(self, channels, kernel_size, activation=nn.ReLU(), bias=True):
+        super().__init__()
+        self.pointwise_conv1 = nn.Conv1d(channels, 2 * channels, kernel_size=1, stride=1, padding=0, bias=bias)
+        self.depthwise_conv = nn.Conv1d(channels, channels, kernel_size, stride=1, padding=(kernel_size - 1) // 2,
+                                        groups=channels, bias=bias)
+        self.norm = nn.GroupNorm(1, channels)
+        self.pointwise_conv2 = nn.Conv1d(channels, channels, kernel_size=1, stride=1, padding=0, bias=bias)
+        self.activation = activation
+
+    def forward(self, x, residual=None):
+        """x [B,L,C] -> [B,L,C]: pointwise conv (a GEMM over channels) + GLU, depthwise conv,
+        GroupNorm(1,C) over the whole [C,L] slab of each utterance, Swish, pointwise conv."""
+        C = x.size(-1)
+        y = ops.linear(x, self.pointwise_conv1.weight.view(2 * C, C), self.pointwise_conv1.bias)
+        y = ops.glu_dwconv_groupnorm_act(y, self.depthwise_conv.weight, self.depthwise_conv.bias,
+                                         self.norm.weight, self.norm.bias, self.norm.eps, _act_name(self.activation))
+        return ops.linear(y, self.pointwise_conv2.weight.view(C, C), self.pointwise_conv2.bias, residual=residual)
+
+
+class ConvEmbedding(nn.Module):
+    """Encoder front-end (embedding.py:89-124).  UPSTREAM of the accelerated path:
+    kept as stock torch ops so that `beam_decode(src, ...)` stays a drop-in; not part of the
+    measured alignment-conditioned path."""
+
+    def __init__(self, input_size, d_model, dropout, pos_enc, causal=False):
+        super().__init__()
+        assert not causal, "causal front-end is not used by CASS-NAT"
+        self.conv = nn.Sequential(nn.Conv2d(1, d_model, 3, 2, 1), nn.ReLU(), nn.Conv2d(d_model, d_model, 3, 2, 1), nn.ReLU())
+        self.d_model = d_model
+        self.linear_out = nn.Linear(d_model * (((input_size - 1) // 2) // 2 + 1), d_model)
+        self.pos_enc = pos_enc
+
+    def forward(self, x, mask):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 like the reference CPU path
+            x = self.conv(x.unsqueeze(1))
+        b, c, t, f = x.size()
+        x = ops.linear(x.transpose(1, 2).contiguous().view(b, t, c * f), self.linear_out.weight, self.linear_out.bias,
+                       alpha=math.sqrt(self.d_model))
+        x = self.pos_enc(x)
+        mask = mask[:, :, ::2][:, :, ::2] if mask.size(1) == 1 else mask[:, ::2, ::2][:, ::2, ::2]
+        return x, mask

@@ -234,3 +234,18 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
          int(left > 0), int(right > 0), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
          ptr(vmean), stream())
     return out
+
+
+def glu_dwconv_groupnorm_act(y, dw_weight, dw_bias, gamma, beta, eps, act):
+    """Core of the conformer ConvModule (conformer_related.py:33-38) on y [B,L,2C] -> [B,L,C]."""
+    require_cuda(y)
+    B, L, C2 = y.shape
+    C = C2 // 2
+    assert y.stride(-1) == 1
+    ksz = dw_weight.shape[-1]
+    out = torch.empty(B, L, C, dtype=torch.float32, device=y.device)
+    ws_bytes = _lib.load().cn_conv_module_workspace_bytes(B, L)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=y.device)
+    call("cn_glu_dwconv_groupnorm_act", ptr(y), y.stride(1), y.stride(0), ptr(dw_weight.reshape(C, ksz).contiguous()),
+         ptr(dw_bias), ptr(gamma), ptr(beta), float(eps), ACT[act], B, L, C, ksz, ptr(out), ptr(ws), ws_bytes, stream())
+    return out

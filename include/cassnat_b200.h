@@ -179,6 +179,18 @@ int cn_segment_attention_f32(const float* Q, int64_t ldq, const float* K, int64_
                              float* out, int64_t ldo, int64_t sbo,
                              float* vmean_ws /* f32 [B, h*dk] scratch */, cn_stream_t stream);
 
+/* Conformer convolution-module core between the two pointwise convolutions (which are GEMMs):
+ * GLU over channels -> depthwise conv (odd kernel <= 63, zero padding) along the token axis ->
+ * GroupNorm(1,C) over the whole padded [C,L] slab of each utterance -> activation.
+ *   replaces: F.glu / depthwise_conv / GroupNorm / Swish      src/models/modules/conformer_related.py:33-38
+ * y f32 [B,L,2C] (row stride ldy, batch stride sby) = pointwise_conv1 output; dw_weight [C,ksz];
+ * out f32 [B,L,C] contiguous.  workspace: cn_conv_module_workspace_bytes(B,L). */
+int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L);
+int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t sby, const float* dw_weight,
+                                const float* dw_bias, const float* gamma, const float* beta, float eps, int act,
+                                int64_t B, int64_t L, int64_t C, int64_t ksz, float* out,
+                                void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,118 @@
+"""GPU parity of the CassNAT mirror (make_model / beam_decode / decode_from_encoder) against the
+fixtures produced by the unmodified reference (tests/golden/blocks_*.npz): alignments and token ids
+bit-exact, embeddings within rel 1e-4 (north_star: 1e-3 in fp32)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from cassnat_asr_public_b200.cassnat import make_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+VOCAB = SimpleNamespace(word2index={"sos": 1, "eos": 2, "blank": 0})
+TOL = 1e-4
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-9)).item()
+
+
+def build(sd, cfg, **over):
+    args = SimpleNamespace(**{**vars(cfg), **over})
+    model = make_model(16, args)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("pos_enc.pe") for k in missing), missing
+    return model.to(DEV).eval(), args
+
+
+def hyps_of(z, tag):
+    flat, lens = z[tag + "::hyp_flat"], z[tag + "::hyp_len"]
+    out, o = [], 0
+    for n in lens:
+        out.append(flat[o:o + n].tolist())
+        o += n
+    return out
+
+
+def test_state_dict_names_match_reference(blocks_golden):
+    name, z, sd, cfg = blocks_golden
+    model = make_model(16, SimpleNamespace(**vars(cfg)))
+    mine = {k for k in model.state_dict() if not k.endswith("pos_enc.pe")}
+    assert mine == set(sd), (sorted(mine - set(sd))[:5], sorted(set(sd) - mine)[:5])
+    for k, v in model.state_dict().items():
+        if k in sd:
+            assert tuple(v.shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.parametrize("tag,left,right", [("greedy", 0, 0), ("greedy_l1r1", 1, 1)])
+def test_decode_from_encoder(blocks_golden, tag, left, right):
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg, left_trigger=left, right_trigger=right)
+    enc_h = torch.from_numpy(z[tag + "::enc_h"]).to(DEV)
+    src_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2].to(DEV)
+    size = torch.from_numpy(z["src_size"]).to(DEV)
+    with torch.no_grad():
+        out, _, keep = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args, return_intermediates=True)
+    assert np.array_equal(keep["aligned"].cpu().numpy(), z[tag + "::aligned"])
+    assert np.array_equal(keep["ylen"].cpu().numpy(), z[tag + "::ylen"])
+    for key in ("ac_embed", "pred_embed", "dec_h"):
+        assert rel(keep[key], z[f"{tag}::{key}"]) < TOL, (name, tag, key)
+    att = torch.from_numpy(z[tag + "::att_out"])
+    assert torch.equal(keep["ids"].cpu().long(), att.argmax(-1))
+    assert (keep["logp"].cpu() - att.max(-1)[0]).abs().max().item() < 1e-4
+    assert [o[0]["hyp"] for o in out] == hyps_of(z, tag)
+    assert np.allclose([o[0]["score"] for o in out], z[tag + "::score"], rtol=1e-5, atol=1e-4)
+
+
+def test_beam_decode_from_features(blocks_golden):
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    enc_h, m2 = model.encode(src, mask)
+    assert rel(enc_h, z["greedy::enc_h"]) < TOL
+    out, args2 = model.beam_decode(src, mask, size, VOCAB, args)
+    assert args2 is args
+    assert [o[0]["hyp"] for o in out] == hyps_of(z, "greedy")
+    assert out[0][0]["ys"].tolist() == [[1]]
+
+
+def test_generator_log_softmax(blocks_golden):
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    enc_h = torch.from_numpy(z["greedy::enc_h"]).to(DEV)
+    ctc_out = model.ctc_generator(enc_h)
+    assert (ctc_out.cpu() - torch.from_numpy(z["greedy::ctc_out"])).abs().max().item() < 1e-4
+
+
+def test_sampled_decode_with_ranker(blocks_golden):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg, sample_num=3, threshold=0.9, rank_model="lm")
+
+    class TinyLM(torch.nn.Module):          # same stand-in ranker as tests/golden/make_golden_blocks.py
+        def __init__(self, V, seed=7):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.emb = torch.nn.Parameter(torch.randn(V, 16, generator=g), requires_grad=False)
+            self.out = torch.nn.Parameter(torch.randn(16, V, generator=g), requires_grad=False)
+
+        def forward(self, ids, mask):
+            x = self.emb[ids]
+            m = (mask != 0).float()
+            ctx = torch.matmul(m / m.sum(-1, keepdim=True).clamp(min=1), x)
+            return torch.log_softmax(ctx @ self.out, -1)
+
+    lm = TinyLM(cfg.vocab_size).to(DEV)
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    torch.manual_seed(555)                   # make_golden_blocks.py seeds the reference the same way
+    with torch.no_grad():
+        enc_h, m2 = model.encode(src, mask)
+        out, _, keep = model.decode_from_encoder(enc_h, m2, size, VOCAB, args, lm_model=lm, return_intermediates=True)
+    assert np.array_equal(keep["aligned"].cpu().numpy(), z["sampled::aligned"])
+    assert np.array_equal(keep["best_sample"].cpu().numpy(), z["sampled::best_sample"])
+    assert [o[0]["hyp"] for o in out] == hyps_of(z, "sampled")

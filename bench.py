@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the CASS-NAT alignment-conditioned decode path (BASELINE.json metric:
+utterances/sec of CASS-NAT decode; alignment-lattice GB/s for the cfg2 microbench).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg1|cfg2]
+
+A "step" is one pass of the path (everything CassNAT.beam_decode does after the encoder output
+`enc_h` exists: CTC head -> best-path alignment -> segment ids -> extractor -> SAD -> MAD -> output
+head -> hypotheses) over one batch of synthetic encoder output of the named shape, random-init
+weights.  N > 1: one process per GPU under torchrun, utterance-sharded, weak scaling (the batch per
+GPU is fixed); the only collective is the hypothesis gather.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOCAB = SimpleNamespace(word2index={"sos": 1, "eos": 2, "blank": 0})
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: LibriSpeech-shaped base model, 64 x 20 s per GPU
+    "cfg3": dict(d_model=512, n_head=8, d_ff=2048, N_enc=12, N_mix_dec=6, batch=64, frames_in=2000, audio_s=20.0,
+                 name="cfg3: CASS-NAT base (512-d, 12 enc / 1+1+6 dec, V=5000) greedy decode, 64 x 20 s per GPU, "
+                      "post-encoder path on synthetic enc_h"),
+    # BASELINE.json configs[0]: small model, 16 x 10 s
+    "cfg1": dict(d_model=256, n_head=4, d_ff=2048, N_enc=12, N_mix_dec=3, batch=16, frames_in=1000, audio_s=10.0,
+                 name="cfg1: CASS-NAT small (256-d, 12 enc / 1+1+3 dec, V=5000) greedy decode, 16 x 10 s"),
+}
+
+
+def model_args(w, **over):
+    a = dict(use_conv_enc=False, use_conv_dec=False, model_type="transformer", pos_type="absolute",
+             n_head=w["n_head"], d_model=w["d_model"], d_encff=w["d_ff"], d_decff=w["d_ff"], d_ff=w["d_ff"],
+             dropout=0.0, N_enc=w["N_enc"], N_extra=1, N_self_dec=1, N_mix_dec=w["N_mix_dec"], vocab_size=5000,
+             interctc_alpha=0, interce_alpha=0, interctc_layer=0, interce_layer=0, padding_idx=0, label_smooth=0.1,
+             share_ff=False, enc_max_relative_len=20, enc_kernel_size=31, dec_max_relative_len=8, dec_kernel_size=3,
+             use_trigger=True, use_best_path=False, sample_topk=0, ctc_alpha=0.5, att_alpha=1.0, save_embedding=False,
+             use_unimask=False, src_trigger=False, left_trigger=0, right_trigger=0, test_hitrate=False, sample_num=0,
+             decode_type="att_only", threshold=0.9, rank_model="lm", lm_weight=0, beam_width=1, length_penalty=0,
+             use_gpu=True)
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+def synth_encoder_output(w, batch, seed):
+    """Synthetic encoder output of the named shape: unit-variance rows (what the encoder's final
+    LayerNorm emits at init), ragged lengths U{60%..100%} with utterance 0 full length."""
+    g = torch.Generator().manual_seed(seed)
+    T = (w["frames_in"] + 3) // 4
+    enc_h = torch.randn(batch, T, w["d_model"], generator=g)
+    lens = torch.randint(int(0.6 * T), T + 1, (batch,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None, :] < lens[:, None]).unsqueeze(1)
+    # exact ratios (cassnat.py:436 truncates): nudge so that (ratio*T).long() == lens
+    ratio = (lens.float() + 0.5) / T
+    return enc_h, mask, ratio, lens
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tensor=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.tmp.flush()
+        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(a, w):
+    """The reference's CPU implementation of the path = the oracle port (the reference is Python and
+    does not travel to the GPU box), all host threads, on a bounded sample of the same workload."""
+    import oracle.nat_torch as O
+    from cassnat_asr_public_b200.cassnat import make_model
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = model_args(w, use_gpu=False)
+    torch.manual_seed(1234)
+    model = make_model(80, args)                    # parameter container only (never runs on this arm)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    sample = a.cpu_sample
+    enc_h, mask, ratio, lens = synth_encoder_output(w, sample, 1234)
+    frames = (ratio * enc_h.size(1)).long()
+    cfg = SimpleNamespace(**vars(args))
+
+    def step():
+        with torch.no_grad():
+            return O.decode_from_encoder(enc_h, mask, frames, sd, cfg)
+
+    for _ in range(max(a.warmup, 1) if a.warmup < 2 else 1):
+        out = step()
+    ts = []
+    for _ in range(a.steps):
+        t0 = time.perf_counter()
+        out = step()
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    value = sample * len(ts) / total
+    line = {"impl": "reference", "metric": "utterances/sec", "value": value, "unit": "utt/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": 1, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "global_batch": sample, "tokens_U": int(out["ymax"])},
+            "rtf": (total / len(ts)) / (sample * w["audio_s"]),
+            "cpu_baseline": {"value": value, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{sample} utterances of the workload per step (oracle/nat_torch.py on CPU)"},
+            "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(a, w):
+    import torch.distributed as dist
+
+    from cassnat_asr_public_b200 import _lib, sharding
+    from cassnat_asr_public_b200.cassnat import make_model
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib.load().cn_device_check() != 0:
+        raise RuntimeError("bench.py needs an sm_100 device (no fallback)")
+    B = a.batch or w["batch"]
+    args = model_args(w, precision=a.precision)
+    torch.manual_seed(1234)
+    model = make_model(80, args).to(dev).eval()
+    if hasattr(model, "set_precision"):
+        model.set_precision(a.precision)
+    enc_h, mask, ratio, lens = synth_encoder_output(w, B, 1234 + rank)        # a different shard per rank
+    T = enc_h.size(1)
+    host = [t.pin_memory() for t in (enc_h, mask, ratio)]
+    dev_in = [t.to(dev) for t in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(inputs):
+        with torch.no_grad():
+            out, _ = model.decode_from_encoder(inputs[0], inputs[1], inputs[2], VOCAB, args)
+        hyps = [o[0]["hyp"] for o in out]
+        if world > 1:      # the hypothesis gather of the decode job (tiny; padded to T+2 tokens)
+            hyps = sharding.gather_hypotheses(hyps, B * world, T + 2, dev)
+        return hyps
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        hyps = step(dev_in)
+    # ---- device-resident throughput: per-step CUDA events, L2 flushed between steps
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.launch_count = 0
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hyps = step(dev_in)
+        e1.record()
+        evs.append((e0, e1))
+    sync_all()
+    launches = _lib.launch_count
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    # ---- end to end: pinned host buffers in, hypotheses (python lists) out, copies inside the clock
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        staged = [t.to(dev, non_blocking=True) for t in host]
+        hyps = step(staged)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = t.tolist()
+    # ---- per-kernel durations for the roofline (separate profiled steps, CUDA events per C-ABI call)
+    prof = None
+    if rank == 0:
+        _lib.start_profile()
+        for _ in range(2):
+            step(dev_in)
+        prof = _lib.stop_profile()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_tok = sum(len(h) - 1 for h in hyps[:B]) / B
+    units = B * world * a.steps
+    value = units / (total_ms / 1e3)
+    pk = peaks()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    name, d = top
+    if d["flops"] > 0:
+        ach = d["flops"] / (d["ms"] / 1e3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor"], "traffic": None}
+    else:
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None}
+    roof["peak_source"] = pk["source"]
+    roof["avg_launch_ms"] = d["ms"] / d["calls"]
+    roof["share_of_step"] = d["ms"] / sum(v["ms"] for v in prof.values())
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        roof["traffic"] = json.load(open(tpath)).get(name)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    ymax = max(len(h) - 1 for h in hyps[:B])
+    d2h = B * ymax * (4 + 8) + B * 8 + 4          # ids i32 + logp f64 + ylen i64 + the ymax scalar
+    line = {"metric": "utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else a.precision, "data": "synthetic",
+            "config": {"workload": w["name"], "global_batch": B * world, "per_gpu_batch": B, "frames_T": T,
+                       "tokens_U_mean": n_tok, "tokens_U_max": ymax, "precision": a.precision,
+                       "parallelism": f"utterance-sharded x{world}", "l2": "flushed (256 MiB write) between steps"},
+            "rtf": (total_ms / 1e3 / a.steps) / (B * w["audio_s"]),
+            "e2e": {"value": units / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "kernels": {k: {"ms_per_step": v["ms"] / 2, "calls_per_step": v["calls"] / 2} for k, v in prof.items()}}
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, w, args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, w, args):
+    """Oracle port on the host cores, bounded sample (rank 0, N=1 only).  Reported, not a target."""
+    import oracle.nat_torch as O
+    from cassnat_asr_public_b200.cassnat import make_model
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    cargs = SimpleNamespace(**{**vars(args), "use_gpu": False})
+    sd = {k: v.detach() for k, v in make_model(80, cargs).state_dict().items()}
+    sample = a.cpu_sample
+    enc_h, mask, ratio, lens = synth_encoder_output(w, sample, 1234)
+    frames = (ratio * enc_h.size(1)).long()
+    with torch.no_grad():
+        O.decode_from_encoder(enc_h[:1], mask[:1], frames[:1], sd, cargs)            # warm-up
+        t0 = time.perf_counter()
+        O.decode_from_encoder(enc_h, mask, frames, sd, cargs)
+        dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "utt/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} utterances of the workload, one pass (oracle/nat_torch.py, torch CPU f32)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--precision", default=os.environ.get("CASSNAT_PRECISION", "fp32"))
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    w = WORKLOADS[a.workload]
+    if a.impl == "reference":
+        run_reference(a, w)
+    else:
+        run_ours(a, w)
+
+
+if __name__ == "__main__":
+    main()

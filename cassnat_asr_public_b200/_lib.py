@@ -76,10 +76,49 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name, *args):
-    rc = getattr(load(), name)(*args)
+# kernels launched per C-ABI call (cn_row_stats: +1 when it also writes log-probs)
+LAUNCHES = {"cn_row_stats": 1, "cn_bestpath_collapse": 1, "cn_bestpath_from_logp": 2, "cn_viterbi_align": 1,
+            "cn_align_to_mask": 1, "cn_expand_trigger_mask": 1, "cn_tgt_length_mask": 1, "cn_gemm_f32": 1,
+            "cn_layernorm": 1, "cn_attention_f32": 1, "cn_segment_attention_f32": 2,
+            "cn_glu_dwconv_groupnorm_act": 2}
+launch_count = 0          # running total of our kernel launches (bench.py reads and resets it)
+_profile = None           # list of (name, start_event, end_event, work) while profiling
+
+
+def start_profile():
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """-> {name: dict(calls, ms, flops, bytes)} measured with CUDA events on the launching stream."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, work in rec:
+        d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += work.get("flops", 0.0)
+        d["bytes"] += work.get("bytes", 0.0)
+    return out
+
+
+def call(name, *args, work=None, tag=None):
+    global launch_count
+    fn = getattr(load(), name)
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.append((tag or name, e0, e1, work or {}))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {status_string(rc)} (cn_status {rc})")
+    launch_count += LAUNCHES.get(name, 1)
 
 
 def require_cuda(*tensors):

@@ -46,7 +46,9 @@ def row_stats(x, top2=False, peak=False, lse=False, logp_out=None):
         out["lse"] = torch.empty(rows, dtype=torch.float32, device=dev)
     lp = logp_out.reshape(-1, V) if logp_out is not None else None
     call("cn_row_stats", ptr(x2), rows, V, x2.stride(0), ptr(out["top1"]), ptr(out.get("top2")),
-         ptr(out.get("peak")), ptr(out.get("lse")), ptr(lp), lp.stride(0) if lp is not None else 0, stream())
+         ptr(out.get("peak")), ptr(out.get("lse")), ptr(lp), lp.stride(0) if lp is not None else 0, stream(),
+         work=dict(bytes=4.0 * rows * V * (3 if lp is not None else 1)))
+    _lib.launch_count += 1 if lp is not None else 0
     lead = x.shape[:-1]
     return {k: v.reshape(lead) for k, v in out.items()}
 
@@ -163,7 +165,7 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
     w = weight if weight.stride(-1) == 1 else weight.contiguous()
     call("cn_gemm_f32", ptr(x2), x2.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(r2),
          r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ACT[act], ptr(o2), o2.stride(0),
-         M, N, K, stream())
+         M, N, K, stream(), work=dict(flops=2.0 * M * N * K, bytes=4.0 * (M * K + N * K + M * N)))
     return out
 
 
@@ -177,7 +179,8 @@ def layer_norm(x, a_2, b_2, eps=1e-6, bf16=False):
     out = torch.empty(x.shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
     o2 = out.reshape(-1, d)
     call("cn_layernorm", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps),
-         None if bf16 else ptr(o2), ptr(o2) if bf16 else None, o2.stride(0), stream())
+         None if bf16 else ptr(o2), ptr(o2) if bf16 else None, o2.stride(0), stream(),
+         work=dict(bytes=float(x2.shape[0] * d * (4 + (2 if bf16 else 4)))))
     return out
 
 
@@ -215,7 +218,8 @@ def attention(q, k, v, mask, n_head, rel=None, out=None):
         rp, ru, rv = rp.contiguous(), ru.contiguous(), rv.contiguous()
     call("cn_attention_f32", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp), ptr(ru), ptr(rv), int(mr),
-         B, n_head, Tq, Tk, dk, ptr(out), out.stride(1), out.stride(0), stream())
+         B, n_head, Tq, Tk, dk, ptr(out), out.stride(1), out.stride(0), stream(),
+         work=dict(flops=4.0 * B * Tq * Tk * d, bytes=4.0 * B * d * (2 * Tq + 2 * Tk)))
     return out
 
 
@@ -232,7 +236,7 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
     call("cn_segment_attention_f32", ptr(q_rows), q_rows.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(seg), ptr(_i64(ylens)), ptr(mask), ptr(_i64(src_size)),
          int(left > 0), int(right > 0), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
-         ptr(vmean), stream())
+         ptr(vmean), stream(), work=dict(flops=4.0 * B * T * d, bytes=4.0 * B * d * (3 * T + U)))
     return out
 
 

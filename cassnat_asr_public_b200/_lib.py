@@ -39,6 +39,8 @@ SIGNATURES = {
     "cn_conv_module_workspace_bytes": (_i64, [_i64, _i64]),
     "cn_glu_dwconv_groupnorm_act": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _int, _i64, _i64, _i64, _i64,
                                            _vp, _vp, _i64, _vp]),
+    "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
 }
 
 _lib = None

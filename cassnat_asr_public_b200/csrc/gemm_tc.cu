@@ -1,0 +1,383 @@
+// bf16 tensor-core GEMM for sm_100a: C[M,N] = residual + alpha * act(A[M,K] * W[N,K]^T + bias)
+//
+//   * persistent, one CTA per SM, warp-specialised (1 TMA producer lane, 1 MMA issuer lane,
+//     4 epilogue warps);
+//   * operands: bf16, both K-major, staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+//     4-stage shared-memory ring guarded by mbarriers;
+//   * math: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, fp32 accumulators in
+//     TMEM, two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
+//     tile i+1;
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation / scale /
+//     residual in registers -> fp32 and/or bf16 rows straight to global memory.
+//
+// Replaces (fast mode) the nn.Linear / Conv1d(k=1) / Generator.proj call sites of
+// src/models/modules/{attention,positionff,conformer_related}.py and src/models/cassnat.py:105,113.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (rows of A per tile)
+constexpr int BK = 64;           // bf16 elements per stage row = 128 bytes = one swizzle atom
+constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups | [46,48) version = 1 (sm_100)
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                  // LBO: ignored for a one-atom-wide swizzled K-major tile (CUTLASS sets 1)
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
+// both K-major (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Epilogue {
+  const float* bias;
+  const float* residual; int64_t ldr; int64_t res_rows;
+  float alpha; int act;
+  float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
+};
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  if (act == CN_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == CN_ACT_SWISH) return v / (1.f + __expf(-v));
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_w,
+                                                                  Epilogue ep, int M, int N, int K) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;                    // two accumulator stages (power of two >= 32)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int k_blocks = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(&map_a, &full[stage], sa, kb * BK, m0);
+          tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);             // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);                       // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advancing K inside the swizzle atom = +32 bytes on the (pre-swizzle) start address
+            umma_bf16(tmem_d, da + (uint64_t)((k * UK * 2) >> 4), db + (uint64_t)((k * UK * 2) >> 4), idesc,
+                      (kb | k) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty[stage]);                        // frees the smem slot when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&acc_full[acc]);                         // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
+    const int quarter = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const int64_t rrow = ep.res_rows > 0 ? (row % ep.res_rows) : row;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+        const int col0 = n0 + c0;
+        if (row < M && col0 < N) {
+          const int ncol = min(32, N - col0);
+          if (ncol == 32 && ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float r[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float x = __uint_as_float(v[j + q]);
+                if (ep.bias) x += __ldg(ep.bias + col0 + j + q);
+                x = act_fn(x, ep.act) * ep.alpha;
+                r[q] = x;
+              }
+              if (ep.residual) {
+                const float4 rs = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0 + j);
+                r[0] += rs.x; r[1] += rs.y; r[2] += rs.z; r[3] += rs.w;
+              }
+              if (ep.out_f32)
+                *reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ldc + col0 + j) =
+                    make_float4(r[0], r[1], r[2], r[3]);
+              if (ep.out_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(ep.out_bf16 + (int64_t)row * ep.ldc + col0 + j) = pk;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j >= ncol) break;
+              float x = __uint_as_float(v[j]);
+              if (ep.bias) x += ep.bias[col0 + j];
+              x = act_fn(x, ep.act) * ep.alpha;
+              if (ep.residual) x += ep.residual[rrow * ep.ldr + col0 + j];
+              if (ep.out_f32) ep.out_f32[(int64_t)row * ep.ldc + col0 + j] = x;
+              if (ep.out_bf16) ep.out_bf16[(int64_t)row * ep.ldc + col0 + j] = __float2bfloat16(x);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, K] (row pitch ld elements) -> 2-D map with a [BK x box_rows] box, 128B swizzle
+bool make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
+              cudaStream_t stream) {
+  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return CN_ERR_LAUNCH;
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_bf16_tc_kernel<BN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+
+}  // namespace
+
+extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                            const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                            float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                            cn_stream_t stream_) {
+  if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || lda < K || ldw < K || ldc < N)
+    return CN_ERR_BAD_ARG;
+  if (residual && ldr < N) return CN_ERR_BAD_ARG;
+  // TMA needs 16-byte aligned bases and row pitches
+  if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return CN_ERR_UNSUPPORTED;
+  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
+  if (M == 0 || N == 0) return CN_OK;
+  const int bn = (N > 128) ? 256 : 128;
+  CUtensorMap ma, mw;
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mw, W, N, K, ldw, bn)) return CN_ERR_DEVICE;
+  Epilogue ep;
+  ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
+  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  return bn == 256 ? launch_tc<256>(ma, mw, ep, (int)M, (int)N, (int)K, stream)
+                   : launch_tc<128>(ma, mw, ep, (int)M, (int)N, (int)K, stream);
+}
+
+// f32 -> bf16 cast (operands of the tensor-core GEMM that arrive in fp32, e.g. enc_h)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                        int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = cn_ld_stream_f32x4(reinterpret_cast<const float4*>(x) + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[i] = pk;
+  }
+}
+
+extern "C" int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream_) {
+  if (!x || !y || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
+    return CN_ERR_BAD_ARG;
+  if (n == 0) return CN_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, (__nv_bfloat16*)y, n / 4);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}

@@ -253,3 +253,48 @@ def glu_dwconv_groupnorm_act(y, dw_weight, dw_bias, gamma, beta, eps, act):
     call("cn_glu_dwconv_groupnorm_act", ptr(y), y.stride(1), y.stride(0), ptr(dw_weight.reshape(C, ksz).contiguous()),
          ptr(dw_bias), ptr(gamma), ptr(beta), float(eps), ACT[act], B, L, C, ksz, ptr(out), ptr(ws), ws_bytes, stream())
     return out
+
+
+# ----------------------------------------------------------------------------- bf16 tensor-core path
+def cast_bf16(x):
+    """f32 -> bf16 copy (operands of the tensor-core GEMMs that arrive in fp32)."""
+    require_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x
+    xc = x.contiguous()
+    out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
+    n = xc.numel()
+    if n % 4 == 0:
+        call("cn_cast_bf16", ptr(xc), ptr(out), n, stream(), work=dict(bytes=6.0 * n))
+    else:
+        out.copy_(xc)
+    return out
+
+
+def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out_dtype=torch.float32,
+                also_bf16=False):
+    """Tensor-core GEMM: residual + alpha * act(x @ W.T + bias), bf16 operands, fp32 accumulation.
+    x bf16 [..., K] (row stride multiple of 8), weight_bf16 [N, K].  Returns f32 or bf16 (or both
+    with also_bf16: the fp32 residual stream plus its bf16 copy for the next GEMM)."""
+    require_cuda(x, weight_bf16)
+    assert x.dtype == torch.bfloat16 and weight_bf16.dtype == torch.bfloat16
+    K = x.shape[-1]
+    N = weight_bf16.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    lead = x.shape[:-1]
+    o32 = torch.empty(*lead, N, dtype=torch.float32, device=x.device) if (out_dtype == torch.float32) else None
+    o16 = torch.empty(*lead, N, dtype=torch.bfloat16, device=x.device) if (out_dtype == torch.bfloat16 or also_bf16) else None
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    call("cn_gemm_bf16", ptr(x2), x2.stride(0), ptr(weight_bf16), weight_bf16.stride(0), ptr(bias), ptr(r2),
+         r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ACT[act], ptr(o32), ptr(o16), N,
+         M, N, K, stream(), work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (4.0 if o32 is not None else 2.0)))
+    if o32 is not None and o16 is not None:
+        return o32, o16
+    return o32 if o32 is not None else o16

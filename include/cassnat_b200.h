@@ -191,6 +191,18 @@ int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t sby, const 
                                 int64_t B, int64_t L, int64_t C, int64_t ksz, float* out,
                                 void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fast mode: bf16 tensor-core GEMM (tcgen05.mma, fp32 accumulation in TMEM, TMA-fed, persistent).
+ * C[M,N] = residual + alpha * act(A[M,K] * W[N,K]^T + bias), A and W bf16 (uint16 storage),
+ * K-major; lda, ldw multiples of 8 and 16-byte aligned bases (TMA).  out_f32 and/or out_bf16.
+ *   replaces (fast mode): the same call sites as cn_gemm_f32. */
+int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                 const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                 float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                 cn_stream_t stream);
+/* y(bf16) = x(f32), n elements (n % 4 == 0, 16-byte aligned x). */
+int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ constexpr int BM = 128;          // UMMA M (rows of A per tile)
 constexpr int BK = 64;           // bf16 elements per stage row = 128 bytes = one swizzle atom
 constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
 constexpr int STAGES = 4;
-constexpr int THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int THREADS = 320;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,20 +117,21 @@ struct Epilogue {
   float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
 };
 
-__device__ __forceinline__ float act_fn(float v, int act) {
-  if (act == CN_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == CN_ACT_SWISH) return v / (1.f + __expf(-v));
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if (ACT == CN_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == CN_ACT_SWISH) return v / (1.f + __expf(-v));
   return v;
 }
 
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;                    // two accumulator stages (power of two >= 32)
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // keeps the shared address space visible
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -204,61 +205,105 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the BN columns.
+    // TMEM hands every thread one ROW (32 consecutive columns).  Writing rows straight to global
+    // memory costs 32 L1 wavefronts per store instruction, so each warp transposes its 32x32 chunk
+    // through a private padded smem buffer and stores 4 rows x 128 contiguous bytes per instruction.
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t stg = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)(warp - 2) * 4096u;   // 32 x 32 fp32, XOR-swizzled 16-byte chunks
+    const int rr = lane >> 3, cc = (lane & 7) * 4;
+    const bool vec_ok = ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0);
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const int64_t rrow = ep.res_rows > 0 ? (row % ep.res_rows) : row;
+      const int row0 = m0 + quarter * 32 + rr;                  // first of the 8 rows (stride 4) this lane stores
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        const int col0 = n0 + c0;
+        if (col0 >= N) break;                                   // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
-        const int col0 = n0 + c0;
-        if (row < M && col0 < N) {
-          const int ncol = min(32, N - col0);
-          if (ncol == 32 && ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float r[4];
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (uint32_t)(lane * 128 + (((j >> 2) ^ (lane & 7)) << 4))), "r"(v[j]),
+                       "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+        __syncwarp();
+        const int gcol = col0 + cc;
+        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) {
+          if (gcol + 3 < N) bz = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol));
+          else {
+            if (gcol < N) bz.x = ep.bias[gcol];
+            if (gcol + 1 < N) bz.y = ep.bias[gcol + 1];
+            if (gcol + 2 < N) bz.z = ep.bias[gcol + 2];
+          }
+        }
+        float x[8][4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float x = __uint_as_float(v[j + q]);
-                if (ep.bias) x += __ldg(ep.bias + col0 + j + q);
-                x = act_fn(x, ep.act) * ep.alpha;
-                r[q] = x;
+        for (int it = 0; it < 8; ++it)
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(x[it][0]), "=f"(x[it][1]), "=f"(x[it][2]), "=f"(x[it][3])
+                       : "r"(stg + (uint32_t)((it * 4 + rr) * 128 + ((((lane & 7)) ^ ((it * 4 + rr) & 7)) << 4))));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          x[it][0] = act_fn<ACT>(x[it][0] + bz.x) * ep.alpha;
+          x[it][1] = act_fn<ACT>(x[it][1] + bz.y) * ep.alpha;
+          x[it][2] = act_fn<ACT>(x[it][2] + bz.z) * ep.alpha;
+          x[it][3] = act_fn<ACT>(x[it][3] + bz.w) * ep.alpha;
+        }
+        if (vec_ok && gcol + 3 < N) {
+          if (ep.residual) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row0 + it * 4;
+              if (grow < M) {
+                const int64_t rrow = ep.res_rows > 0 ? (int64_t)(grow % (int)ep.res_rows) : (int64_t)grow;
+                const float4 rs = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + gcol);
+                x[it][0] += rs.x; x[it][1] += rs.y; x[it][2] += rs.z; x[it][3] += rs.w;
               }
-              if (ep.residual) {
-                const float4 rs = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0 + j);
-                r[0] += rs.x; r[1] += rs.y; r[2] += rs.z; r[3] += rs.w;
-              }
-              if (ep.out_f32)
-                *reinterpret_cast<float4*>(ep.out_f32 + (int64_t)row * ep.ldc + col0 + j) =
-                    make_float4(r[0], r[1], r[2], r[3]);
-              if (ep.out_bf16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+            }
+          }
+          if (ep.out_f32) {
+            float* o = ep.out_f32 + (int64_t)row0 * ep.ldc + gcol;
+#pragma unroll
+            for (int it = 0; it < 8; ++it, o += 4 * ep.ldc)
+              if (row0 + it * 4 < M) *reinterpret_cast<float4*>(o) = make_float4(x[it][0], x[it][1], x[it][2], x[it][3]);
+          }
+          if (ep.out_bf16) {
+            __nv_bfloat16* o = ep.out_bf16 + (int64_t)row0 * ep.ldc + gcol;
+#pragma unroll
+            for (int it = 0; it < 8; ++it, o += 4 * ep.ldc) {
+              if (row0 + it * 4 < M) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(x[it][0], x[it][1]), hi = __floats2bfloat162_rn(x[it][2], x[it][3]);
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(ep.out_bf16 + (int64_t)row * ep.ldc + col0 + j) = pk;
+                *reinterpret_cast<uint2*>(o) = pk;
               }
             }
-          } else {
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j >= ncol) break;
-              float x = __uint_as_float(v[j]);
-              if (ep.bias) x += ep.bias[col0 + j];
-              x = act_fn(x, ep.act) * ep.alpha;
-              if (ep.residual) x += ep.residual[rrow * ep.ldr + col0 + j];
-              if (ep.out_f32) ep.out_f32[(int64_t)row * ep.ldc + col0 + j] = x;
-              if (ep.out_bf16) ep.out_bf16[(int64_t)row * ep.ldc + col0 + j] = __float2bfloat16(x);
+          for (int it = 0; it < 8; ++it) {
+            const int grow = row0 + it * 4;
+            if (grow >= M) continue;
+            const int64_t rrow = ep.res_rows > 0 ? (int64_t)(grow % (int)ep.res_rows) : (int64_t)grow;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (gcol + q < N) {
+                float y = x[it][q];
+                if (ep.residual) y += ep.residual[rrow * ep.ldr + gcol + q];
+                if (ep.out_f32) ep.out_f32[(int64_t)grow * ep.ldc + gcol + q] = y;
+                if (ep.out_bf16) ep.out_bf16[(int64_t)grow * ep.ldc + gcol + q] = __float2bfloat16(y);
+              }
             }
           }
         }
+        __syncwarp();                                            // staging buffer is reused by the next chunk
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -317,19 +362,19 @@ int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, int ACT>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 16 * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  gemm_bf16_tc_kernel<BN, ACT><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
@@ -354,8 +399,15 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
   cudaStream_t stream = (cudaStream_t)stream_;
-  return bn == 256 ? launch_tc<256>(ma, mw, ep, (int)M, (int)N, (int)K, stream)
-                   : launch_tc<128>(ma, mw, ep, (int)M, (int)N, (int)K, stream);
+  const int m = (int)M, n = (int)N, k = (int)K;
+  if (bn == 256) {
+    if (act == CN_ACT_RELU) return launch_tc<256, CN_ACT_RELU>(ma, mw, ep, m, n, k, stream);
+    if (act == CN_ACT_SWISH) return launch_tc<256, CN_ACT_SWISH>(ma, mw, ep, m, n, k, stream);
+    return launch_tc<256, CN_ACT_NONE>(ma, mw, ep, m, n, k, stream);
+  }
+  if (act == CN_ACT_RELU) return launch_tc<128, CN_ACT_RELU>(ma, mw, ep, m, n, k, stream);
+  if (act == CN_ACT_SWISH) return launch_tc<128, CN_ACT_SWISH>(ma, mw, ep, m, n, k, stream);
+  return launch_tc<128, CN_ACT_NONE>(ma, mw, ep, m, n, k, stream);
 }
 
 // f32 -> bf16 cast (operands of the tensor-core GEMM that arrive in fp32, e.g. enc_h)

@@ -300,7 +300,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
-    ap.add_argument("--precision", default=os.environ.get("CASSNAT_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("CASSNAT_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

@@ -41,6 +41,8 @@ SIGNATURES = {
                                            _vp, _vp, _i64, _vp]),
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
+    "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
+                                 _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
 }
 
 _lib = None

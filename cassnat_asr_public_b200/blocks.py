@@ -23,9 +23,9 @@ def clones(module, n):
 
 def _self_attention_block(x, norm, attn, mask, pos_embed=None):
     """x + self_attn(norm(x)) with the residual fused into the output projection."""
-    y = norm(x)
+    y = norm.for_gemm(x)
     if pos_embed is None:
-        q, k, v = attn.project_qkv(y)
+        q, k, v = attn.project_qkv(y, out_bf16=ops.is_bf16())     # bf16 -> tcgen05 attention
         ctx = ops.attention(q, k, v, mask, attn.h)
     else:
         from .modules import distinct_rel_rows
@@ -37,14 +37,14 @@ def _self_attention_block(x, norm, attn, mask, pos_embed=None):
 
 
 def _src_attention_block(x, norm, attn, memory, mask, kv=None):
-    y = norm(x)
-    q = attn.project_q(y)
-    k, v = kv if kv is not None else attn.project_kv(memory)
+    y = norm.for_gemm(x)
+    q = attn.project_q(y, out_bf16=ops.is_bf16())
+    k, v = kv if kv is not None else attn.project_kv(memory, out_bf16=ops.is_bf16())
     return attn.output(ops.attention(q, k, v, mask, attn.h), residual=x)
 
 
 def _ffn_block(x, norm, ff, scale=1.0):
-    return ff(norm(x), residual=x, scale=scale)
+    return ff(norm.for_gemm(x), residual=x, scale=scale)
 
 
 # =============================================================================== transformer family
@@ -81,7 +81,7 @@ class SrcAttLayer(nn.Module):
         """Same result as forward(pe_rows repeated over the batch, m, trigger_mask) with the
         trigger mask given implicitly by `seg_ctx` = (seg, ylens, src_mask, src_size, left, right)."""
         attn = self.src_attn
-        q_rows = attn.project_q(self.sublayer[0].norm(pe_rows))           # batch independent [U,d]
+        q_rows = attn.project_q(self.sublayer[0].norm.for_gemm(pe_rows))           # batch independent [U,d]
         k, v = kv if kv is not None else attn.project_kv(m)
         ctx = ops.segment_attention(q_rows, k, v, *seg_ctx, attn.h)
         x = attn.output(ctx, residual=pe_rows, res_rows=pe_rows.size(0))
@@ -191,7 +191,7 @@ def _project_memory_all(dec, memory):
     attns = [layer.src_attn for layer in dec.layers]
     w = _cat_cached(dec, "kv_all_w", [t for a in attns for t in (a.linears[1].weight, a.linears[2].weight)])
     b = _cat_cached(dec, "kv_all_b", [t for a in attns for t in (a.linears[1].bias, a.linears[2].bias)])
-    kv = ops.linear(memory, w, b)                      # [B,T,2d*N]
+    kv = ops.linear(memory, w, b, out_bf16=ops.is_bf16())                      # [B,T,2d*N]
     d = memory.size(-1)
     return [(kv[..., 2 * i * d:(2 * i + 1) * d], kv[..., (2 * i + 1) * d:(2 * i + 2) * d]) for i in range(len(attns))]
 
@@ -214,7 +214,7 @@ class ConSelfAttLayer(nn.Module):
         self.ff_scale = ff_scale
 
     def _conv(self, x):
-        return self.conv_module(self.sublayer[1].norm(x), residual=x)
+        return self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
 
     def forward(self, x, mask, pos_embed):
         x = _ffn_block(x, self.sublayer[0].norm, self.feed_forward1, self.ff_scale)
@@ -279,11 +279,11 @@ class ConMixAttLayer(nn.Module):
     def forward(self, x, memory, src_mask, self_mask, pos_embed, kv=None):
         x = _ffn_block(x, self.sublayer[0].norm, self.feed_forward1, self.ff_scale)
         if self.pos_type == "absolute":
-            x = self.conv_module(self.sublayer[1].norm(x), residual=x)
+            x = self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
             x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, self_mask, None)
         else:
             x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, self_mask, pos_embed)
-            x = self.conv_module(self.sublayer[1].norm(x), residual=x)
+            x = self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
         x = _src_attention_block(x, self.sublayer[3].norm, self.src_attn, memory, src_mask, kv)
         return _ffn_block(x, self.sublayer[4].norm, self.feed_forward2, self.ff_scale)
 

@@ -151,9 +151,14 @@ class CassNAT(nn.Module):
         return torch.tril(ret, out=ret).unsqueeze(0)
 
     def _pe_rows(self, like, n):
-        if self.pe.device != like.device or self.pe.dtype != like.dtype:
-            self.pe = self.pe.to(device=like.device, dtype=like.dtype)
+        if self.pe.device != like.device:
+            self.pe = self.pe.to(device=like.device)
         return self.pe[:n]
+
+    def set_precision(self, mode):
+        """'fp32' (parity mode, FFMA) or 'bf16' (tcgen05 tensor cores, fp32 accumulate); process-wide."""
+        ops.set_precision(mode)
+        return self
 
     # ------------------------------------------------------------------ the accelerated path
     def encode(self, src, x_mask):
@@ -177,6 +182,8 @@ class CassNAT(nn.Module):
         mask2 = src_mask.reshape(B, T)
         frames = (src_size.to(dev) * T).long()                                       # :436 / :471
         keep = {}
+        if ops.is_bf16():
+            enc_h = ops.cast_bf16(enc_h)     # one bf16 copy feeds the CTC head and every K/V projection
 
         # ---- K1 + K2: CTC head -> per-frame argmax/top-2 -> collapsed, shifted alignment
         if args.use_trigger and args.decode_type == "oracle_att":

@@ -66,6 +66,10 @@ class LayerNorm(nn.Module):
     def forward(self, x):
         return ops.layer_norm(x, self.a_2, self.b_2, self.eps)
 
+    def for_gemm(self, x):
+        """Same normalisation, emitted in the operand type of the next GEMM (bf16 in fast mode)."""
+        return ops.layer_norm(x, self.a_2, self.b_2, self.eps, bf16=ops.is_bf16())
+
 
 class PositionwiseFeedForward(nn.Module):
     def __init__(self, d_model, d_ff, dropout=0.1, activation=nn.ReLU()):
@@ -79,7 +83,7 @@ class PositionwiseFeedForward(nn.Module):
         """w_2(act(w_1 x)); with `residual` the pre-norm residual add (and the conformer's 1/2
         scale) is fused into the second GEMM's epilogue."""
         _no_dropout(self, self.p_drop)
-        hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation))
+        hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation), out_bf16=ops.is_bf16())
         return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale)
 
 
@@ -107,21 +111,21 @@ class MultiHeadedAttention(nn.Module):
         self.p_drop = dropout
 
     # -- pieces the fused decode plan reuses --------------------------------------------
-    def project_q(self, x):
-        return ops.linear(x, self.linears[0].weight, self.linears[0].bias)
+    def project_q(self, x, out_bf16=False):
+        return ops.linear(x, self.linears[0].weight, self.linears[0].bias, out_bf16=out_bf16)
 
-    def project_kv(self, memory):
+    def project_kv(self, memory, out_bf16=False):
         """One GEMM for K and V: [B,T,2d]; returns the two strided views."""
         w = _cat_cached(self, "kv_w", [self.linears[1].weight, self.linears[2].weight])
         b = _cat_cached(self, "kv_b", [self.linears[1].bias, self.linears[2].bias])
-        kv = ops.linear(memory, w, b)
+        kv = ops.linear(memory, w, b, out_bf16=out_bf16)
         d = self.h * self.d_k
         return kv[..., :d], kv[..., d:]
 
-    def project_qkv(self, x):
+    def project_qkv(self, x, out_bf16=False):
         w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
         b = _cat_cached(self, "qkv_b", [l.bias for l in self.linears[:3]])
-        qkv = ops.linear(x, w, b)
+        qkv = ops.linear(x, w, b, out_bf16=out_bf16)
         d = self.h * self.d_k
         return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
 

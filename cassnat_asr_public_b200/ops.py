@@ -145,9 +145,50 @@ def tgt_length_mask(ylen, ymax, as_u8=False):
 
 
 # ----------------------------------------------------------------------------- fp32 blocks
-def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None):
-    """residual + alpha * act(x @ weight.T + bias) over the last dim of x (f32)."""
+_PRECISION = "fp32"          # "fp32": FFMA GEMMs (parity mode) | "bf16": tcgen05 GEMMs, fp32 accumulate
+_BF16_WEIGHTS = {}           # id(tensor) -> (version stamp, bf16 copy)
+
+
+def set_precision(mode):
+    """Selects the arithmetic of every linear layer on the path.  'fp32' is the parity mode
+    (bit-exact hypotheses vs the reference); 'bf16' feeds the 5th-gen tensor cores (bf16 operands,
+    fp32 accumulation in TMEM) under the stated bf16 tolerance."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+def is_bf16():
+    return _PRECISION == "bf16"
+
+
+def bf16_weight(w):
+    """bf16 copy of a weight, converted once and refreshed when the parameter changes."""
+    stamp = (w.data_ptr(), w._version, tuple(w.shape))
+    hit = _BF16_WEIGHTS.get(id(w))
+    if hit is None or hit[0] != stamp:
+        with torch.no_grad():
+            src = w.detach()
+            hit = (stamp, cast_bf16(src if src.is_contiguous() else src.contiguous()), w)
+        _BF16_WEIGHTS[id(w)] = hit
+    return hit[1]
+
+
+def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False):
+    """residual + alpha * act(x @ weight.T + bias) over the last dim of x.
+    fp32 mode: FFMA kernel on f32 operands.  bf16 mode: x (f32 or bf16) and the weight go through the
+    tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains)."""
     require_cuda(x, weight)
+    if _PRECISION == "bf16" and x.shape[-1] % 8 == 0:
+        return linear_bf16(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, act, res_rows,
+                           torch.bfloat16 if out_bf16 else torch.float32)
+    if x.dtype != torch.float32:
+        x = x.float()
     K = x.shape[-1]
     N = weight.shape[0]
     x2 = x.reshape(-1, K)
@@ -208,6 +249,10 @@ def attention(q, k, v, mask, n_head, rel=None, out=None):
     dk = d // n_head
     for t in (q, k, v):
         assert t.stride(-1) == 1
+    if q.dtype == torch.bfloat16:
+        if rel is None and dk == 64 and Tk <= 512 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16:
+            return _attention_bf16(q, k, v, mask, n_head)
+        q, k, v = q.float(), k.float(), v.float()
     if out is None:
         out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
@@ -298,3 +343,16 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     if o32 is not None and o16 is not None:
         return o32, o16
     return o32 if o32 is not None else o16
+
+
+def _attention_bf16(q, k, v, mask, n_head):
+    """tcgen05 attention: bf16 q/k/v (strided views of fused projection buffers are fine) -> bf16 ctx."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    out = torch.empty(B, Tq, d, dtype=torch.bfloat16, device=q.device)
+    m, mb, mi = _mask_strides(mask, B, Tq, Tk)
+    call("cn_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
+         ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, B, n_head, Tq, Tk, d // n_head,
+         ptr(out), out.stride(1), out.stride(0), stream(),
+         work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
+    return out

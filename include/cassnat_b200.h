@@ -203,6 +203,15 @@ int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
 /* y(bf16) = x(f32), n elements (n % 4 == 0, 16-byte aligned x). */
 int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream);
 
+/* Fast mode: masked multi-head attention on tcgen05 (bf16 Q/K/V in, bf16 context out, fp32 softmax).
+ * Same semantics as cn_attention_f32 without the relative-position terms; d_k == 64, Tk <= 512,
+ * row/batch pitches multiples of 8 elements and 16-byte aligned bases (TMA).
+ *   replaces (fast mode): attention()                          src/models/modules/attention.py:13-24 */
+int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                      const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
+                      int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                      void* out, int64_t ldo, int64_t sbo, cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

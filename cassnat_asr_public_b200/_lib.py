@@ -41,6 +41,9 @@ SIGNATURES = {
                                            _vp, _vp, _i64, _vp]),
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
+    "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,
+                           _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
 }

@@ -309,4 +309,62 @@ class CassNAT(nn.Module):
             return self.decode_from_encoder(enc_h, src_mask, src_size, vocab, args, lm_model, labels, label_sizes)
 
     def forward(self, src, src_mask, src_size, tgt_label, label_sizes, args):
-        raise NotImplementedError("training forward (cassnat.py:136-257) lands with the CTC-loss / backward kernels")
+        """cassnat.py:136-257 -> (ctc_out, att_out, loss, ctc_loss, att_loss), forward values only.
+        The kernels are not autograd-aware yet: `loss` carries no graph.  What IS provided for the
+        backward pass is the fused CTC gradient: `self.last_ctc_grad` = ctc_alpha * d ctc_loss / d ctc
+        logits (K10), the [B,T,V] tensor the reference's backward spends its HBM time on."""
+        with torch.no_grad():
+            enc_h, x_mask = self.encode(src, src_mask)
+            return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args)
+
+    def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args):
+        """Post-encoder part of CassNAT.forward (cassnat.py:148-257): CTC posteriors, Viterbi forced
+        alignment, trigger segments, extractor -> SAD -> MAD -> log-probs, CTC + label-smoothing loss."""
+        if not args.use_trigger or args.use_best_path or args.interctc_alpha > 0 or args.interce_alpha > 0:
+            raise NotImplementedError("only the shipped training configuration is provided: use_trigger, Viterbi "
+                                      "alignment, no intermediate CTC/CE losses (use_best_path is broken upstream)")
+        assert args.ctc_alpha > 0
+        B, T, d = enc_h.shape
+        dev = enc_h.device
+        blank = args.padding_idx
+        tgt_label, label_sizes = tgt_label.to(dev), label_sizes.to(dev)
+        frames = (src_size.to(dev) * T).long()                                          # :165
+        mask2 = x_mask.reshape(B, T)
+        mem = ops.cast_bf16(enc_h) if ops.is_bf16() else enc_h
+        ctc_out = self.ctc_generator(mem)                                               # :148 (K1, materialised)
+        aligned, ylen, ymax = ops.viterbi_align(ctc_out, x_mask, frames, tgt_label[:, :-1], label_sizes, blank,
+                                                args.sample_topk)                       # :170 (K3)
+        _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
+                                               want_seg=True)                           # :172-175 (K4, implicit mask)
+        seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
+        dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
+                                                  args.left_trigger, args.right_trigger, True)[0]
+        tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)             # :185-187 (K5)
+        ac_embed = self.acembed_extractor.forward_segments(self._pe_rows(enc_h, ymax), mem, seg_ctx, dense_trigger)
+        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
+        if args.use_unimask:
+            raise NotImplementedError("use_unimask in training")
+        mem_mask = dense_trigger() if args.src_trigger else x_mask
+        dec_h = self.decoder(pred_embed, mem, mem_mask, tgt_mask)
+        att_out = self.att_generator(dec_h)                                             # :226
+        ctc_loss, _, grad = ops.ctc_loss(ctc_out, tgt_label, frames, label_sizes, blank,
+                                         want_grad=True, grad_out=float(args.ctc_alpha))   # :232 (K10)
+        self.last_ctc_grad = grad
+        att_loss = label_smoothing_loss(att_out.view(-1, att_out.size(-1)), tgt_label.reshape(-1),
+                                        args.vocab_size, args.padding_idx, args.label_smooth)   # :248
+        loss = args.ctc_alpha * ctc_loss + args.att_alpha * att_loss
+        return ctc_out, att_out, loss, ctc_loss, att_loss
+
+
+def label_smoothing_loss(logp, target, size, padding_idx, smoothing):
+    """LabelSmoothing.forward of src/utils/loss.py:21-35 in closed form (no [N,V] true_dist clone):
+    KL(smoothed one-hot || p) summed over non-pad tokens / #tokens.  Adjacent to the accelerated
+    path: a handful of torch reductions over the already materialised log-probs."""
+    keep = target != padding_idx
+    tokens = keep.sum()
+    tgt = target.masked_fill(~keep, 0)
+    lp_t = logp.gather(1, tgt.unsqueeze(1)).squeeze(1)
+    conf, eps = 1.0 - smoothing, smoothing / (size - 1)
+    const = (conf * math.log(conf) if conf > 0 else 0.0) + ((size - 1) * eps * math.log(eps) if eps > 0 else 0.0)
+    per_tok = const - conf * lp_t - eps * (logp.sum(1) - lp_t)
+    return per_tok.masked_fill(~keep, 0).sum() / tokens

@@ -356,3 +356,29 @@ def _attention_bf16(q, k, v, mask, n_head):
          ptr(out), out.stride(1), out.stride(0), stream(),
          work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
     return out
+
+
+# ----------------------------------------------------------------------------- K10 CTC loss
+def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, want_grad=True, grad_out=1.0):
+    """CTC loss of cassnat.py:232 — torch.nn.CTCLoss(reduction='mean', zero_infinity=True) — on
+    log_probs [B,T,V] (batch-first; the reference passes the transposed [T,B,V] view of the same
+    tensor).  Returns (loss scalar, nll [B], d loss / d logits [B,T,V] or None); the gradient is with
+    respect to the logits that log_probs = log_softmax(logits) came from."""
+    require_cuda(log_probs)
+    B, T, V = log_probs.shape
+    lp = log_probs if log_probs.stride(-1) == 1 else log_probs.contiguous()
+    tg = _i64(targets.to(lp.device))
+    L = tg.shape[1]
+    il, tl = _i64(input_lengths.to(lp.device)), _i64(target_lengths.to(lp.device))
+    loss = torch.empty(1, dtype=torch.float32, device=lp.device)
+    nll = torch.empty(B, dtype=torch.float32, device=lp.device)
+    grad = torch.empty(B, T, V, dtype=torch.float32, device=lp.device) if want_grad else None
+    ws_bytes = _lib.load().cn_ctc_loss_workspace_bytes(B, T, L)
+    if ws_bytes < 0:
+        raise RuntimeError(f"ctc_loss: unsupported target length L={L} (<= 511)")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lp.device)
+    call("cn_ctc_loss", ptr(lp), B, T, V, lp.stride(0), lp.stride(1), ptr(tg), L, tg.stride(0), ptr(il), ptr(tl),
+         int(blank), float(grad_out), ptr(loss), ptr(nll), ptr(grad), grad.stride(0) if want_grad else 0,
+         grad.stride(1) if want_grad else 0, ptr(ws), ws_bytes, stream(),
+         work=dict(bytes=4.0 * B * T * V * (2 if want_grad else 0) + 8.0 * B * T * (2 * L + 1)))
+    return loss[0], nll, grad

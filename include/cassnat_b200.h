@@ -212,6 +212,21 @@ int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, in
                       int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                       void* out, int64_t ldo, int64_t sbo, cn_stream_t stream);
 
+/* K10  CTC loss (alpha-beta in log space) fused with the log-softmax backward.
+ *   replaces: torch.nn.CTCLoss(reduction='mean', zero_infinity=True)   src/models/cassnat.py:126,232
+ * logp f32 [B,T,V] log-posteriors (strides sb, st; the reference passes the [T,B,V] transposed view
+ * of the same storage); targets i64 [B,L] padded (row stride tgt_stride); input_lengths,
+ * target_lengths i64 [B]; blank id.  Outputs: loss f32 [1] = mean_b(nll_b / max(L_b,1)) with inf -> 0;
+ * nll f32 [B]; grad_logits f32 [B,T,V] (strides gsb, gst; may be NULL) = grad_out * d loss / d logits
+ * where logp = log_softmax(logits) (what autograd delivers after log_softmax.backward).
+ * Supported: L <= 511.  workspace: cn_ctc_loss_workspace_bytes(B,T,L). */
+int64_t cn_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t L);
+int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
+                const int64_t* targets, int64_t L, int64_t tgt_stride, const int64_t* input_lengths,
+                const int64_t* target_lengths, int64_t blank, float grad_out, float* loss, float* nll,
+                float* grad_logits, int64_t gsb, int64_t gst, void* workspace, int64_t workspace_bytes,
+                cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,26 @@ def test_bf16_tensor_core_mode(blocks_golden):
     clear = (top2[..., 0] - top2[..., 1]) > 0.1
     assert torch.equal(keep["ids"].cpu().long()[clear], att.argmax(-1)[clear])
     assert (keep["logp"].cpu() - att.max(-1)[0])[clear].abs().max().item() < 0.05
+
+
+def test_training_forward(blocks_golden):
+    """CassNAT.forward values (cassnat.py:136-257): Viterbi alignment bit-exact, log-probs and the three
+    losses within rel 1e-4, fused CTC gradient (ctc_alpha * d ctc_loss / d logits) within rel 1e-3."""
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    enc_h = torch.from_numpy(z["train::enc_h"]).to(DEV)
+    x_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2].to(DEV)
+    size = torch.from_numpy(z["src_size"]).to(DEV)
+    labels, sizes = torch.from_numpy(z["train::labels"]), torch.from_numpy(z["train::label_sizes"])
+    with torch.no_grad():
+        ctc_out, att_out, loss, ctc_loss, att_loss = model.train_forward_from_encoder(enc_h, x_mask, size, labels, sizes, args)
+    assert rel(ctc_out, z["train::ctc_out"]) < TOL and rel(att_out, z["train::att_out"]) < TOL
+    for got, key in ((loss, "loss"), (ctc_loss, "ctc_loss"), (att_loss, "att_loss")):
+        want = float(z["train::" + key])
+        assert abs(float(got) - want) < 1e-4 * max(1.0, abs(want)), key
+    want_grad = torch.from_numpy(z["train::dctc_dlogits"]) * args.ctc_alpha
+    assert rel(model.last_ctc_grad, want_grad) < 1e-3
+    # whole call from features
+    src, mask = torch.from_numpy(z["src"]).to(DEV), torch.from_numpy(z["src_mask"]).to(DEV)
+    out = model(src, mask, size, labels, sizes, args)
+    assert abs(float(out[2]) - float(z["train::loss"])) < 1e-3 * abs(float(z["train::loss"]))

@@ -1,0 +1,65 @@
+"""CPU: the multi-GPU host logic (utterance sharding, hypothesis gather, WER count reduction) on a
+world_size-2 gloo group — the N > 1 path of bench.py without GPUs."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cassnat_asr_public_b200 import sharding
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 64, 65, 1000):
+        for w in (1, 2, 3, 8):
+            spans = [sharding.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_roundtrip_and_edit_distance():
+    hyps = [[1, 5, 6], [1], [1, 2, 3, 4, 5, 6, 7]]
+    ids, lens = sharding.pack_hypotheses(hyps, 9, "cpu")
+    assert sharding.unpack_hypotheses(ids, lens) == hyps
+    assert sharding.edit_distance([1, 2, 3], [1, 3]) == 1 and sharding.edit_distance([], [4, 4]) == 2
+    assert sharding.edit_distance([7, 8, 9], [7, 8, 9]) == 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_total, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_bounds(n_total, rank, world)
+    mine = [[1] + [10 * i + k for k in range(i % 5)] for i in range(lo, hi)]       # hypothesis of utterance i
+    everything = sharding.gather_hypotheses(mine, n_total, 8, "cpu")
+    errs, toks = sharding.reduce_error_counts(errors=rank + 1, tokens=10 * (rank + 1), device="cpu")
+    out_q.put((rank, everything, errs, toks))
+    dist.destroy_process_group()
+
+
+def test_gather_two_ranks_gloo():
+    world, n_total = 2, 7                       # uneven shards: 4 + 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[1] + [10 * i + k for k in range(i % 5)] for i in range(n_total)]
+    for rank, everything, errs, toks in results:
+        assert everything == want, rank
+        assert (errs, toks) == (3, 30)

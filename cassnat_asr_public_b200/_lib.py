@@ -90,6 +90,7 @@ LAUNCHES = {"cn_row_stats": 1, "cn_bestpath_collapse": 1, "cn_bestpath_from_logp
             "cn_glu_dwconv_groupnorm_act": 2}
 launch_count = 0          # running total of our kernel launches (bench.py reads and resets it)
 _profile = None           # list of (name, start_event, end_event, work) while profiling
+PROFILE_SHAPES = False     # tag GEMM records with their shape (diagnostics)
 
 
 def start_profile():

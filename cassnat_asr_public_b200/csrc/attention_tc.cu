@@ -126,11 +126,13 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const __grid_c
   const uint32_t bars = sbase + OFF_BAR;
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 128);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 160);     // 16 words: key mask of this utterance
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT, hh = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Tk + KT - 1) / KT;
 
+  if (threadIdx.x < 16) kbits[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 9; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(9), 1); mbar_init(bar(10), 1);
@@ -199,55 +201,105 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const __grid_c
 #pragma unroll
     for (int d = 0; d < DK; ++d) o[d] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    if (p.mask && p.mi == 0) {
+      // key-mask bits of this utterance, built by the 128 softmax threads while the TMA loads fly
+      const uint8_t* mk = p.mask + (int64_t)b * p.mb;
+      for (int k0 = 0; k0 < p.Tk; k0 += 128) {
+        const int k = k0 + (int)threadIdx.x;
+        const uint32_t bits = __ballot_sync(0xffffffffu, k < p.Tk && mk[k] != 0);
+        if (lane == 0) kbits[k >> 5] = bits;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     const uint8_t* mrow = p.mask ? p.mask + (int64_t)b * p.mb + (int64_t)(qi < p.Tq ? qi : 0) * p.mi : nullptr;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(bar(9 + (j & 1)), (j >> 1) & 1);
       fence_after();
-      float s[KT];
-#pragma unroll
-      for (int c = 0; c < KT; c += 32) tmem_ld32(TM_S + lane_addr + (j & 1) * 128 + c, s + c);
-      tmem_wait_ld();
-      float mx = -INFINITY;
+      // Two sweeps over S_j straight out of TMEM, 32 columns at a time (keeps the loop body small
+      // enough for the instruction cache and the row out of the register file): max, then exp/P.
       const int k0 = j * KT;
-#pragma unroll
-      for (int c = 0; c < KT; c += 4) {
-        uint32_t mk = 0x01010101u;
-        if (mrow && k0 + c + 3 < p.Tk) {
-          mk = (uint32_t)mrow[k0 + c] | ((uint32_t)mrow[k0 + c + 1] << 8) | ((uint32_t)mrow[k0 + c + 2] << 16) |
-               ((uint32_t)mrow[k0 + c + 3] << 24);
-        } else if (mrow) {
-          mk = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (k0 + c + q < p.Tk) mk |= (uint32_t)mrow[k0 + c + q] << (8 * q);
+      const uint32_t s_addr = TM_S + lane_addr + (j & 1) * 128;
+      auto chunk_bits = [&](int c, uint32_t& keep, uint32_t& valid) {
+        const int n = p.Tk - (k0 + c);
+        valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+        if (!p.mask) keep = 0xffffffffu;
+        else if (p.mi == 0) keep = kbits[(k0 + c) >> 5];              // key mask: shared by all rows
+        else {
+          keep = 0;
+          for (int q = 0; q < 32; ++q)
+            if (k0 + c + q < p.Tk && mrow[k0 + c + q]) keep |= 1u << q;
         }
+      };
+      // Software pipeline over the four 32-column chunks: the tcgen05.ld of chunk i+1 is in flight
+      // while chunk i is processed (tcgen05.wait::ld waits for ALL outstanding loads of the thread).
+      // four independent max / sum chains: one softmax warp per scheduler has to supply its own ILP
+      float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
+      auto sweep_max = [&](const float* t, int c) {
+        uint32_t keep, valid;
+        chunk_bits(c, keep, valid);
+        if ((keep & valid) == 0xffffffffu) {                            // common case: nothing masked in this chunk
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float t = s[c + q] * scale;
-          if (((mk >> (8 * q)) & 0xffu) == 0) t = CN_F32_MIN;      // masked: finfo.min, like the reference
-          if (k0 + c + q >= p.Tk) t = -INFINITY;                    // beyond the key range: no weight at all
-          s[c + q] = t;
-          mx = fmaxf(mx, t);
+          for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
+        } else {
+          float mm = -INFINITY;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            float v = t[q] * scale;
+            v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
+            v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
+            mm = fmaxf(mm, v);
+          }
+          mx_masked = fmaxf(mx_masked, mm);
         }
-      }
+      };
+      float ta[32], tb[32];
+      tmem_ld32(s_addr, ta); tmem_wait_ld();
+      tmem_ld32(s_addr + 32, tb); sweep_max(ta, 0); tmem_wait_ld();
+      tmem_ld32(s_addr + 64, ta); sweep_max(tb, 32); tmem_wait_ld();
+      tmem_ld32(s_addr + 96, tb); sweep_max(ta, 64); tmem_wait_ld();
+      tmem_ld32(s_addr, ta); sweep_max(tb, 96);                          // chunk 0 again, for the exp sweep
+      const float mx = fmaxf(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])) * scale, mx_masked);   // scale > 0
       const float m_new = fmaxf(m_run, mx);
       const float corr = ex2(m_run - m_new);
-      float lsum = 0.f;
+      float lsv[4] = {0.f, 0.f, 0.f, 0.f};
       if (j > 0) mbar_wait(bar(12), (j - 1) & 1);                    // PV_{j-1} finished reading the P buffer
       uint8_t* prow = smem + OFF_P + row * 128;
+      auto sweep_exp = [&](float* t, int c) {
+        uint32_t keep, valid;
+        chunk_bits(c, keep, valid);
+        if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
-      for (int c = 0; c < KT; c += 8) {
-        float e[8];
+          for (int q = 0; q < 32; ++q) {
+            t[q] = ex2(fmaf(t[q], scale, -m_new));
+            lsv[q & 3] += t[q];
+          }
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { e[q] = ex2(s[c + q] - m_new); lsum += e[q]; }
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(e[0], e[1]), b1 = __floats2bfloat162_rn(e[2], e[3]),
-                       b2 = __floats2bfloat162_rn(e[4], e[5]), b3 = __floats2bfloat162_rn(e[6], e[7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-        const int atom = c >> 6, chunk = (c & 63) >> 3;               // 64-key swizzle atoms, 16-byte chunks
-        *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (row & 7)) << 4)) = pk;
-      }
+          for (int q = 0; q < 32; ++q) {
+            float v = t[q] * scale;
+            v = ((keep >> q) & 1u) ? v : CN_F32_MIN;
+            v = ((valid >> q) & 1u) ? v : -INFINITY;
+            t[q] = ex2(v - m_new);
+            lsv[q & 3] += t[q];
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(t[g], t[g + 1]), b1 = __floats2bfloat162_rn(t[g + 2], t[g + 3]),
+                         b2 = __floats2bfloat162_rn(t[g + 4], t[g + 5]), b3 = __floats2bfloat162_rn(t[g + 6], t[g + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+          pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+          const int col = c + g;
+          const int atom = col >> 6, chunk = (col & 63) >> 3;         // 64-key swizzle atoms, 16-byte chunks
+          *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (row & 7)) << 4)) = pk;
+        }
+      };
+      tmem_wait_ld();
+      tmem_ld32(s_addr + 32, tb); sweep_exp(ta, 0); tmem_wait_ld();
+      tmem_ld32(s_addr + 64, ta); sweep_exp(tb, 32); tmem_wait_ld();
+      tmem_ld32(s_addr + 96, tb); sweep_exp(ta, 64); tmem_wait_ld();
+      sweep_exp(tb, 96);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
       fence_before();                                                  // S_j (TMEM) fully read before it is handed back
       mbar_arrive(bar(11));
@@ -262,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const __grid_c
 #pragma unroll
         for (int d = 0; d < DK; ++d) o[d] = o[d] * corr_prev + part[d];
       }
-      l_run = l_run * corr + lsum;
+      l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
       m_run = m_new;
       corr_prev = corr;
       fence_before();

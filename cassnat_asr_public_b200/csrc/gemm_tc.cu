@@ -124,7 +124,7 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, bool RES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K) {
@@ -217,13 +217,32 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int row0 = m0 + quarter * 32 + rr;                  // first of the 8 rows (stride 4) this lane stores
+      // Residual rows do not depend on the accumulator: fetch them one chunk ahead so their HBM
+      // latency hides behind the MMAs / the previous chunk instead of stalling the epilogue.
+      auto load_res = [&](int c0, float4 (&r)[8]) {
+        const int gc = n0 + c0 + cc;
+        const bool ok = RES && ep.residual && vec_ok && gc + 3 < N;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4;
+          if (ok && grow < M) {
+            const int64_t rrow = ep.res_rows > 0 ? (int64_t)(grow % (int)ep.res_rows) : (int64_t)grow;
+            r[it] = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + gc);
+          } else {
+            r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      float4 res_cur[8], res_next[8];
+      if (RES) load_res(half * (BN / 2), res_cur);
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row0 = m0 + quarter * 32 + rr;                  // first of the 8 rows (stride 4) this lane stores
 #pragma unroll 1
       for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         const int col0 = n0 + c0;
         if (col0 >= N) break;                                   // warp-uniform
+        if (RES && c0 + 32 < (half + 1) * (BN / 2) && col0 + 32 < N) load_res(c0 + 32, res_next);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
 #pragma unroll
@@ -256,15 +275,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           x[it][3] = act_fn<ACT>(x[it][3] + bz.w) * ep.alpha;
         }
         if (vec_ok && gcol + 3 < N) {
-          if (ep.residual) {
+          if (RES) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int grow = row0 + it * 4;
-              if (grow < M) {
-                const int64_t rrow = ep.res_rows > 0 ? (int64_t)(grow % (int)ep.res_rows) : (int64_t)grow;
-                const float4 rs = *reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + gcol);
-                x[it][0] += rs.x; x[it][1] += rs.y; x[it][2] += rs.z; x[it][3] += rs.w;
-              }
+              x[it][0] += res_cur[it].x; x[it][1] += res_cur[it].y; x[it][2] += res_cur[it].z; x[it][3] += res_cur[it].w;
             }
           }
           if (ep.out_f32) {
@@ -304,6 +318,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           }
         }
         __syncwarp();                                            // staging buffer is reused by the next chunk
+        if (RES) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -362,19 +380,19 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, bool RES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  gemm_bf16_tc_kernel<BN, ACT, RES><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
@@ -400,14 +418,20 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
-  if (bn == 256) {
-    if (act == CN_ACT_RELU) return launch_tc<256, CN_ACT_RELU>(ma, mw, ep, m, n, k, stream);
-    if (act == CN_ACT_SWISH) return launch_tc<256, CN_ACT_SWISH>(ma, mw, ep, m, n, k, stream);
-    return launch_tc<256, CN_ACT_NONE>(ma, mw, ep, m, n, k, stream);
-  }
-  if (act == CN_ACT_RELU) return launch_tc<128, CN_ACT_RELU>(ma, mw, ep, m, n, k, stream);
-  if (act == CN_ACT_SWISH) return launch_tc<128, CN_ACT_SWISH>(ma, mw, ep, m, n, k, stream);
-  return launch_tc<128, CN_ACT_NONE>(ma, mw, ep, m, n, k, stream);
+#define CN_TC_DISPATCH(BN_)                                                                              \
+  do {                                                                                                   \
+    if (residual) {                                                                                      \
+      if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, true>(ma, mw, ep, m, n, k, stream);    \
+      if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, true>(ma, mw, ep, m, n, k, stream);  \
+      return launch_tc<BN_, CN_ACT_NONE, true>(ma, mw, ep, m, n, k, stream);                            \
+    }                                                                                                    \
+    if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, false>(ma, mw, ep, m, n, k, stream);     \
+    if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, false>(ma, mw, ep, m, n, k, stream);   \
+    return launch_tc<BN_, CN_ACT_NONE, false>(ma, mw, ep, m, n, k, stream);                             \
+  } while (0)
+  if (bn == 256) CN_TC_DISPATCH(256);
+  CN_TC_DISPATCH(128);
+#undef CN_TC_DISPATCH
 }
 
 // f32 -> bf16 cast (operands of the tensor-core GEMM that arrive in fp32, e.g. enc_h)

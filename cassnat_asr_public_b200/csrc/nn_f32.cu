@@ -150,13 +150,64 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// Fast path: the row lives in registers (NV float4 per lane), 128-bit loads and stores.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int64_t ldx,
+                                                            const float* __restrict__ a, const float* __restrict__ b,
+                                                            float eps, float* __restrict__ of32,
+                                                            __nv_bfloat16* __restrict__ obf, int64_t ldo) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float4* row = reinterpret_cast<const float4*>(x + r * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = cn_ld_stream_f32x4(row + lane + 32 * i);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = cn_warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q); q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
+  }
+  const float denom = sqrtf(cn_warp_sum(q) / (float)(D - 1)) + eps;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(a + c)), be = __ldg(reinterpret_cast<const float4*>(b + c));
+    float4 y;
+    y.x = ga.x * v[i].x / denom + be.x; y.y = ga.y * v[i].y / denom + be.y;
+    y.z = ga.z * v[i].z / denom + be.z; y.w = ga.w * v[i].w / denom + be.w;
+    if (of32) *reinterpret_cast<float4*>(of32 + r * ldo + c) = y;
+    if (obf) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(obf + r * ldo + c) = pk;
+    }
+  }
+}
+
 extern "C" int cn_layernorm(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
                             float eps, float* out_f32, void* out_bf16, int64_t ldo, cn_stream_t stream_) {
   if (!x || !a || !b || rows < 0 || d < 2 || ldx < d || ldo < d || (!out_f32 && !out_bf16)) return CN_ERR_BAD_ARG;
   if (rows == 0) return CN_OK;
   const int64_t blocks = (rows + 7) / 8;
-  layernorm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, rows, (int)d, ldx, a, b, eps, out_f32,
-                                                                         (__nv_bfloat16*)out_bf16, ldo);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  __nv_bfloat16* obf = (__nv_bfloat16*)out_bf16;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                         reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0;
+  if (aligned && d == 128) layernorm_vec_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo);
+  else if (aligned && d == 256) layernorm_vec_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo);
+  else if (aligned && d == 512) layernorm_vec_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo);
+  else if (aligned && d == 1024) layernorm_vec_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo);
+  else layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, (int)d, ldx, a, b, eps, out_f32, obf, ldo);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -35,12 +35,15 @@ SIGNATURES = {
     "cn_attention_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                 _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "cn_segment_attention_f32": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int,
-                                        _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+                                        _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "cn_segment_attention_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_conv_module_workspace_bytes": (_i64, [_i64, _i64]),
     "cn_glu_dwconv_groupnorm_act": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _int, _i64, _i64, _i64, _i64,
                                            _vp, _vp, _i64, _vp]),
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
+    "cn_gemm_rowstats_workspace_bytes": (_i64, [_i64, _i64]),
+    "cn_gemm_bf16_rowstats": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,
                            _vp, _i64, _i64, _vp, _i64, _vp]),
@@ -86,8 +89,8 @@ def stream():
 # kernels launched per C-ABI call (cn_row_stats: +1 when it also writes log-probs)
 LAUNCHES = {"cn_row_stats": 1, "cn_bestpath_collapse": 1, "cn_bestpath_from_logp": 2, "cn_viterbi_align": 1,
             "cn_align_to_mask": 1, "cn_expand_trigger_mask": 1, "cn_tgt_length_mask": 1, "cn_gemm_f32": 1,
-            "cn_layernorm": 1, "cn_attention_f32": 1, "cn_segment_attention_f32": 2,
-            "cn_glu_dwconv_groupnorm_act": 2}
+            "cn_layernorm": 1, "cn_attention_f32": 1, "cn_segment_attention_f32": 3,
+            "cn_glu_dwconv_groupnorm_act": 2, "cn_gemm_bf16_rowstats": 2}
 launch_count = 0          # running total of our kernel launches (bench.py reads and resets it)
 _profile = None           # list of (name, start_event, end_event, work) while profiling
 PROFILE_SHAPES = False     # tag GEMM records with their shape (diagnostics)

@@ -53,7 +53,10 @@ class Generator(nn.Module):
 
     def greedy(self, x, want_top2=False):
         """argmax id, its log-probability (and runner-up id) per row without writing log-probs."""
-        st = ops.row_stats(self.logits(x), top2=want_top2, peak=True, lse=True)
+        if ops.is_bf16() and not self.add_norm and x.shape[-1] % 8 == 0:
+            st = ops.head_rowstats(x, self.proj.weight, self.proj.bias, top2=want_top2)    # logits stay on chip
+        else:
+            st = ops.row_stats(self.logits(x), top2=want_top2, peak=True, lse=True)
         st["logp"] = st["peak"] - st["lse"]
         return st
 
@@ -247,17 +250,17 @@ class CassNAT(nn.Module):
             ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
             keep["best_sample"] = best
         # ---- hypothesis assembly (cassnat.py:574-637 for beam_width 1): one D2H copy
-        ids_h, logp_h, ylen_h = ids.cpu(), logp.double().cpu(), ylen.cpu()
+        ids_h, ylen_h = ids.cpu().numpy(), ylen.cpu().tolist()
+        # sequential float64 running sum == the reference's `seq['score'] + token_score` chain
+        csum = logp.cpu().numpy().astype("float64").cumsum(axis=1)
         ys0 = torch.ones(1, 1).fill_(sos).long()
         if getattr(args, "use_gpu", False):
             ys0 = ys0.to(dev)
         out = []
         for b in range(B):
             n = min(int(ylen_h[b]) + 1, ymax)          # the reference keeps i <= ylen[b] (one past eos)
-            score = 0.0
-            for s_ in logp_h[b, :n].tolist():
-                score = score + s_
-            out.append([{"ys": ys0, "score": score if n else 0.0, "hyp": [sos] + ids_h[b, :n].tolist()}])
+            out.append([{"ys": ys0, "score": float(csum[b, n - 1]) if n else 0.0,
+                         "hyp": [sos] + ids_h[b, :n].tolist()}])
         if return_intermediates:
             return out, args, keep
         return out, args

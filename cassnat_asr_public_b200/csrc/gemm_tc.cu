@@ -115,6 +115,8 @@ struct Epilogue {
   const float* residual; int64_t ldr; int64_t res_rows;
   float alpha; int act;
   float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
+  // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
+  float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
 };
 
 template <int ACT>
@@ -124,7 +126,7 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-template <int BN, int ACT, bool RES>
+template <int BN, int ACT, bool RES, bool STATS>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K) {
@@ -211,6 +213,81 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     // memory costs 32 L1 wavefronts per store instruction, so each warp transposes its 32x32 chunk
     // through a private padded smem buffer and stores 4 rows x 128 contiguous bytes per instruction.
     const int quarter = warp & 3, half = (warp - 2) >> 2;
+    if constexpr (STATS) {
+      // Fused row statistics (K1/K9): every thread owns one output ROW of the tile (its TMEM lane) and
+      // scans its half of the tile's columns: running (max, first index), runner-up and online
+      // sum of exp.  Partials go to [row][part] arrays; a tiny second kernel merges the parts.
+      // The logits themselves never leave the SM.
+      float* bias_s = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES + 256);       // [2][BN]
+      const int tid_e = threadIdx.x - 64;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        if (tid_e < BN) bias_s[acc * BN + tid_e] = (ep.bias && n0 + tid_e < N) ? ep.bias[n0 + tid_e] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(&acc_full[acc], acc_phase);
+        tcgen05_fence_after();
+        const int row = m0 + quarter * 32 + lane;
+        float m1 = -INFINITY, m2 = -INFINITY, ssum = 0.f;
+        int i1 = 0x7fffffff, i2 = 0x7fffffff;
+#pragma unroll 1
+        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+          const int col0 = n0 + c0;
+          if (col0 >= N) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+          const float* bz = bias_s + acc * BN + c0;
+          float x[32];
+          float cm = -INFINITY;
+          const float m_old = m1;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bz + j);
+            x[j] = (__uint_as_float(v[j]) + b4.x) * ep.alpha;
+            x[j + 1] = (__uint_as_float(v[j + 1]) + b4.y) * ep.alpha;
+            x[j + 2] = (__uint_as_float(v[j + 2]) + b4.z) * ep.alpha;
+            x[j + 3] = (__uint_as_float(v[j + 3]) + b4.w) * ep.alpha;
+          }
+          if (col0 + 32 > N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j >= N) x[j] = -INFINITY;
+          }
+          if (ep.st_idx2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (x[j] > m1) { m2 = m1; i2 = i1; m1 = x[j]; i1 = col0 + j; }
+              else if (x[j] > m2) { m2 = x[j]; i2 = col0 + j; }
+              cm = fmaxf(cm, x[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, x[j]);
+            if (cm > m1) {                                   // strictly greater: earlier columns keep ties
+              int ci = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j) ci = (x[j] == cm) ? j : ci;
+              i1 = col0 + ci;
+            }
+          }
+          const float m_new = fmaxf(m_old, cm);
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part += __expf(x[j] - m_new);
+          ssum = ssum * __expf(m_old - m_new) + part;          // m_old: the max ssum was relative to so far
+          m1 = m_new;
+        }
+        if (row < M) {
+          const int64_t o = (int64_t)row * ep.n_parts + (tile % tiles_n) * 2 + half;
+          ep.st_max[o] = m1; ep.st_idx[o] = i1; ep.st_sum[o] = ssum;
+          if (ep.st_idx2) { ep.st_max2[o] = m2; ep.st_idx2[o] = i2; }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
     const uint32_t stg = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)(warp - 2) * 4096u;   // 32 x 32 fp32, XOR-swizzled 16-byte chunks
     const int rr = lane >> 3, cc = (lane & 7) * 4;
     const bool vec_ok = ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0);
@@ -328,6 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }  // !STATS
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -380,19 +458,19 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int ACT, bool RES>
+template <int BN, int ACT, bool RES, bool STATS = false>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  gemm_bf16_tc_kernel<BN, ACT, RES, STATS><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
@@ -416,6 +494,7 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   Epilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
+  ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
 #define CN_TC_DISPATCH(BN_)                                                                              \
@@ -432,6 +511,75 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   if (bn == 256) CN_TC_DISPATCH(256);
   CN_TC_DISPATCH(128);
 #undef CN_TC_DISPATCH
+}
+
+// ---------------------------------------------------------------- fused head + row statistics
+namespace {
+__global__ void __launch_bounds__(256) merge_row_parts_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx,
+                                                              const float* __restrict__ psum, const float* __restrict__ pmax2,
+                                                              const int32_t* __restrict__ pidx2, int n_parts, int64_t rows,
+                                                              int32_t* __restrict__ top1, int32_t* __restrict__ top2,
+                                                              float* __restrict__ peak, float* __restrict__ lse) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int64_t o = r * n_parts;
+  float m1 = -INFINITY, m2 = -INFINITY;
+  int i1 = 0x7fffffff, i2 = 0x7fffffff;
+  for (int q = 0; q < n_parts; ++q) {                     // parts are in increasing column order
+    const float v = pmax[o + q];
+    const int i = pidx[o + q];
+    if (v > m1) { m2 = m1; i2 = i1; m1 = v; i1 = i; }
+    else if (v > m2) { m2 = v; i2 = i; }
+    if (pidx2) {
+      const float w = pmax2[o + q];
+      const int k = pidx2[o + q];
+      if (cn_better(w, k, m2, i2) && k != i1) { m2 = w; i2 = k; }
+    }
+  }
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += psum[o + q] * expf(pmax[o + q] - m1);
+  top1[r] = i1;
+  if (top2) top2[r] = i2;
+  if (peak) peak[r] = m1;
+  if (lse) lse[r] = m1 + logf(s);
+}
+}  // namespace
+
+extern "C" int64_t cn_gemm_rowstats_workspace_bytes(int64_t M, int64_t N) {
+  const int64_t parts = ((N + 255) / 256) * 2;
+  return M * parts * 5 * 4 + 256;
+}
+
+extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                     float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
+                                     float* peak, float* lse, void* workspace, int64_t workspace_bytes,
+                                     cn_stream_t stream_) {
+  if (!A || !W || !top1 || !workspace || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K) return CN_ERR_BAD_ARG;
+  if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return CN_ERR_UNSUPPORTED;
+  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
+  if (workspace_bytes < cn_gemm_rowstats_workspace_bytes(M, N)) return CN_ERR_WORKSPACE;
+  if (M == 0) return CN_OK;
+  CUtensorMap ma, mw;
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mw, W, N, K, ldw, 256)) return CN_ERR_DEVICE;
+  const int parts = (int)(((N + 255) / 256) * 2);
+  float* pmax = (float*)workspace;
+  int32_t* pidx = (int32_t*)(pmax + M * parts);
+  float* psum = (float*)(pidx + M * parts);
+  float* pmax2 = psum + M * parts;
+  int32_t* pidx2 = (int32_t*)(pmax2 + M * parts);
+  Epilogue ep;
+  ep.bias = bias; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = alpha; ep.act = CN_ACT_NONE;
+  ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0;
+  ep.st_max = pmax; ep.st_idx = pidx; ep.st_sum = psum; ep.st_max2 = top2 ? pmax2 : nullptr;
+  ep.st_idx2 = top2 ? pidx2 : nullptr; ep.n_parts = parts;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = launch_tc<256, CN_ACT_NONE, false, true>(ma, mw, ep, (int)M, (int)N, (int)K, stream);
+  if (rc != CN_OK) return rc;
+  merge_row_parts_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(pmax, pidx, psum, ep.st_max2, ep.st_idx2, parts, M,
+                                                                          top1, top2, peak, lse);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
 }
 
 // f32 -> bf16 cast (operands of the tensor-core GEMM that arrive in fp32, e.g. enc_h)

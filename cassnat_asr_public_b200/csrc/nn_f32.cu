@@ -413,7 +413,26 @@ struct SegArgs {
   const int32_t* seg; const int64_t* ylens; const uint8_t* src_mask; const int64_t* src_size;
   int left, right, h, U, T;
   float* out; int64_t ldo, sbo; const float* vmean;
+  const int32_t* run_first; const int32_t* run_last;
 };
+
+// first / last frame of every segment id (run) of every utterance: one CTA per utterance
+__global__ void __launch_bounds__(256) segment_bounds_kernel(const int32_t* __restrict__ seg, int T, int U,
+                                                             int32_t* __restrict__ run_first,
+                                                             int32_t* __restrict__ run_last) {
+  const int b = blockIdx.x;
+  const int32_t* s = seg + (int64_t)b * T;
+  int32_t* f = run_first + (int64_t)b * U;
+  int32_t* l = run_last + (int64_t)b * U;
+  for (int u = threadIdx.x; u < U; u += blockDim.x) { f[u] = T; l[u] = -1; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int v = s[t];
+    if (v < 0 || v >= U) continue;
+    if (t == 0 || s[t - 1] != v) f[v] = t;
+    if (t == T - 1 || s[t + 1] != v) l[v] = t;
+  }
+}
 
 // one warp per (token row, head); lanes own 2 of the 64 head dims
 __global__ void __launch_bounds__(256) segment_attention_kernel(SegArgs p) {
@@ -436,13 +455,9 @@ __global__ void __launch_bounds__(256) segment_attention_kernel(SegArgs p) {
     if (p.left) m = m || base(t + 1);
     return m && src[t];
   };
-  // frames whose segment id equals u form one contiguous run (seg is non-decreasing): binary search
-  int lo = 0, hi = T;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] < u) lo = mid + 1; else hi = mid; }
-  const int first = lo;
-  hi = T;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] <= u) lo = mid + 1; else hi = mid; }
-  const int last = lo - 1;                         // empty run: last < first
+  // frames whose segment id equals u form one contiguous run (seg is non-decreasing); its bounds
+  // were tabulated per utterance by segment_bounds_kernel (empty run: last < first)
+  const int first = p.run_first[(int64_t)b * p.U + u], last = p.run_last[(int64_t)b * p.U + u];
   const float2 q = *reinterpret_cast<const float2*>(p.Q + (int64_t)u * p.ldq + hh * 64 + lane * 2);
   const float* Kb = p.K + (int64_t)b * p.sbk + hh * 64 + lane * 2;
   const float* Vb = p.V + (int64_t)b * p.sbv + hh * 64 + lane * 2;
@@ -479,12 +494,21 @@ __global__ void __launch_bounds__(256) segment_attention_kernel(SegArgs p) {
 }
 }  // namespace
 
+extern "C" int64_t cn_segment_attention_workspace_bytes(int64_t B, int64_t U, int64_t d) {
+  return (((B * d + 63) / 64) * 64 + 2 * B * U) * 4;
+}
+
 extern "C" int cn_segment_attention_f32(const float* Q, int64_t ldq, const float* K, int64_t ldk, int64_t sbk,
                                         const float* V, int64_t ldv, int64_t sbv, const int32_t* seg,
                                         const int64_t* ylens, const uint8_t* src_mask, const int64_t* src_size,
                                         int left, int right, int64_t B, int64_t h, int64_t U, int64_t T, int64_t dk,
-                                        float* out, int64_t ldo, int64_t sbo, float* vmean_ws, cn_stream_t stream_) {
-  if (!Q || !K || !V || !seg || !ylens || !src_mask || !src_size || !out || !vmean_ws) return CN_ERR_BAD_ARG;
+                                        float* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
+                                        cn_stream_t stream_) {
+  if (!Q || !K || !V || !seg || !ylens || !src_mask || !src_size || !out || !workspace) return CN_ERR_BAD_ARG;
+  if (workspace_bytes < cn_segment_attention_workspace_bytes(B, U, h * dk)) return CN_ERR_WORKSPACE;
+  float* vmean_ws = (float*)workspace;
+  int32_t* run_first = (int32_t*)(vmean_ws + ((B * h * dk + 63) / 64) * 64);
+  int32_t* run_last = run_first + B * U;
   if (B < 0 || U < 0 || T <= 0 || h <= 0) return CN_ERR_BAD_ARG;
   if (dk != 64 || h > 8 || B > 65535) return CN_ERR_UNSUPPORTED;
   if (((ldq | ldk | ldv | ldo | sbk | sbv | sbo) & 1) != 0) return CN_ERR_UNSUPPORTED;
@@ -493,11 +517,13 @@ extern "C" int cn_segment_attention_f32(const float* Q, int64_t ldq, const float
   const int d = (int)(h * dk);
   column_mean_kernel<<<dim3((unsigned)((d + 255) / 256), (unsigned)B), 256, 0, stream>>>(V, ldv, sbv, (int)T, d, vmean_ws);
   CN_CHECK_LAUNCH();
+  segment_bounds_kernel<<<(unsigned)B, 256, 0, stream>>>(seg, (int)T, (int)U, run_first, run_last);
+  CN_CHECK_LAUNCH();
   SegArgs p;
   p.Q = Q; p.K = K; p.V = V; p.ldq = ldq; p.ldk = ldk; p.sbk = sbk; p.ldv = ldv; p.sbv = sbv;
   p.seg = seg; p.ylens = ylens; p.src_mask = src_mask; p.src_size = src_size;
   p.left = left > 0; p.right = right > 0; p.h = (int)h; p.U = (int)U; p.T = (int)T;
-  p.out = out; p.ldo = ldo; p.sbo = sbo; p.vmean = vmean_ws;
+  p.out = out; p.ldo = ldo; p.sbo = sbo; p.vmean = vmean_ws; p.run_first = run_first; p.run_last = run_last;
   segment_attention_kernel<<<dim3((unsigned)U, (unsigned)B), (unsigned)(32 * h), 0, stream>>>(p);
   CN_CHECK_LAUNCH();
   return CN_OK;

@@ -276,12 +276,13 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
     B, T, _ = k.shape
     if out is None:
         out = torch.empty(B, U, d, dtype=torch.float32, device=k.device)
-    vmean = torch.empty(B, d, dtype=torch.float32, device=k.device)
+    ws_bytes = _lib.load().cn_segment_attention_workspace_bytes(B, U, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=k.device)
     mask = _u8(src_mask, B, T)
     call("cn_segment_attention_f32", ptr(q_rows), q_rows.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(seg), ptr(_i64(ylens)), ptr(mask), ptr(_i64(src_size)),
          int(left > 0), int(right > 0), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
-         ptr(vmean), stream(), work=dict(flops=4.0 * B * T * d, bytes=4.0 * B * d * (3 * T + U)))
+         ptr(ws), ws_bytes, stream(), work=dict(flops=4.0 * B * T * d, bytes=4.0 * B * d * (3 * T + U)))
     return out
 
 
@@ -383,3 +384,29 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, want_gr
          grad.stride(1) if want_grad else 0, ptr(ws), ws_bytes, stream(),
          work=dict(bytes=4.0 * B * T * V * (2 if want_grad else 0) + 8.0 * B * T * (2 * L + 1)))
     return loss[0], nll, grad
+
+
+def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False):
+    """K1/K9 fused (fast mode): argmax / runner-up / max / log-sum-exp of every row of
+    alpha * (x @ weight.T + bias) straight out of the tcgen05 GEMM's epilogue; the logits are never
+    written.  Returns the same dict as row_stats."""
+    require_cuda(x, weight)
+    xb, wb = cast_bf16(x), bf16_weight(weight)
+    K, N = xb.shape[-1], wb.shape[0]
+    x2 = xb.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    dev = x.device
+    out = {"top1": torch.empty(M, dtype=torch.int32, device=dev), "peak": torch.empty(M, dtype=torch.float32, device=dev),
+           "lse": torch.empty(M, dtype=torch.float32, device=dev)}
+    if top2:
+        out["top2"] = torch.empty(M, dtype=torch.int32, device=dev)
+    ws_bytes = _lib.load().cn_gemm_rowstats_workspace_bytes(M, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("cn_gemm_bf16_rowstats", ptr(x2), x2.stride(0), ptr(wb), wb.stride(0), ptr(bias), float(alpha), M, N, K,
+         ptr(out["top1"]), ptr(out.get("top2")), ptr(out["peak"]), ptr(out["lse"]), ptr(ws), ws_bytes, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K)),
+         tag=(f"cn_gemm_bf16_rowstats[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+    lead = x.shape[:-1]
+    return {k: v.reshape(lead) for k, v in out.items()}

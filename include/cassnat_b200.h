@@ -177,7 +177,8 @@ int cn_segment_attention_f32(const float* Q, int64_t ldq, const float* K, int64_
                              const int64_t* src_size, int left, int right,
                              int64_t B, int64_t h, int64_t U, int64_t T, int64_t dk,
                              float* out, int64_t ldo, int64_t sbo,
-                             float* vmean_ws /* f32 [B, h*dk] scratch */, cn_stream_t stream);
+                             void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+int64_t cn_segment_attention_workspace_bytes(int64_t B, int64_t U, int64_t d /* = h*dk */);
 
 /* Conformer convolution-module core between the two pointwise convolutions (which are GEMMs):
  * GLU over channels -> depthwise conv (odd kernel <= 63, zero padding) along the token axis ->
@@ -226,6 +227,16 @@ int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, 
                 const int64_t* target_lengths, int64_t blank, float grad_out, float* loss, float* nll,
                 float* grad_logits, int64_t gsb, int64_t gst, void* workspace, int64_t workspace_bytes,
                 cn_stream_t stream);
+
+/* K1/K9 fused: head GEMM (bf16 tcgen05, fp32 accumulate) whose epilogue keeps only the row
+ * statistics of  z = alpha * (A W^T + bias):  first-index argmax, runner-up, max and log-sum-exp.
+ * The [M,N] logits never reach HBM.
+ *   replaces: Generator.forward + argmax/max/topk(2)       src/models/cassnat.py:110-113,371-378,501,611
+ * top2 / peak / lse may be NULL.  workspace: cn_gemm_rowstats_workspace_bytes(M,N). */
+int64_t cn_gemm_rowstats_workspace_bytes(int64_t M, int64_t N);
+int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha,
+                          int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak, float* lse,
+                          void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -49,3 +49,31 @@ def test_gemm_bf16_strided_views_and_res_rows():
 def test_cast_bf16():
     x = torch.randn(1000, 512, device=DEV)
     assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 5000, 512), (129, 120, 128), (1000, 4990, 256), (32, 257, 64)])
+def test_fused_head_rowstats(M, N, K):
+    """K1/K9 fused epilogue vs row_stats on the materialised logits of the same bf16 GEMM."""
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K).bfloat16().to(DEV)
+    w = (torch.randn(N, K) / K ** 0.5).bfloat16().to(DEV)
+    w[N // 3] = w[0]                                   # exact duplicate column -> argmax / top-2 ties
+    b = torch.randn(N).to(DEV)
+    b[N // 3] = b[0]
+    logits = ops.linear_bf16(x, w, b)
+    want = ops.row_stats(logits, top2=True, peak=True, lse=True)
+    from cassnat_asr_public_b200 import _lib
+    from cassnat_asr_public_b200._lib import call, ptr, stream
+    got = {k: torch.empty(M, dtype=(torch.int32 if k.startswith("top") else torch.float32), device=DEV)
+           for k in ("top1", "top2", "peak", "lse")}
+    nbytes = _lib.load().cn_gemm_rowstats_workspace_bytes(M, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    call("cn_gemm_bf16_rowstats", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), 1.0, M, N, K, ptr(got["top1"]),
+         ptr(got["top2"]), ptr(got["peak"]), ptr(got["lse"]), ptr(ws), nbytes, stream())
+    assert torch.equal(got["top1"], want["top1"]) and torch.equal(got["top2"], want["top2"])
+    assert torch.equal(got["peak"], want["peak"])
+    assert (got["lse"] - want["lse"]).abs().max().item() < 1e-4
+    # and without the runner-up (the greedy decode configuration)
+    call("cn_gemm_bf16_rowstats", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), 1.0, M, N, K, ptr(got["top1"]),
+         None, ptr(got["peak"]), ptr(got["lse"]), ptr(ws), nbytes, stream())
+    assert torch.equal(got["top1"], want["top1"]) and (got["lse"] - want["lse"]).abs().max().item() < 1e-4

@@ -1,18 +1,19 @@
 // Masked multi-head attention on the 5th-gen tensor cores (fast mode), d_k = 64, Tk <= 512.
 //
-// One CTA per (128-query tile, head, utterance).  Warps 0-3 (one thread per query row = one TMEM
-// lane) run the softmax; warp 4 issues TMA and tcgen05.mma:
-//   * Q tile and ALL K/V tiles of this (utterance, head) are fetched up front by TMA (3-D tensor
-//     maps over [B, T, row], 128-byte swizzle), one mbarrier per tile, so S_0 starts as soon as
-//     K_0 lands;
-//   * S_j = Q K_j^T  (128 x 128 x 64, K-major operands) into a double-buffered TMEM accumulator;
-//   * softmax warps read S_j with tcgen05.ld, apply 1/sqrt(d_k) and the mask with the reference's
-//     finfo.min semantics (fully masked rows stay uniform over all Tk keys, modules/attention.py:19-21),
-//     keep a running max / sum, and write P_j as bf16 into shared memory in the K-major swizzled
-//     layout the next MMA reads;
-//   * O_j = P_j V_j (128 x 64 x 128; V tile used in place as an MN-major operand) into a
+// Persistent kernel, one CTA per SM looping over (utterance, head) items; per item the K/V tiles
+// are loaded once (3-D TMA maps over [B, T, row], 128-byte swizzle, per-tile mbarriers) and shared
+// by all query tiles.  Two softmax warpgroups ping-pong on two query tiles (A/B) so that the
+// tensor pipe computes S_B while group A is in its softmax and vice versa:
+//   * S_g = Q_g K_j^T  (128 x 128 x 64, K-major operands) into TMEM;
+//   * the softmax group reads S_g with tcgen05.ld (32-column chunks, software pipelined), applies
+//     1/sqrt(d_k) and the mask with the reference's finfo.min semantics (fully masked rows stay
+//     uniform over all Tk keys, modules/attention.py:19-21), keeps a running max / sum and writes
+//     P_g as bf16 into shared memory in the K-major swizzled layout the next MMA reads;
+//   * O_g = P_g V_j (128 x 64 x 128; the V tile is used in place as an MN-major operand) into a
 //     double-buffered TMEM slot, folded into per-row fp32 registers with the online-softmax
-//     correction.
+//     correction while the next MMAs run;
+//   * a dedicated TMA warp runs ahead through the schedule (next Q tiles, next item's K/V as soon
+//     as the last MMA that reads a slot has retired).
 // Replaces (fast mode) attention() of src/models/modules/attention.py:13-24.
 #include <cuda.h>
 
@@ -24,7 +25,6 @@ constexpr int QT = 128;        // queries per CTA
 constexpr int KT = 128;        // keys per tile
 constexpr int DK = 64;
 constexpr int MAX_TILES = 4;   // Tk <= 512
-constexpr int THREADS = 160;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -107,40 +107,46 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major)
 
 struct AttnTcArgs {
   const uint8_t* mask; int64_t mb, mi;      // u8, element (b,i,j) at mask[b*mb + i*mi + j]; mi == 0 -> key mask
-  int h, Tq, Tk;
+  int B, h, Tq, Tk;
   __nv_bfloat16* out; int64_t ldo, sbo;
 };
 
-// smem map (bytes): Q 16K | K 4x16K | V 4x16K | P 32K | barriers
-constexpr uint32_t OFF_Q = 0, OFF_K = 16384, OFF_V = OFF_K + MAX_TILES * 16384, OFF_P = OFF_V + MAX_TILES * 16384,
-                   OFF_BAR = OFF_P + 32768, SMEM_BYTES = OFF_BAR + 256 + 1024;
+// Persistent, ping-pong design (v2):
+//   warps 0-3  softmax group A (query tile 2p of the current (utterance, head) item)
+//   warps 4-7  softmax group B (query tile 2p+1)          -> two softmax warps per scheduler
+//   warp 8     tcgen05.mma issuer (one lane)
+//   warp 9     TMA producer (one lane), runs ahead through the whole schedule
+// smem: Q_A | Q_B | K 4x16K | V 4x16K | P_A 32K | P_B 32K | barriers ; TMEM: S_A S_B O_A[2] O_B[2]
+constexpr uint32_t OFF_Q = 0, OFF_K = 2 * 16384, OFF_V = OFF_K + MAX_TILES * 16384, OFF_P = OFF_V + MAX_TILES * 16384,
+                   OFF_BAR = OFF_P + 2 * 32768, SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int NTHREADS = 320;
+// barrier indices
+constexpr int B_QFULL = 0, B_QFREE = 2, B_KFULL = 4, B_VFULL = 8, B_KFREE = 12, B_VFREE = 16, B_SFULL = 20,
+              B_PREADY = 22, B_PFREE = 24, B_OFULL = 26, N_BARS = 30;
 
-__global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
-                                                                  const __grid_constant__ CUtensorMap map_k,
-                                                                  const __grid_constant__ CUtensorMap map_v,
-                                                                  AttnTcArgs p) {
+__global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                   const __grid_constant__ CUtensorMap map_k,
+                                                                   const __grid_constant__ CUtensorMap map_v,
+                                                                   AttnTcArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
-  // barriers: 0 q_full | 1..4 k_full[j] | 5..8 v_full[j] | 9,10 s_full[2] | 11 p_ready | 12 p_free | 13,14 o_full[2]
   const uint32_t bars = sbase + OFF_BAR;
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 128);
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 160);     // 16 words: key mask of this utterance
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 256);
+  uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 288);   // [2 groups][16 words]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QT, hh = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.Tk + KT - 1) / KT;
+  const int n_tiles = (p.Tk + KT - 1) / KT;            // key tiles (<= 4)
+  const int nq = (p.Tq + QT - 1) / QT;                 // query tiles
+  const int n_pairs = (nq + 1) / 2;
+  const int n_items = p.B * p.h;
 
-  if (threadIdx.x < 16) kbits[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(bar(i), 1);
-    mbar_init(bar(9), 1); mbar_init(bar(10), 1);
-    mbar_init(bar(11), 128); mbar_init(bar(12), 1);
-    mbar_init(bar(13), 1); mbar_init(bar(14), 1);
+    for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), (i == B_PREADY || i == B_PREADY + 1) ? 128 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -148,205 +154,244 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const __grid_c
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t TM_S = tmem, TM_O = tmem + 256;          // S: 2 x 128 columns, O: 2 x 64 columns
+  // TMEM columns: S_A 0..127 | S_B 128..255 | O_A[0] 256 | O_A[1] 320 | O_B[0] 384 | O_B[1] 448
+  auto tm_s = [&](int g) { return tmem + g * 128; };
+  auto tm_o = [&](int g, int buf) { return tmem + 256 + g * 128 + buf * 64; };
 
-  if (warp == 4) {
+  if (warp == 9) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      // ---- TMA: Q, then K_j / V_j for every key tile
-      mbar_expect_tx(bar(0), QT * DK * 2);
-      tma_load_3d(&map_q, bar(0), sbase + OFF_Q, hh * DK, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_expect_tx(bar(1 + j), KT * DK * 2);
-        tma_load_3d(&map_k, bar(1 + j), sbase + OFF_K + j * 16384, hh * DK, j * KT, b);
+      uint32_t it_cnt = 0, q_cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+        const int b = item / p.h, hh = item % p.h;
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(bar(B_KFREE + j), (it_cnt & 1) ^ 1);
+          mbar_expect_tx(bar(B_KFULL + j), KT * DK * 2);
+          tma_load_3d(&map_k, bar(B_KFULL + j), sbase + OFF_K + j * 16384, hh * DK, j * KT, b);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(bar(B_VFREE + j), (it_cnt & 1) ^ 1);
+          mbar_expect_tx(bar(B_VFULL + j), KT * DK * 2);
+          tma_load_3d(&map_v, bar(B_VFULL + j), sbase + OFF_V + j * 16384, hh * DK, j * KT, b);
+        }
+        for (int pr = 0; pr < n_pairs; ++pr) {
+          for (int g = 0; g < 2; ++g) {
+            const int qt = 2 * pr + g;
+            if (qt >= nq) continue;
+            mbar_wait(bar(B_QFREE + g), (q_cnt[g] & 1) ^ 1);
+            mbar_expect_tx(bar(B_QFULL + g), QT * DK * 2);
+            tma_load_3d(&map_q, bar(B_QFULL + g), sbase + OFF_Q + g * 16384, hh * DK, qt * QT, b);
+            ++q_cnt[g];
+          }
+        }
       }
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_expect_tx(bar(5 + j), KT * DK * 2);
-        tma_load_3d(&map_v, bar(5 + j), sbase + OFF_V + j * 16384, hh * DK, j * KT, b);
-      }
-      // ---- MMA issue
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(QT, KT, false);
       constexpr uint32_t idesc_o = idesc_bf16(QT, DK, true);
-      mbar_wait(bar(0), 0);
-      auto issue_s = [&](int j) {
-        mbar_wait(bar(1 + j), 0);
-        fence_after();
-        const uint64_t dq = desc_kmajor(sbase + OFF_Q), dkk = desc_kmajor(sbase + OFF_K + j * 16384);
+      uint32_t it_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+        for (int pr = 0; pr < n_pairs; ++pr) {
+          const bool has[2] = {2 * pr < nq, 2 * pr + 1 < nq};
+          const bool last_pair = pr == n_pairs - 1;
+          const int last_g = has[1] ? 1 : 0;
+          auto issue_s = [&](int g, int j) {
+            if (j == 0) mbar_wait(bar(B_QFULL + g), q_cnt[g] & 1);
+            mbar_wait(bar(B_KFULL + j), it_cnt & 1);
+            fence_after();
+            const uint64_t dq = desc_kmajor(sbase + OFF_Q + g * 16384), dkk = desc_kmajor(sbase + OFF_K + j * 16384);
 #pragma unroll
-        for (int k = 0; k < DK / 16; ++k) umma(TM_S + (j & 1) * 128, dq + (uint64_t)(k * 2), dkk + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
-        tcgen05_commit(bar(9 + (j & 1)));
-      };
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);               // S_{j+1} overlaps the softmax of tile j
-        mbar_wait(bar(11), j & 1);                          // P_j written by all 128 softmax threads
-        mbar_wait(bar(5 + j), 0);                           // V_j landed
-        fence_after();
-        const uint64_t dv = desc_mnmajor(sbase + OFF_V + j * 16384);
+            for (int k = 0; k < DK / 16; ++k) umma(tm_s(g), dq + (uint64_t)(k * 2), dkk + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+            tcgen05_commit(bar(B_SFULL + g));
+            if (j == n_tiles - 1) { tcgen05_commit(bar(B_QFREE + g)); ++q_cnt[g]; }   // Q tile no longer needed
+            if (last_pair && g == last_g) tcgen05_commit(bar(B_KFREE + j));           // K_j done for this item
+          };
+          for (int g = 0; g < 2; ++g)
+            if (has[g]) issue_s(g, 0);
+          for (int j = 0; j < n_tiles; ++j) {
+            for (int g = 0; g < 2; ++g) {
+              if (!has[g]) continue;
+              mbar_wait(bar(B_PREADY + g), p_cnt[g] & 1);       // P_g(j) written, S_g(j) consumed
+              ++p_cnt[g];
+              mbar_wait(bar(B_VFULL + j), it_cnt & 1);
+              fence_after();
+              const uint64_t dv = desc_mnmajor(sbase + OFF_V + j * 16384);
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k) {
-          const uint64_t dp = desc_kmajor(sbase + OFF_P + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
-          umma(TM_O + (j & 1) * 64, dp, dv + (uint64_t)((k * 16 * 128) >> 4), idesc_o, k ? 1u : 0u);
+              for (int k = 0; k < KT / 16; ++k) {
+                const uint64_t dp = desc_kmajor(sbase + OFF_P + g * 32768 + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
+                umma(tm_o(g, j & 1), dp, dv + (uint64_t)((k * 16 * 128) >> 4), idesc_o, k ? 1u : 0u);
+              }
+              tcgen05_commit(bar(B_PFREE + g));
+              tcgen05_commit(bar(B_OFULL + g * 2 + (j & 1)));
+              if (last_pair && g == last_g) tcgen05_commit(bar(B_VFREE + j));
+              if (j + 1 < n_tiles) issue_s(g, j + 1);           // S_g(j+1) while group g folds O_g(j-1)
+            }
+          }
         }
-        tcgen05_commit(bar(12));                            // P buffer free again
-        tcgen05_commit(bar(13 + (j & 1)));                  // O_j ready
       }
     }
   } else {
-    // ---- softmax warps: thread = query row = TMEM lane
-    const int row = warp * 32 + lane;
-    const int qi = q0 + row;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    // ===================== softmax groups: thread = query row = TMEM lane =====================
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float scale = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
-    float o[DK];
-#pragma unroll
-    for (int d = 0; d < DK; ++d) o[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-    if (p.mask && p.mi == 0) {
-      // key-mask bits of this utterance, built by the 128 softmax threads while the TMA loads fly
-      const uint8_t* mk = p.mask + (int64_t)b * p.mb;
-      for (int k0 = 0; k0 < p.Tk; k0 += 128) {
-        const int k = k0 + (int)threadIdx.x;
-        const uint32_t bits = __ballot_sync(0xffffffffu, k < p.Tk && mk[k] != 0);
-        if (lane == 0) kbits[k >> 5] = bits;
+    uint32_t* kbits = kbits_all + g * 16;
+    uint32_t s_cnt = 0, pf_cnt = 0, o_cnt[2] = {0, 0};
+    uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / p.h, hh = item % p.h;
+      if (p.mask && p.mi == 0) {
+        // key-mask bits of this utterance (one private copy per group)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // previous item's readers are done
+        const uint8_t* mk = p.mask + (int64_t)b * p.mb;
+        for (int k0 = 0; k0 < p.Tk; k0 += 128) {
+          const int k = k0 + row;
+          const uint32_t bits = __ballot_sync(0xffffffffu, k < p.Tk && mk[k] != 0);
+          if (lane == 0) kbits[k >> 5] = bits;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    const uint8_t* mrow = p.mask ? p.mask + (int64_t)b * p.mb + (int64_t)(qi < p.Tq ? qi : 0) * p.mi : nullptr;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(bar(9 + (j & 1)), (j >> 1) & 1);
-      fence_after();
-      // Two sweeps over S_j straight out of TMEM, 32 columns at a time (keeps the loop body small
-      // enough for the instruction cache and the row out of the register file): max, then exp/P.
-      const int k0 = j * KT;
-      const uint32_t s_addr = TM_S + lane_addr + (j & 1) * 128;
-      auto chunk_bits = [&](int c, uint32_t& keep, uint32_t& valid) {
-        const int n = p.Tk - (k0 + c);
-        valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
-        if (!p.mask) keep = 0xffffffffu;
-        else if (p.mi == 0) keep = kbits[(k0 + c) >> 5];              // key mask: shared by all rows
-        else {
-          keep = 0;
-          for (int q = 0; q < 32; ++q)
-            if (k0 + c + q < p.Tk && mrow[k0 + c + q]) keep |= 1u << q;
-        }
-      };
-      // Software pipeline over the four 32-column chunks: the tcgen05.ld of chunk i+1 is in flight
-      // while chunk i is processed (tcgen05.wait::ld waits for ALL outstanding loads of the thread).
-      // four independent max / sum chains: one softmax warp per scheduler has to supply its own ILP
-      float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
-      auto sweep_max = [&](const float* t, int c) {
-        uint32_t keep, valid;
-        chunk_bits(c, keep, valid);
-        if ((keep & valid) == 0xffffffffu) {                            // common case: nothing masked in this chunk
+      for (int pr = 0; pr < n_pairs; ++pr) {
+        const int qt = 2 * pr + g;
+        if (qt >= nq) continue;
+        const int qi = qt * QT + row;
+        const uint8_t* mrow = p.mask ? p.mask + (int64_t)b * p.mb + (int64_t)(qi < p.Tq ? qi : 0) * p.mi : nullptr;
+        float o[DK];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
-        } else {
-          float mm = -INFINITY;
+        for (int d = 0; d < DK; ++d) o[d] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+        auto fold = [&](int j, float extra) {
+          mbar_wait(bar(B_OFULL + g * 2 + (j & 1)), o_cnt[j & 1] & 1);
+          ++o_cnt[j & 1];
+          fence_after();
+          float part[DK];
+          tmem_ld32(tm_o(g, j & 1) + lane_addr, part);
+          tmem_ld32(tm_o(g, j & 1) + lane_addr + 32, part + 32);
+          tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            float v = t[q] * scale;
-            v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
-            v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
-            mm = fmaxf(mm, v);
+          for (int d = 0; d < DK; ++d) o[d] = (o[d] * corr_prev + part[d]) * extra;
+        };
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(bar(B_SFULL + g), s_cnt & 1);
+          ++s_cnt;
+          fence_after();
+          const int k0 = j * KT;
+          const uint32_t s_addr = tm_s(g) + lane_addr;
+          auto chunk_bits = [&](int c, uint32_t& keep, uint32_t& valid) {
+            const int n = p.Tk - (k0 + c);
+            valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+            if (!p.mask) keep = 0xffffffffu;
+            else if (p.mi == 0) keep = kbits[(k0 + c) >> 5];              // key mask: shared by all rows
+            else {
+              keep = 0;
+              for (int q = 0; q < 32; ++q)
+                if (k0 + c + q < p.Tk && mrow[k0 + c + q]) keep |= 1u << q;
+            }
+          };
+          // ---- sweep 1: row max (four independent chains; masked chunks take the slow path)
+          float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
+          auto sweep_max = [&](const float* t, int c) {
+            uint32_t keep, valid;
+            chunk_bits(c, keep, valid);
+            if ((keep & valid) == 0xffffffffu) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
+            } else {
+              float mm = -INFINITY;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                float v = t[q] * scale;
+                v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
+                v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
+                mm = fmaxf(mm, v);
+              }
+              mx_masked = fmaxf(mx_masked, mm);
+            }
+          };
+          float ta[32], tb[32];
+          tmem_ld32(s_addr, ta); tmem_wait_ld();
+#pragma unroll 1
+          for (int c = 0; c < KT; c += 64) {                              // software pipeline, 2 chunks / iteration
+            tmem_ld32(s_addr + c + 32, tb); sweep_max(ta, c); tmem_wait_ld();
+            tmem_ld32(s_addr + ((c + 64) & (KT - 1)), ta); sweep_max(tb, c + 32); tmem_wait_ld();   // wraps to chunk 0
           }
-          mx_masked = fmaxf(mx_masked, mm);
-        }
-      };
-      float ta[32], tb[32];
-      tmem_ld32(s_addr, ta); tmem_wait_ld();
-      tmem_ld32(s_addr + 32, tb); sweep_max(ta, 0); tmem_wait_ld();
-      tmem_ld32(s_addr + 64, ta); sweep_max(tb, 32); tmem_wait_ld();
-      tmem_ld32(s_addr + 96, tb); sweep_max(ta, 64); tmem_wait_ld();
-      tmem_ld32(s_addr, ta); sweep_max(tb, 96);                          // chunk 0 again, for the exp sweep
-      const float mx = fmaxf(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])) * scale, mx_masked);   // scale > 0
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = ex2(m_run - m_new);
-      float lsv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (j > 0) mbar_wait(bar(12), (j - 1) & 1);                    // PV_{j-1} finished reading the P buffer
-      uint8_t* prow = smem + OFF_P + row * 128;
-      auto sweep_exp = [&](float* t, int c) {
-        uint32_t keep, valid;
-        chunk_bits(c, keep, valid);
-        if ((keep & valid) == 0xffffffffu) {
+          const float mx = fmaxf(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])) * scale, mx_masked);   // scale > 0
+          const float m_new = fmaxf(m_run, mx);
+          const float corr = ex2(m_run - m_new);
+          float lsv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (pf_cnt > 0) mbar_wait(bar(B_PFREE + g), (pf_cnt - 1) & 1);   // previous PV finished reading P_g
+          ++pf_cnt;
+          // ---- sweep 2: exp, row sum, P (bf16) into the K-major swizzled layout of the PV MMA
+          auto sweep_exp = [&](float* t, int c) {
+            uint32_t keep, valid;
+            chunk_bits(c, keep, valid);
+            if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            t[q] = ex2(fmaf(t[q], scale, -m_new));
-            lsv[q & 3] += t[q];
+              for (int q = 0; q < 32; ++q) {
+                t[q] = ex2(fmaf(t[q], scale, -m_new));
+                lsv[q & 3] += t[q];
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                float v = t[q] * scale;
+                v = ((keep >> q) & 1u) ? v : CN_F32_MIN;
+                v = ((valid >> q) & 1u) ? v : -INFINITY;
+                t[q] = ex2(v - m_new);
+                lsv[q & 3] += t[q];
+              }
+            }
+#pragma unroll
+            for (int gq = 0; gq < 32; gq += 8) {
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(t[gq], t[gq + 1]), b1 = __floats2bfloat162_rn(t[gq + 2], t[gq + 3]),
+                             b2 = __floats2bfloat162_rn(t[gq + 4], t[gq + 5]), b3 = __floats2bfloat162_rn(t[gq + 6], t[gq + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              const int col = c + gq;
+              const int atom = col >> 6, chunk = (col & 63) >> 3;         // 64-key swizzle atoms, 16-byte chunks
+              *reinterpret_cast<uint4*>(pbase + atom * 16384 + ((chunk ^ (row & 7)) << 4)) = pk;
+            }
+          };
+#pragma unroll 1
+          for (int c = 0; c < KT; c += 64) {                              // ta holds chunk c on entry
+            tmem_ld32(s_addr + c + 32, tb); sweep_exp(ta, c); tmem_wait_ld();
+            if (c + 64 < KT) tmem_ld32(s_addr + c + 64, ta);
+            sweep_exp(tb, c + 32);
+            tmem_wait_ld();
           }
-        } else {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
+          fence_before();                                                  // S_g fully read before it is handed back
+          mbar_arrive(bar(B_PREADY + g));
+          if (j > 0) fold(j - 1, 1.f);                                     // O_g(j-1) while PV_g(j) / S_g(j+1) run
+          l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
+          m_run = m_new;
+          corr_prev = corr;
+          fence_before();
+        }
+        fold(n_tiles - 1, 1.f / l_run);
+        fence_before();
+        if (qi < p.Tq) {
+          __nv_bfloat16* dst = p.out + (int64_t)b * p.sbo + (int64_t)qi * p.ldo + hh * DK;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            float v = t[q] * scale;
-            v = ((keep >> q) & 1u) ? v : CN_F32_MIN;
-            v = ((valid >> q) & 1u) ? v : -INFINITY;
-            t[q] = ex2(v - m_new);
-            lsv[q & 3] += t[q];
+          for (int d = 0; d < DK; d += 8) {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(o[d], o[d + 1]), b1 = __floats2bfloat162_rn(o[d + 2], o[d + 3]),
+                           b2 = __floats2bfloat162_rn(o[d + 4], o[d + 5]), b3 = __floats2bfloat162_rn(o[d + 6], o[d + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(dst + d) = pk;
           }
         }
-#pragma unroll
-        for (int g = 0; g < 32; g += 8) {
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(t[g], t[g + 1]), b1 = __floats2bfloat162_rn(t[g + 2], t[g + 3]),
-                         b2 = __floats2bfloat162_rn(t[g + 4], t[g + 5]), b3 = __floats2bfloat162_rn(t[g + 6], t[g + 7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-          pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-          const int col = c + g;
-          const int atom = col >> 6, chunk = (col & 63) >> 3;         // 64-key swizzle atoms, 16-byte chunks
-          *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (row & 7)) << 4)) = pk;
-        }
-      };
-      tmem_wait_ld();
-      tmem_ld32(s_addr + 32, tb); sweep_exp(ta, 0); tmem_wait_ld();
-      tmem_ld32(s_addr + 64, ta); sweep_exp(tb, 32); tmem_wait_ld();
-      tmem_ld32(s_addr + 96, tb); sweep_exp(ta, 64); tmem_wait_ld();
-      sweep_exp(tb, 96);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
-      fence_before();                                                  // S_j (TMEM) fully read before it is handed back
-      mbar_arrive(bar(11));
-      // fold O_{j-1} (finished long ago) while PV_j runs
-      if (j > 0) {
-        mbar_wait(bar(13 + ((j - 1) & 1)), ((j - 1) >> 1) & 1);
-        fence_after();
-        float part[DK];
-        tmem_ld32(TM_O + lane_addr + ((j - 1) & 1) * 64, part);
-        tmem_ld32(TM_O + lane_addr + ((j - 1) & 1) * 64 + 32, part + 32);
-        tmem_wait_ld();
-#pragma unroll
-        for (int d = 0; d < DK; ++d) o[d] = o[d] * corr_prev + part[d];
-      }
-      l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
-      m_run = m_new;
-      corr_prev = corr;
-      fence_before();
-    }
-    {
-      const int j = n_tiles - 1;
-      mbar_wait(bar(13 + (j & 1)), (j >> 1) & 1);
-      fence_after();
-      float part[DK];
-      tmem_ld32(TM_O + lane_addr + (j & 1) * 64, part);
-      tmem_ld32(TM_O + lane_addr + (j & 1) * 64 + 32, part + 32);
-      tmem_wait_ld();
-      const float inv = 1.f / l_run;
-#pragma unroll
-      for (int d = 0; d < DK; ++d) o[d] = (o[d] * corr_prev + part[d]) * inv;
-    }
-    if (qi < p.Tq) {
-      __nv_bfloat16* dst = p.out + (int64_t)b * p.sbo + (int64_t)qi * p.ldo + hh * DK;
-#pragma unroll
-      for (int d = 0; d < DK; d += 8) {
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(o[d], o[d + 1]), b1 = __floats2bfloat162_rn(o[d + 2], o[d + 3]),
-                       b2 = __floats2bfloat162_rn(o[d + 4], o[d + 5]), b3 = __floats2bfloat162_rn(o[d + 6], o[d + 7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-        *reinterpret_cast<uint4*>(dst + d) = pk;
       }
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -401,7 +446,7 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
       !make_map3(&mv, V, B, Tk, width, ldv, sbv))
     return CN_ERR_DEVICE;
   AttnTcArgs p;
-  p.mask = mask; p.mb = mb; p.mi = mi; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
+  p.mask = mask; p.mb = mb; p.mi = mi; p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo;
   static bool configured = false;
   if (!configured) {
@@ -409,8 +454,12 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
       return CN_ERR_LAUNCH;
     configured = true;
   }
-  dim3 grid((unsigned)((Tq + QT - 1) / QT), (unsigned)h, (unsigned)B);
-  attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t items = B * h;
+  const unsigned grid = (unsigned)(items < sms ? items : sms);           // persistent: one CTA per SM
+  attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

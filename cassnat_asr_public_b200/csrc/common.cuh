@@ -10,10 +10,14 @@
 #define CN_LOGZERO (-1e10f)          // reference: src/utils/ctc_prefix.py:12
 #define CN_F32_MIN (-FLT_MAX)        // reference: np.finfo(float32).min, modules/attention.py:19
 
-#define CN_CHECK_LAUNCH()                                   \
-  do {                                                      \
-    cudaError_t e__ = cudaGetLastError();                   \
-    if (e__ != cudaSuccess) return CN_ERR_LAUNCH;           \
+#include <stdio.h>
+#define CN_CHECK_LAUNCH()                                                                    \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) {                                                                \
+      fprintf(stderr, "[cassnat_b200] %s:%d CUDA error: %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return CN_ERR_LAUNCH;                                                                  \
+    }                                                                                        \
   } while (0)
 
 static inline int cn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

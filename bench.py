@@ -178,11 +178,11 @@ def run_ours(a, w):
     dev_in = [t.to(dev) for t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(inputs):
+    def step(inputs, gather=True):
         with torch.no_grad():
             out, _ = model.decode_from_encoder(inputs[0], inputs[1], inputs[2], VOCAB, args)
         hyps = [o[0]["hyp"] for o in out]
-        if world > 1:      # the hypothesis gather of the decode job (tiny; padded to T+2 tokens)
+        if world > 1 and gather:      # the hypothesis gather of the decode job (tiny; padded to T+2 tokens)
             hyps = sharding.gather_hypotheses(hyps, B * world, T + 2, dev)
         return hyps
 
@@ -191,11 +191,11 @@ def run_ours(a, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # samples during warm-up + timed steps (all under load)
     for _ in range(a.warmup):
         hyps = step(dev_in)
     # ---- device-resident throughput: per-step CUDA events, L2 flushed between steps
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count = 0
     evs = []
     for _ in range(a.steps):
@@ -226,7 +226,7 @@ def run_ours(a, w):
     if rank == 0:
         _lib.start_profile()
         for _ in range(2):
-            step(dev_in)
+            step(dev_in, gather=False)          # rank 0 only: no collective in here
         prof = _lib.stop_profile()
     if rank != 0:
         if world > 1:
@@ -267,9 +267,56 @@ def run_ours(a, w):
             "kernels": {k: {"ms_per_step": v["ms"] / 2, "calls_per_step": v["calls"] / 2} for k, v in prof.items()}}
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
+    if world == 1 and not a.no_lattice:
+        del model, dev_in, flush
+        torch.cuda.empty_cache()
+        line["alignment_lattice"] = alignment_lattice(dev, pk)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
+    """BASELINE configs[1]: CTC best-path + Viterbi forced alignment + trigger masks on synthetic
+    posteriors (T=1000, V=5000, U=200, batch 256; 5.12 GB).  Kernel times from CUDA events around the
+    C-ABI calls.  "lattice bytes" follow SURVEY §8d: B*T*S*5 + B*T*9 (S = 2U+1)."""
+    from cassnat_asr_public_b200 import _lib, ops
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ys = torch.randint(4, V, (B, U), device=dev, generator=g)
+    logits = torch.randn(B, T, V, device=dev, generator=g)
+    t_idx = (torch.arange(U, device=dev) * 5)[None, :, None] + torch.arange(1, 4, device=dev)[None, None, :]
+    b_idx = torch.arange(B, device=dev)[:, None, None].expand(B, U, 3)
+    logits[b_idx, t_idx.expand(B, U, 3), ys[:, :, None].expand(B, U, 3)] += 8.0        # planted alignment
+    lp = torch.log_softmax(logits, -1)
+    del logits
+    mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
+    xl = torch.full((B,), T, dtype=torch.int64, device=dev)
+    yls = torch.full((B,), U, dtype=torch.int64, device=dev)
+
+    def once():
+        a, yl, ym = ops.best_path_align(lp, mask, xl, 0)
+        ops.align_to_mask(a, yl, ym, mask, xl, 0)
+        va, _, _ = ops.viterbi_align(lp, mask, xl, ys, yls, 0)
+        ops.align_to_mask(va, yls, U, mask, xl, 0)
+
+    for _ in range(2):
+        once()
+    _lib.start_profile()
+    for _ in range(iters):
+        once()
+    prof = _lib.stop_profile()
+    ms = {k: v["ms"] / v["calls"] for k, v in prof.items()}
+    S = 2 * U + 1
+    lattice = B * T * S * 5 + B * T * 9
+    vit, bp = ms["cn_viterbi_align"], ms["cn_bestpath_from_logp"]
+    return {"workload": f"cfg2: B={B} T={T} V={V} U={U} planted posteriors ({4 * B * T * V / 1e9:.2f} GB f32)",
+            "viterbi_ms": vit, "viterbi_utt_per_s": B / (vit / 1e3),
+            "viterbi_lattice_GBps": lattice / (vit / 1e3) / 1e9, "viterbi_lattice_frac_of_hbm": lattice / (vit / 1e3) / 1e9 / pk["hbm"],
+            "viterbi_note": "emission gather touches one 64-B DRAM atom per (frame, label): see DESIGN.md §4",
+            "bestpath_ms": bp, "bestpath_GBps": 4.0 * B * T * V / (bp / 1e3) / 1e9,
+            "bestpath_frac_of_hbm": 4.0 * B * T * V / (bp / 1e3) / 1e9 / pk["hbm"],
+            "align_to_mask_ms": ms["cn_align_to_mask"],
+            "align_to_mask_GBps": (8.0 * B * T + B * (U + 1) * T) / (ms["cn_align_to_mask"] / 1e3) / 1e9}
 
 
 def cpu_baseline(a, w, args):
@@ -295,7 +342,7 @@ def cpu_baseline(a, w, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
@@ -303,6 +350,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CASSNAT_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lattice", action="store_true", help="skip the cfg2 alignment-lattice microbench")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     w = WORKLOADS[a.workload]

@@ -21,20 +21,21 @@ def shard_bounds(n_items, rank, world_size):
 
 def pack_hypotheses(hyps, pad_len, device):
     """list of token-id lists -> (ids int32 [n, pad_len] zero padded, lens int32 [n])."""
+    import numpy as np
     n = len(hyps)
-    ids = torch.zeros(n, pad_len, dtype=torch.int32)
-    lens = torch.zeros(n, dtype=torch.int32)
+    ids = np.zeros((n, pad_len), dtype=np.int32)
+    lens = np.zeros(n, dtype=np.int32)
     for i, h in enumerate(hyps):
         if len(h) > pad_len:
             raise ValueError(f"hypothesis of length {len(h)} exceeds pad_len {pad_len}")
-        ids[i, :len(h)] = torch.tensor(h, dtype=torch.int32)
+        ids[i, :len(h)] = h
         lens[i] = len(h)
-    return ids.to(device), lens.to(device)
+    return torch.from_numpy(ids).to(device), torch.from_numpy(lens).to(device)
 
 
 def unpack_hypotheses(ids, lens):
-    ids, lens = ids.cpu(), lens.cpu()
-    return [ids[i, :int(lens[i])].tolist() for i in range(ids.size(0))]
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    return [ids[i, :int(lens[i])].tolist() for i in range(ids.shape[0])]
 
 
 def gather_hypotheses(hyps, n_total, pad_len, device, group=None):
@@ -46,17 +47,17 @@ def gather_hypotheses(hyps, n_total, pad_len, device, group=None):
     rank = dist.get_rank(group)
     per_rank = max(shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world))
     ids, lens = pack_hypotheses(hyps, pad_len, device)
-    if ids.size(0) < per_rank:                      # equalise shapes for all_gather
-        ids = torch.cat([ids, ids.new_zeros(per_rank - ids.size(0), pad_len)], 0)
-        lens = torch.cat([lens, lens.new_zeros(per_rank - lens.size(0))], 0)
-    all_ids = [torch.empty_like(ids) for _ in range(world)]
-    all_lens = [torch.empty_like(lens) for _ in range(world)]
-    dist.all_gather(all_ids, ids, group=group)
-    dist.all_gather(all_lens, lens, group=group)
+    packed = torch.cat([ids, lens.unsqueeze(1)], 1)            # lengths ride in the last column: one collective
+    if packed.size(0) < per_rank:                                # equalise shapes for all_gather
+        packed = torch.cat([packed, packed.new_zeros(per_rank - packed.size(0), pad_len + 1)], 0)
+    everything = torch.empty(world * per_rank, pad_len + 1, dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(everything, packed.contiguous(), group=group)
+    everything = everything.cpu().numpy()
     out = []
     for r in range(world):
         lo, hi = shard_bounds(n_total, r, world)
-        out.extend(unpack_hypotheses(all_ids[r][:hi - lo], all_lens[r][:hi - lo]))
+        blk = everything[r * per_rank:r * per_rank + (hi - lo)]
+        out.extend(blk[i, :int(blk[i, pad_len])].tolist() for i in range(hi - lo))
     return out
 
 

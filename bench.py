@@ -170,8 +170,8 @@ def run_ours(a, w):
     args = model_args(w, precision=a.precision)
     torch.manual_seed(1234)
     model = make_model(80, args).to(dev).eval()
-    if hasattr(model, "set_precision"):
-        model.set_precision(a.precision)
+    model.set_precision(a.precision)
+    model.use_cuda_graphs = not a.no_graphs
     enc_h, mask, ratio, lens = synth_encoder_output(w, B, 1234 + rank)        # a different shard per rank
     T = enc_h.size(1)
     host = [t.pin_memory() for t in (enc_h, mask, ratio)]
@@ -210,10 +210,26 @@ def run_ours(a, w):
     clocks = sampler.stop() if sampler else None
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     # ---- end to end: pinned host buffers in, hypotheses (python lists) out, copies inside the clock
+    # (double-buffered: the copy of step i+1 runs on a side stream while step i computes)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def stage():
+        with torch.cuda.stream(copy_stream):
+            bufs = [t.to(dev, non_blocking=True) for t in host]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs, ev
+
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        staged = [t.to(dev, non_blocking=True) for t in host]
+    nxt = stage()
+    for i in range(a.steps):
+        staged, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        for t in staged:
+            t.record_stream(torch.cuda.current_stream())
+        if i + 1 < a.steps:
+            nxt = stage()
         hyps = step(staged)
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -224,10 +240,16 @@ def run_ours(a, w):
     # ---- per-kernel durations for the roofline (separate profiled steps, CUDA events per C-ABI call)
     prof = None
     if rank == 0:
+        model.use_cuda_graphs = False           # per-call CUDA events need eager launches
         _lib.start_profile()
         for _ in range(2):
             step(dev_in, gather=False)          # rank 0 only: no collective in here
         prof = _lib.stop_profile()
+        _lib.PROFILE_SHAPES = True
+        _lib.start_profile()
+        step(dev_in, gather=False)
+        prof_shapes = _lib.stop_profile()
+        _lib.PROFILE_SHAPES = False
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -259,12 +281,15 @@ def run_ours(a, w):
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else a.precision, "data": "synthetic",
             "config": {"workload": w["name"], "global_batch": B * world, "per_gpu_batch": B, "frames_T": T,
-                       "tokens_U_mean": n_tok, "tokens_U_max": ymax, "precision": a.precision,
+                       "tokens_U_mean": n_tok, "tokens_U_max": ymax, "precision": a.precision, "cuda_graph": not a.no_graphs,
                        "parallelism": f"utterance-sharded x{world}", "l2": "flushed (256 MiB write) between steps"},
             "rtf": (total_ms / 1e3 / a.steps) / (B * w["audio_s"]),
             "e2e": {"value": units / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "kernels": {k: {"ms_per_step": v["ms"] / 2, "calls_per_step": v["calls"] / 2} for k, v in prof.items()}}
+            "kernels": {k: {"ms_per_step": round(v["ms"], 4), "calls_per_step": v["calls"],
+                            **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] else
+                               {"GBps": round(v["bytes"] / v["ms"] / 1e6, 1)})}
+                        for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]["ms"])}}
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
     if world == 1 and not a.no_lattice:
@@ -351,6 +376,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lattice", action="store_true", help="skip the cfg2 alignment-lattice microbench")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     w = WORKLOADS[a.workload]

@@ -203,48 +203,18 @@ class CassNAT(nn.Module):
             enc_h, src_mask, mask2, frames = rep(enc_h), rep(src_mask), rep(mask2), rep(frames)
         BS = B * S
 
-        # ---- K4/K5: segment ids (trigger mask stays implicit), ylen+1, target-length mask
-        if args.use_trigger:
-            _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
-                                                   want_seg=True)
-            seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
-            dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
-                                                      args.left_trigger, args.right_trigger, True)[0]
-        else:                                                                          # :470-473
-            seg_ctx = None
-        tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)            # [BS,1,U]
-
-        # ---- K6: token acoustic extractor
-        pe_rows = self._pe_rows(enc_h, ymax)
-        if seg_ctx is not None:
-            ac_embed = self.acembed_extractor.forward_segments(pe_rows, enc_h, seg_ctx, dense_trigger)
+        # ---- K4..K9: segments -> extractor -> SAD -> MAD -> head (optionally replayed as a CUDA graph)
+        graphable = (self.use_cuda_graphs and args.use_trigger and S == 1 and not args.use_unimask and
+                     not args.src_trigger and not getattr(args, "save_embedding", False) and not return_intermediates)
+        if graphable:
+            ids, logp, ylen, ymax = self._stage_b_graphed(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
+            ac_embed = pred_embed = dec_h = seg = None
         else:
-            ac_embed = self.acembed_extractor(pe_rows.unsqueeze(0).repeat(BS, 1, 1), enc_h, src_mask)
-        # ---- K7: SAD
-        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
-        if getattr(args, "save_embedding", False) and S == 1:
-            first = lambda x: x[0] if isinstance(x, tuple) else x
-            args.ac_embed, args.pred_embed = first(ac_embed)[0].cpu(), first(pred_embed)[0].cpu()
-        # ---- K8: MAD
-        if args.use_unimask:                                                           # :486-489
-            pos = None
-            if isinstance(pred_embed, tuple):
-                pred_embed, pos = pred_embed
-            pred_embed = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
-            causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=dev)).unsqueeze(0)
-            dec_mask = tgt_mask & causal
-            if pos is not None:
-                pred_embed = (pred_embed, pos)
-        else:
-            dec_mask = tgt_mask
-        mem_mask = dense_trigger() if (args.src_trigger and seg_ctx is not None) else src_mask
-        dec_h = self.decoder(pred_embed, enc_h, mem_mask, dec_mask)
-        # ---- K9: output head + greedy pick
-        st = self.att_generator.greedy(dec_h)
-        ids, logp = st["top1"], st["logp"]                                             # [BS,U]
+            ids, logp, ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask = self._stage_b(
+                enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
         if return_intermediates:
             first = lambda x: x[0] if isinstance(x, tuple) else x
-            keep.update(aligned=aligned, seg=seg_ctx[0] if seg_ctx else None, ylen=ylen, ymax=ymax,
+            keep.update(aligned=aligned, seg=seg, ylen=ylen, ymax=ymax,
                         ac_embed=first(ac_embed), pred_embed=first(pred_embed), dec_h=dec_h, ids=ids, logp=logp)
         if S > 1:
             ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
@@ -264,6 +234,85 @@ class CassNAT(nn.Module):
         if return_intermediates:
             return out, args, keep
         return out, args
+
+    def _stage_b(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank):
+        """cassnat.py:465-497 after the alignment: no host synchronisation in here (CUDA-graph safe)."""
+        BS, T, _ = enc_h.shape
+        dev = enc_h.device
+        mask2 = src_mask.reshape(BS, T)
+        # ---- K4/K5: segment ids (trigger mask stays implicit), ylen+1, target-length mask
+        seg = None
+        if args.use_trigger:
+            _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
+                                                   want_seg=True)
+            seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
+            dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
+                                                      args.left_trigger, args.right_trigger, True)[0]
+        else:                                                                          # :470-473
+            seg_ctx = None
+        tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)            # [BS,1,U]
+        # ---- K6: token acoustic extractor
+        pe_rows = self._pe_rows(enc_h, ymax)
+        if seg_ctx is not None:
+            ac_embed = self.acembed_extractor.forward_segments(pe_rows, enc_h, seg_ctx, dense_trigger)
+        else:
+            ac_embed = self.acembed_extractor(pe_rows.unsqueeze(0).repeat(BS, 1, 1), enc_h, src_mask)
+        # ---- K7: SAD
+        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
+        if getattr(args, "save_embedding", False) and getattr(args, "sample_num", 0) <= 1:
+            first = lambda x: x[0] if isinstance(x, tuple) else x
+            args.ac_embed, args.pred_embed = first(ac_embed)[0].cpu(), first(pred_embed)[0].cpu()
+        # ---- K8: MAD
+        if args.use_unimask:                                                           # :486-489
+            pos = None
+            if isinstance(pred_embed, tuple):
+                pred_embed, pos = pred_embed
+            pred_embed = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
+            causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=dev)).unsqueeze(0)
+            dec_mask = tgt_mask & causal
+            if pos is not None:
+                pred_embed = (pred_embed, pos)
+        else:
+            dec_mask = tgt_mask
+        mem_mask = dense_trigger() if (args.src_trigger and seg_ctx is not None) else src_mask
+        dec_h = self.decoder(pred_embed, enc_h, mem_mask, dec_mask)
+        # ---- K9: output head + greedy pick
+        st = self.att_generator.greedy(dec_h)
+        return st["top1"], st["logp"], ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask
+
+    use_cuda_graphs = False          # opt-in: replay the sync-free part of the decode as a CUDA graph
+    _GRAPH_CACHE_SIZE = 4
+
+    def _stage_b_graphed(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank):
+        """Same as _stage_b, captured once per (batch, frames, tokens, precision) shape and replayed:
+        ~150 kernel launches become one graph launch.  The first call of a shape runs eagerly (it also
+        warms the weight caches) and captures for the following calls."""
+        key = (tuple(enc_h.shape), str(enc_h.dtype), int(ymax), ops.get_precision(), int(args.left_trigger),
+               int(args.right_trigger), int(blank), str(src_mask.dtype))
+        cache = self.__dict__.setdefault("_graphs", {})
+        hit = cache.get(key)
+        if hit is None:
+            out = self._stage_b(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
+            statics = [t.clone() for t in (enc_h, src_mask, frames, aligned, ylen)]
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            from . import _lib
+            before = _lib.launch_count
+            with torch.cuda.graph(graph):
+                res = self._stage_b(statics[0], statics[1], statics[2], statics[3], statics[4], ymax, args, blank)
+            n_kernels = _lib.launch_count - before          # our kernels recorded into the graph
+            _lib.launch_count = before                       # capture launched nothing
+            if len(cache) >= self._GRAPH_CACHE_SIZE:
+                cache.pop(next(iter(cache)))
+            cache[key] = (graph, statics, res[:4], n_kernels)
+            return out[:4]
+        graph, statics, res, n_kernels = hit
+        for dst, src in zip(statics, (enc_h, src_mask, frames, aligned, ylen)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        from . import _lib
+        _lib.launch_count += n_kernels
+        return res
 
     def _collapse(self, st, mask2, B, T, S, blank, threshold):
         dev = mask2.device

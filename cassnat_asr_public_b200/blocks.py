@@ -30,8 +30,9 @@ def _self_attention_block(x, norm, attn, mask, pos_embed=None):
     else:
         from .modules import distinct_rel_rows
         table, m = distinct_rel_rows(pos_embed, x.size(1))
+        fast = ops.is_bf16() and x.size(1) <= 512 and attn.h <= 8 and m <= 64
         rel_pos = ops.linear(table, attn.linear_pos.weight)
-        q, k, v = attn.project_qkv(y)
+        q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
         ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m))
     return attn.output(ctx, residual=x)
 

@@ -109,6 +109,7 @@ struct AttnTcArgs {
   const uint8_t* mask; int64_t mb, mi;      // u8, element (b,i,j) at mask[b*mb + i*mi + j]; mi == 0 -> key mask
   int B, h, Tq, Tk;
   __nv_bfloat16* out; int64_t ldo, sbo;
+  const float* relbias; int max_rel;         // REL: [B,h,Tq,2m+1] = (q_i + v_h) . P[r,h]  (pre-kernel)
 };
 
 // Persistent, ping-pong design (v2):
@@ -124,6 +125,7 @@ constexpr int NTHREADS = 320;
 constexpr int B_QFULL = 0, B_QFREE = 2, B_KFULL = 4, B_VFULL = 8, B_KFREE = 12, B_VFREE = 16, B_SFULL = 20,
               B_PREADY = 22, B_PFREE = 24, B_OFULL = 26, N_BARS = 30;
 
+template <bool REL>
 __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                    const __grid_constant__ CUtensorMap map_k,
                                                                    const __grid_constant__ CUtensorMap map_v,
@@ -263,6 +265,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
 #pragma unroll
         for (int d = 0; d < DK; ++d) o[d] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+        // relative-position term (modules/attention.py:104-143): score += (q_i+v).P[clamp(j-i,-m,m)+m]
+        const int nrel = 2 * p.max_rel + 1;
+        const float* rb = REL ? p.relbias + (((int64_t)b * p.h + hh) * p.Tq + (qi < p.Tq ? qi : p.Tq - 1)) * nrel : nullptr;
+        const float rel_left = REL ? rb[0] : 0.f, rel_right = REL ? rb[nrel - 1] : 0.f;
+        bool any_keep = false;
         auto fold = [&](int j, float extra) {
           mbar_wait(bar(B_OFULL + g * 2 + (j & 1)), o_cnt[j & 1] & 1);
           ++o_cnt[j & 1];
@@ -291,11 +298,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
                 if (k0 + c + q < p.Tk && mrow[k0 + c + q]) keep |= 1u << q;
             }
           };
+          auto add_rel = [&](float* t, int c) {
+            const int d_lo = k0 + c - qi;                                   // j - i of the chunk's first key
+            if (d_lo + 31 <= -p.max_rel) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) t[q] += rel_left;
+            } else if (d_lo >= p.max_rel) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) t[q] += rel_right;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                int r = d_lo + q;
+                r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
+                t[q] += __ldg(rb + r + p.max_rel);
+              }
+            }
+          };
           // ---- sweep 1: row max (four independent chains; masked chunks take the slow path)
           float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
-          auto sweep_max = [&](const float* t, int c) {
+          auto sweep_max = [&](float* t, int c) {
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
+            if (REL) { add_rel(t, c); any_keep = any_keep || ((keep & valid) != 0u); }
             if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
@@ -328,6 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           auto sweep_exp = [&](float* t, int c) {
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
+            if (REL) add_rel(t, c);
             if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
@@ -372,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           corr_prev = corr;
           fence_before();
         }
-        fold(n_tiles - 1, 1.f / l_run);
+        fold(n_tiles - 1, (REL && !any_keep) ? 0.f : 1.f / l_run);      // REL: masked probabilities are re-zeroed
         fence_before();
         if (qi < p.Tq) {
           __nv_bfloat16* dst = p.out + (int64_t)b * p.sbo + (int64_t)qi * p.ldo + hh * DK;
@@ -426,12 +452,31 @@ bool make_map3(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// (q_i + v_h) . P[r, h, :] for every query row and the 2m+1 clamped offsets; Q holds q + u_h.
+__global__ void __launch_bounds__(256) rel_bias_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, int64_t sbq,
+                                                       const float* __restrict__ rel_pos, const float* __restrict__ rel_u,
+                                                       const float* __restrict__ rel_v, int h, int Tq, int nrel,
+                                                       float* __restrict__ out) {
+  const int i = blockIdx.x, b = blockIdx.y, hh = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (hh >= h) return;
+  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(Q + (int64_t)b * sbq + (int64_t)i * ldq + hh * 64 + lane * 2);
+  const float2 u = *reinterpret_cast<const float2*>(rel_u + hh * 64 + lane * 2);
+  const float2 v = *reinterpret_cast<const float2*>(rel_v + hh * 64 + lane * 2);
+  const float qx = __bfloat162float(q2.x) + (v.x - u.x), qy = __bfloat162float(q2.y) + (v.y - u.y);
+  float* o = out + (((int64_t)b * h + hh) * Tq + i) * nrel;
+  for (int r = 0; r < nrel; ++r) {
+    const float2 pr = *reinterpret_cast<const float2*>(rel_pos + (int64_t)r * h * 64 + hh * 64 + lane * 2);
+    const float s = cn_warp_sum(fmaf(qx, pr.x, qy * pr.y));
+    if (lane == 0) o[r] = s;
+  }
+}
+
 }  // namespace
 
-extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
-                                 const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
-                                 int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
-                                 int64_t sbo, cn_stream_t stream_) {
+static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                               const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
+                               int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
+                               int64_t sbo, const float* relbias, int max_rel, cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   if (dk != DK || Tk > MAX_TILES * KT || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
   // TMA: 16-byte aligned bases and pitches; 16-byte vector stores of the output rows
@@ -447,10 +492,11 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
     return CN_ERR_DEVICE;
   AttnTcArgs p;
   p.mask = mask; p.mb = mb; p.mi = mi; p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
-  p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo;
+  p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
@@ -459,7 +505,38 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t items = B * h;
   const unsigned grid = (unsigned)(items < sms ? items : sms);           // persistent: one CTA per SM
-  attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  if (relbias) attention_tc_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  else attention_tc_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
   CN_CHECK_LAUNCH();
   return CN_OK;
+}
+
+extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                                 const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
+                                 int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
+                                 int64_t sbo, cn_stream_t stream_) {
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
+                             nullptr, 0, stream_);
+}
+
+extern "C" int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel) {
+  return B * h * Tq * (2 * max_rel + 1) * 4 + 256;
+}
+
+extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                                     const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb,
+                                     int64_t mi, const float* rel_pos, const float* rel_bias_u, const float* rel_bias_v,
+                                     int64_t max_rel, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                                     void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
+                                     cn_stream_t stream_) {
+  if (!rel_pos || !rel_bias_u || !rel_bias_v || !workspace || max_rel < 0 || !Q) return CN_ERR_BAD_ARG;
+  if (h > 8 || max_rel > 64 || dk != DK) return CN_ERR_UNSUPPORTED;
+  if (workspace_bytes < cn_rel_attention_workspace_bytes(B, h, Tq, max_rel)) return CN_ERR_WORKSPACE;
+  if (B == 0 || Tq == 0) return CN_OK;
+  float* relbias = (float*)workspace;
+  rel_bias_kernel<<<dim3((unsigned)Tq, (unsigned)B), (unsigned)(32 * h), 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)h, (int)Tq, (int)(2 * max_rel + 1), relbias);
+  CN_CHECK_LAUNCH();
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
+                             relbias, (int)max_rel, stream_);
 }

@@ -165,6 +165,16 @@ class RelMultiHeadedAttention(nn.Module):
     project_qkv = MultiHeadedAttention.project_qkv
     output = MultiHeadedAttention.output
 
+    def project_qkv_rel(self, x):
+        """Fused QKV projection for the tcgen05 relative attention: bf16 out, pos_bias_u folded into
+        the query bias so that the kernel's Q operand is q + u."""
+        w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
+        bq_u = _cat_cached(self, "q_bias_u", [self.linears[0].bias, self.pos_bias_u.reshape(-1)])
+        d = self.h * self.d_k
+        b = _cat_cached(self, "qkv_b_rel", [bq_u[:d] + bq_u[d:], self.linears[1].bias, self.linears[2].bias])
+        qkv = ops.linear(x, w, b, out_bf16=True)
+        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+
     def forward(self, query, key, value, mask=None, pos_embed=None):
         """pos_embed: [2L-1, d] rows of the clamped relative-position table (what
         RelativePositionalEncoding returns).  Only 2m+1 of them are distinct; the kernel works on

@@ -169,13 +169,15 @@ def is_bf16():
 
 def bf16_weight(w):
     """bf16 copy of a weight, converted once and refreshed when the parameter changes."""
-    stamp = (w.data_ptr(), w._version, tuple(w.shape))
-    hit = _BF16_WEIGHTS.get(id(w))
+    base = w._base if w._base is not None else w          # views of a parameter share its cache entry
+    key = (id(base), w.storage_offset(), tuple(w.shape), tuple(w.stride()))
+    stamp = (base.data_ptr(), base._version)
+    hit = _BF16_WEIGHTS.get(key)
     if hit is None or hit[0] != stamp:
         with torch.no_grad():
             src = w.detach()
-            hit = (stamp, cast_bf16(src if src.is_contiguous() else src.contiguous()), w)
-        _BF16_WEIGHTS[id(w)] = hit
+            hit = (stamp, cast_bf16(src if src.is_contiguous() else src.contiguous()), base)
+        _BF16_WEIGHTS[key] = hit
     return hit[1]
 
 
@@ -250,8 +252,11 @@ def attention(q, k, v, mask, n_head, rel=None, out=None):
     for t in (q, k, v):
         assert t.stride(-1) == 1
     if q.dtype == torch.bfloat16:
-        if rel is None and dk == 64 and Tk <= 512 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16:
-            return _attention_bf16(q, k, v, mask, n_head)
+        if dk == 64 and Tk <= 512 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
+                (rel is None or (n_head <= 8 and rel[3] <= 64)):
+            return _attention_bf16(q, k, v, mask, n_head, rel)      # rel: q must already hold q + pos_bias_u
+        if rel is not None:
+            raise RuntimeError("bf16 relative attention outside the tcgen05 kernel's range (Tk<=512, h<=8, m<=64)")
         q, k, v = q.float(), k.float(), v.float()
     if out is None:
         out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
@@ -347,12 +352,22 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     return o32 if o32 is not None else o16
 
 
-def _attention_bf16(q, k, v, mask, n_head):
+def _attention_bf16(q, k, v, mask, n_head, rel=None):
     """tcgen05 attention: bf16 q/k/v (strided views of fused projection buffers are fine) -> bf16 ctx."""
     B, Tq, d = q.shape
     Tk = k.shape[1]
     out = torch.empty(B, Tq, d, dtype=torch.bfloat16, device=q.device)
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
+    if rel is not None:
+        rp, ru, rv, mr = rel
+        ws_bytes = _lib.load().cn_rel_attention_workspace_bytes(B, n_head, Tq, int(mr))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+        call("cn_rel_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
+             ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp.float().contiguous()), ptr(ru.contiguous()),
+             ptr(rv.contiguous()), int(mr), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1), out.stride(0),
+             ptr(ws), ws_bytes, stream(),
+             work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
+        return out
     call("cn_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, B, n_head, Tq, Tk, d // n_head,
          ptr(out), out.stride(1), out.stride(0), stream(),

@@ -238,6 +238,21 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak, float* lse,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* Fast mode: relative-position (Transformer-XL style) self-attention on tcgen05.
+ *   replaces (fast mode): RelMultiHeadedAttention.forward      src/models/modules/attention.py:104-143
+ * Q must hold q + pos_bias_u (fold u into the query bias of the projection); rel_pos f32
+ * [2m+1, h*64] = linear_pos(embedding rows); rel_bias_u / rel_bias_v f32 [h,64].  A pre-kernel
+ * tabulates (q_i + v_h).P[r,h] into the workspace; the attention kernel adds
+ * table[clamp(j-i,-m,m)+m] to the scores and re-zeroes fully masked rows (attention.py:138).
+ * h <= 8, max_rel <= 64.  workspace: cn_rel_attention_workspace_bytes(B,h,Tq,max_rel). */
+int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel);
+int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                          const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
+                          const float* rel_pos, const float* rel_bias_u, const float* rel_bias_v, int64_t max_rel,
+                          int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                          void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
+                          cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

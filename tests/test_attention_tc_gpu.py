@@ -51,3 +51,33 @@ def test_attention_tc_on_fused_buffers():
     got = ops.attention(q, k, v, None, h)
     want = ref_attention(q.float().cpu(), k.float().cpu(), v.float().cpu(), None, h)
     assert rel(got.float(), want) < 2e-2
+
+
+@pytest.mark.parametrize("B,U,h,m", [(2, 90, 2, 8), (3, 300, 4, 20), (2, 500, 8, 8)])
+def test_rel_attention_tc(B, U, h, m):
+    """tcgen05 relative-position attention vs the oracle's rel_mha core on bf16-rounded q/k/v."""
+    d = 64 * h
+    torch.manual_seed(U + m)
+    q, k, v = (torch.randn(B, U, d).bfloat16() for _ in range(3))
+    u_b, v_b = torch.randn(h, 64) * 0.3, torch.randn(h, 64) * 0.3
+    relp = torch.randn(2 * m + 1, d)
+    lens = torch.randint(U // 2, U + 1, (B,))
+    mask = (torch.arange(U)[None] < lens[:, None]).unsqueeze(1)
+    # reference (fp64): scores = ((q+u).k + (q+v).P[clamp(j-i)]) / 8, masked -> finfo.min, softmax, re-zero, @ v
+    qh, kh, vh = (t.double().view(B, U, h, 64).transpose(1, 2) for t in (q, k, v))
+    ac = (qh + u_b.double()[None, :, None, :]) @ kh.transpose(-1, -2)
+    P = relp.double().view(2 * m + 1, h, 64).permute(1, 0, 2)                       # [h, 2m+1, 64]
+    qp = (qh + v_b.double()[None, :, None, :]) @ P.transpose(-1, -2)[None]          # [B,h,U,2m+1]
+    idx = (torch.arange(U)[None, :] - torch.arange(U)[:, None]).clamp(-m, m) + m    # [i,j]
+    bd = torch.gather(qp, -1, idx[None, None].expand(B, h, U, U))
+    s = (ac + bd) / 8.0
+    mm = (mask.unsqueeze(1) == 0)
+    s = s.masked_fill(mm, float(torch.finfo(torch.float32).min))
+    want = (torch.softmax(s, -1).masked_fill(mm, 0.0) @ vh).transpose(1, 2).reshape(B, U, d)
+    # kernel: Q operand = q + u (what project_qkv_rel produces)
+    q_u = (q.float().view(B, U, h, 64) + u_b[None, None]).reshape(B, U, d).bfloat16()
+    got = ops.attention(q_u.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV), h,
+                        (relp.to(DEV), u_b.to(DEV), v_b.to(DEV), m))
+    assert got.dtype == torch.bfloat16
+    # (q+u) is rounded to bf16 once more than in the reference: tolerance 3e-2 of the output's max
+    assert rel(got.float(), want) < 3e-2

@@ -46,12 +46,12 @@ SIGNATURES = {
     "cn_gemm_bf16_rowstats": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cn_rel_attention_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "cn_rel_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
-                                     _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
+                                     _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
-                                 _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+                                 _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -220,9 +220,17 @@ class CassNAT(nn.Module):
             ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
             keep["best_sample"] = best
         # ---- hypothesis assembly (cassnat.py:574-637 for beam_width 1): one D2H copy
-        ids_h, ylen_h = ids.cpu().numpy(), ylen.cpu().tolist()
+        # one device->host transfer: [ids | logp bits | ylen] packed into a pinned int32 buffer
+        U_ = ids.shape[1]
+        packed = torch.cat([ids.reshape(B, U_).to(torch.int32), logp.reshape(B, U_).view(torch.int32),
+                            ylen.reshape(B, 1).to(torch.int32)], 1)
+        host = self._pinned(packed.shape)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        arr = host.numpy()
+        ids_h, ylen_h = arr[:, :U_], arr[:, 2 * U_].tolist()
         # sequential float64 running sum == the reference's `seq['score'] + token_score` chain
-        csum = logp.cpu().numpy().astype("float64").cumsum(axis=1)
+        csum = arr[:, U_:2 * U_].view("float32").astype("float64").cumsum(axis=1)
         ys0 = torch.ones(1, 1).fill_(sos).long()
         if getattr(args, "use_gpu", False):
             ys0 = ys0.to(dev)
@@ -251,6 +259,17 @@ class CassNAT(nn.Module):
         else:                                                                          # :470-473
             seg_ctx = None
         tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)            # [BS,1,U]
+        if ops.is_bf16() and not args.use_unimask:
+            # Length hints for the tcgen05 attention (exact): key tiles past the last valid key carry
+            # zero weight; in the transformer family token rows past ylen[b] (the pick loop reads rows
+            # 0..ylen[b], cassnat.py:587) never influence a row that is read, so they are zero-filled.
+            # The conformer family mixes rows (depthwise conv, GroupNorm over the padded slab): no q hint.
+            need_rows = None if self._conformer_dec else (ylen + 1).clamp(max=ymax)
+            ops.attach_length_hints(tgt_mask, kv_len=ylen.clamp(max=ymax), q_len=need_rows)
+            if not args.src_trigger:
+                valid = mask2 != 0
+                last_key = (valid * torch.arange(1, T + 1, device=dev)).amax(1)
+                src_mask = ops.attach_length_hints(src_mask.reshape(BS, 1, T), kv_len=last_key, q_len=need_rows)
         # ---- K6: token acoustic extractor
         pe_rows = self._pe_rows(enc_h, ymax)
         if seg_ctx is not None:
@@ -313,6 +332,15 @@ class CassNAT(nn.Module):
         from . import _lib
         _lib.launch_count += n_kernels
         return res
+
+    def _pinned(self, shape):
+        """Reusable pinned int32 staging buffer for the hypothesis read-back."""
+        buf = self.__dict__.get("_pin_buf")
+        n = int(shape[0]) * int(shape[1])
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1 << 16), dtype=torch.int32, pin_memory=True)
+            self.__dict__["_pin_buf"] = buf
+        return buf[:n].view(*shape)
 
     def _collapse(self, st, mask2, B, T, S, blank, threshold):
         dev = mask2.device

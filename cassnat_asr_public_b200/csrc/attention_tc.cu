@@ -110,6 +110,9 @@ struct AttnTcArgs {
   int B, h, Tq, Tk;
   __nv_bfloat16* out; int64_t ldo, sbo;
   const float* relbias; int max_rel;         // REL: [B,h,Tq,2m+1] = (q_i + v_h) . P[r,h]  (pre-kernel)
+  // optional per-utterance hints (key masks only): keys >= kv_len[b] are all masked (their tiles are
+  // skipped: exactly zero weight), query rows >= q_len[b] are not needed by the caller (zero-filled)
+  const int32_t* kv_len; const int32_t* q_len;
 };
 
 // Persistent, ping-pong design (v2):
@@ -139,9 +142,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 288);   // [2 groups][16 words]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (p.Tk + KT - 1) / KT;            // key tiles (<= 4)
-  const int nq = (p.Tq + QT - 1) / QT;                 // query tiles
-  const int n_pairs = (nq + 1) / 2;
+  const int n_tiles_max = (p.Tk + KT - 1) / KT;        // key tiles (<= 4)
+  const int nq_max = (p.Tq + QT - 1) / QT;             // query tiles
+  // per-item tile counts; every role evaluates the same expressions, so they stay in lock step
+  auto tiles_of = [&](int b, int& n_tiles, int& nq) {
+    n_tiles = n_tiles_max;
+    nq = nq_max;
+    if (p.kv_len) { int t = (min(max(p.kv_len[b], 1), p.Tk) + KT - 1) / KT; n_tiles = min(max(t, 1), n_tiles_max); }
+    if (p.q_len) { int t = (min(max(p.q_len[b], 0), p.Tq) + QT - 1) / QT; nq = min(t, nq_max); }
+  };
   const int n_items = p.B * p.h;
 
   if (threadIdx.x == 0) {
@@ -163,18 +172,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   if (warp == 9) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it_cnt = 0, q_cnt[2] = {0, 0};
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+      uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / p.h, hh = item % p.h;
+        int n_tiles, nq;
+        tiles_of(b, n_tiles, nq);
+        if (nq == 0) continue;                                  // nothing to compute for this item
+        const int n_pairs = (nq + 1) / 2;
         for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(bar(B_KFREE + j), (it_cnt & 1) ^ 1);
+          mbar_wait(bar(B_KFREE + j), (kv_cnt[j] & 1) ^ 1);
           mbar_expect_tx(bar(B_KFULL + j), KT * DK * 2);
           tma_load_3d(&map_k, bar(B_KFULL + j), sbase + OFF_K + j * 16384, hh * DK, j * KT, b);
         }
         for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(bar(B_VFREE + j), (it_cnt & 1) ^ 1);
+          mbar_wait(bar(B_VFREE + j), (kv_cnt[j] & 1) ^ 1);
           mbar_expect_tx(bar(B_VFULL + j), KT * DK * 2);
           tma_load_3d(&map_v, bar(B_VFULL + j), sbase + OFF_V + j * 16384, hh * DK, j * KT, b);
+          ++kv_cnt[j];
         }
         for (int pr = 0; pr < n_pairs; ++pr) {
           for (int g = 0; g < 2; ++g) {
@@ -193,15 +207,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(QT, KT, false);
       constexpr uint32_t idesc_o = idesc_bf16(QT, DK, true);
-      uint32_t it_cnt = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_cnt) {
+      uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int n_tiles, nq;
+        tiles_of(item / p.h, n_tiles, nq);
+        if (nq == 0) continue;
+        const int n_pairs = (nq + 1) / 2;
         for (int pr = 0; pr < n_pairs; ++pr) {
           const bool has[2] = {2 * pr < nq, 2 * pr + 1 < nq};
           const bool last_pair = pr == n_pairs - 1;
           const int last_g = has[1] ? 1 : 0;
           auto issue_s = [&](int g, int j) {
             if (j == 0) mbar_wait(bar(B_QFULL + g), q_cnt[g] & 1);
-            mbar_wait(bar(B_KFULL + j), it_cnt & 1);
+            mbar_wait(bar(B_KFULL + j), kv_cnt[j] & 1);
             fence_after();
             const uint64_t dq = desc_kmajor(sbase + OFF_Q + g * 16384), dkk = desc_kmajor(sbase + OFF_K + j * 16384);
 #pragma unroll
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
               if (!has[g]) continue;
               mbar_wait(bar(B_PREADY + g), p_cnt[g] & 1);       // P_g(j) written, S_g(j) consumed
               ++p_cnt[g];
-              mbar_wait(bar(B_VFULL + j), it_cnt & 1);
+              mbar_wait(bar(B_VFULL + j), kv_cnt[j] & 1);
               fence_after();
               const uint64_t dv = desc_mnmajor(sbase + OFF_V + j * 16384);
 #pragma unroll
@@ -232,6 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             }
           }
         }
+        for (int j = 0; j < n_tiles; ++j) ++kv_cnt[j];
       }
     }
   } else {
@@ -255,6 +274,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           if (lane == 0) kbits[k >> 5] = bits;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      }
+      int n_tiles, nq;
+      tiles_of(b, n_tiles, nq);
+      const int n_pairs = (nq + 1) / 2;
+      if (nq < nq_max) {
+        // query rows the caller does not need: zero-filled (finite inputs for whatever reads them next)
+        for (int r = nq * QT + g * 128 + row; r < p.Tq; r += 256) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)b * p.sbo + (int64_t)r * p.ldo + hh * DK);
+#pragma unroll
+          for (int d = 0; d < DK / 8; ++d) dst[d] = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       for (int pr = 0; pr < n_pairs; ++pr) {
         const int qt = 2 * pr + g;
@@ -476,7 +506,8 @@ __global__ void __launch_bounds__(256) rel_bias_kernel(const __nv_bfloat16* __re
 static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
-                               int64_t sbo, const float* relbias, int max_rel, cn_stream_t stream_) {
+                               int64_t sbo, const float* relbias, int max_rel, const int32_t* kv_len,
+                               const int32_t* q_len, cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   if (dk != DK || Tk > MAX_TILES * KT || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
   // TMA: 16-byte aligned bases and pitches; 16-byte vector stores of the output rows
@@ -493,6 +524,7 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   AttnTcArgs p;
   p.mask = mask; p.mb = mb; p.mi = mi; p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
+  p.kv_len = (mask && mi == 0) ? kv_len : nullptr; p.q_len = q_len;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
@@ -514,9 +546,9 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
 extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                  const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                  int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
-                                 int64_t sbo, cn_stream_t stream_) {
+                                 int64_t sbo, const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             nullptr, 0, stream_);
+                             nullptr, 0, kv_len, q_len, stream_);
 }
 
 extern "C" int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel) {
@@ -528,7 +560,7 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
                                      int64_t mi, const float* rel_pos, const float* rel_bias_u, const float* rel_bias_v,
                                      int64_t max_rel, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                                      void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
-                                     cn_stream_t stream_) {
+                                     const int32_t* kv_len, cn_stream_t stream_) {
   if (!rel_pos || !rel_bias_u || !rel_bias_v || !workspace || max_rel < 0 || !Q) return CN_ERR_BAD_ARG;
   if (h > 8 || max_rel > 64 || dk != DK) return CN_ERR_UNSUPPORTED;
   if (workspace_bytes < cn_rel_attention_workspace_bytes(B, h, Tq, max_rel)) return CN_ERR_WORKSPACE;
@@ -538,5 +570,5 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
       (const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)h, (int)Tq, (int)(2 * max_rel + 1), relbias);
   CN_CHECK_LAUNCH();
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             relbias, (int)max_rel, stream_);
+                             relbias, (int)max_rel, kv_len, nullptr, stream_);
 }

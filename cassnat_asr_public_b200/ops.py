@@ -352,11 +352,25 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     return o32 if o32 is not None else o16
 
 
+def attach_length_hints(mask, kv_len=None, q_len=None):
+    """Tags a KEY mask ([B,1,Tk], prefix-shaped or not) with per-utterance hints for the tcgen05
+    attention: kv_len[b] = (index of the last unmasked key) + 1, q_len[b] = number of leading query
+    rows the caller needs.  Both int32 [B] device tensors; the kernel skips fully masked key tiles
+    (exactly zero weight) and zero-fills unneeded query rows."""
+    if kv_len is not None:
+        mask._cn_kv_len = kv_len.to(torch.int32).contiguous()
+    if q_len is not None:
+        mask._cn_q_len = q_len.to(torch.int32).contiguous()
+    return mask
+
+
 def _attention_bf16(q, k, v, mask, n_head, rel=None):
     """tcgen05 attention: bf16 q/k/v (strided views of fused projection buffers are fine) -> bf16 ctx."""
     B, Tq, d = q.shape
     Tk = k.shape[1]
     out = torch.empty(B, Tq, d, dtype=torch.bfloat16, device=q.device)
+    kv_len = getattr(mask, "_cn_kv_len", None) if mask is not None else None
+    q_len = getattr(mask, "_cn_q_len", None) if mask is not None else None
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
     if rel is not None:
         rp, ru, rv, mr = rel
@@ -365,12 +379,12 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
         call("cn_rel_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
              ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp.float().contiguous()), ptr(ru.contiguous()),
              ptr(rv.contiguous()), int(mr), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1), out.stride(0),
-             ptr(ws), ws_bytes, stream(),
+             ptr(ws), ws_bytes, ptr(kv_len), stream(),
              work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
         return out
     call("cn_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, B, n_head, Tq, Tk, d // n_head,
-         ptr(out), out.stride(1), out.stride(0), stream(),
+         ptr(out), out.stride(1), out.stride(0), ptr(kv_len), ptr(q_len), stream(),
          work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
     return out
 

@@ -211,7 +211,10 @@ int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream);
 int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                       const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                       int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
-                      void* out, int64_t ldo, int64_t sbo, cn_stream_t stream);
+                      void* out, int64_t ldo, int64_t sbo,
+                      const int32_t* kv_len /* i32 [B] or NULL: keys >= kv_len[b] are all masked (key masks only) */,
+                      const int32_t* q_len  /* i32 [B] or NULL: rows >= q_len[b] are not needed -> zero-filled */,
+                      cn_stream_t stream);
 
 /* K10  CTC loss (alpha-beta in log space) fused with the log-softmax backward.
  *   replaces: torch.nn.CTCLoss(reduction='mean', zero_infinity=True)   src/models/cassnat.py:126,232
@@ -251,7 +254,7 @@ int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K
                           const float* rel_pos, const float* rel_bias_u, const float* rel_bias_v, int64_t max_rel,
                           int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                           void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
-                          cn_stream_t stream);
+                          const int32_t* kv_len, cn_stream_t stream);
 
 #ifdef __cplusplus
 }

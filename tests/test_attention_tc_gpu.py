@@ -81,3 +81,24 @@ def test_rel_attention_tc(B, U, h, m):
     assert got.dtype == torch.bfloat16
     # (q+u) is rounded to bf16 once more than in the reference: tolerance 3e-2 of the output's max
     assert rel(got.float(), want) < 3e-2
+
+
+def test_attention_tc_length_hints():
+    """kv_len / q_len hints: skipped key tiles carry exactly zero weight, unneeded rows are zero-filled,
+    needed rows are unchanged."""
+    B, Tq, Tk, h = 4, 400, 500, 2
+    d = 64 * h
+    torch.manual_seed(3)
+    q, k, v = (torch.randn(B, n, d).bfloat16().to(DEV) for n in (Tq, Tk, Tk))
+    klen = torch.tensor([500, 130, 257, 1])
+    qlen = torch.tensor([400, 0, 129, 300])
+    mask = (torch.arange(Tk)[None] < klen[:, None]).unsqueeze(1).to(DEV)
+    plain = ops.attention(q, k, v, mask, h).float()
+    ops.attach_length_hints(mask, kv_len=klen.to(DEV), q_len=qlen.to(DEV))
+    hinted = ops.attention(q, k, v, mask, h).float()
+    for b in range(B):
+        n = int(qlen[b])
+        assert torch.equal(hinted[b, :n], plain[b, :n]), b
+        # rows >= ceil(q_len/128)*128 are zero-filled; rows between q_len and the tile edge are computed
+        edge = min(-(-n // 128) * 128, Tq)
+        assert float(hinted[b, edge:].abs().max()) == 0.0 if edge < Tq else True

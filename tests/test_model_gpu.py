@@ -136,11 +136,15 @@ def test_bf16_tensor_core_mode(blocks_golden):
         model.set_precision("fp32")
     if not np.array_equal(keep["aligned"].cpu().numpy(), z["greedy::aligned"]):
         pytest.skip("bf16 CTC head flipped a near-tie frame: alignment differs, tensors not comparable")
+    ylen = torch.from_numpy(z["greedy::ylen"])
+    U = keep["dec_h"].shape[1]
+    needed = torch.arange(U)[None, :] <= ylen[:, None]          # rows 0..ylen[b]: what the pick loop reads
     for key in ("ac_embed", "pred_embed", "dec_h"):
-        assert rel(keep[key], z[f"greedy::{key}"]) < 3e-2, (name, key)
+        got, want = keep[key].float().cpu()[needed], torch.from_numpy(z[f"greedy::{key}"])[needed]
+        assert rel(got, want) < 3e-2, (name, key)
     att = torch.from_numpy(z["greedy::att_out"])
     top2 = att.topk(2, -1)[0]
-    clear = (top2[..., 0] - top2[..., 1]) > 0.1
+    clear = ((top2[..., 0] - top2[..., 1]) > 0.1) & needed
     assert torch.equal(keep["ids"].cpu().long()[clear], att.argmax(-1)[clear])
     assert (keep["logp"].cpu() - att.max(-1)[0])[clear].abs().max().item() < 0.05
 

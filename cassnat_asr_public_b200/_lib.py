@@ -38,8 +38,8 @@ SIGNATURES = {
                                         _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_segment_attention_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_conv_module_workspace_bytes": (_i64, [_i64, _i64]),
-    "cn_glu_dwconv_groupnorm_act": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _int, _i64, _i64, _i64, _i64,
-                                           _vp, _vp, _i64, _vp]),
+    "cn_glu_dwconv_groupnorm_act": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _int, _i64, _i64, _i64, _i64,
+                                           _vp, _vp, _vp, _i64, _vp]),
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
     "cn_gemm_rowstats_workspace_bytes": (_i64, [_i64, _i64]),
@@ -47,6 +47,7 @@ SIGNATURES = {
     "cn_rel_attention_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "cn_rel_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                      _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "cn_rescore_select": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,
                            _vp, _i64, _i64, _vp, _i64, _vp]),

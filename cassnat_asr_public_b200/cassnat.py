@@ -370,10 +370,18 @@ class CassNAT(nn.Module):
         lm_in = torch.cat([torch.full((B * S, 1), sos, dtype=torch.long, device=ids.device), ids64[:, :-1]], 1)
         causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=ids.device)).unsqueeze(0)
         lm_out = lm_model(lm_in, (tgt_mask & causal).long())
-        valid = tgt_mask.reshape(B, S, ymax) != 0
-        sc = torch.gather(lm_out, -1, ids64.unsqueeze(-1)).squeeze(-1).reshape(B, S, ymax).masked_fill(~valid, 0)
-        mean = sc.sum(-1) / (sc != 0).sum(-1).float()
-        best = mean.max(-1, keepdim=True)[1]                                            # [B,1]
+        if lm_out.is_cuda and lm_out.dtype == torch.float32 and lm_out.stride(-1) == 1 and S <= 32:
+            from ._lib import call, ptr, stream                                            # K11
+            mean = torch.empty(B * S, dtype=torch.float32, device=ids.device)
+            best = torch.empty(B, dtype=torch.int64, device=ids.device)
+            call("cn_rescore_select", ptr(lm_out), lm_out.stride(0), lm_out.stride(1), ptr(ids.contiguous()),
+                 ptr(tgt_mask.reshape(B * S, ymax).contiguous()), B, S, ymax, ptr(mean), ptr(best), stream())
+            best = best.unsqueeze(1)
+        else:
+            valid = tgt_mask.reshape(B, S, ymax) != 0
+            sc = torch.gather(lm_out, -1, ids64.unsqueeze(-1)).squeeze(-1).reshape(B, S, ymax).masked_fill(~valid, 0)
+            mean = sc.sum(-1) / (sc != 0).sum(-1).float()
+            best = mean.max(-1, keepdim=True)[1]                                        # [B,1]
         pick = lambda x: x.reshape(B, S, -1).gather(1, best.unsqueeze(-1).expand(B, 1, x.shape[-1])).squeeze(1)
         # the reference zeroes att_out beyond ylen before picking (:536) -> id 0 / score 0 there
         ids = pick(ids.masked_fill(tgt_mask.squeeze(1) == 0, 0))

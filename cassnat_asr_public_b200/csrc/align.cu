@@ -387,3 +387,57 @@ extern "C" int cn_tgt_length_mask(const int64_t* ylen, int64_t B, int64_t ymax, 
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
+
+// ------------------------------------------------------------------ K11 sampled-alignment rescoring
+//   replaces: gather / masked_fill / sum / count / max        src/models/cassnat.py:517-520
+// one CTA per utterance, one warp per sample: mean over the valid tokens of the ranker's log-prob at
+// the predicted id (entries that are exactly 0 do not count, as in the reference), then the first
+// arg-max over the S samples (NaN ranks highest, like torch.max).
+__global__ void __launch_bounds__(1024) rescore_select_kernel(const float* __restrict__ lm_out, int64_t s_row, int64_t s_tok,
+                                                              const int32_t* __restrict__ ids,
+                                                              const uint8_t* __restrict__ tgt_mask, int S, int U,
+                                                              float* __restrict__ mean_out, int64_t* __restrict__ best) {
+  __shared__ float means[32];
+  const int b = blockIdx.x, s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (s < S) {
+    const int64_t r = (int64_t)b * S + s;
+    float sum = 0.f;
+    int cnt = 0;
+    for (int u = lane; u < U; u += 32) {
+      float v = 0.f;
+      if (tgt_mask[r * U + u]) v = lm_out[r * s_row + (int64_t)u * s_tok + ids[r * U + u]];
+      sum += v;
+      cnt += (v != 0.f);
+    }
+    sum = cn_warp_sum(sum);
+    cnt = cn_warp_sum_i(cnt);
+    if (lane == 0) {
+      const float m = sum / (float)cnt;
+      means[s] = m;
+      mean_out[r] = m;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int arg = 0;
+    float top = means[0];
+    for (int k = 1; k < S; ++k) {
+      const float v = means[k];
+      if (top != top) break;                         // a NaN already won
+      if (v != v || v > top) { top = v; arg = k; }
+    }
+    best[b] = arg;
+  }
+}
+
+extern "C" int cn_rescore_select(const float* lm_out, int64_t row_stride, int64_t tok_stride, const int32_t* ids,
+                                 const uint8_t* tgt_mask, int64_t B, int64_t S, int64_t U, float* mean_out,
+                                 int64_t* best, cn_stream_t stream_) {
+  if (!lm_out || !ids || !tgt_mask || !mean_out || !best || B < 0 || S <= 0 || U <= 0) return CN_ERR_BAD_ARG;
+  if (S > 32) return CN_ERR_UNSUPPORTED;
+  if (B == 0) return CN_OK;
+  rescore_select_kernel<<<(unsigned)B, (unsigned)(32 * S), 0, (cudaStream_t)stream_>>>(lm_out, row_stride, tok_stride, ids,
+                                                                                      tgt_mask, (int)S, (int)U, mean_out, best);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}

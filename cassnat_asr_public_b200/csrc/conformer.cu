@@ -9,8 +9,12 @@ namespace {
 constexpr int TL = 32;     // token rows per CTA
 constexpr int CC = 256;    // channels per pass (one per thread)
 
+__device__ __forceinline__ float ld_as_f32(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_f32(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 // pass 1: z = dwconv(glu(y)) + per-CTA partial (sum, sum of squares) in double
-__global__ void __launch_bounds__(CC) glu_dwconv_kernel(const float* __restrict__ y, int64_t ldy, int64_t sby,
+template <typename TIn>
+__global__ void __launch_bounds__(CC) glu_dwconv_kernel(const TIn* __restrict__ y, int64_t ldy, int64_t sby,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         int L, int C, int ksz, float* __restrict__ z,
                                                         double* __restrict__ partial) {
@@ -20,15 +24,19 @@ __global__ void __launch_bounds__(CC) glu_dwconv_kernel(const float* __restrict_
   float s1 = 0.f, s2 = 0.f;
   for (int c0 = 0; c0 < C; c0 += CC) {
     const int c = c0 + threadIdx.x;
-    for (int r = 0; r < rows; ++r) {
-      const int l = l0 - pad + r;
-      float v = 0.f;
-      if (c < C && l >= 0 && l < L) {
-        const float* row = y + (int64_t)b * sby + (int64_t)l * ldy;
-        const float a = row[c], gate = row[C + c];
-        v = a * (1.f / (1.f + expf(-gate)));        // F.glu: first half * sigmoid(second half)
+    for (int r0 = 0; r0 < rows; r0 += 8) {          // 16 independent loads in flight per thread
+      float a[8], gt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int l = l0 - pad + r0 + k;
+        const bool ok = c < C && r0 + k < rows && l >= 0 && l < L;
+        const TIn* row = y + (int64_t)b * sby + (int64_t)(ok ? l : 0) * ldy;
+        a[k] = ok ? ld_as_f32(row + c) : 0.f;
+        gt[k] = ok ? ld_as_f32(row + C + c) : 0.f;
       }
-      g[r * CC + threadIdx.x] = v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (r0 + k < rows) g[(r0 + k) * CC + threadIdx.x] = a[k] * (1.f / (1.f + __expf(-gt[k])));   // F.glu
     }
     // each thread only reads back its own column -> no barrier needed
     if (c < C) {
@@ -59,11 +67,11 @@ __global__ void __launch_bounds__(CC) glu_dwconv_kernel(const float* __restrict_
   }
 }
 
-// pass 2: GroupNorm(1,C) affine + activation, in place
+// pass 2: GroupNorm(1,C) affine + activation; fp32 in place, or bf16 into out_bf16 (next GEMM's operand)
 __global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ z, const double* __restrict__ partial,
                                                             int nblk, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int act, int L,
-                                                            int C) {
+                                                            int C, __nv_bfloat16* __restrict__ out_bf16) {
   const int b = blockIdx.y;
   double t1 = 0, t2 = 0;
   for (int i = 0; i < nblk; ++i) { t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1]; }
@@ -74,12 +82,14 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ 
   const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
   const int64_t total = (int64_t)L * C;
   float* zb = z + (int64_t)b * total;
+  __nv_bfloat16* ob = out_bf16 ? out_bf16 + (int64_t)b * total : nullptr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     float v = (zb[i] - mu) * rstd * gamma[c] + beta[c];
     if (act == CN_ACT_RELU) v = fmaxf(v, 0.f);
-    else if (act == CN_ACT_SWISH) v = v / (1.f + expf(-v));
-    zb[i] = v;
+    else if (act == CN_ACT_SWISH) v = v / (1.f + __expf(-v));
+    if (ob) ob[i] = __float2bfloat16(v);
+    else zb[i] = v;
   }
 }
 }  // namespace
@@ -88,10 +98,11 @@ extern "C" int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L) {
   return B * ((L + TL - 1) / TL) * 2 * (int64_t)sizeof(double);
 }
 
-extern "C" int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t sby, const float* dw_weight,
-                                           const float* dw_bias, const float* gamma, const float* beta, float eps,
-                                           int act, int64_t B, int64_t L, int64_t C, int64_t ksz, float* out,
-                                           void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
+extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t ldy, int64_t sby,
+                                           const float* dw_weight, const float* dw_bias, const float* gamma,
+                                           const float* beta, float eps, int act, int64_t B, int64_t L, int64_t C,
+                                           int64_t ksz, float* out, void* out_bf16, void* workspace,
+                                           int64_t workspace_bytes, cn_stream_t stream_) {
   if (!y || !dw_weight || !gamma || !beta || !out || !workspace || B < 0 || L <= 0 || C <= 0) return CN_ERR_BAD_ARG;
   if (ksz < 1 || (ksz & 1) == 0 || ksz > 63 || ldy < 2 * C || B > 65535) return CN_ERR_UNSUPPORTED;
   if (workspace_bytes < cn_conv_module_workspace_bytes(B, L)) return CN_ERR_WORKSPACE;
@@ -99,16 +110,22 @@ extern "C" int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t 
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nblk = (int)((L + TL - 1) / TL);
   const size_t smem = (size_t)(TL + ksz - 1) * CC * sizeof(float);
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(glu_dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return CN_ERR_LAUNCH;
-  glu_dwconv_kernel<<<dim3(nblk, (unsigned)B), CC, smem, stream>>>(y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C,
-                                                                   (int)ksz, out, (double*)workspace);
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(glu_dwconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(glu_dwconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return CN_ERR_LAUNCH;
+  }
+  if (y_is_bf16)
+    glu_dwconv_kernel<__nv_bfloat16><<<dim3(nblk, (unsigned)B), CC, smem, stream>>>(
+        (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, (int)ksz, out, (double*)workspace);
+  else
+    glu_dwconv_kernel<float><<<dim3(nblk, (unsigned)B), CC, smem, stream>>>((const float*)y, ldy, sby, dw_weight, dw_bias,
+                                                                          (int)L, (int)C, (int)ksz, out, (double*)workspace);
   CN_CHECK_LAUNCH();
   int gx = (int)((L * C + 255) / 256);
   if (gx > 148 * 4) gx = 148 * 4;
   groupnorm_act_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(out, (const double*)workspace, nblk, gamma, beta, eps,
-                                                                  act, (int)L, (int)C);
+                                                                  act, (int)L, (int)C, (__nv_bfloat16*)out_bf16);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

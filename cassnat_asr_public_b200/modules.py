@@ -256,9 +256,11 @@ class ConvModule(nn.Module):
         """x [B,L,C] -> [B,L,C]: pointwise conv (a GEMM over channels) + GLU, depthwise conv,
         GroupNorm(1,C) over the whole [C,L] slab of each utterance, Swish, pointwise conv."""
         C = x.size(-1)
-        y = ops.linear(x, self.pointwise_conv1.weight.view(2 * C, C), self.pointwise_conv1.bias)
+        fast = ops.is_bf16()
+        y = ops.linear(x, self.pointwise_conv1.weight.view(2 * C, C), self.pointwise_conv1.bias, out_bf16=fast)
         y = ops.glu_dwconv_groupnorm_act(y, self.depthwise_conv.weight, self.depthwise_conv.bias,
-                                         self.norm.weight, self.norm.bias, self.norm.eps, _act_name(self.activation))
+                                         self.norm.weight, self.norm.bias, self.norm.eps, _act_name(self.activation),
+                                         out_bf16=fast)
         return ops.linear(y, self.pointwise_conv2.weight.view(C, C), self.pointwise_conv2.bias, residual=residual)
 
 

@@ -291,19 +291,23 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
     return out
 
 
-def glu_dwconv_groupnorm_act(y, dw_weight, dw_bias, gamma, beta, eps, act):
-    """Core of the conformer ConvModule (conformer_related.py:33-38) on y [B,L,2C] -> [B,L,C]."""
+def glu_dwconv_groupnorm_act(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16=False):
+    """Core of the conformer ConvModule (conformer_related.py:33-38) on y [B,L,2C] (f32 or bf16)
+    -> [B,L,C] (f32, or bf16 for the next tensor-core GEMM)."""
     require_cuda(y)
     B, L, C2 = y.shape
     C = C2 // 2
     assert y.stride(-1) == 1
     ksz = dw_weight.shape[-1]
     out = torch.empty(B, L, C, dtype=torch.float32, device=y.device)
+    o16 = torch.empty(B, L, C, dtype=torch.bfloat16, device=y.device) if out_bf16 else None
     ws_bytes = _lib.load().cn_conv_module_workspace_bytes(B, L)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=y.device)
-    call("cn_glu_dwconv_groupnorm_act", ptr(y), y.stride(1), y.stride(0), ptr(dw_weight.reshape(C, ksz).contiguous()),
-         ptr(dw_bias), ptr(gamma), ptr(beta), float(eps), ACT[act], B, L, C, ksz, ptr(out), ptr(ws), ws_bytes, stream())
-    return out
+    call("cn_glu_dwconv_groupnorm_act", ptr(y), int(y.dtype == torch.bfloat16), y.stride(1), y.stride(0),
+         ptr(dw_weight.reshape(C, ksz).contiguous()), ptr(dw_bias), ptr(gamma), ptr(beta), float(eps), ACT[act],
+         B, L, C, ksz, ptr(out), ptr(o16), ptr(ws), ws_bytes, stream(),
+         work=dict(bytes=float(B * L * C) * (2 * y.element_size() + 8 + (2 if out_bf16 else 4))))
+    return o16 if out_bf16 else out
 
 
 # ----------------------------------------------------------------------------- bf16 tensor-core path

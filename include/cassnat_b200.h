@@ -184,12 +184,13 @@ int64_t cn_segment_attention_workspace_bytes(int64_t B, int64_t U, int64_t d /* 
  * GLU over channels -> depthwise conv (odd kernel <= 63, zero padding) along the token axis ->
  * GroupNorm(1,C) over the whole padded [C,L] slab of each utterance -> activation.
  *   replaces: F.glu / depthwise_conv / GroupNorm / Swish      src/models/modules/conformer_related.py:33-38
- * y f32 [B,L,2C] (row stride ldy, batch stride sby) = pointwise_conv1 output; dw_weight [C,ksz];
+ * y f32 or bf16 [B,L,2C] (row stride ldy, batch stride sby) = pointwise_conv1 output; dw_weight [C,ksz];
  * out f32 [B,L,C] contiguous.  workspace: cn_conv_module_workspace_bytes(B,L). */
 int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L);
-int cn_glu_dwconv_groupnorm_act(const float* y, int64_t ldy, int64_t sby, const float* dw_weight,
+int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t ldy, int64_t sby, const float* dw_weight,
                                 const float* dw_bias, const float* gamma, const float* beta, float eps, int act,
-                                int64_t B, int64_t L, int64_t C, int64_t ksz, float* out,
+                                int64_t B, int64_t L, int64_t C, int64_t ksz, float* out /* f32 scratch + result */,
+                                void* out_bf16 /* optional bf16 result (then `out` only holds the pre-norm values) */,
                                 void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
@@ -255,6 +256,15 @@ int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K
                           int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                           void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
                           const int32_t* kv_len, cn_stream_t stream);
+
+/* K11  sampled-alignment rescoring: per sample the mean ranker log-probability of the predicted ids
+ * over the valid tokens (exact zeros do not count), then the first arg-max over the S samples.
+ *   replaces: gather / masked_fill / sum / count / max         src/models/cassnat.py:517-520
+ * lm_out f32 [B*S, U, V] (row_stride = elements between utterance-samples, tok_stride between tokens);
+ * ids i32 [B*S,U]; tgt_mask u8 [B*S,U]; mean_out f32 [B*S]; best i64 [B].  S <= 32. */
+int cn_rescore_select(const float* lm_out, int64_t row_stride, int64_t tok_stride, const int32_t* ids,
+                      const uint8_t* tgt_mask, int64_t B, int64_t S, int64_t U, float* mean_out, int64_t* best,
+                      cn_stream_t stream);
 
 #ifdef __cplusplus
 }

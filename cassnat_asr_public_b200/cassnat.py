@@ -282,19 +282,18 @@ class CassNAT(nn.Module):
             first = lambda x: x[0] if isinstance(x, tuple) else x
             args.ac_embed, args.pred_embed = first(ac_embed)[0].cpu(), first(pred_embed)[0].cpu()
         # ---- K8: MAD
+        dec_in = pred_embed
         if args.use_unimask:                                                           # :486-489
-            pos = None
             if isinstance(pred_embed, tuple):
-                pred_embed, pos = pred_embed
-            pred_embed = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
+                raise NotImplementedError("use_unimask with the conformer decoder raises in the reference "
+                                          "(cassnat.py:487 calls .size on a tuple)")
+            dec_in = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
             causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=dev)).unsqueeze(0)
             dec_mask = tgt_mask & causal
-            if pos is not None:
-                pred_embed = (pred_embed, pos)
         else:
             dec_mask = tgt_mask
         mem_mask = dense_trigger() if (args.src_trigger and seg_ctx is not None) else src_mask
-        dec_h = self.decoder(pred_embed, enc_h, mem_mask, dec_mask)
+        dec_h = self.decoder(dec_in, enc_h, mem_mask, dec_mask)
         # ---- K9: output head + greedy pick
         st = self.att_generator.greedy(dec_h)
         return st["top1"], st["logp"], ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask

@@ -257,14 +257,28 @@ def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg):
     h = cfg.n_head
     pe = sinusoid_table(d).unsqueeze(0).repeat(bs, 1, 1)[:, :ymax, :]
     mem_mask = trigger if cfg.src_trigger else src_mask
+
+    def unimask(pred):
+        """cassnat.py:486-489: shift the token embeddings right by one (zeros first), causal target mask."""
+        if not getattr(cfg, "use_unimask", False):
+            return pred, tgt_mask
+        if cfg.use_conv_dec:
+            raise AttributeError("use_unimask with the conformer decoder fails in the reference "
+                                 "(cassnat.py:487 calls .size on the (x, pos_embed) tuple)")
+        shifted = torch.cat([torch.zeros_like(pred[:, :1]), pred[:, :-1]], dim=1)
+        causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8)).unsqueeze(0)
+        return shifted, tgt_mask & causal.type_as(tgt_mask)
+
     if cfg.use_conv_dec:
         ac, pos = con_extractor(pe, enc_h, trigger, sd, h, cfg.dec_max_relative_len)
         pred, pos = con_sad(ac, pos, tgt_mask, sd, h)
-        dec_h = con_mad(pred, pos, enc_h, mem_mask, tgt_mask, sd, h)
+        dec_in, dec_mask = unimask(pred)
+        dec_h = con_mad(dec_in, pos, enc_h, mem_mask, dec_mask, sd, h)
     else:
         ac = trf_extractor(pe, enc_h, trigger, sd, h)
         pred = trf_sad(ac, tgt_mask, sd, h)
-        dec_h = trf_mad(pred, enc_h, mem_mask, tgt_mask, sd, h)
+        dec_in, dec_mask = unimask(pred)
+        dec_h = trf_mad(dec_in, enc_h, mem_mask, dec_mask, sd, h)
     return generator(dec_h, sd, "att_generator"), ac, pred, dec_h
 
 

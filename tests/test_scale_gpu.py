@@ -1,0 +1,93 @@
+"""GPU: end-to-end parity at shapes the golden fixtures do not cover (4 heads, odd lengths, deeper MAD),
+CUDA path vs the oracle port run on the same seeded inputs, plus randomised shape sweeps of the
+tensor-core kernels."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.nat_torch as O
+from cassnat_asr_public_b200 import ops
+from cassnat_asr_public_b200.cassnat import make_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+VOCAB = SimpleNamespace(word2index={"sos": 1, "eos": 2, "blank": 0})
+
+
+def _args(**kw):
+    a = dict(use_conv_enc=False, use_conv_dec=False, model_type="transformer", pos_type="absolute", n_head=4,
+             d_model=256, d_encff=512, d_decff=512, d_ff=512, dropout=0.0, N_enc=1, N_extra=1, N_self_dec=2, N_mix_dec=3,
+             vocab_size=501, interctc_alpha=0, interce_alpha=0, interctc_layer=0, interce_layer=0, padding_idx=0,
+             label_smooth=0.1, share_ff=False, enc_max_relative_len=20, enc_kernel_size=7, dec_max_relative_len=8,
+             dec_kernel_size=3, use_trigger=True, use_best_path=False, sample_topk=0, ctc_alpha=0.5, att_alpha=1.0,
+             save_embedding=False, use_unimask=False, src_trigger=False, left_trigger=0, right_trigger=0,
+             test_hitrate=False, sample_num=0, decode_type="att_only", threshold=0.9, rank_model="lm", lm_weight=0,
+             beam_width=1, length_penalty=0, use_gpu=True)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+@pytest.mark.parametrize("family", ["trf", "con"])
+@pytest.mark.parametrize("flags", [dict(), dict(left_trigger=1, right_trigger=1, src_trigger=True), dict(use_unimask=True)])
+def test_decode_vs_oracle_port(family, flags):
+    over = dict(flags)
+    if family == "con" and flags.get("use_unimask"):
+        pytest.skip("use_unimask + conformer decoder raises in the reference (cassnat.py:487)")
+    if family == "con":
+        over.update(use_conv_dec=True, use_conv_enc=True, pos_type="relative")
+    args = _args(**over)
+    torch.manual_seed(11)
+    model = make_model(16, args)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    B, T = 5, 77
+    enc_h = torch.randn(B, T, 256, generator=g)
+    lens = torch.tensor([77, 50, 63, 41, 70])
+    mask = (torch.arange(T)[None] < lens[:, None]).unsqueeze(1)
+    ratio = (lens.float() + 0.5) / T
+    with torch.no_grad():
+        want = O.decode_from_encoder(enc_h, mask, (ratio * T).long(), sd, SimpleNamespace(**vars(args)))
+        out, _, keep = model.decode_from_encoder(enc_h.to(DEV), mask.to(DEV), ratio.to(DEV), VOCAB, args,
+                                                 return_intermediates=True)
+    assert np.array_equal(keep["aligned"].cpu().numpy(), want["aligned"])
+    for key in ("ac_embed", "pred_embed", "dec_h"):
+        a, b = keep[key].cpu().double(), want[key].double()
+        assert ((a - b).abs().max() / b.abs().max()).item() < 1e-4, (family, flags, key)
+    # token ids: identical except where the oracle's own top-2 margin is within fp32 round-off
+    ids, ref = keep["ids"].cpu().long(), want["att_out"].argmax(-1)
+    top2 = want["att_out"].topk(2, -1)[0]
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert torch.equal(ids[clear], ref[clear])
+    if bool(clear.all()):
+        assert [o[0]["hyp"] for o in out] == want["hyps"]
+
+
+def test_random_gemm_shapes():
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        M, N, K = int(rng.integers(1, 700)), int(rng.integers(1, 80)) * 8, int(rng.integers(1, 40)) * 8
+        x = torch.randn(M, K).bfloat16()
+        w = (torch.randn(N, K) / K ** 0.5).bfloat16()
+        b, r = torch.randn(N), torch.randn(M, N)
+        y = ops.linear_bf16(x.to(DEV), w.to(DEV), b.to(DEV), r.to(DEV), 1.0, None)
+        ref = x.double() @ w.double().t() + b.double() + r.double()
+        assert ((y.cpu().double() - ref).abs().max() / ref.abs().max()).item() < 2e-5, (M, N, K)
+
+
+def test_random_attention_shapes():
+    rng = np.random.default_rng(1)
+    for _ in range(8):
+        B, h = int(rng.integers(1, 5)), int(rng.integers(1, 9))
+        Tq, Tk = int(rng.integers(1, 513)), int(rng.integers(1, 513))
+        d = 64 * h
+        q, k, v = (torch.randn(B, n, d).bfloat16() for n in (Tq, Tk, Tk))
+        lens = torch.randint(1, Tk + 1, (B,))
+        mask = (torch.arange(Tk)[None] < lens[:, None]).unsqueeze(1)
+        got = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV), h).float().cpu()
+        qh, kh, vh = (t.double().view(B, -1, h, 64).transpose(1, 2) for t in (q, k, v))
+        s = (qh @ kh.transpose(-1, -2) / 8.0).masked_fill(mask.unsqueeze(1) == 0, float(torch.finfo(torch.float32).min))
+        want = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, d)
+        assert ((got.double() - want).abs().max() / want.abs().max()).item() < 2e-2, (B, h, Tq, Tk)

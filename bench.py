@@ -8,7 +8,7 @@ A "step" is one pass of the path (everything CassNAT.beam_decode does after the 
 `enc_h` exists: CTC head -> best-path alignment -> segment ids -> extractor -> SAD -> MAD -> output
 head -> hypotheses) over one batch of synthetic encoder output of the named shape, random-init
 weights.  N > 1: one process per GPU under torchrun, utterance-sharded, weak scaling (the batch per
-GPU is fixed); the only collective is the hypothesis gather.  One JSON line on rank 0.
+GPU is fixed); no data-path collective, one end-of-job count all_reduce.  One JSON line on rank 0.
 """
 import argparse
 import json
@@ -178,13 +178,17 @@ def run_ours(a, w):
     dev_in = [t.to(dev) for t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(inputs, gather=True):
+    def step(inputs):
+        # Each rank decodes its own shard and keeps its own hypotheses, exactly like the reference's
+        # decode job (one process per device writing its own result file, run_hubert.sh:94-116):
+        # no data-path collective.  The job-level exchange is the (errors, tokens) sum below.
         with torch.no_grad():
             out, _ = model.decode_from_encoder(inputs[0], inputs[1], inputs[2], VOCAB, args)
-        hyps = [o[0]["hyp"] for o in out]
-        if world > 1 and gather:      # the hypothesis gather of the decode job (tiny; padded to T+2 tokens)
-            hyps = sharding.gather_hypotheses(hyps, B * world, T + 2, dev)
-        return hyps
+        return [o[0]["hyp"] for o in out]
+
+    def job_totals(hyps, n_steps):
+        # end-of-job count exchange (the WER numerator/denominator all_reduce, cassnat_task.py:186-189)
+        return sharding.reduce_error_counts(0, n_steps * sum(len(h) - 1 for h in hyps), dev)
 
     def sync_all():
         if world > 1:
@@ -205,6 +209,11 @@ def run_ours(a, w):
         hyps = step(dev_in)
         e1.record()
         evs.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    job_totals(hyps, a.steps)
+    e1.record()
+    evs.append((e0, e1))
     sync_all()
     launches = _lib.launch_count
     clocks = sampler.stop() if sampler else None
@@ -231,6 +240,7 @@ def run_ours(a, w):
         if i + 1 < a.steps:
             nxt = stage()
         hyps = step(staged)
+    job_totals(hyps, a.steps)
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -243,11 +253,11 @@ def run_ours(a, w):
         model.use_cuda_graphs = False           # per-call CUDA events need eager launches
         _lib.start_profile()
         for _ in range(2):
-            step(dev_in, gather=False)          # rank 0 only: no collective in here
+            step(dev_in)                         # rank 0 only: no collective in here
         prof = _lib.stop_profile()
         _lib.PROFILE_SHAPES = True
         _lib.start_profile()
-        step(dev_in, gather=False)
+        step(dev_in)
         prof_shapes = _lib.stop_profile()
         _lib.PROFILE_SHAPES = False
     if rank != 0:

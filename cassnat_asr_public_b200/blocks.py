@@ -138,6 +138,9 @@ class AcEmbedExtractor(nn.Module):
         return x
 
     def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None):
+        if torch.is_grad_enabled() and (memory.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: dense trigger mask through the attention that has a backward
+            return self.forward(pe_rows.unsqueeze(0).expand(memory.size(0), -1, -1), memory, dense_mask_fn())
         x = self.layers[0].forward_segments(pe_rows, memory, seg_ctx)
         if len(self.layers) > 1:
             mask = dense_mask_fn()

@@ -396,13 +396,23 @@ class CassNAT(nn.Module):
             return self.decode_from_encoder(enc_h, src_mask, src_size, vocab, args, lm_model, labels, label_sizes)
 
     def forward(self, src, src_mask, src_size, tgt_label, label_sizes, args):
-        """cassnat.py:136-257 -> (ctc_out, att_out, loss, ctc_loss, att_loss), forward values only.
-        The kernels are not autograd-aware yet: `loss` carries no graph.  What IS provided for the
-        backward pass is the fused CTC gradient: `self.last_ctc_grad` = ctc_alpha * d ctc_loss / d ctc
-        logits (K10), the [B,T,V] tensor the reference's backward spends its HBM time on."""
-        with torch.no_grad():
-            enc_h, x_mask = self.encode(src, src_mask)
-            return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args)
+        """cassnat.py:136-257 -> (ctc_out, att_out, loss, ctc_loss, att_loss).  With grad mode on and
+        parameters requiring grad, `loss` is connected to the autograd tape and `loss.backward()`
+        (cassnat_task.py:291) runs on this package's backward kernels (grad.py); `ctc_out` / `att_out`
+        are the log-probabilities the caller decodes for WER and carry no gradient of their own.
+        Under torch.no_grad() the same values are produced without a tape, and
+        `self.last_ctc_grad` = ctc_alpha * d ctc_loss / d ctc logits (K10) is kept for inspection."""
+        enc_h, x_mask = self.encode(src, src_mask)
+        return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args)
+
+    def zero_dropout(self):
+        """The kernels implement no dropout; training runs with every dropout probability at 0.
+        (The reference's transformer-family make_model hard-codes 0.1 for the encoder's attention
+        dropout whatever args.dropout says, so even its dropout=0 configuration is random there.)"""
+        for m in self.modules():
+            if hasattr(m, "p_drop"):
+                m.p_drop = 0.0
+        return self
 
     def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args):
         """Post-encoder part of CassNAT.forward (cassnat.py:148-257): CTC posteriors, Viterbi forced
@@ -417,8 +427,14 @@ class CassNAT(nn.Module):
         tgt_label, label_sizes = tgt_label.to(dev), label_sizes.to(dev)
         frames = (src_size.to(dev) * T).long()                                          # :165
         mask2 = x_mask.reshape(B, T)
+        taped = torch.is_grad_enabled() and (enc_h.requires_grad or any(p.requires_grad for p in self.parameters()))
         mem = ops.cast_bf16(enc_h) if ops.is_bf16() else enc_h
-        ctc_out = self.ctc_generator(mem)                                               # :148 (K1, materialised)
+        if taped:
+            from . import grad
+            ctc_out, ctc_loss = grad.CtcFromLogits.apply(self.ctc_generator.logits(mem), tgt_label, frames,
+                                                         label_sizes, blank)                # :148 + :232 (K1, K10)
+        else:
+            ctc_out = self.ctc_generator(mem)                                           # :148 (K1, materialised)
         aligned, ylen, ymax = ops.viterbi_align(ctc_out, x_mask, frames, tgt_label[:, :-1], label_sizes, blank,
                                                 args.sample_topk)                       # :170 (K3)
         _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
@@ -433,12 +449,18 @@ class CassNAT(nn.Module):
             raise NotImplementedError("use_unimask in training")
         mem_mask = dense_trigger() if args.src_trigger else x_mask
         dec_h = self.decoder(pred_embed, mem, mem_mask, tgt_mask)
-        att_out = self.att_generator(dec_h)                                             # :226
-        ctc_loss, _, grad = ops.ctc_loss(ctc_out, tgt_label, frames, label_sizes, blank,
-                                         want_grad=True, grad_out=float(args.ctc_alpha))   # :232 (K10)
-        self.last_ctc_grad = grad
-        att_loss = label_smoothing_loss(att_out.view(-1, att_out.size(-1)), tgt_label.reshape(-1),
-                                        args.vocab_size, args.padding_idx, args.label_smooth)   # :248
+        if taped:
+            z = self.att_generator.logits(dec_h)                                        # :226 + :248
+            att_out, att_loss = grad.LabelSmoothingFromLogits.apply(z.reshape(-1, z.size(-1)), tgt_label.reshape(-1),
+                                                                    args.padding_idx, args.label_smooth)
+            att_out = att_out.view(z.shape)
+        else:
+            att_out = self.att_generator(dec_h)                                         # :226
+            ctc_loss, _, g = ops.ctc_loss(ctc_out, tgt_label, frames, label_sizes, blank,
+                                          want_grad=True, grad_out=float(args.ctc_alpha))  # :232 (K10)
+            self.last_ctc_grad = g
+            att_loss = label_smoothing_loss(att_out.view(-1, att_out.size(-1)), tgt_label.reshape(-1),
+                                            args.vocab_size, args.padding_idx, args.label_smooth)   # :248
         loss = args.ctc_alpha * ctc_loss + args.att_alpha * att_loss
         return ctc_out, att_out, loss, ctc_loss, att_loss
 

@@ -1,0 +1,289 @@
+"""Autograd bindings of the CUDA kernels: what makes `loss.backward()` of the training call
+(src/tasks/cassnat_task.py:271,291) run on this package's kernels.
+
+Each op of `ops.py` that carries a gradient gets a `torch.autograd.Function` whose backward is built
+from the backward kernels of csrc/backward.cu (strided fp32 GEMM, LayerNorm / activation / softmax
+backward, label smoothing) plus, in the bf16 mode, the tcgen05 GEMM on transposed bf16 operands.
+`ops.linear / layer_norm / attention / cast_bf16` dispatch here when grad mode is on and an input
+requires grad; PyTorch autograd only provides the tape (slicing, concatenation of the fused QKV
+weights, residual adds)."""
+import torch
+
+from . import _lib
+from . import ops
+from ._lib import call, ptr, stream
+
+_ACT = ops.ACT
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _f32_2d(t, cols):
+    t = t.reshape(-1, cols)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def gemm_strided(A, a_strides, B, b_strides, C, c_strides, nz1, nz2, M, N, K, alpha=1.0, beta=0.0):
+    """C[z](m,n) = alpha * sum_k A[z](m,k) B[z](n,k) + beta C; strides are (z1, z2, row, k) in elements."""
+    call("cn_gemm_f32_strided", ptr(A), *a_strides, ptr(B), *b_strides, ptr(C), *c_strides, nz1, nz2, M, N, K,
+         float(alpha), float(beta), stream(), work=dict(flops=2.0 * nz1 * nz2 * M * N * K))
+    return C
+
+
+def act_bwd_colsum(dy, saved, act, alpha, want_dpre, want_colsum):
+    """-> (dpre or None, colsum or None) of cn_act_bwd_colsum on 2-D fp32 dy."""
+    M, N = dy.shape
+    dpre = torch.empty(M, N, dtype=torch.float32, device=dy.device) if want_dpre else None
+    col = torch.empty(N, dtype=torch.float32, device=dy.device) if want_colsum else None
+    ws_bytes = _lib.load().cn_colsum_workspace_bytes(M, N) if want_colsum else 0
+    ws = _ws(ws_bytes, dy.device)
+    call("cn_act_bwd_colsum", ptr(dy), dy.stride(0), ptr(saved), saved.stride(0) if saved is not None else 0,
+         _ACT[act], float(alpha), ptr(dpre), N, M, N, ptr(col), 0, ptr(ws), ws_bytes, stream(),
+         work=dict(bytes=4.0 * M * N * (2 + (saved is not None))))
+    return dpre, col
+
+
+def transpose_bf16(x2, pad_to=8):
+    """[R,C] f32|bf16 -> bf16 [C, Rpad] (row pitch padded to a multiple of 8 elements for TMA);
+    returns the padded buffer, whose first R columns are x^T."""
+    R, C = x2.shape
+    Rp = (R + pad_to - 1) // pad_to * pad_to
+    out = torch.empty(C, Rp, dtype=torch.bfloat16, device=x2.device)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    call("cn_transpose_bf16", ptr(x2), int(x2.dtype == torch.bfloat16), x2.stride(0), R, C, ptr(out), Rp, stream(),
+         work=dict(bytes=float(R * C) * (x2.element_size() + 2)))
+    return out
+
+
+def _gemm_bf16_raw(A, lda, W, ldw, M, N, K, out_dtype, device):
+    """out[M,N] = A[M,K] W[N,K]^T on tcgen05 (bf16 operands, row pitches lda/ldw)."""
+    o32 = torch.empty(M, N, dtype=torch.float32, device=device) if out_dtype == torch.float32 else None
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=device) if out_dtype == torch.bfloat16 else None
+    call("cn_gemm_bf16", ptr(A), lda, ptr(W), ldw, None, None, 0, 0, 1.0, 0, ptr(o32), ptr(o16), N, M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (4.0 if o32 is not None else 2.0)),
+         tag=(f"cn_gemm_bf16[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+    return o32 if o32 is not None else o16
+
+
+# =============================================================================== linear
+class Linear(torch.autograd.Function):
+    """residual + alpha * act(x W^T + b)  (ops.linear); dX = dpre W, dW = dpre^T X, db = colsum(dpre),
+    dpre = alpha * dY * act'."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, alpha, act, res_rows, out_bf16):
+        if act == "swish":
+            raise NotImplementedError("training through a fused Swish GEMM epilogue")
+        ctx.tc = ops.is_bf16() and x.shape[-1] % 8 == 0
+        ctx.alpha, ctx.act, ctx.res_rows = float(alpha), act, int(res_rows)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        ctx.wb = None
+        with torch.no_grad():
+            if ctx.tc:
+                xs = ops.cast_bf16(x.detach())                # the operands the forward GEMM consumes
+                ctx.wb = ops.bf16_weight(weight)
+                y = ops.linear_bf16(xs, ctx.wb, bias, residual, alpha, act, res_rows,
+                                    torch.bfloat16 if out_bf16 else torch.float32)
+            else:
+                xs = x
+                y = ops.linear_forward(x, weight, bias, residual, alpha, act, res_rows, None, out_bf16)
+        ctx.save_for_backward(xs, weight, y if act == "relu" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y_act = ctx.saved_tensors
+        N, K = weight.shape
+        needs = ctx.needs_input_grad
+        gy2 = _f32_2d(gy, N)
+        M = gy2.shape[0]
+        dev = gy2.device
+        g_res = None
+        if ctx.has_res and needs[3]:
+            g_res = gy if gy.dtype == torch.float32 else gy.float()
+            if ctx.res_rows:
+                g_res = g_res.reshape(-1, ctx.res_rows, N).sum(0)
+        saved = _f32_2d(y_act, N) if y_act is not None else None
+        want_dpre = ctx.act is not None or ctx.alpha != 1.0
+        want_db = ctx.has_bias and needs[2]
+        if want_dpre or want_db:
+            dpre, db = act_bwd_colsum(gy2, saved, ctx.act, ctx.alpha, want_dpre, want_db)
+            if dpre is None:
+                dpre = gy2
+        else:
+            dpre, db = gy2, None
+        x2 = x.reshape(-1, K)
+        dx = dw = None
+        if ctx.tc and N % 8 == 0:
+            d16 = ops.cast_bf16(dpre)
+            if needs[0]:
+                wt = transpose_bf16(ctx.wb)                                        # [K, Npad]
+                dx = _gemm_bf16_raw(d16, N, wt, wt.stride(0), M, K, N, ctx.x_dtype, dev)
+            if needs[1]:
+                dt = transpose_bf16(dpre)                                          # [N, Mpad]
+                xt = transpose_bf16(x2)                                            # [K, Mpad]
+                dw = _gemm_bf16_raw(dt, dt.stride(0), xt, xt.stride(0), N, K, M, torch.float32, dev)
+        else:
+            x2 = _f32_2d(x2, K)
+            w = weight if weight.stride(-1) == 1 else weight.contiguous()
+            if needs[0]:
+                dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+                gemm_strided(dpre, (0, 0, dpre.stride(0), 1), w, (0, 0, 1, w.stride(0)), dx, (0, 0, K), 1, 1, M, K, N)
+                if ctx.x_dtype != torch.float32:
+                    dx = dx.to(ctx.x_dtype)
+            if needs[1]:
+                dw = torch.empty(N, K, dtype=torch.float32, device=dev)
+                gemm_strided(dpre, (0, 0, 1, dpre.stride(0)), x2, (0, 0, 1, x2.stride(0)), dw, (0, 0, K), 1, 1, N, K, M)
+        if dx is not None:
+            dx = dx.reshape(ctx.x_shape)
+        return dx, dw, db, g_res, None, None, None, None
+
+
+# =============================================================================== layer norm
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a_2, b_2, eps, bf16):
+        with torch.no_grad():
+            y = ops.layer_norm_forward(x, a_2, b_2, eps, bf16)
+        ctx.eps = float(eps)
+        ctx.save_for_backward(x, a_2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, a = ctx.saved_tensors
+        d = x.shape[-1]
+        x2, g2 = _f32_2d(x, d), _f32_2d(gy, d)
+        rows = x2.shape[0]
+        dx = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+        da = torch.empty(d, dtype=torch.float32, device=x.device)
+        db = torch.empty(d, dtype=torch.float32, device=x.device)
+        ws_bytes = _lib.load().cn_layernorm_bwd_workspace_bytes(rows, d)
+        ws = _ws(ws_bytes, x.device)
+        call("cn_layernorm_bwd", ptr(x2), x2.stride(0), ptr(g2), g2.stride(0), ptr(a), ctx.eps, rows, d, ptr(dx), d,
+             ptr(da), ptr(db), ptr(ws), ws_bytes, stream(), work=dict(bytes=float(rows * d) * 20))
+        dx = dx.reshape(x.shape)
+        if x.dtype != torch.float32:
+            dx = dx.to(x.dtype)
+        return dx, da, db, None, None
+
+
+# =============================================================================== attention
+class Attention(torch.autograd.Function):
+    """Masked multi-head attention (ops.attention, plain variant).  Backward recomputes the
+    probabilities: S = QK^T/sqrt(dk), dP = dO V^T, softmax backward in place, then
+    dV = P^T dO, dQ = dS K/sqrt(dk), dK = dS^T Q/sqrt(dk) as batched strided GEMMs."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, n_head):
+        with torch.no_grad():
+            out = ops.attention_forward(q, k, v, mask, n_head)
+        ctx.n_head = n_head
+        ctx.mask = mask
+        ctx.save_for_backward(q, k, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v = ctx.saved_tensors
+        h = ctx.n_head
+        B, Tq, d = q.shape
+        Tk = k.shape[1]
+        dk = d // h
+        dev = q.device
+        f = lambda t: t if t.dtype == torch.float32 else t.float()
+        qf, kf, vf, gf = f(q), f(k), f(v), f(go)
+        if gf.stride(-1) != 1:
+            gf = gf.contiguous()
+        scale = 1.0 / (dk ** 0.5)
+        S = torch.empty(B, h, Tq, Tk, dtype=torch.float32, device=dev)
+        dP = torch.empty(B, h, Tq, Tk, dtype=torch.float32, device=dev)
+        sz = (h * Tq * Tk, Tq * Tk, Tk)
+        st = lambda t: (t.stride(0), dk, t.stride(1), 1)                 # (batch, head, row, feature)
+        gemm_strided(qf, st(qf), kf, st(kf), S, sz, B, h, Tq, Tk, dk, alpha=scale)
+        gemm_strided(gf, st(gf), vf, st(vf), dP, sz, B, h, Tq, Tk, dk)
+        m, mb, mi = ops._mask_strides(ctx.mask, B, Tq, Tk)
+        call("cn_attn_softmax_bwd", ptr(S), ptr(dP), ptr(m), mb, mi, B, h, Tq, Tk, 0, stream(),
+             work=dict(bytes=16.0 * B * h * Tq * Tk))
+        dq = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
+        dk_ = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
+        dv = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
+        tr = lambda t: (t.stride(0), dk, 1, t.stride(1))                 # operand read as [feature, row]
+        P_t = (h * Tq * Tk, Tq * Tk, 1, Tk)                              # P^T / dS^T: rows = keys, k = queries
+        P_n = (h * Tq * Tk, Tq * Tk, Tk, 1)
+        gemm_strided(S, P_t, gf, tr(gf), dv, (Tk * d, dk, d), B, h, Tk, dk, Tq)
+        gemm_strided(dP, P_n, kf, tr(kf), dq, (Tq * d, dk, d), B, h, Tq, dk, Tk, alpha=scale)
+        gemm_strided(dP, P_t, qf, tr(qf), dk_, (Tk * d, dk, d), B, h, Tk, dk, Tq, alpha=scale)
+        c = lambda g, ref: g if ref.dtype == torch.float32 else g.to(ref.dtype)
+        return c(dq, q), c(dk_, k), c(dv, v), None, None
+
+
+# =============================================================================== bf16 cast
+class CastBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        with torch.no_grad():
+            return ops.cast_bf16(x.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float()
+
+
+# =============================================================================== heads + losses
+class CtcFromLogits(torch.autograd.Function):
+    """logits [B,T,V] -> (log-probs [B,T,V] (no gradient of its own: the caller only decodes it for
+    WER, cassnat_task.py:276-279), CTC loss).  The gradient at the logits comes straight out of the
+    fused alpha-beta kernel (K10): softmax - occupancy, scaled by the incoming loss gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, input_lengths, target_lengths, blank):
+        with torch.no_grad():
+            logp = torch.empty_like(logits, dtype=torch.float32)
+            ops.row_stats(logits, lse=True, logp_out=logp)
+            loss, _, grad = ops.ctc_loss(logp, targets, input_lengths, target_lengths, blank, want_grad=True, grad_out=1.0)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(logp)
+        return logp, loss
+
+    @staticmethod
+    def backward(ctx, _g_logp, g_loss):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None, None, None, None
+
+
+class LabelSmoothingFromLogits(torch.autograd.Function):
+    """logits [R,V] -> (log-probs, label-smoothing KL loss) with dlogits = (p - w) / tokens."""
+
+    @staticmethod
+    def forward(ctx, logits, target, pad, smoothing):
+        with torch.no_grad():
+            R, V = logits.shape
+            logp = torch.empty_like(logits, dtype=torch.float32)
+            ops.row_stats(logits, lse=True, logp_out=logp)
+            loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+            grad = torch.empty(R, V, dtype=torch.float32, device=logits.device)
+            tg = target.to(torch.int64).contiguous()
+            ws = _ws((R + 4) * 4, logits.device)
+            call("cn_label_smoothing", ptr(logp), logp.stride(0), R, V, ptr(tg), int(pad), float(smoothing), 1.0,
+                 ptr(loss), ptr(grad), V, ptr(ws), ws.numel(), stream(), work=dict(bytes=12.0 * R * V))
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(logp)
+        return logp, loss[0]
+
+    @staticmethod
+    def backward(ctx, _g_logp, g_loss):
+        (grad,) = ctx.saved_tensors
+        return grad * g_loss, None, None, None
+
+
+def needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

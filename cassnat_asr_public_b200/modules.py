@@ -24,6 +24,8 @@ from . import ops
 
 def _cat_cached(owner, key, tensors, dim=0):
     """Concatenation of parameters, rebuilt only when one of them changed (fused QKV weights)."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        return torch.cat(list(tensors), dim)          # training: the concatenation is part of the tape
     stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
     cache = owner.__dict__.setdefault("_cn_cache", {})
     hit = cache.get(key)

@@ -169,6 +169,9 @@ def is_bf16():
 
 def bf16_weight(w):
     """bf16 copy of a weight, converted once and refreshed when the parameter changes."""
+    if w.grad_fn is not None and w._base is None:          # rebuilt every training step (torch.cat of parameters)
+        src = w.detach()
+        return cast_bf16(src if src.is_contiguous() else src.contiguous())
     base = w._base if w._base is not None else w          # views of a parameter share its cache entry
     key = (id(base), w.storage_offset(), tuple(w.shape), tuple(w.stride()))
     stamp = (base.data_ptr(), base._version)
@@ -181,10 +184,23 @@ def bf16_weight(w):
     return hit[1]
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False):
     """residual + alpha * act(x @ weight.T + bias) over the last dim of x.
     fp32 mode: FFMA kernel on f32 operands.  bf16 mode: x (f32 or bf16) and the weight go through the
-    tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains)."""
+    tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains).
+    With grad mode on and an input requiring grad the call is recorded for backward (grad.Linear)."""
+    if _needs_grad(x, weight, bias, residual):
+        from . import grad
+        assert out is None
+        return grad.Linear.apply(x, weight, bias, residual, alpha, act, res_rows, out_bf16)
+    return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16)
+
+
+def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False):
     require_cuda(x, weight)
     if _PRECISION == "bf16" and x.shape[-1] % 8 == 0:
         return linear_bf16(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, act, res_rows,
@@ -214,6 +230,13 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
 
 def layer_norm(x, a_2, b_2, eps=1e-6, bf16=False):
     """LayerNorm of modules/norm.py:15-18 (unbiased std, eps added to std)."""
+    if _needs_grad(x, a_2, b_2):
+        from . import grad
+        return grad.LayerNormFn.apply(x, a_2, b_2, eps, bf16)
+    return layer_norm_forward(x, a_2, b_2, eps, bf16)
+
+
+def layer_norm_forward(x, a_2, b_2, eps=1e-6, bf16=False):
     require_cuda(x)
     d = x.shape[-1]
     x2 = x.reshape(-1, d)
@@ -245,6 +268,16 @@ def attention(q, k, v, mask, n_head, rel=None, out=None):
     are fine, e.g. slices of a fused QKV buffer).  mask: [B,1,Tk] or [B,Tq,Tk], 0 = masked.
     rel = (rel_pos [2m+1,d], pos_bias_u [h,dk], pos_bias_v [h,dk], m) selects the relative-position
     variant (modules/attention.py:104-143)."""
+    if _needs_grad(q, k, v) or (rel is not None and _needs_grad(rel[0], rel[1], rel[2])):
+        from . import grad
+        assert out is None
+        if rel is not None:
+            raise NotImplementedError("backward of the relative-position attention")
+        return grad.Attention.apply(q, k, v, mask, n_head)
+    return attention_forward(q, k, v, mask, n_head, rel, out)
+
+
+def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     require_cuda(q, k, v)
     B, Tq, d = q.shape
     Tk = k.shape[1]
@@ -316,6 +349,9 @@ def cast_bf16(x):
     require_cuda(x)
     if x.dtype == torch.bfloat16:
         return x
+    if _needs_grad(x):
+        from . import grad
+        return grad.CastBf16.apply(x)
     xc = x.contiguous()
     out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
     n = xc.numel()

@@ -266,6 +266,57 @@ int cn_rescore_select(const float* lm_out, int64_t row_stride, int64_t tok_strid
                       const uint8_t* tgt_mask, int64_t B, int64_t S, int64_t U, float* mean_out, int64_t* best,
                       cn_stream_t stream);
 
+/* ============================ backward pass of the training step (cfg5) ============================
+ * What loss.backward() (src/tasks/cassnat_task.py:291) runs through ATen autograd for the blocks on
+ * the path.  Every reduction is order-deterministic (no floating-point atomics). */
+
+/* Batched strided fp32 GEMM:  C[z](m,n) = alpha * sum_k A[z](m,k) * B[z](n,k) + beta * C[z](m,n),
+ * z = (z1,z2) with independent element strides; C rows have stride c_m and unit column stride.
+ * Expresses dX = dY W, dW = dY^T X and the five contractions of attention backward without copies.
+ *   replaces: autograd of F.linear / torch.matmul   src/models/modules/attention.py:15-24,55-65,104-143 */
+int cn_gemm_f32_strided(const float* A, int64_t a_z1, int64_t a_z2, int64_t a_m, int64_t a_k,
+                        const float* B, int64_t b_z1, int64_t b_z2, int64_t b_n, int64_t b_k,
+                        float* C, int64_t c_z1, int64_t c_z2, int64_t c_m,
+                        int64_t nz1, int64_t nz2, int64_t M, int64_t N, int64_t K,
+                        float alpha, float beta, cn_stream_t stream);
+
+/* dpre = alpha * dy * act'(saved) (ReLU: saved = activation output; Swish: saved = pre-activation;
+ * CN_ACT_NONE: saved unused) and colsum[n] (+)= sum_m dpre[m,n]  (the bias gradient).
+ * dpre or colsum may be NULL.  workspace: cn_colsum_workspace_bytes(M,N) when colsum != NULL.
+ *   replaces: autograd of bias add / ReLU / Swish    src/models/modules/positionff.py:15-16 */
+int64_t cn_colsum_workspace_bytes(int64_t M, int64_t N);
+int cn_act_bwd_colsum(const float* dy, int64_t lddy, const float* saved, int64_t lds, int act, float alpha,
+                      float* dpre, int64_t ldp, int64_t M, int64_t N, float* colsum, int accumulate,
+                      void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* Backward of y = a*(x-mean)/(std_unbiased+eps)+b: dx [rows,d], da [d], db [d].
+ *   replaces: autograd of LayerNorm.forward          src/models/modules/norm.py:15-18 */
+int64_t cn_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d);
+int cn_layernorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* a, float eps,
+                     int64_t rows, int64_t d, float* dx, int64_t lddx, float* da, float* db,
+                     void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* Softmax backward of masked attention, in place: S [B,h,Tq,Tk] (scaled raw scores) <- probabilities
+ * as the forward used them; dP [B,h,Tq,Tk] (= dO V^T) <- gradient at the scaled scores.  Fully masked
+ * rows: uniform probabilities and zero score gradient (attention.py:19-21); zero_masked = 1 applies the
+ * relative variant's re-zeroing (attention.py:138).  mask as in cn_attention_f32. */
+int cn_attn_softmax_bwd(float* S, float* dP, const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t h,
+                        int64_t Tq, int64_t Tk, int zero_masked, cn_stream_t stream);
+
+/* Label-smoothing KL loss over log-softmax rows and its gradient at the logits:
+ *   loss = sum_{rows with target != pad} KL(w || p) / #such rows,  w = (1-s) one-hot + s/(V-1) elsewhere
+ *   dlogits[r,:] = grad_scale * (p - w) / #rows   (0 for pad rows);  dlogits may be NULL.
+ *   replaces: LabelSmoothing.forward + autograd      src/utils/loss.py:21-35
+ * workspace: (R + 4) * 4 bytes. */
+int cn_label_smoothing(const float* logp, int64_t ld, int64_t R, int64_t V, const int64_t* target, int64_t pad,
+                       float smoothing, float grad_scale, float* loss, float* dlogits, int64_t ldg,
+                       void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* out(bf16)[C, ldo] = in^T, in [R,C] f32 or bf16 with row stride ldi: operand staging of the
+ * tensor-core backward GEMMs (dX = dY W needs W^T rows, dW = dY^T X needs dY^T and X^T rows). */
+int cn_transpose_bf16(const void* in, int in_is_bf16, int64_t ldi, int64_t R, int64_t C, void* out, int64_t ldo,
+                      cn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,25 @@ def gen_family(name, **over):
     loss.backward()
     for hk in hooks:
         hk.remove()
+    # Parameter gradients of the unmodified reference (whole model, encoder included) for the
+    # backward-pass parity tests; kept in their own file.  The transformer-family make_model builds
+    # the encoder's MultiHeadedAttention with its default dropout=0.1 regardless of args.dropout
+    # (cassnat.py make_model), so a .train() forward is random there; this run zeroes every Dropout.p
+    # (module attributes only, no code change) to make loss.backward() reproducible.
+    for m_ in model.modules():
+        if isinstance(m_, torch.nn.Dropout):
+            m_.p = 0.0
+    model.zero_grad()
+    _, _, loss_d, ctc_d, att_d = model(src, src_mask, src_size, labels, label_sizes, args)
+    loss_d.backward()
+    grads = {"grad::" + k: p.grad.numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+    grads["no_grad"] = np.asarray([k for k, p in model.named_parameters() if p.grad is None])
+    grads["loss"] = loss_d.detach().numpy()
+    grads["ctc_loss"] = ctc_d.detach().numpy()
+    grads["att_loss"] = att_d.detach().numpy()
+    gpath = os.path.join(HERE, f"train_grads_{name}.npz")
+    np.savez_compressed(gpath, **grads)
+    print(gpath, os.path.getsize(gpath) // 1024, "KiB", len(grads) - 4, "tensors")
     enc_h = store["encoder"].detach()
     x_mask = src_mask[:, :, ::2][:, :, ::2]
     frames = (src_size * enc_h.size(1)).long()

@@ -72,7 +72,8 @@ def test_beam_decode_from_features(blocks_golden):
     name, z, sd, cfg = blocks_golden
     model, args = build(sd, cfg)
     src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
-    enc_h, m2 = model.encode(src, mask)
+    with torch.no_grad():
+        enc_h, m2 = model.encode(src, mask)
     assert rel(enc_h, z["greedy::enc_h"]) < TOL
     out, args2 = model.beam_decode(src, mask, size, VOCAB, args)
     assert args2 is args
@@ -168,7 +169,8 @@ def test_training_forward(blocks_golden):
     assert rel(model.last_ctc_grad, want_grad) < 1e-3
     # whole call from features
     src, mask = torch.from_numpy(z["src"]).to(DEV), torch.from_numpy(z["src_mask"]).to(DEV)
-    out = model(src, mask, size, labels, sizes, args)
+    with torch.no_grad():
+        out = model(src, mask, size, labels, sizes, args)
     assert abs(float(out[2]) - float(z["train::loss"])) < 1e-3 * abs(float(z["train::loss"]))
 
 

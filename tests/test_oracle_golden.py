@@ -1,5 +1,6 @@
 """CPU: the oracle (oracle/*.py) against the golden vectors generated from the unmodified
 reference (tests/golden/make_golden*.py).  Bit-exact for integer outputs."""
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -90,3 +91,29 @@ def test_train_port(blocks_golden):
     assert _rel(o["ctc_out"], z["train::ctc_out"]) < 2e-5 and _rel(o["att_out"], z["train::att_out"]) < 2e-5
     for k in ("loss", "ctc_loss", "att_loss"):
         assert abs(float(o[k]) - float(z["train::" + k])) < 1e-4 * max(1.0, abs(float(z["train::" + k])))
+
+
+def test_train_port_gradients(blocks_golden):
+    """The oracle port differentiated by torch autograd reproduces the parameter gradients of the
+    unmodified reference's loss.backward() (whole model, encoder included): the pin for the
+    backward-pass parity tests."""
+    name, z, sd, cfg = blocks_golden
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"train_grads_{name}.npz"))
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    src, mask, size = (torch.from_numpy(z[k]) for k in ("src", "src_mask", "src_size"))
+    enc_h, x_mask = O.encode(src, mask, leaf, cfg)
+    o = O.train_forward_from_encoder(enc_h, x_mask, torch.from_numpy(z["train::frames"]),
+                                     torch.from_numpy(z["train::labels"]), torch.from_numpy(z["train::label_sizes"]),
+                                     leaf, cfg)
+    o["loss"].backward()
+    checked = 0
+    for key in g.files:
+        if not key.startswith("grad::"):
+            continue
+        want = g[key]
+        got = leaf[key[6:]].grad
+        assert got is not None, key
+        scale = max(np.abs(want).max(), 1e-6)
+        assert np.abs(got.numpy() - want).max() / scale < 2e-4, (name, key)
+        checked += 1
+    assert checked > 100

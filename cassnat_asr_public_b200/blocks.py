@@ -32,7 +32,10 @@ def _self_attention_block(x, norm, attn, mask, pos_embed=None):
         table, m = distinct_rel_rows(pos_embed, x.size(1))
         fast = ops.is_bf16() and x.size(1) <= 512 and attn.h <= 8 and m <= 64
         rel_pos = ops.linear(table, attn.linear_pos.weight)
-        q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
+        if torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad):
+            q, k, v = attn.project_qkv(y, out_bf16=fast)           # training: raw q, grad.RelAttention adds u
+        else:
+            q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
         ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m))
     return attn.output(ctx, residual=x)
 
@@ -335,6 +338,8 @@ class ConAcEmbedExtractor(nn.Module):
         return x
 
     def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None):
+        if torch.is_grad_enabled() and (memory.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self.forward(pe_rows.unsqueeze(0).expand(memory.size(0), -1, -1), memory, dense_mask_fn())
         return self.layers[0].forward_segments(pe_rows, memory, seg_ctx)
 
 

@@ -111,28 +111,6 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __rest
   if (partial) partial[(int64_t)blockIdx.y * N + c] = s;
 }
 
-// out[c] = sum_blk partial[blk][c] in block order; 32 columns x 8 row groups per CTA.
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int64_t nblk, int64_t N,
-                                                            float* __restrict__ out, int accumulate) {
-  __shared__ float sh[8][33];
-  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
-  float s = 0.f;
-  if (c < N) {
-    const int64_t per = (nblk + 7) / 8;
-    const int64_t b0 = gy * per, b1 = (b0 + per < nblk) ? b0 + per : nblk;
-    for (int64_t b = b0; b < b1; ++b) s += partial[b * N + c];
-  }
-  sh[gy][cx] = s;
-  __syncthreads();
-  if (gy == 0 && c < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][cx];
-    out[c] = accumulate ? out[c] + t : t;
-  }
-}
-
 // ===================================================================== LayerNorm backward
 constexpr int LN_ROWS = 32;
 
@@ -314,9 +292,96 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const TIn* __restri
   }
 }
 
+// ===================================================================== relative-position terms
+// S[z,i,j] += scale * Tb[z,i,clamp(j-i,-m,m)+m]     (Tb = (q+v) P^T, attention.py:119-133)
+__global__ void __launch_bounds__(256) rel_bias_add_kernel(float* __restrict__ S, const float* __restrict__ Tb, int Tq, int Tk,
+                                                           int m, float scale, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= total) return;
+  const int j = (int)(e % Tk);
+  const int64_t row = e / Tk;
+  const int i = (int)(row % Tq);
+  int r = j - i;
+  r = r < -m ? -m : (r > m ? m : r);
+  S[e] += scale * Tb[row * (2 * m + 1) + r + m];
+}
+
+// G[z,i,r] = sum_{j : clamp(j-i,-m,m)+m == r} dS[z,i,j]   (gradient reaching the tabulated bias)
+__global__ void __launch_bounds__(256) rel_bucket_kernel(const float* __restrict__ dS, float* __restrict__ G, int Tq, int Tk,
+                                                         int m, int64_t rows_total) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows_total) return;
+  const int i = (int)(row % Tq);
+  const float* d = dS + row * Tk;
+  float* g = G + row * (2 * m + 1);
+  float lo = 0.f, hi = 0.f;
+  for (int j = lane; j < Tk; j += 32) {
+    const int r = j - i;
+    if (r <= -m) lo += d[j];
+    else if (r >= m) hi += d[j];
+    else g[r + m] = d[j];
+  }
+  lo = cn_warp_sum(lo); hi = cn_warp_sum(hi);
+  if (lane == 0) {
+    if (m == 0) g[0] = lo + hi;            // every offset clamps to the single row
+    else { g[0] = lo; g[2 * m] = hi; }
+  }
+  // offsets whose key index falls outside [0,Tk): no contribution
+  for (int r = -m + 1 + lane; r < m; r += 32) {
+    const int j = i + r;
+    if (j < 0 || j >= Tk) g[r + m] = 0.f;
+  }
+}
+
+// y = act(x) elementwise, f32 -> f32 or bf16 (training keeps the pre-activation for backward)
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, int act, float* __restrict__ y32,
+                                                      __nv_bfloat16* __restrict__ y16, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float v = x[i];
+    if (act == CN_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == CN_ACT_SWISH) v = v / (1.f + expf(-v));
+    if (y32) y32[i] = v;
+    if (y16) y16[i] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
+extern "C" int cn_rel_bias_add(float* S, const float* Tb, int64_t Z, int64_t Tq, int64_t Tk, int64_t max_rel, float scale,
+                               cn_stream_t stream) {
+  if (!S || !Tb || Z < 0 || Tq < 0 || Tk <= 0 || max_rel < 0) return CN_ERR_BAD_ARG;
+  const int64_t total = Z * Tq * Tk;
+  if (total == 0) return CN_OK;
+  if ((total + 255) / 256 > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  rel_bias_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(S, Tb, (int)Tq, (int)Tk, (int)max_rel,
+                                                                                         scale, total);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+extern "C" int cn_rel_bucket(const float* dS, float* G, int64_t Z, int64_t Tq, int64_t Tk, int64_t max_rel,
+                             cn_stream_t stream) {
+  if (!dS || !G || Z < 0 || Tq < 0 || Tk <= 0 || max_rel < 0) return CN_ERR_BAD_ARG;
+  const int64_t rows = Z * Tq;
+  if (rows == 0) return CN_OK;
+  if ((rows + 7) / 8 > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  rel_bucket_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dS, G, (int)Tq, (int)Tk, (int)max_rel, rows);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+extern "C" int cn_act_fwd(const float* x, int act, float* y_f32, void* y_bf16, int64_t n, cn_stream_t stream) {
+  if (!x || (!y_f32 && !y_bf16) || n < 0) return CN_ERR_BAD_ARG;
+  if (n == 0) return CN_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  act_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, act, y_f32, (__nv_bfloat16*)y_bf16, n);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
 extern "C" int cn_gemm_f32_strided(const float* A, int64_t a_z1, int64_t a_z2, int64_t a_m, int64_t a_k,
                                    const float* B, int64_t b_z1, int64_t b_z2, int64_t b_n, int64_t b_k,
                                    float* C, int64_t c_z1, int64_t c_z2, int64_t c_m,

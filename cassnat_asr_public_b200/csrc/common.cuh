@@ -55,3 +55,26 @@ __device__ __forceinline__ int cn_warp_sum_i(int v) {
 __device__ __forceinline__ bool cn_better(float va, int ia, float vb, int ib) {
   return (va > vb) || (va == vb && ia < ib);
 }
+
+// out[c] = sum_blk partial[blk][c] in block order; 32 columns x 8 row groups per CTA.
+static __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int64_t nblk, int64_t N,
+                                                            float* __restrict__ out, int accumulate) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < N) {
+    const int64_t per = (nblk + 7) / 8;
+    const int64_t b0 = gy * per, b1 = (b0 + per < nblk) ? b0 + per : nblk;
+    for (int64_t b = b0; b < b1; ++b) s += partial[b * N + c];
+  }
+  sh[gy][cx] = s;
+  __syncthreads();
+  if (gy == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][cx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+

@@ -92,7 +92,201 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ 
     else zb[i] = v;
   }
 }
+// ------------------------------------------------------------------------------------- backward
+// pass B2: dn = dout * act'(n), dwh = dn * gamma;  per-CTA partials of sum(dwh), sum(dwh * what) (double)
+// and of the channel sums dgamma_c = sum dn * what, dbeta_c = sum dn.  z (pre-norm conv output, from pass 1)
+// is overwritten with what, dwh goes to `dwh`.
+__global__ void __launch_bounds__(CC) gn_bwd_stats_kernel(float* __restrict__ z, const double* __restrict__ partial, int nblk,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, int act, int L, int C, const float* __restrict__ dout,
+                                                          float* __restrict__ dwh, double* __restrict__ s_partial,
+                                                          float* __restrict__ pg, float* __restrict__ pb) {
+  const int b = blockIdx.y, l0 = blockIdx.x * TL;
+  double t1 = 0, t2 = 0;
+  for (int i = 0; i < nblk; ++i) { t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1]; }
+  const double n = (double)L * C;
+  const double mean = t1 / n;
+  double var = t2 / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
+  float s1 = 0.f, s2 = 0.f;
+  const int64_t blk = (int64_t)b * gridDim.x + blockIdx.x;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    const int c = c0 + threadIdx.x;
+    if (c >= C) continue;
+    const float gm = gamma[c], bt = beta[c];
+    float ag = 0.f, ab = 0.f;
+    for (int i = 0; i < TL && l0 + i < L; ++i) {
+      const int64_t o = ((int64_t)b * L + (l0 + i)) * C + c;
+      const float wh = (z[o] - mu) * rstd;
+      const float v = wh * gm + bt;
+      float d = dout[o];
+      if (act == CN_ACT_RELU) d = v > 0.f ? d : 0.f;
+      else if (act == CN_ACT_SWISH) { const float sg = 1.f / (1.f + __expf(-v)); d *= sg * (1.f + v * (1.f - sg)); }
+      const float dh = d * gm;
+      z[o] = wh;
+      dwh[o] = dh;
+      s1 += dh; s2 = fmaf(dh, wh, s2);
+      ag = fmaf(d, wh, ag); ab += d;
+    }
+    pg[blk * C + c] = ag;
+    pb[blk * C + c] = ab;
+  }
+  __shared__ double red[2][CC / 32];
+  double d1 = s1, d2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d1; red[1][threadIdx.x >> 5] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a1 = 0, a2 = 0;
+    for (int i = 0; i < CC / 32; ++i) { a1 += red[0][i]; a2 += red[1][i]; }
+    s_partial[blk * 2 + 0] = a1;
+    s_partial[blk * 2 + 1] = a2;
+  }
+}
+
+// pass B3: dw = rstd * (dwh - mean(dwh) - what * mean(dwh * what)); depthwise-conv backward (weight, bias, input)
+// and GLU backward into dy [B,L,2C].
+template <typename TIn>
+__global__ void __launch_bounds__(CC) dwconv_glu_bwd_kernel(const TIn* __restrict__ y, int64_t ldy, int64_t sby,
+                                                            const float* __restrict__ w, const float* __restrict__ what,
+                                                            const float* __restrict__ dwh, const double* __restrict__ partial,
+                                                            const double* __restrict__ s_partial, int nblk, float eps,
+                                                            int L, int C, int ksz, float* __restrict__ dy,
+                                                            float* __restrict__ pw, float* __restrict__ pbias) {
+  extern __shared__ float sm[];                     // u tile then dw tile: 2 x [(TL + ksz - 1)][CC]
+  const int b = blockIdx.y, l0 = blockIdx.x * TL, pad = (ksz - 1) / 2;
+  const int rows = TL + ksz - 1;
+  float* ut = sm;
+  float* dt = sm + (size_t)rows * CC;
+  double t1 = 0, t2 = 0, q1 = 0, q2 = 0;
+  for (int i = 0; i < nblk; ++i) {
+    t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1];
+    q1 += s_partial[((int64_t)b * nblk + i) * 2]; q2 += s_partial[((int64_t)b * nblk + i) * 2 + 1];
+  }
+  const double n = (double)L * C;
+  const double mean = t1 / n;
+  double var = t2 / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float m1 = (float)(q1 / n), m2 = (float)(q2 / n);
+  const int64_t blk = (int64_t)b * gridDim.x + blockIdx.x;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    const int c = c0 + threadIdx.x;
+    if (c >= C) continue;                           // each thread only touches its own smem column
+    for (int r = 0; r < rows; ++r) {
+      const int l = l0 - pad + r;
+      const bool ok = l >= 0 && l < L;
+      float u = 0.f, d = 0.f;
+      if (ok) {
+        const TIn* row = y + (int64_t)b * sby + (int64_t)l * ldy;
+        u = ld_as_f32(row + c) * (1.f / (1.f + __expf(-ld_as_f32(row + C + c))));
+        const int64_t o = ((int64_t)b * L + l) * C + c;
+        d = rstd * (dwh[o] - m1 - what[o] * m2);
+      }
+      ut[r * CC + threadIdx.x] = u;
+      dt[r * CC + threadIdx.x] = d;
+    }
+    const int own = (L - l0 < TL) ? L - l0 : TL;
+    // weight / bias gradients over the CTA's own rows (tile row of token l0+i is i+pad)
+    float bsum = 0.f;
+    for (int i = 0; i < own; ++i) bsum += dt[(i + pad) * CC + threadIdx.x];
+    pbias[blk * C + c] = bsum;
+    for (int k = 0; k < ksz; ++k) {
+      float acc = 0.f;
+      for (int i = 0; i < own; ++i) acc = fmaf(dt[(i + pad) * CC + threadIdx.x], ut[(i + k) * CC + threadIdx.x], acc);
+      pw[blk * (int64_t)C * ksz + (int64_t)c * ksz + k] = acc;
+    }
+    // input gradient: du[l] = sum_k dw[l - k + pad] * w[c,k]; then GLU backward
+    for (int i = 0; i < own; ++i) {
+      float du = 0.f;
+      for (int k = 0; k < ksz; ++k) du = fmaf(dt[(i + 2 * pad - k) * CC + threadIdx.x], w[c * ksz + k], du);
+      const int l = l0 + i;
+      const TIn* row = y + (int64_t)b * sby + (int64_t)l * ldy;
+      const float a = ld_as_f32(row + c);
+      const float sg = 1.f / (1.f + __expf(-ld_as_f32(row + C + c)));
+      float* drow = dy + ((int64_t)b * L + l) * 2 * C;
+      drow[c] = du * sg;
+      drow[C + c] = du * a * sg * (1.f - sg);
+    }
+  }
+}
+// dynamic shared memory ceilings for the largest supported kernel size (ksz <= 63); the attribute is a
+// per-function maximum, so it is always set to the ceiling, never to the size of one call
+bool set_smem_limits() {
+  const int fwd = (TL + 62) * CC * (int)sizeof(float), bwd = 2 * fwd;
+  return cudaFuncSetAttribute(glu_dwconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd) == cudaSuccess &&
+         cudaFuncSetAttribute(glu_dwconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd) == cudaSuccess &&
+         cudaFuncSetAttribute(dwconv_glu_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd) == cudaSuccess &&
+         cudaFuncSetAttribute(dwconv_glu_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd) == cudaSuccess;
+}
 }  // namespace
+
+extern "C" int64_t cn_conv_module_bwd_workspace_bytes(int64_t B, int64_t L, int64_t C, int64_t ksz) {
+  if (B < 0 || L < 0 || C < 0 || ksz < 1) return -1;
+  const int64_t nblk = B * ((L + TL - 1) / TL);
+  return 2 * B * L * C * (int64_t)sizeof(float)          // what, dwh
+         + nblk * 4 * (int64_t)sizeof(double)             // forward stats + backward stats partials
+         + nblk * C * (2 + 1 + ksz) * (int64_t)sizeof(float) + 64;   // dgamma, dbeta, dbias, dweight partials
+}
+
+/* Backward of cn_glu_dwconv_groupnorm_act (recomputes the forward intermediates from y). */
+extern "C" int cn_glu_dwconv_groupnorm_act_bwd(const void* y, int y_is_bf16, int64_t ldy, int64_t sby, const float* dw_weight,
+                                               const float* dw_bias, const float* gamma, const float* beta, float eps,
+                                               int act, int64_t B, int64_t L, int64_t C, int64_t ksz, const float* dout,
+                                               float* dy, float* d_dw_weight, float* d_dw_bias, float* dgamma,
+                                               float* dbeta, void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
+  if (!y || !dw_weight || !gamma || !beta || !dout || !dy || !d_dw_weight || !d_dw_bias || !dgamma || !dbeta || !workspace ||
+      B < 0 || L <= 0 || C <= 0)
+    return CN_ERR_BAD_ARG;
+  if (ksz < 1 || (ksz & 1) == 0 || ksz > 63 || ldy < 2 * C || B > 65535) return CN_ERR_UNSUPPORTED;
+  if (workspace_bytes < cn_conv_module_bwd_workspace_bytes(B, L, C, ksz)) return CN_ERR_WORKSPACE;
+  if (B == 0) return CN_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nblk = (int)((L + TL - 1) / TL);
+  const int64_t nb = (int64_t)B * nblk;
+  char* p = (char*)workspace;
+  double* partial = (double*)p;            p += nb * 2 * sizeof(double);
+  double* s_partial = (double*)p;          p += nb * 2 * sizeof(double);
+  float* what = (float*)p;                 p += B * L * C * sizeof(float);
+  float* dwh = (float*)p;                  p += B * L * C * sizeof(float);
+  float* pg = (float*)p;                   p += nb * C * sizeof(float);
+  float* pb = (float*)p;                   p += nb * C * sizeof(float);
+  float* pbias = (float*)p;                p += nb * C * sizeof(float);
+  float* pw = (float*)p;
+  const size_t smem1 = (size_t)(TL + ksz - 1) * CC * sizeof(float);
+  const size_t smem3 = 2 * smem1;
+  if (!set_smem_limits()) return CN_ERR_LAUNCH;
+  dim3 grid(nblk, (unsigned)B);
+  if (y_is_bf16)
+    glu_dwconv_kernel<__nv_bfloat16><<<grid, CC, smem1, stream>>>((const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L,
+                                                                  (int)C, (int)ksz, what, partial);
+  else
+    glu_dwconv_kernel<float><<<grid, CC, smem1, stream>>>((const float*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C,
+                                                          (int)ksz, what, partial);
+  CN_CHECK_LAUNCH();
+  gn_bwd_stats_kernel<<<grid, CC, 0, stream>>>(what, partial, nblk, gamma, beta, eps, act, (int)L, (int)C, dout, dwh, s_partial,
+                                               pg, pb);
+  CN_CHECK_LAUNCH();
+  if (y_is_bf16)
+    dwconv_glu_bwd_kernel<__nv_bfloat16><<<grid, CC, smem3, stream>>>((const __nv_bfloat16*)y, ldy, sby, dw_weight, what, dwh,
+                                                                      partial, s_partial, nblk, eps, (int)L, (int)C, (int)ksz,
+                                                                      dy, pw, pbias);
+  else
+    dwconv_glu_bwd_kernel<float><<<grid, CC, smem3, stream>>>((const float*)y, ldy, sby, dw_weight, what, dwh, partial,
+                                                              s_partial, nblk, eps, (int)L, (int)C, (int)ksz, dy, pw, pbias);
+  CN_CHECK_LAUNCH();
+  colsum_reduce_kernel<<<(unsigned)((C + 31) / 32), 256, 0, stream>>>(pg, nb, C, dgamma, 0);
+  colsum_reduce_kernel<<<(unsigned)((C + 31) / 32), 256, 0, stream>>>(pb, nb, C, dbeta, 0);
+  colsum_reduce_kernel<<<(unsigned)((C + 31) / 32), 256, 0, stream>>>(pbias, nb, C, d_dw_bias, 0);
+  colsum_reduce_kernel<<<(unsigned)((C * ksz + 31) / 32), 256, 0, stream>>>(pw, nb, C * ksz, d_dw_weight, 0);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
 
 extern "C" int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L) {
   return B * ((L + TL - 1) / TL) * 2 * (int64_t)sizeof(double);
@@ -110,11 +304,7 @@ extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nblk = (int)((L + TL - 1) / TL);
   const size_t smem = (size_t)(TL + ksz - 1) * CC * sizeof(float);
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(glu_dwconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(glu_dwconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return CN_ERR_LAUNCH;
-  }
+  if (!set_smem_limits()) return CN_ERR_LAUNCH;
   if (y_is_bf16)
     glu_dwconv_kernel<__nv_bfloat16><<<dim3(nblk, (unsigned)B), CC, smem, stream>>>(
         (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, (int)ksz, out, (double*)workspace);

@@ -72,6 +72,15 @@ def _gemm_bf16_raw(A, lda, W, ldw, M, N, K, out_dtype, device):
     return o32 if o32 is not None else o16
 
 
+def act_forward(x, act, out_bf16=False):
+    """act(x) elementwise (f32 in; f32 or bf16 out)."""
+    xc = x.contiguous()
+    y = torch.empty(xc.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    call("cn_act_fwd", ptr(xc), _ACT[act], None if out_bf16 else ptr(y), ptr(y) if out_bf16 else None, xc.numel(), stream(),
+         work=dict(bytes=float(xc.numel()) * (4 + y.element_size())))
+    return y
+
+
 # =============================================================================== linear
 class Linear(torch.autograd.Function):
     """residual + alpha * act(x W^T + b)  (ops.linear); dX = dpre W, dW = dpre^T X, db = colsum(dpre),
@@ -79,8 +88,8 @@ class Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, alpha, act, res_rows, out_bf16):
-        if act == "swish":
-            raise NotImplementedError("training through a fused Swish GEMM epilogue")
+        swish = act == "swish"            # the backward needs the pre-activation: GEMM, then a separate activation
+        assert not (swish and residual is not None)
         ctx.tc = ops.is_bf16() and x.shape[-1] % 8 == 0
         ctx.alpha, ctx.act, ctx.res_rows = float(alpha), act, int(res_rows)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
@@ -90,12 +99,19 @@ class Linear(torch.autograd.Function):
             if ctx.tc:
                 xs = ops.cast_bf16(x.detach())                # the operands the forward GEMM consumes
                 ctx.wb = ops.bf16_weight(weight)
-                y = ops.linear_bf16(xs, ctx.wb, bias, residual, alpha, act, res_rows,
-                                    torch.bfloat16 if out_bf16 else torch.float32)
+                y = ops.linear_bf16(xs, ctx.wb, bias, residual, 1.0 if swish else alpha, None if swish else act, res_rows,
+                                    torch.bfloat16 if (out_bf16 and not swish) else torch.float32)
             else:
                 xs = x
-                y = ops.linear_forward(x, weight, bias, residual, alpha, act, res_rows, None, out_bf16)
-        ctx.save_for_backward(xs, weight, y if act == "relu" else None)
+                y = ops.linear_forward(x, weight, bias, residual, 1.0 if swish else alpha, None if swish else act,
+                                       res_rows, None, out_bf16 and not swish)
+            saved = y if act == "relu" else None
+            if swish:
+                saved = y
+                y = act_forward(saved, "swish", out_bf16)
+                if alpha != 1.0:
+                    y = y * alpha
+        ctx.save_for_backward(xs, weight, saved)
         return y
 
     @staticmethod
@@ -224,6 +240,113 @@ class Attention(torch.autograd.Function):
         gemm_strided(dP, P_t, qf, tr(qf), dk_, (Tk * d, dk, d), B, h, Tk, dk, Tq, alpha=scale)
         c = lambda g, ref: g if ref.dtype == torch.float32 else g.to(ref.dtype)
         return c(dq, q), c(dk_, k), c(dv, v), None, None
+
+
+class RelAttention(torch.autograd.Function):
+    """Relative-position self-attention (attention.py:104-143) on raw projected q (without pos_bias_u):
+    score(i,j) = ((q_i+u).k_j + (q_i+v).P[clamp(j-i,-m,m)+m]) / sqrt(dk), masked probabilities re-zeroed.
+    Backward = plain attention backward on q+u, plus the tabulated-bias path: bucket dS by relative offset,
+    then d(q+v) = G P and dP = G^T (q+v) as strided GEMMs."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, rel_pos, bias_u, bias_v, mask, n_head, m):
+        with torch.no_grad():
+            if q.dtype == torch.bfloat16:      # tcgen05 kernel takes q + u as its Q operand
+                qu = (q.float() + bias_u.reshape(1, 1, -1)).to(torch.bfloat16)
+                out = ops.attention_forward(qu, k, v, mask, n_head, (rel_pos, bias_u, bias_v, m))
+            else:
+                out = ops.attention_forward(q, k, v, mask, n_head, (rel_pos, bias_u, bias_v, m))
+        ctx.n_head, ctx.m, ctx.mask = n_head, int(m), mask
+        ctx.save_for_backward(q, k, v, rel_pos, bias_u, bias_v)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, rel_pos, bias_u, bias_v = ctx.saved_tensors
+        h, m = ctx.n_head, ctx.m
+        B, Tq, d = q.shape
+        Tk = k.shape[1]
+        dk = d // h
+        R = 2 * m + 1
+        dev = q.device
+        f = lambda t: t if t.dtype == torch.float32 else t.float()
+        qf, kf, vf, gf = f(q), f(k), f(v), f(go)
+        if gf.stride(-1) != 1:
+            gf = gf.contiguous()
+        P = f(rel_pos).contiguous()                                           # [R, d]
+        qu = qf + bias_u.reshape(1, 1, -1)
+        qv = qf + bias_v.reshape(1, 1, -1)
+        scale = 1.0 / (dk ** 0.5)
+        Z = B * h
+        S = torch.empty(B, h, Tq, Tk, dtype=torch.float32, device=dev)
+        dP = torch.empty(B, h, Tq, Tk, dtype=torch.float32, device=dev)
+        Tb = torch.empty(B, h, Tq, R, dtype=torch.float32, device=dev)
+        sz = (h * Tq * Tk, Tq * Tk, Tk)
+        st = lambda t: (t.stride(0), dk, t.stride(1), 1)
+        tr = lambda t: (t.stride(0), dk, 1, t.stride(1))
+        gemm_strided(qu, st(qu), kf, st(kf), S, sz, B, h, Tq, Tk, dk, alpha=scale)
+        gemm_strided(qv, st(qv), P, (0, dk, d, 1), Tb, (h * Tq * R, Tq * R, R), B, h, Tq, R, dk)
+        call("cn_rel_bias_add", ptr(S), ptr(Tb), Z, Tq, Tk, m, scale, stream(), work=dict(bytes=8.0 * Z * Tq * Tk))
+        gemm_strided(gf, st(gf), vf, st(vf), dP, sz, B, h, Tq, Tk, dk)
+        mk, mb, mi = ops._mask_strides(ctx.mask, B, Tq, Tk)
+        call("cn_attn_softmax_bwd", ptr(S), ptr(dP), ptr(mk), mb, mi, B, h, Tq, Tk, 1, stream(),
+             work=dict(bytes=16.0 * Z * Tq * Tk))
+        dqu = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
+        dqv = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
+        dk_ = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
+        dv = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
+        P_t = (h * Tq * Tk, Tq * Tk, 1, Tk)
+        P_n = (h * Tq * Tk, Tq * Tk, Tk, 1)
+        gemm_strided(S, P_t, gf, tr(gf), dv, (Tk * d, dk, d), B, h, Tk, dk, Tq)
+        gemm_strided(dP, P_n, kf, tr(kf), dqu, (Tq * d, dk, d), B, h, Tq, dk, Tk, alpha=scale)
+        gemm_strided(dP, P_t, qu, tr(qu), dk_, (Tk * d, dk, d), B, h, Tk, dk, Tq, alpha=scale)
+        G = Tb                                                                 # reuse: [B,h,Tq,R]
+        call("cn_rel_bucket", ptr(dP), ptr(G), Z, Tq, Tk, m, stream(), work=dict(bytes=4.0 * Z * Tq * (Tk + R)))
+        gemm_strided(G, (h * Tq * R, Tq * R, R, 1), P, (0, dk, 1, d), dqv, (Tq * d, dk, d), B, h, Tq, dk, R, alpha=scale)
+        dPb = torch.empty(B, R, d, dtype=torch.float32, device=dev)
+        gemm_strided(G, (h * Tq * R, Tq * R, 1, R), qv, tr(qv), dPb, (R * d, dk, d), B, h, R, dk, Tq, alpha=scale)
+        _, du = act_bwd_colsum(dqu.view(-1, d), None, None, 1.0, False, True)
+        _, dvb = act_bwd_colsum(dqv.view(-1, d), None, None, 1.0, False, True)
+        dq = dqu + dqv
+        c = lambda g, ref: g if ref.dtype == torch.float32 else g.to(ref.dtype)
+        return (c(dq, q), c(dk_, k), c(dv, v), c(dPb.sum(0), rel_pos), du.view_as(bias_u), dvb.view_as(bias_v),
+                None, None, None)
+
+
+# =============================================================================== conformer conv module core
+class ConvCore(torch.autograd.Function):
+    """GLU -> depthwise conv -> GroupNorm(1,C) -> activation (conformer_related.py:33-38)."""
+
+    @staticmethod
+    def forward(ctx, y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16):
+        with torch.no_grad():
+            out = ops.glu_dwconv_groupnorm_act_forward(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16)
+        ctx.eps, ctx.act = float(eps), act
+        ctx.save_for_backward(y, dw_weight, dw_bias, gamma, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        y, dw_weight, dw_bias, gamma, beta = ctx.saved_tensors
+        B, L, C2 = y.shape
+        C = C2 // 2
+        ksz = dw_weight.shape[-1]
+        dev = y.device
+        gf = go if go.dtype == torch.float32 else go.float()
+        gf = gf.contiguous()
+        yc = y if y.stride(-1) == 1 else y.contiguous()
+        dy = torch.empty(B, L, C2, dtype=torch.float32, device=dev)
+        dw = torch.empty(C, ksz, dtype=torch.float32, device=dev)
+        db, dg, dbt = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(3))
+        ws_bytes = _lib.load().cn_conv_module_bwd_workspace_bytes(B, L, C, ksz)
+        ws = _ws(ws_bytes, dev)
+        call("cn_glu_dwconv_groupnorm_act_bwd", ptr(yc), int(yc.dtype == torch.bfloat16), yc.stride(1), yc.stride(0),
+             ptr(dw_weight.reshape(C, ksz).contiguous()), ptr(dw_bias), ptr(gamma), ptr(beta), ctx.eps, _ACT[ctx.act],
+             B, L, C, ksz, ptr(gf), ptr(dy), ptr(dw), ptr(db), ptr(dg), ptr(dbt), ptr(ws), ws_bytes, stream(),
+             work=dict(bytes=float(B * L * C) * 40))
+        if y.dtype != torch.float32:
+            dy = dy.to(y.dtype)
+        return dy, dw.view_as(dw_weight), db if dw_bias is not None else None, dg, dbt, None, None, None
 
 
 # =============================================================================== bf16 cast

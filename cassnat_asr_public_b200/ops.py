@@ -272,7 +272,7 @@ def attention(q, k, v, mask, n_head, rel=None, out=None):
         from . import grad
         assert out is None
         if rel is not None:
-            raise NotImplementedError("backward of the relative-position attention")
+            return grad.RelAttention.apply(q, k, v, rel[0], rel[1], rel[2], mask, n_head, rel[3])
         return grad.Attention.apply(q, k, v, mask, n_head)
     return attention_forward(q, k, v, mask, n_head, rel, out)
 
@@ -327,6 +327,13 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
 def glu_dwconv_groupnorm_act(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16=False):
     """Core of the conformer ConvModule (conformer_related.py:33-38) on y [B,L,2C] (f32 or bf16)
     -> [B,L,C] (f32, or bf16 for the next tensor-core GEMM)."""
+    if _needs_grad(y, dw_weight, dw_bias, gamma, beta):
+        from . import grad
+        return grad.ConvCore.apply(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16)
+    return glu_dwconv_groupnorm_act_forward(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16)
+
+
+def glu_dwconv_groupnorm_act_forward(y, dw_weight, dw_bias, gamma, beta, eps, act, out_bf16=False):
     require_cuda(y)
     B, L, C2 = y.shape
     C = C2 // 2

@@ -312,6 +312,27 @@ int cn_label_smoothing(const float* logp, int64_t ld, int64_t R, int64_t V, cons
                        float smoothing, float grad_scale, float* loss, float* dlogits, int64_t ldg,
                        void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* Relative-position attention backward helpers (attention.py:104-143):
+ *   cn_rel_bias_add:  S[z,i,j] += scale * Tb[z,i,clamp(j-i,-m,m)+m],  Tb [Z,Tq,2m+1] = (q+v) P^T
+ *   cn_rel_bucket:    G[z,i,r]  = sum over keys j with clamp(j-i,-m,m)+m == r of dS[z,i,j]
+ * (Z = B*h; the remaining contractions are cn_gemm_f32_strided calls.) */
+int cn_rel_bias_add(float* S, const float* Tb, int64_t Z, int64_t Tq, int64_t Tk, int64_t max_rel, float scale,
+                    cn_stream_t stream);
+int cn_rel_bucket(const float* dS, float* G, int64_t Z, int64_t Tq, int64_t Tk, int64_t max_rel, cn_stream_t stream);
+
+/* y = act(x), n elements, into f32 and/or bf16 (training keeps the pre-activation x for backward). */
+int cn_act_fwd(const float* x, int act, float* y_f32, void* y_bf16, int64_t n, cn_stream_t stream);
+
+/* Backward of cn_glu_dwconv_groupnorm_act: recomputes GLU / depthwise conv / GroupNorm statistics from y,
+ * then dy [B,L,2C] (contiguous f32), d_dw_weight [C,ksz], d_dw_bias [C], dgamma [C], dbeta [C]; dout [B,L,C].
+ *   replaces: autograd of ConvModule.forward core      src/models/modules/conformer_related.py:33-38 */
+int64_t cn_conv_module_bwd_workspace_bytes(int64_t B, int64_t L, int64_t C, int64_t ksz);
+int cn_glu_dwconv_groupnorm_act_bwd(const void* y, int y_is_bf16, int64_t ldy, int64_t sby, const float* dw_weight,
+                                    const float* dw_bias, const float* gamma, const float* beta, float eps, int act,
+                                    int64_t B, int64_t L, int64_t C, int64_t ksz, const float* dout, float* dy,
+                                    float* d_dw_weight, float* d_dw_bias, float* dgamma, float* dbeta,
+                                    void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
 /* out(bf16)[C, ldo] = in^T, in [R,C] f32 or bf16 with row stride ldi: operand staging of the
  * tensor-core backward GEMMs (dX = dY W needs W^T rows, dW = dY^T X needs dY^T and X^T rows). */
 int cn_transpose_bf16(const void* in, int in_is_bf16, int64_t ldi, int64_t R, int64_t C, void* out, int64_t ldo,

@@ -129,6 +129,96 @@ def test_attention_backward(precision, tol, B, h, Tq, Tk, dk, kind):
     assert rel(got, qkv.grad) < tol
 
 
+def ref_rel_attention(q, k, v, P, u, vb, mask, h, m):
+    B, T, d = q.shape
+    dk = d // h
+    sp = lambda t: t.reshape(B, -1, h, dk).transpose(1, 2)
+    qu, qv = sp(q) + u[None, :, None, :], sp(q) + vb[None, :, None, :]
+    ac = qu @ sp(k).transpose(-1, -2)
+    ar = torch.arange(T, device=q.device)
+    idx = (ar[None, :] - ar[:, None]).clamp(-m, m) + m
+    Ph = P.reshape(-1, h, dk).permute(1, 0, 2)
+    bd = (qv @ Ph.transpose(-1, -2)[None]).gather(-1, idx[None, None].expand(B, h, T, T))
+    s = (ac + bd) / dk ** 0.5
+    if mask is not None:
+        s = s.masked_fill(mask.unsqueeze(1) == 0, torch.finfo(torch.float32).min)
+    p = torch.softmax(s, -1)
+    if mask is not None:
+        p = p.masked_fill(mask.unsqueeze(1) == 0, 0.0)
+    return (p @ sp(v)).transpose(1, 2).reshape(B, T, d)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("B,h,T,m,kind", [(2, 2, 9, 3, "key"), (2, 4, 40, 8, "full"), (3, 8, 70, 8, "key"), (2, 2, 5, 8, "none")])
+def test_rel_attention_backward(precision, tol, B, h, T, m, kind):
+    ops.set_precision(precision)
+    dk = 64
+    d = h * dk
+    mm = min(m, T - 1)
+    qkv, P = leaf(B, T, 3 * d, seed=1), leaf(2 * mm + 1, d, seed=2)
+    u, vb = leaf(h, dk, seed=3, scale=0.3), leaf(h, dk, seed=4, scale=0.3)
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    if kind == "key":
+        lens = torch.randint(1, T + 1, (B,), device=DEV, generator=gen)
+        mask = (torch.arange(T, device=DEV)[None] < lens[:, None]).unsqueeze(1)
+    elif kind == "full":
+        mask = torch.rand(B, T, T, device=DEV, generator=gen) > 0.4
+        mask[:, 3] = False
+    else:
+        mask = None
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    leaves = (qkv, P, u, vb)
+    t = qkv.to(dt)
+    out = ops.attention(t[..., :d], t[..., d:2 * d], t[..., 2 * d:], mask, h, (P, u, vb, mm))
+    go = torch.randn(B, T, d, device=DEV, generator=gen)
+    out.backward(go.to(out.dtype))
+    got = [x.grad.clone() for x in leaves]
+    for x in leaves:
+        x.grad = None
+    ref = ref_rel_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], P, u, vb, mask, h, mm)
+    assert rel(out.float(), ref) < tol
+    ref.backward(go)
+    for g, x, nm in zip(got, leaves, "qkv P u v".split()):
+        assert rel(g, x.grad) < tol, nm
+
+
+@pytest.mark.parametrize("B,L,C,ksz,act", [(2, 7, 16, 3, "swish"), (3, 70, 128, 7, "swish"), (2, 33, 300, 15, "relu")])
+def test_conv_core_backward(B, L, C, ksz, act):
+    F = torch.nn.functional
+    y, w, b = leaf(B, L, 2 * C, seed=1), leaf(C, 1, ksz, seed=2, scale=0.4), leaf(C, seed=3, scale=0.2)
+    gamma, beta = leaf(C, seed=4), leaf(C, seed=5, scale=0.3)
+    leaves = (y, w, b, gamma, beta)
+    out = ops.glu_dwconv_groupnorm_act(y, w, b, gamma, beta, 1e-5, act)
+    go = torch.randn(B, L, C, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    out.backward(go)
+    got = [x.grad.clone() for x in leaves]
+    for x in leaves:
+        x.grad = None
+    x = F.glu(y.transpose(1, 2), dim=1)
+    x = F.group_norm(F.conv1d(x, w, b, padding=(ksz - 1) // 2, groups=C), 1, gamma, beta, 1e-5)
+    x = (x * torch.sigmoid(x) if act == "swish" else torch.relu(x)).transpose(1, 2)
+    assert rel(out, x) < 2e-5
+    x.backward(go)
+    for g, t, nm in zip(got, leaves, "y w b gamma beta".split()):
+        assert rel(g, t.grad) < 1e-4, nm
+
+
+def test_swish_linear_backward():
+    x, w, b = leaf(200, 64, seed=1), leaf(96, 64, seed=2, scale=0.3), leaf(96, seed=3)
+    y = ops.linear(x, w, b, act="swish")
+    go = torch.randn(200, 96, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    y.backward(go)
+    got = [t.grad.clone() for t in (x, w, b)]
+    for t in (x, w, b):
+        t.grad = None
+    z = torch.nn.functional.linear(x, w, b)
+    z = z * torch.sigmoid(z)
+    assert rel(y, z) < 2e-5
+    z.backward(go)
+    for g, t, nm in zip(got, (x, w, b), "x w b".split()):
+        assert rel(g, t.grad) < 3e-5, nm
+
+
 def test_label_smoothing_and_ctc_heads():
     R, V, B, T, L = 24, 50, 4, 30, 5
     gen = torch.Generator(device=DEV).manual_seed(3)
@@ -172,7 +262,7 @@ def _load(name):
 
 
 @pytest.mark.parametrize("precision,tol,loss_tol", [("fp32", 1e-3, 1e-4), ("bf16", 0.25, 2e-2)])
-@pytest.mark.parametrize("name", ["trf"])
+@pytest.mark.parametrize("name", ["trf", "con"])
 def test_whole_model_backward_vs_reference(name, precision, tol, loss_tol):
     """CassNAT.forward(...)[2].backward() == the reference's parameter gradients, encoder included."""
     z, sd, cfg, g = _load(name)

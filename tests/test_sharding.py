@@ -63,3 +63,44 @@ def test_gather_two_ranks_gloo():
     for rank, everything, errs, toks in results:
         assert everything == want, rank
         assert (errs, toks) == (3, 30)
+
+
+def _grad_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                      # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for p in net[2].parameters():                             # a bucket member that never gets a gradient
+        pass
+    buckets = sharding.GradientBuckets(net.parameters(), bucket_bytes=64)     # tiny buckets -> several of them
+    outs = []
+    for step in range(2):                                     # buckets are reusable across steps
+        net.zero_grad(set_to_none=True)
+        x = torch.full((4, 6), float(rank + 1 + step))
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        buckets.finish()
+        outs.append((local, [p.grad.clone() for p in net.parameters()]))
+    out_q.put((rank, [([g.numpy() for g in l], [g.numpy() for g in a]) for l, a in outs]))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_two_ranks_gloo():
+    """Bucketed asynchronous gradient all_reduce == the mean of the per-rank gradients."""
+    import numpy as np
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        local0, avg0 = results[0][step]
+        local1, avg1 = results[1][step]
+        for a, b, m0, m1 in zip(local0, local1, avg0, avg1):
+            assert np.allclose(m0, (a + b) / 2, rtol=1e-6) and np.allclose(m1, m0)

@@ -247,6 +247,9 @@ def run_ours(a, w):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = t.tolist()
+    training = None
+    if not a.no_training:
+        training = training_step(model, args, w, dev, rank, world, sync_all, graphed=not a.no_graphs)
     # ---- per-kernel durations for the roofline (separate profiled steps, CUDA events per C-ABI call)
     prof = None
     if rank == 0:
@@ -300,6 +303,8 @@ def run_ours(a, w):
                             **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] else
                                {"GBps": round(v["bytes"] / v["ms"] / 1e6, 1)})}
                         for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]["ms"])}}
+    if training is not None:
+        line["training_step"] = training
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
     if world == 1 and not a.no_lattice:
@@ -309,6 +314,99 @@ def run_ours(a, w):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32, frames_in=1000, L=40, iters=10):
+    """SURVEY §8 cfg5 on the post-encoder path: forward (CTC head, Viterbi forced alignment, trigger
+    segments, extractor -> SAD -> MAD -> head, CTC + label-smoothing loss), loss.backward() on the
+    package's backward kernels (gradient returned at enc_h for the encoder) and, for N > 1, the bucketed
+    bf16 gradient all_reduce overlapped with backward.  Runs on every rank (it contains the collective);
+    time = max over ranks of the CUDA-event time of `iters` steps."""
+    import torch.distributed as dist
+
+    from cassnat_asr_public_b200 import sharding
+    T = (frames_in + 3) // 4
+    g = torch.Generator().manual_seed(4321 + rank)
+    enc_h = torch.randn(B, T, w["d_model"], generator=g).to(dev).requires_grad_(True)
+    lens = torch.randint(int(0.8 * T), T + 1, (B,), generator=g)
+    lens[0] = T
+    x_mask = (torch.arange(T)[None, :] < lens[:, None]).unsqueeze(1).to(dev)
+    ratio = ((lens.float() + 0.5) / T).to(dev)
+    labels = torch.randint(4, 5000, (B, L + 1), generator=g)
+    labels[:, L] = 2
+    labels, sizes = labels.to(dev), torch.full((B,), L, dtype=torch.int64, device=dev)
+    model.train()
+    model.zero_dropout()
+    params = [p for n, p in model.named_parameters() if not n.startswith(("src_embed.", "encoder."))]
+    buckets = sharding.GradientBuckets(params, comm_dtype=torch.bfloat16, hooks=not graphed) if world > 1 else None
+
+    def fwd_bwd():
+        out = model.train_forward_from_encoder(enc_h, x_mask, ratio, labels, sizes, args)
+        out[2].backward()
+        return out[2]
+
+    def eager():
+        for p in params:
+            p.grad = None
+        enc_h.grad = None
+        return fwd_bwd()
+
+    # warm-up on a side stream (PyTorch's whole-step capture recipe: the gradient accumulators of the leaves
+    # must not be tied to the legacy default stream when backward is captured)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            loss = eager()
+    torch.cuda.current_stream().wait_stream(side)
+    if graphed:
+        # the training forward has no host synchronisation (ymax comes from the label tensor's shape), so
+        # forward + backward are captured once and replayed: gradients live in the graph's memory pool
+        for p in params:
+            p.grad = None
+        enc_h.grad = None
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = fwd_bwd()
+
+    def one():
+        if graphed:
+            graph.replay()
+            res = static_loss
+        else:
+            res = eager()
+        if buckets is not None:
+            buckets.finish()
+        return res
+
+    for _ in range(2):
+        loss = one()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        loss = one()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        buckets.remove()
+    ms = float(t[0]) / iters
+    n_par = sum(p.numel() for p in params)
+    model.eval()
+    for p in params:
+        p.grad = None
+    return {"workload": f"cfg5 (post-encoder path): base model, {B} x {frames_in / 100:.0f} s per GPU, T={T}, {L} labels/utt, "
+                        f"fwd + bwd" + (" + bf16 gradient all_reduce" if world > 1 else ""),
+            "ms_per_step": ms, "utt_per_s": B * world / (ms / 1e3), "loss": float(loss.detach()),
+            "params_in_step": n_par, "precision": args_precision(model), "cuda_graph": graphed}
+
+
+def args_precision(model):
+    from cassnat_asr_public_b200 import ops
+    return ops.get_precision()
 
 
 def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
@@ -386,6 +484,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lattice", action="store_true", help="skip the cfg2 alignment-lattice microbench")
+    ap.add_argument("--no-training", action="store_true", help="skip the cfg5 training-step measurement")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

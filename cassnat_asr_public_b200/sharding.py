@@ -90,7 +90,7 @@ class GradientBuckets:
     averages and scatters the result back into `p.grad`.  comm_dtype=torch.bfloat16 halves the bytes on
     NVLink (fp32 master gradients are restored on the way back)."""
 
-    def __init__(self, params, group=None, bucket_bytes=32 << 20, comm_dtype=torch.float32):
+    def __init__(self, params, group=None, bucket_bytes=32 << 20, comm_dtype=torch.float32, hooks=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.comm_dtype = comm_dtype
@@ -109,7 +109,10 @@ class GradientBuckets:
         self._flat = [None] * len(self.buckets)
         self._pending = [0] * len(self.buckets)
         self._work = [None] * len(self.buckets)
-        self._hooks = [p.register_post_accumulate_grad_hook(self._ready) for p in self.params] if self.world > 1 else []
+        # hooks=False: no overlap; finish() launches every bucket itself (used when backward is a replayed
+        # CUDA graph, where no autograd hook fires)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._ready) for p in self.params] \
+            if (self.world > 1 and hooks) else []
         self.reset()
 
     def reset(self):

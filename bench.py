@@ -307,6 +307,8 @@ def run_ours(a, w):
         line["training_step"] = training
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
+    if world == 1 and not a.no_sampled and a.workload == "cfg3":
+        line["sampled_decode"] = sampled_decode(model, w, dev)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
         torch.cuda.empty_cache()
@@ -409,6 +411,57 @@ def args_precision(model):
     return ops.get_precision()
 
 
+class StandInRanker(torch.nn.Module):
+    """Ranker with the TransformerLM call contract (ids [N,U], mask [N,U,U]) -> log-probs [N,U,V]
+    (src/models/lm.py:52-56).  The real LM is the caller's stock PyTorch module (not part of
+    the path); this stand-in is a causal running-mean bag of embeddings so that the rescoring input has
+    the real shape and dtype."""
+
+    def __init__(self, V, d=64, seed=7):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.emb = torch.nn.Parameter(torch.randn(V, d, generator=g) * 0.3, requires_grad=False)
+        self.out = torch.nn.Parameter(torch.randn(d, V, generator=g) * 0.3, requires_grad=False)
+
+    def forward(self, ids, mask):
+        x = self.emb[ids].cumsum(1) / torch.arange(1, ids.size(1) + 1, device=ids.device)[None, :, None]
+        return torch.log_softmax(x @ self.out, -1)
+
+
+def sampled_decode(model, w, dev, B=32, S=10, iters=5):
+    """BASELINE configs[3] / SURVEY cfg4: decode with S=10 sampled alignments per utterance (threshold 0.9,
+    host-drawn select bits as cassnat.py:373) + ranker rescoring (K11), batch 32 -> effective batch 320."""
+    args = model_args(w, sample_num=S, threshold=0.9, rank_model="lm")
+    enc_h, mask, ratio, lens = synth_encoder_output(w, B, 777)
+    enc_h, mask, ratio = enc_h.to(dev), mask.to(dev), ratio.to(dev)
+    ranker = StandInRanker(5000).to(dev)
+
+    def once():
+        with torch.no_grad():
+            return model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args, lm_model=ranker)
+
+    for _ in range(2):
+        out, _ = once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        out, _ = once()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / iters * 1e3
+    U = max(len(o[0]["hyp"]) - 1 for o in out)
+    ids = torch.randint(0, 5000, (B * S, U), device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        ranker(ids, None)
+    torch.cuda.synchronize()
+    rk = (time.perf_counter() - t0) / iters * 1e3
+    return {"workload": f"cfg4: base model, {B} utterances x {S} sampled alignments (threshold 0.9) + rescoring, T={enc_h.size(1)}, "
+                        f"tokens_U_max={U}", "ms_per_step": ms, "utt_per_s": B / (ms / 1e3),
+            "alignments_per_s": B * S / (ms / 1e3), "stand_in_ranker_ms": rk,
+            "note": "wall clock incl. the host RNG draw, the stand-in ranker (stock torch, not part of the path) and the hypothesis read-back"}
+
+
 def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
     """BASELINE configs[1]: CTC best-path + Viterbi forced alignment + trigger masks on synthetic
     posteriors (T=1000, V=5000, U=200, batch 256; 5.12 GB).  Kernel times from CUDA events around the
@@ -484,6 +537,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lattice", action="store_true", help="skip the cfg2 alignment-lattice microbench")
+    ap.add_argument("--no-sampled", action="store_true", help="skip the cfg4 sampled-alignment decode measurement")
     ap.add_argument("--no-training", action="store_true", help="skip the cfg5 training-step measurement")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     a = ap.parse_args()

@@ -308,6 +308,8 @@ def run_ours(a, w):
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
     if world == 1 and not a.no_sampled and a.workload == "cfg3":
+        model.use_cuda_graphs = not a.no_graphs
+        line["speechlike_decode"] = speechlike_decode(model, args, w, dev_in, B, dev)
         line["sampled_decode"] = sampled_decode(model, w, dev)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
@@ -409,6 +411,48 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
 def args_precision(model):
     from cassnat_asr_public_b200 import ops
     return ops.get_precision()
+
+
+def speechlike_decode(model, args, w, dev_in, B, dev, iters=20, target=0.15):
+    """The headline workload has U ~ T because random-init CTC posteriors start a new token on almost every
+    frame; real speech has U ~ 0.1-0.2 T.  Same model, same inputs, but the CTC head's blank
+    bias is raised (bisection on the measured token rate) until tokens/frames ~ 0.15: what the path costs
+    at a speech-like token rate.  Restores the bias afterwards."""
+    bias = model.ctc_generator.proj.bias
+    saved = bias.detach().clone()
+    enc_h, mask, ratio = dev_in
+    frames = float(mask.sum())
+
+    def rate(b):
+        with torch.no_grad():
+            bias.copy_(saved)
+            bias[0] += b
+            out, _ = model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+        return sum(len(o[0]["hyp"]) - 2 for o in out) / frames, out
+
+    lo, hi = 0.0, 8.0
+    for _ in range(10):
+        mid = 0.5 * (lo + hi)
+        r, _ = rate(mid)
+        lo, hi = (mid, hi) if r > target else (lo, mid)
+    r, out = rate(hi)
+    for _ in range(3):
+        model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    with torch.no_grad():
+        for _ in range(iters):
+            out, _ = model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    with torch.no_grad():
+        bias.copy_(saved)
+    toks = [len(o[0]["hyp"]) - 1 for o in out]
+    return {"workload": f"cfg3 model and inputs, CTC blank bias +{hi:.2f} so that tokens/frames = {r:.3f}",
+            "ms_per_step": ms, "utt_per_s": B / (ms / 1e3), "tokens_U_mean": sum(toks) / len(toks), "tokens_U_max": max(toks),
+            "note": "no L2 flush between steps; everything else as the headline run"}
 
 
 class StandInRanker(torch.nn.Module):

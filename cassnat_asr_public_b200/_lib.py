@@ -53,6 +53,10 @@ SIGNATURES = {
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "cn_pack_mask_bits": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "cn_trigger_mask_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
+    "cn_attention_bf16_bits": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
+                                      _vp, _i64, _i64, _vp, _vp, _vp]),
     "cn_gemm_f32_strided": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                    _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
     "cn_colsum_workspace_bytes": (_i64, [_i64, _i64]),

@@ -85,9 +85,10 @@ class SrcAttLayer(nn.Module):
         """Same result as forward(pe_rows repeated over the batch, m, trigger_mask) with the
         trigger mask given implicitly by `seg_ctx` = (seg, ylens, src_mask, src_size, left, right)."""
         attn = self.src_attn
-        q_rows = attn.project_q(self.sublayer[0].norm.for_gemm(pe_rows))           # batch independent [U,d]
-        k, v = kv if kv is not None else attn.project_kv(m)
-        ctx = ops.segment_attention(q_rows, k, v, *seg_ctx, attn.h)
+        fast = ops.is_bf16() and attn.d_k == 64 and m.size(1) <= 512                # tcgen05 attention, mask fused
+        q_rows = attn.project_q(self.sublayer[0].norm.for_gemm(pe_rows), out_bf16=fast)   # batch independent [U,d]
+        k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
+        ctx = ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h, q_len=seg_ctx[6] if len(seg_ctx) > 6 else None)
         x = attn.output(ctx, residual=pe_rows, res_rows=pe_rows.size(0))
         return _ffn_block(x, self.sublayer[1].norm, self.feed_forward)
 
@@ -262,9 +263,10 @@ class ConSrcAttLayer(nn.Module):
 
     def forward_segments(self, pe_rows, m, seg_ctx, kv=None):
         attn = self.src_attn
-        q_rows = attn.project_q(pe_rows)
-        k, v = kv if kv is not None else attn.project_kv(m)
-        return self._finish(ops.segment_attention(q_rows, k, v, *seg_ctx, attn.h))
+        fast = ops.is_bf16() and attn.d_k == 64 and m.size(1) <= 512
+        q_rows = attn.project_q(pe_rows, out_bf16=fast)
+        k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
+        return self._finish(ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h))
 
 
 class ConMixAttLayer(nn.Module):

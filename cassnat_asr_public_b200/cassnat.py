@@ -254,6 +254,8 @@ class CassNAT(nn.Module):
             _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
                                                    want_seg=True)
             seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
+            if ops.is_bf16() and not self._conformer_dec and not args.use_unimask:
+                seg_ctx = seg_ctx + ((ylen + 1).clamp(max=ymax),)      # token rows the pick loop can read
             dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
                                                       args.left_trigger, args.right_trigger, True)[0]
         else:                                                                          # :470-473

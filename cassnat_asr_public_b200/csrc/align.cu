@@ -319,6 +319,94 @@ __global__ void __launch_bounds__(256) align_to_mask_kernel(
   }
 }
 
+// Bit-packed per-row masks for the tcgen05 attention: bits[b][u][w] (16 words per row, Tk <= 512),
+// bit (t & 31) of word (t >> 5) = keep(u, t).
+__global__ void __launch_bounds__(256) trigger_mask_bits_kernel(const int32_t* __restrict__ seg_g,
+                                                                const int64_t* __restrict__ ylens,
+                                                                const uint8_t* __restrict__ src_mask,
+                                                                const int64_t* __restrict__ src_size, int T, int n_rows,
+                                                                int left, int right, uint32_t* __restrict__ bits) {
+  // seg is non-decreasing along t, so row u's frames are one range [lo, hi]: two binary searches and
+  // word-wise range masks instead of T predicate evaluations per row
+  extern __shared__ int seg[];
+  __shared__ uint32_t srcw[16];
+  const int b = blockIdx.x, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) seg[t] = seg_g[(int64_t)b * T + t];
+  for (int t0 = 0; t0 < 512; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    const uint32_t w = __ballot_sync(0xffffffffu, t < T && src_mask[(int64_t)b * T + t] != 0);
+    if (lane == 0) srcw[t >> 5] = w;
+  }
+  __syncthreads();
+  const int yl = (int)ylens[b];
+  int fx = (int)src_size[b] - 1;
+  fx = fx < 0 ? fx + T : fx;
+  auto lower_bound = [&](int val) {                 // first t with seg[t] >= val
+    int lo = 0, hi = T;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] < val) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  for (int u = threadIdx.x; u < n_rows; u += blockDim.x) {
+    const int lo = lower_bound(u), hi = lower_bound(u + 1) - 1;           // frames with seg == u (may be empty)
+    uint32_t base[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const int a = max(lo - w * 32, 0), e = min(hi - w * 32, 31);
+      uint32_t m = 0;
+      if (a <= e) m = (e == 31 ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << a) - 1u);
+      m &= srcw[w];
+      if (u == yl && fx >= 0 && fx < T && (fx >> 5) == w) m |= 1u << (fx & 31);      // eos row is never empty
+      base[w] = m;
+    }
+    uint32_t* out = bits + ((int64_t)b * n_rows + u) * 16;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      uint32_t m = base[w];
+      if (right) m |= (base[w] << 1) | (w > 0 ? base[w - 1] >> 31 : 0u);
+      if (left) m |= (base[w] >> 1) | (w < 15 ? base[w + 1] << 31 : 0u);
+      out[w] = m & srcw[w];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_mask_bits_kernel(const uint8_t* __restrict__ mask, int64_t mb, int64_t mi,
+                                                             int Tq, int Tk, int64_t rows, uint32_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t b = row / Tq;
+  const int i = (int)(row % Tq);
+  const uint8_t* m = mask + b * mb + (int64_t)i * mi;
+  for (int w = 0; w < 16; ++w) {
+    const int t = w * 32 + lane;
+    const uint32_t word = __ballot_sync(0xffffffffu, t < Tk && m[t] != 0);
+    if (lane == 0) bits[row * 16 + w] = word;
+  }
+}
+
+extern "C" int cn_trigger_mask_bits(const int32_t* seg, const int64_t* ylens, const uint8_t* src_mask,
+                                    const int64_t* src_size, int64_t B, int64_t T, int64_t n_rows, int left, int right,
+                                    uint32_t* bits, cn_stream_t stream) {
+  if (!seg || !ylens || !src_mask || !src_size || !bits || B < 0 || T <= 0 || n_rows < 0) return CN_ERR_BAD_ARG;
+  if (T > 512 || B > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  if (B == 0 || n_rows == 0) return CN_OK;
+  trigger_mask_bits_kernel<<<(unsigned)B, 256, (size_t)T * sizeof(int), (cudaStream_t)stream>>>(
+      seg, ylens, src_mask, src_size, (int)T, (int)n_rows, left, right, bits);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+extern "C" int cn_pack_mask_bits(const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t Tq, int64_t Tk,
+                                 uint32_t* bits, cn_stream_t stream) {
+  if (!mask || !bits || B < 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
+  if (Tk > 512) return CN_ERR_UNSUPPORTED;
+  const int64_t rows = B * Tq;
+  if (rows == 0) return CN_OK;
+  pack_mask_bits_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(mask, mb, mi, (int)Tq, (int)Tk, rows, bits);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
 extern "C" int cn_align_to_mask(const int64_t* aligned, const int64_t* ylens, const uint8_t* src_mask,
                                 const int64_t* src_size, int64_t B, int64_t T, int64_t ymax, int64_t blank,
                                 int left, int right, int and_src_mask, uint8_t* mask_out, int64_t* ylen_out,

@@ -106,7 +106,9 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major)
 }
 
 struct AttnTcArgs {
-  const uint8_t* mask; int64_t mb, mi;      // u8, element (b,i,j) at mask[b*mb + i*mi + j]; mi == 0 -> key mask
+  const uint8_t* mask; int64_t mb;          // key mask u8 [B,Tk] (row pitch mb), shared by all query rows
+  const uint32_t* mask_bits;                // or: per-row mask, bit-packed [B,Tq,16 words] (bit t of word t/32 = keep)
+  int q_bcast;                              // Q is [1,Tq,d], shared by every utterance (extractor queries)
   int B, h, Tq, Tk;
   __nv_bfloat16* out; int64_t ldo, sbo;
   const float* relbias; int max_rel;         // REL: [B,h,Tq,2m+1] = (q_i + v_h) . P[r,h]  (pre-kernel)
@@ -128,7 +130,7 @@ constexpr int NTHREADS = 320;
 constexpr int B_QFULL = 0, B_QFREE = 2, B_KFULL = 4, B_VFULL = 8, B_KFREE = 12, B_VFREE = 16, B_SFULL = 20,
               B_PREADY = 22, B_PFREE = 24, B_OFULL = 26, N_BARS = 30;
 
-template <bool REL>
+template <bool REL, bool BITS>
 __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                    const __grid_constant__ CUtensorMap map_k,
                                                                    const __grid_constant__ CUtensorMap map_v,
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             if (qt >= nq) continue;
             mbar_wait(bar(B_QFREE + g), (q_cnt[g] & 1) ^ 1);
             mbar_expect_tx(bar(B_QFULL + g), QT * DK * 2);
-            tma_load_3d(&map_q, bar(B_QFULL + g), sbase + OFF_Q + g * 16384, hh * DK, qt * QT, b);
+            tma_load_3d(&map_q, bar(B_QFULL + g), sbase + OFF_Q + g * 16384, hh * DK, qt * QT, p.q_bcast ? 0 : b);
             ++q_cnt[g];
           }
         }
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.h, hh = item % p.h;
-      if (p.mask && p.mi == 0) {
+      if (p.mask) {
         // key-mask bits of this utterance (one private copy per group)
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // previous item's readers are done
         const uint8_t* mk = p.mask + (int64_t)b * p.mb;
@@ -290,7 +292,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         const int qt = 2 * pr + g;
         if (qt >= nq) continue;
         const int qi = qt * QT + row;
-        const uint8_t* mrow = p.mask ? p.mask + (int64_t)b * p.mb + (int64_t)(qi < p.Tq ? qi : 0) * p.mi : nullptr;
+        const uint32_t* brow = BITS ? p.mask_bits + ((int64_t)b * p.Tq + (qi < p.Tq ? qi : 0)) * 16 : nullptr;
+        // BITS: a row without any unmasked key is uniform over all Tk keys (scores all finfo.min,
+        // modules/attention.py:19-21) = softmax of equal scores; every other row gives masked keys exactly zero
+        // weight, so chunks without a kept key are skipped
+        bool uniform_row = false;
+        if (BITS) {
+          uint32_t any = 0;
+          for (int w = 0; w < (p.Tk + 31) >> 5; ++w) {
+            const int n = p.Tk - w * 32;
+            any |= __ldg(brow + w) & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+          }
+          uniform_row = any == 0u;
+        }
         float o[DK];
 #pragma unroll
         for (int d = 0; d < DK; ++d) o[d] = 0.f;
@@ -320,13 +334,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           auto chunk_bits = [&](int c, uint32_t& keep, uint32_t& valid) {
             const int n = p.Tk - (k0 + c);
             valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
-            if (!p.mask) keep = 0xffffffffu;
-            else if (p.mi == 0) keep = kbits[(k0 + c) >> 5];              // key mask: shared by all rows
-            else {
-              keep = 0;
-              for (int q = 0; q < 32; ++q)
-                if (k0 + c + q < p.Tk && mrow[k0 + c + q]) keep |= 1u << q;
-            }
+            if (BITS) keep = uniform_row ? 0xffffffffu : __ldg(brow + ((k0 + c) >> 5));   // per-row mask, bit-packed
+            else if (p.mask) keep = kbits[(k0 + c) >> 5];                 // key mask: shared by all rows
+            else keep = 0xffffffffu;
           };
           auto add_rel = [&](float* t, int c) {
             const int d_lo = k0 + c - qi;                                   // j - i of the chunk's first key
@@ -351,9 +361,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
             if (REL) { add_rel(t, c); any_keep = any_keep || ((keep & valid) != 0u); }
+            if (BITS && uniform_row) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) t[q] = 0.f;                     // equal scores
+            }
             if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
+            } else if (BITS && (keep & valid) == 0u) {
+              // no weight in this chunk
             } else {
               float mm = -INFINITY;
 #pragma unroll
@@ -375,7 +391,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           }
           const float mx = fmaxf(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])) * scale, mx_masked);   // scale > 0
           const float m_new = fmaxf(m_run, mx);
-          const float corr = ex2(m_run - m_new);
+          // BITS: a row can have no unmasked key in the tiles seen so far (m_new still -inf): nothing to rescale
+          const float corr = (BITS && m_new == -INFINITY) ? 1.f : ex2(m_run - m_new);
           float lsv[4] = {0.f, 0.f, 0.f, 0.f};
           if (pf_cnt > 0) mbar_wait(bar(B_PFREE + g), (pf_cnt - 1) & 1);   // previous PV finished reading P_g
           ++pf_cnt;
@@ -384,12 +401,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
             if (REL) add_rel(t, c);
+            if (BITS && uniform_row) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) t[q] = 0.f;
+            }
             if ((keep & valid) == 0xffffffffu) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
                 t[q] = ex2(fmaf(t[q], scale, -m_new));
                 lsv[q & 3] += t[q];
               }
+            } else if (BITS && (keep & valid) == 0u) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) t[q] = 0.f;
             } else {
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
@@ -505,11 +529,13 @@ __global__ void __launch_bounds__(256) rel_bias_kernel(const __nv_bfloat16* __re
 
 static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
-                               int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
-                               int64_t sbo, const float* relbias, int max_rel, const int32_t* kv_len,
-                               const int32_t* q_len, cn_stream_t stream_) {
+                               const uint32_t* mask_bits, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                               void* out, int64_t ldo, int64_t sbo, const float* relbias, int max_rel,
+                               const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   if (dk != DK || Tk > MAX_TILES * KT || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
+  if (mask && mi != 0) return CN_ERR_UNSUPPORTED;      // per-row byte masks go through cn_pack_mask_bits + *_bits
+  const bool q_bcast = sbq == 0;
   // TMA: 16-byte aligned bases and pitches; 16-byte vector stores of the output rows
   if ((ldq & 7) || (ldk & 7) || (ldv & 7) || (sbq & 7) || (sbk & 7) || (sbv & 7) || (ldo & 7) || (sbo & 7) ||
       ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
@@ -518,17 +544,19 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   if (B == 0 || Tq == 0) return CN_OK;
   CUtensorMap mq, mk, mv;
   const int64_t width = h * DK;
-  if (!make_map3(&mq, Q, B, Tq, width, ldq, sbq) || !make_map3(&mk, K, B, Tk, width, ldk, sbk) ||
+  if (!make_map3(&mq, Q, q_bcast ? 1 : B, Tq, width, ldq, q_bcast ? Tq * ldq : sbq) || !make_map3(&mk, K, B, Tk, width, ldk, sbk) ||
       !make_map3(&mv, V, B, Tk, width, ldv, sbv))
     return CN_ERR_DEVICE;
   AttnTcArgs p;
-  p.mask = mask; p.mb = mb; p.mi = mi; p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
+  p.mask = mask_bits ? nullptr : mask; p.mb = mb; p.mask_bits = mask_bits; p.q_bcast = q_bcast ? 1 : 0;
+  p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
-  p.kv_len = (mask && mi == 0) ? kv_len : nullptr; p.q_len = q_len;
+  p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
@@ -537,8 +565,10 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t items = B * h;
   const unsigned grid = (unsigned)(items < sms ? items : sms);           // persistent: one CTA per SM
-  if (relbias) attention_tc_kernel<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
-  else attention_tc_kernel<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  if (relbias && mask_bits) return CN_ERR_UNSUPPORTED;
+  if (relbias) attention_tc_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  else if (mask_bits) attention_tc_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  else attention_tc_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
@@ -547,8 +577,17 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
                                  const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                  int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
                                  int64_t sbo, const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
-  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
                              nullptr, 0, kv_len, q_len, stream_);
+}
+
+extern "C" int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                                      const void* V, int64_t ldv, int64_t sbv, const uint32_t* mask_bits, int64_t B,
+                                      int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo, int64_t sbo,
+                                      const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
+  if (!mask_bits) return CN_ERR_BAD_ARG;
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, nullptr, 0, 0, mask_bits, B, h, Tq, Tk, dk, out, ldo,
+                             sbo, nullptr, 0, kv_len, q_len, stream_);
 }
 
 extern "C" int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel) {
@@ -569,6 +608,6 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
   rel_bias_kernel<<<dim3((unsigned)Tq, (unsigned)B), (unsigned)(32 * h), 0, (cudaStream_t)stream_>>>(
       (const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)h, (int)Tq, (int)(2 * max_rel + 1), relbias);
   CN_CHECK_LAUNCH();
-  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, B, h, Tq, Tk, dk, out, ldo, sbo,
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
                              relbias, (int)max_rel, kv_len, nullptr, stream_);
 }

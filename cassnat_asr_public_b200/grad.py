@@ -251,11 +251,15 @@ class RelAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, rel_pos, bias_u, bias_v, mask, n_head, m):
         with torch.no_grad():
-            if q.dtype == torch.bfloat16:      # tcgen05 kernel takes q + u as its Q operand
+            key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
+            fast = (q.dtype == torch.bfloat16 and key_mask and q.shape[-1] // n_head == 64 and k.shape[1] <= 512
+                    and n_head <= 8 and m <= 64)
+            if fast:                           # tcgen05 kernel takes q + u as its Q operand
                 qu = (q.float() + bias_u.reshape(1, 1, -1)).to(torch.bfloat16)
                 out = ops.attention_forward(qu, k, v, mask, n_head, (rel_pos, bias_u, bias_v, m))
             else:
-                out = ops.attention_forward(q, k, v, mask, n_head, (rel_pos, bias_u, bias_v, m))
+                out = ops.attention_forward(q.float(), k.float(), v.float(), mask, n_head, (rel_pos, bias_u, bias_v, m))
+                out = out.to(q.dtype)
         ctx.n_head, ctx.m, ctx.mask = n_head, int(m), mask
         ctx.save_for_backward(q, k, v, rel_pos, bias_u, bias_v)
         return out

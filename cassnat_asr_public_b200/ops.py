@@ -285,12 +285,13 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     for t in (q, k, v):
         assert t.stride(-1) == 1
     if q.dtype == torch.bfloat16:
+        key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
         if dk == 64 and Tk <= 512 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
-                (rel is None or (n_head <= 8 and rel[3] <= 64)):
+                (rel is None or (n_head <= 8 and rel[3] <= 64 and key_mask)):
             return _attention_bf16(q, k, v, mask, n_head, rel)      # rel: q must already hold q + pos_bias_u
-        if rel is not None:
+        if rel is not None and key_mask:
             raise RuntimeError("bf16 relative attention outside the tcgen05 kernel's range (Tk<=512, h<=8, m<=64)")
-        q, k, v = q.float(), k.float(), v.float()
+        q, k, v = q.float(), k.float(), v.float()        # (rel + per-row mask: fp32 kernel, q without pos_bias_u)
     if out is None:
         out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
@@ -306,12 +307,19 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     return out
 
 
-def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, out=None):
+def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, out=None, q_len=None):
     """Extractor attention with the trigger mask evaluated on the fly from segment ids
-    (cassnat.py:465-468 + modules/attention.py:13-24).  q_rows [U,d] is batch independent."""
+    (cassnat.py:465-468 + modules/attention.py:13-24).  q_rows [U,d] is batch independent.
+    bf16 operands (fast mode, d_k = 64, T <= 512): the mask is generated bit-packed from the segment ids
+    and fused into the tcgen05 attention; otherwise the fp32 segment-sparse kernel."""
     require_cuda(q_rows, k, v, seg)
     U, d = q_rows.shape
     B, T, _ = k.shape
+    if q_rows.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
+            d // n_head == 64 and T <= 512 and out is None:
+        return _segment_attention_bf16(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, q_len)
+    if q_rows.dtype != torch.float32:
+        q_rows, k, v = q_rows.float(), k.float(), v.float()
     if out is None:
         out = torch.empty(B, U, d, dtype=torch.float32, device=k.device)
     ws_bytes = _lib.load().cn_segment_attention_workspace_bytes(B, U, d)
@@ -411,6 +419,27 @@ def attach_length_hints(mask, kv_len=None, q_len=None):
     return mask
 
 
+def _segment_attention_bf16(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, q_len=None):
+    U, d = q_rows.shape
+    B, T, _ = k.shape
+    dev = k.device
+    bits = torch.empty(B, U, 16, dtype=torch.int32, device=dev)
+    call("cn_trigger_mask_bits", ptr(seg), ptr(_i64(ylens)), ptr(_u8(src_mask, B, T)), ptr(_i64(src_size)), B, T, U,
+         int(left > 0), int(right > 0), ptr(bits), stream(), work=dict(bytes=4.0 * B * T + 64.0 * B * U))
+    out = torch.empty(B, U, d, dtype=torch.bfloat16, device=dev)
+    # no kv_len hint: the first row past eos is fully masked and must stay uniform over ALL T frames
+    # (modules/attention.py:19-21); q_len only drops whole query tiles the caller never reads
+    kv_len = None
+    if q_len is not None:
+        q_len = q_len.to(torch.int32).contiguous()
+    if q_rows.stride(-1) != 1 or q_rows.stride(0) % 8:
+        q_rows = q_rows.contiguous()
+    call("cn_attention_bf16_bits", ptr(q_rows), q_rows.stride(0), 0, ptr(k), k.stride(1), k.stride(0),
+         ptr(v), v.stride(1), v.stride(0), ptr(bits), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
+         ptr(kv_len), ptr(q_len), stream(), work=dict(flops=4.0 * B * U * T * d, bytes=2.0 * B * d * (2 * T + U)))
+    return out
+
+
 def _attention_bf16(q, k, v, mask, n_head, rel=None):
     """tcgen05 attention: bf16 q/k/v (strided views of fused projection buffers are fine) -> bf16 ctx."""
     B, Tq, d = q.shape
@@ -419,6 +448,16 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
     kv_len = getattr(mask, "_cn_kv_len", None) if mask is not None else None
     q_len = getattr(mask, "_cn_q_len", None) if mask is not None else None
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
+    if m is not None and mi != 0:                    # per-row mask: bit-pack it for the tensor-core kernel
+        if rel is not None:
+            raise RuntimeError("bf16 relative attention takes key masks only")
+        bits = torch.empty(B, Tq, 16, dtype=torch.int32, device=q.device)
+        call("cn_pack_mask_bits", ptr(m), mb, mi, B, Tq, Tk, ptr(bits), stream(), work=dict(bytes=float(B * Tq * (Tk + 64))))
+        call("cn_attention_bf16_bits", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
+             ptr(v), v.stride(1), v.stride(0), ptr(bits), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1),
+             out.stride(0), None, None, stream(),
+             work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
+        return out
     if rel is not None:
         rp, ru, rv, mr = rel
         ws_bytes = _lib.load().cn_rel_attention_workspace_bytes(B, n_head, Tq, int(mr))

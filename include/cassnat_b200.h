@@ -242,6 +242,23 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak, float* lse,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* Fast mode, per-row masks: the mask arrives bit-packed, bits[b][i][w] (16 uint32 words per query row,
+ * bit (t&31) of word (t>>5) = keep(i,t)); cn_attention_bf16 itself only takes key masks (mi == 0).
+ *   cn_pack_mask_bits      u8 [B,Tq,Tk] (strides mb, mi) -> bits        (dense masks: src_trigger, unimask)
+ *   cn_trigger_mask_bits   segment ids + lengths -> bits of the trigger mask of cassnat.py:355-365,259-270,:468
+ *                          (the [B,U+1,T] byte mask is never materialised; eos fix-up, +-1 dilation, & src_mask)
+ *   cn_attention_bf16_bits the tcgen05 attention with that mask; sbq == 0 shares one [Tq, h*64] query block
+ *                          between all utterances (the extractor's positional queries).
+ *   replaces (fast mode): AcEmbedExtractor's masked cross-attention  fanat_blocks.py:24-37,101-113 */
+int cn_pack_mask_bits(const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t Tq, int64_t Tk, uint32_t* bits,
+                      cn_stream_t stream);
+int cn_trigger_mask_bits(const int32_t* seg, const int64_t* ylens, const uint8_t* src_mask, const int64_t* src_size,
+                         int64_t B, int64_t T, int64_t n_rows, int left, int right, uint32_t* bits, cn_stream_t stream);
+int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                           const void* V, int64_t ldv, int64_t sbv, const uint32_t* mask_bits, int64_t B, int64_t h,
+                           int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo, int64_t sbo,
+                           const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream);
+
 /* Fast mode: relative-position (Transformer-XL style) self-attention on tcgen05.
  *   replaces (fast mode): RelMultiHeadedAttention.forward      src/models/modules/attention.py:104-143
  * Q must hold q + pos_bias_u (fold u into the query bias of the projection); rel_pos f32

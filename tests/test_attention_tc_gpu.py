@@ -102,3 +102,49 @@ def test_attention_tc_length_hints():
         # rows >= ceil(q_len/128)*128 are zero-filled; rows between q_len and the tile edge are computed
         edge = min(-(-n // 128) * 128, Tq)
         assert float(hinted[b, edge:].abs().max()) == 0.0 if edge < Tq else True
+
+
+@pytest.mark.parametrize("left,right", [(0, 0), (1, 1), (1, 0)])
+def test_segment_attention_tc_matches_fp32_segment_kernel(left, right):
+    """Extractor attention on tcgen05 with the trigger mask generated bit-packed from segment ids
+    (cn_trigger_mask_bits + cn_attention_bf16_bits, shared query block) == the fp32 segment-sparse kernel,
+    and the bit mask itself == the dense byte mask of cn_align_to_mask (bit-exact)."""
+    import numpy as np
+
+    import oracle.align_np as A
+    B, T, h, V = 4, 300, 2, 30
+    d = 64 * h
+    rng = np.random.default_rng(5)
+    lp = rng.standard_normal((B, T, V)).astype(np.float32)
+    lp[:, :, 0] += 2.0
+    xl = np.array([T, 190, 161, 240])
+    mask = (np.arange(T)[None] < xl[:, None])[:, None]
+    al, yl, ym = A.best_path_align(lp, mask, 0)
+    c = lambda t: t.to(DEV)
+    al_t, yl_t, mk_t, xl_t = (c(torch.from_numpy(x)) for x in (al, yl, mask, xl))
+    dense, _, ym1, seg = ops.align_to_mask(al_t, yl_t, ym, mk_t, xl_t, 0, left, right, True, want_mask=True, want_seg=True)
+    U = ym1 + 3                                                   # extra fully masked rows
+    torch.manual_seed(3)
+    q_rows = torch.randn(U, d).bfloat16().to(DEV)
+    kv = torch.randn(B, T, 2 * d).bfloat16().to(DEV)
+    k, v = kv[..., :d], kv[..., d:]
+    got = ops.segment_attention(q_rows, k, v, seg, yl_t, mk_t, xl_t, left, right, h)
+    assert got.dtype == torch.bfloat16
+    want = ops.segment_attention(q_rows.float(), k.float(), v.float(), seg, yl_t, mk_t, xl_t, left, right, h)
+    assert rel(got.float(), want) < 2e-2
+    # the packed bits against the dense mask
+    from cassnat_asr_public_b200._lib import call, ptr, stream
+    bits = torch.empty(B, U, 16, dtype=torch.int32, device=DEV)
+    call("cn_trigger_mask_bits", ptr(seg), ptr(yl_t), ptr(mk_t.reshape(B, T).to(torch.uint8).contiguous()), ptr(xl_t), B, T, U,
+         int(left > 0), int(right > 0), ptr(bits), stream())
+    b = bits.cpu().numpy().view(np.uint32)
+    unpacked = ((b[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(B, U, 512)[..., :T].astype(bool)
+    want_mask = np.zeros((B, U, T), bool)
+    want_mask[:, :ym1] = dense.cpu().numpy() != 0
+    assert np.array_equal(unpacked, want_mask)
+    # q_len hint: rows below the hint unchanged
+    q_len = (yl_t + 2).clamp(max=U)
+    hinted = ops.segment_attention(q_rows, k, v, seg, yl_t, mk_t, xl_t, left, right, h, q_len=q_len)
+    for bi in range(B):
+        n = int(q_len[bi])
+        assert torch.equal(hinted[bi, :n], got[bi, :n])

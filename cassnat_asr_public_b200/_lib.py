@@ -52,7 +52,7 @@ SIGNATURES = {
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
-                                 _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp]),
+                                 _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cn_pack_mask_bits": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "cn_trigger_mask_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "cn_attention_bf16_bits": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64,

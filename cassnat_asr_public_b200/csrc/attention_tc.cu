@@ -115,6 +115,9 @@ struct AttnTcArgs {
   // optional per-utterance hints (key masks only): keys >= kv_len[b] are all masked (their tiles are
   // skipped: exactly zero weight), query rows >= q_len[b] are not needed by the caller (zero-filled)
   const int32_t* kv_len; const int32_t* q_len;
+  // optional processing order: utterance order[i] is the i-th to be scheduled (heaviest first), so that the
+  // static round-robin over the persistent CTAs hands every CTA a similar amount of work
+  const int32_t* order;
 };
 
 // Persistent, ping-pong design (v2):
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     if (lane == 0) {
       uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = item / p.h, hh = item % p.h;
+        const int b = p.order ? p.order[item / p.h] : item / p.h, hh = item % p.h;
         int n_tiles, nq;
         tiles_of(b, n_tiles, nq);
         if (nq == 0) continue;                                  // nothing to compute for this item
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int n_tiles, nq;
-        tiles_of(item / p.h, n_tiles, nq);
+        tiles_of(p.order ? p.order[item / p.h] : item / p.h, n_tiles, nq);
         if (nq == 0) continue;
         const int n_pairs = (nq + 1) / 2;
         for (int pr = 0; pr < n_pairs; ++pr) {
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     uint32_t s_cnt = 0, pf_cnt = 0, o_cnt[2] = {0, 0};
     uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = item / p.h, hh = item % p.h;
+      const int b = p.order ? p.order[item / p.h] : item / p.h, hh = item % p.h;
       if (p.mask) {
         // key-mask bits of this utterance (one private copy per group)
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // previous item's readers are done
@@ -531,7 +534,7 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                const uint32_t* mask_bits, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                                void* out, int64_t ldo, int64_t sbo, const float* relbias, int max_rel,
-                               const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
+                               const int32_t* kv_len, const int32_t* q_len, const int32_t* order, cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   if (dk != DK || Tk > MAX_TILES * KT || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
   if (mask && mi != 0) return CN_ERR_UNSUPPORTED;      // per-row byte masks go through cn_pack_mask_bits + *_bits
@@ -551,7 +554,7 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   p.mask = mask_bits ? nullptr : mask; p.mb = mb; p.mask_bits = mask_bits; p.q_bcast = q_bcast ? 1 : 0;
   p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
-  p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len;
+  p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len; p.order = order;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
@@ -576,9 +579,10 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
 extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                  const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                  int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo,
-                                 int64_t sbo, const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
+                                 int64_t sbo, const int32_t* kv_len, const int32_t* q_len, const int32_t* order,
+                                 cn_stream_t stream_) {
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             nullptr, 0, kv_len, q_len, stream_);
+                             nullptr, 0, kv_len, q_len, order, stream_);
 }
 
 extern "C" int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
@@ -587,7 +591,7 @@ extern "C" int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, c
                                       const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
   if (!mask_bits) return CN_ERR_BAD_ARG;
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, nullptr, 0, 0, mask_bits, B, h, Tq, Tk, dk, out, ldo,
-                             sbo, nullptr, 0, kv_len, q_len, stream_);
+                             sbo, nullptr, 0, kv_len, q_len, nullptr, stream_);
 }
 
 extern "C" int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel) {
@@ -609,5 +613,5 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
       (const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)h, (int)Tq, (int)(2 * max_rel + 1), relbias);
   CN_CHECK_LAUNCH();
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             relbias, (int)max_rel, kv_len, nullptr, stream_);
+                             relbias, (int)max_rel, kv_len, nullptr, nullptr, stream_);
 }

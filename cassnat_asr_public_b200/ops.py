@@ -416,6 +416,14 @@ def attach_length_hints(mask, kv_len=None, q_len=None):
         mask._cn_kv_len = kv_len.to(torch.int32).contiguous()
     if q_len is not None:
         mask._cn_q_len = q_len.to(torch.int32).contiguous()
+    if kv_len is not None or q_len is not None:
+        # heaviest utterances first: (key tiles) x (query tiles) of 128, so that the static round-robin over the
+        # persistent CTAs balances the ragged batch
+        B = mask.shape[0]
+        one = torch.ones(B, dtype=torch.int32, device=mask.device)
+        kt = (mask._cn_kv_len + 127) // 128 if kv_len is not None else one
+        qt = (mask._cn_q_len + 127) // 128 if q_len is not None else one
+        mask._cn_order = torch.argsort(kt * qt, descending=True, stable=True).to(torch.int32).contiguous()
     return mask
 
 
@@ -447,6 +455,7 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
     out = torch.empty(B, Tq, d, dtype=torch.bfloat16, device=q.device)
     kv_len = getattr(mask, "_cn_kv_len", None) if mask is not None else None
     q_len = getattr(mask, "_cn_q_len", None) if mask is not None else None
+    order = getattr(mask, "_cn_order", None) if mask is not None else None
     m, mb, mi = _mask_strides(mask, B, Tq, Tk)
     if m is not None and mi != 0:                    # per-row mask: bit-pack it for the tensor-core kernel
         if rel is not None:
@@ -470,7 +479,7 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
         return out
     call("cn_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, B, n_head, Tq, Tk, d // n_head,
-         ptr(out), out.stride(1), out.stride(0), ptr(kv_len), ptr(q_len), stream(),
+         ptr(out), out.stride(1), out.stride(0), ptr(kv_len), ptr(q_len), ptr(order), stream(),
          work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
     return out
 

@@ -215,6 +215,8 @@ int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, in
                       void* out, int64_t ldo, int64_t sbo,
                       const int32_t* kv_len /* i32 [B] or NULL: keys >= kv_len[b] are all masked (key masks only) */,
                       const int32_t* q_len  /* i32 [B] or NULL: rows >= q_len[b] are not needed -> zero-filled */,
+                      const int32_t* order  /* i32 [B] or NULL: a permutation of the utterances, heaviest first,
+                                               so that the persistent CTAs get balanced work */,
                       cn_stream_t stream);
 
 /* K10  CTC loss (alpha-beta in log space) fused with the log-softmax backward.

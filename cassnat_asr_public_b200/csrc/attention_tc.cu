@@ -156,7 +156,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     if (p.kv_len) { int t = (min(max(p.kv_len[b], 1), p.Tk) + KT - 1) / KT; n_tiles = min(max(t, 1), n_tiles_max); }
     if (p.q_len) { int t = (min(max(p.q_len[b], 0), p.Tq) + QT - 1) / QT; nq = min(t, nq_max); }
   };
-  const int n_items = p.B * p.h;
+  // work item = (utterance, head, pair of 128-query tiles): finer than (utterance, head) so that the tail of
+  // the static round-robin over 148 CTAs stays short (K/V of an item are re-fetched per pair, from L2)
+  const int np_max = (nq_max + 1) / 2;
+  const int n_items = p.B * p.h * np_max;
+  auto decode_item = [&](int item, int& b, int& hh, int& pr) {
+    const int u = item / (p.h * np_max), rem = item % (p.h * np_max);
+    b = p.order ? p.order[u] : u;
+    hh = rem / np_max;
+    pr = rem % np_max;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), (i == B_PREADY || i == B_PREADY + 1) ? 128 : 1);
@@ -179,11 +188,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     if (lane == 0) {
       uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = p.order ? p.order[item / p.h] : item / p.h, hh = item % p.h;
+        int b, hh, pr0;
+        decode_item(item, b, hh, pr0);
         int n_tiles, nq;
         tiles_of(b, n_tiles, nq);
-        if (nq == 0) continue;                                  // nothing to compute for this item
-        const int n_pairs = (nq + 1) / 2;
+        if (2 * pr0 >= nq) continue;                            // nothing to compute for this item
         for (int j = 0; j < n_tiles; ++j) {
           mbar_wait(bar(B_KFREE + j), (kv_cnt[j] & 1) ^ 1);
           mbar_expect_tx(bar(B_KFULL + j), KT * DK * 2);
@@ -195,7 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           tma_load_3d(&map_v, bar(B_VFULL + j), sbase + OFF_V + j * 16384, hh * DK, j * KT, b);
           ++kv_cnt[j];
         }
-        for (int pr = 0; pr < n_pairs; ++pr) {
+        {
+          const int pr = pr0;
           for (int g = 0; g < 2; ++g) {
             const int qt = 2 * pr + g;
             if (qt >= nq) continue;
@@ -214,13 +224,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       constexpr uint32_t idesc_o = idesc_bf16(QT, DK, true);
       uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int b_, hh_, pr;
+        decode_item(item, b_, hh_, pr);
         int n_tiles, nq;
-        tiles_of(p.order ? p.order[item / p.h] : item / p.h, n_tiles, nq);
-        if (nq == 0) continue;
-        const int n_pairs = (nq + 1) / 2;
-        for (int pr = 0; pr < n_pairs; ++pr) {
+        tiles_of(b_, n_tiles, nq);
+        if (2 * pr >= nq) continue;
+        {
           const bool has[2] = {2 * pr < nq, 2 * pr + 1 < nq};
-          const bool last_pair = pr == n_pairs - 1;
+          const bool last_pair = true;                          // one pair per item: K/V are released at its end
           const int last_g = has[1] ? 1 : 0;
           auto issue_s = [&](int g, int j) {
             if (j == 0) mbar_wait(bar(B_QFULL + g), q_cnt[g] & 1);
@@ -268,8 +279,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     uint32_t s_cnt = 0, pf_cnt = 0, o_cnt[2] = {0, 0};
     uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = p.order ? p.order[item / p.h] : item / p.h, hh = item % p.h;
-      if (p.mask) {
+      int b, hh, pr0;
+      decode_item(item, b, hh, pr0);
+      int n_tiles, nq;
+      tiles_of(b, n_tiles, nq);
+      if (2 * pr0 >= nq && !(pr0 == 0 && nq < nq_max)) continue;
+      if (p.mask && 2 * pr0 < nq) {
         // key-mask bits of this utterance (one private copy per group)
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // previous item's readers are done
         const uint8_t* mk = p.mask + (int64_t)b * p.mb;
@@ -280,10 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
-      int n_tiles, nq;
-      tiles_of(b, n_tiles, nq);
-      const int n_pairs = (nq + 1) / 2;
-      if (nq < nq_max) {
+      if (pr0 == 0 && nq < nq_max) {
         // query rows the caller does not need: zero-filled (finite inputs for whatever reads them next)
         for (int r = nq * QT + g * 128 + row; r < p.Tq; r += 256) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)b * p.sbo + (int64_t)r * p.ldo + hh * DK);
@@ -291,7 +303,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           for (int d = 0; d < DK / 8; ++d) dst[d] = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      for (int pr = 0; pr < n_pairs; ++pr) {
+      {
+        const int pr = pr0;
         const int qt = 2 * pr + g;
         if (qt >= nq) continue;
         const int qi = qt * QT + row;

@@ -30,7 +30,7 @@ def _self_attention_block(x, norm, attn, mask, pos_embed=None):
     else:
         from .modules import distinct_rel_rows
         table, m = distinct_rel_rows(pos_embed, x.size(1))
-        fast = ops.is_bf16() and x.size(1) <= 512 and attn.h <= 8 and m <= 64
+        fast = ops.is_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= 64
         rel_pos = ops.linear(table, attn.linear_pos.weight)
         if torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad):
             q, k, v = attn.project_qkv(y, out_bf16=fast)           # training: raw q, grad.RelAttention adds u

@@ -24,7 +24,8 @@ namespace {
 constexpr int QT = 128;        // queries per CTA
 constexpr int KT = 128;        // keys per tile
 constexpr int DK = 64;
-constexpr int MAX_TILES = 4;   // Tk <= 512
+constexpr int MAX_TILES = 4;   // K/V ring slots (all of Tk <= 512 stays resident)
+constexpr int MAX_TK = 2048;   // key-mask words kept in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -127,13 +128,13 @@ struct AttnTcArgs {
 //   warp 9     TMA producer (one lane), runs ahead through the whole schedule
 // smem: Q_A | Q_B | K 4x16K | V 4x16K | P_A 32K | P_B 32K | barriers ; TMEM: S_A S_B O_A[2] O_B[2]
 constexpr uint32_t OFF_Q = 0, OFF_K = 2 * 16384, OFF_V = OFF_K + MAX_TILES * 16384, OFF_P = OFF_V + MAX_TILES * 16384,
-                   OFF_BAR = OFF_P + 2 * 32768, SMEM_BYTES = OFF_BAR + 512 + 1024;
+                   OFF_BAR = OFF_P + 2 * 32768, SMEM_BYTES = OFF_BAR + 1024 + 1024;   // barriers + key-mask words, alignment slack
 constexpr int NTHREADS = 320;
 // barrier indices
 constexpr int B_QFULL = 0, B_QFREE = 2, B_KFULL = 4, B_VFULL = 8, B_KFREE = 12, B_VFREE = 16, B_SFULL = 20,
               B_PREADY = 22, B_PFREE = 24, B_OFULL = 26, N_BARS = 30;
 
-template <bool REL, bool BITS>
+template <bool REL, bool BITS, bool RING>
 __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                    const __grid_constant__ CUtensorMap map_k,
                                                                    const __grid_constant__ CUtensorMap map_v,
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   const uint32_t bars = sbase + OFF_BAR;
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 256);
-  uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 288);   // [2 groups][16 words]
+  uint32_t* kbits_all = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 288);   // [2 groups][MAX_TK / 32 words]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_max = (p.Tk + KT - 1) / KT;        // key tiles (<= 4)
@@ -186,24 +187,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   if (warp == 9) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0};
+      // K/V tiles go through a ring of MAX_TILES slots each (tile j -> slot j % MAX_TILES); up to MAX_TILES
+      // tiles of the next item are prefetched before its Q tiles, later ones follow as slots are released
+      uint32_t k_fill = 0, v_fill = 0, q_cnt[2] = {0, 0};      // phase bit per slot, kept in one register each
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b, hh, pr0;
         decode_item(item, b, hh, pr0);
         int n_tiles, nq;
         tiles_of(b, n_tiles, nq);
         if (2 * pr0 >= nq) continue;                            // nothing to compute for this item
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(bar(B_KFREE + j), (kv_cnt[j] & 1) ^ 1);
-          mbar_expect_tx(bar(B_KFULL + j), KT * DK * 2);
-          tma_load_3d(&map_k, bar(B_KFULL + j), sbase + OFF_K + j * 16384, hh * DK, j * KT, b);
-        }
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(bar(B_VFREE + j), (kv_cnt[j] & 1) ^ 1);
-          mbar_expect_tx(bar(B_VFULL + j), KT * DK * 2);
-          tma_load_3d(&map_v, bar(B_VFULL + j), sbase + OFF_V + j * 16384, hh * DK, j * KT, b);
-          ++kv_cnt[j];
-        }
+        auto load_k = [&](int j) {
+          const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
+          mbar_wait(bar(B_KFREE + sl), ((k_fill >> sl) & 1) ^ 1);
+          mbar_expect_tx(bar(B_KFULL + sl), KT * DK * 2);
+          tma_load_3d(&map_k, bar(B_KFULL + sl), sbase + OFF_K + sl * 16384, hh * DK, j * KT, b);
+          k_fill ^= 1u << sl;
+        };
+        auto load_v = [&](int j) {
+          const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
+          mbar_wait(bar(B_VFREE + sl), ((v_fill >> sl) & 1) ^ 1);
+          mbar_expect_tx(bar(B_VFULL + sl), KT * DK * 2);
+          tma_load_3d(&map_v, bar(B_VFULL + sl), sbase + OFF_V + sl * 16384, hh * DK, j * KT, b);
+          v_fill ^= 1u << sl;
+        };
+        const int n_first = n_tiles < MAX_TILES ? n_tiles : MAX_TILES;
+        for (int j = 0; j < n_first; ++j) load_k(j);
+        for (int j = 0; j < n_first; ++j) load_v(j);
         {
           const int pr = pr0;
           for (int g = 0; g < 2; ++g) {
@@ -215,6 +224,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             ++q_cnt[g];
           }
         }
+        if (RING)
+          for (int j = n_first; j < n_tiles; ++j) { load_k(j); load_v(j); }   // Tk > 512: stream through the ring
       }
     }
   } else if (warp == 8) {
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(QT, KT, false);
       constexpr uint32_t idesc_o = idesc_bf16(QT, DK, true);
-      uint32_t kv_cnt[MAX_TILES] = {0, 0, 0, 0}, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};
+      uint32_t k_seen = 0, v_seen = 0, q_cnt[2] = {0, 0}, p_cnt[2] = {0, 0};   // phase bit per K/V slot
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int b_, hh_, pr;
         decode_item(item, b_, hh_, pr);
@@ -234,15 +245,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           const bool last_pair = true;                          // one pair per item: K/V are released at its end
           const int last_g = has[1] ? 1 : 0;
           auto issue_s = [&](int g, int j) {
+            const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
             if (j == 0) mbar_wait(bar(B_QFULL + g), q_cnt[g] & 1);
-            mbar_wait(bar(B_KFULL + j), kv_cnt[j] & 1);
+            mbar_wait(bar(B_KFULL + sl), (k_seen >> sl) & 1);
             fence_after();
-            const uint64_t dq = desc_kmajor(sbase + OFF_Q + g * 16384), dkk = desc_kmajor(sbase + OFF_K + j * 16384);
+            const uint64_t dq = desc_kmajor(sbase + OFF_Q + g * 16384), dkk = desc_kmajor(sbase + OFF_K + sl * 16384);
 #pragma unroll
             for (int k = 0; k < DK / 16; ++k) umma(tm_s(g), dq + (uint64_t)(k * 2), dkk + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
             tcgen05_commit(bar(B_SFULL + g));
             if (j == n_tiles - 1) { tcgen05_commit(bar(B_QFREE + g)); ++q_cnt[g]; }   // Q tile no longer needed
-            if (last_pair && g == last_g) tcgen05_commit(bar(B_KFREE + j));           // K_j done for this item
+            if (last_pair && g == last_g) { tcgen05_commit(bar(B_KFREE + sl)); k_seen ^= 1u << sl; }   // K_j consumed
           };
           for (int g = 0; g < 2; ++g)
             if (has[g]) issue_s(g, 0);
@@ -251,9 +263,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
               if (!has[g]) continue;
               mbar_wait(bar(B_PREADY + g), p_cnt[g] & 1);       // P_g(j) written, S_g(j) consumed
               ++p_cnt[g];
-              mbar_wait(bar(B_VFULL + j), kv_cnt[j] & 1);
+              const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
+              mbar_wait(bar(B_VFULL + sl), (v_seen >> sl) & 1);
               fence_after();
-              const uint64_t dv = desc_mnmajor(sbase + OFF_V + j * 16384);
+              const uint64_t dv = desc_mnmajor(sbase + OFF_V + sl * 16384);
 #pragma unroll
               for (int k = 0; k < KT / 16; ++k) {
                 const uint64_t dp = desc_kmajor(sbase + OFF_P + g * 32768 + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
@@ -261,12 +274,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
               }
               tcgen05_commit(bar(B_PFREE + g));
               tcgen05_commit(bar(B_OFULL + g * 2 + (j & 1)));
-              if (last_pair && g == last_g) tcgen05_commit(bar(B_VFREE + j));
+              if (last_pair && g == last_g) { tcgen05_commit(bar(B_VFREE + sl)); v_seen ^= 1u << sl; }
               if (j + 1 < n_tiles) issue_s(g, j + 1);           // S_g(j+1) while group g folds O_g(j-1)
             }
           }
         }
-        for (int j = 0; j < n_tiles; ++j) ++kv_cnt[j];
       }
     }
   } else {
@@ -275,8 +287,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float scale = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
-    uint32_t* kbits = kbits_all + g * 16;
-    uint32_t s_cnt = 0, pf_cnt = 0, o_cnt[2] = {0, 0};
+    uint32_t* kbits = kbits_all + g * (MAX_TK / 32);
+    uint32_t s_cnt = 0, pf_cnt = 0, o_par = 0;              // o_par: phase bit of each of the two O buffers
     uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, hh, pr0;
@@ -331,8 +343,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         const float rel_left = REL ? rb[0] : 0.f, rel_right = REL ? rb[nrel - 1] : 0.f;
         bool any_keep = false;
         auto fold = [&](int j, float extra) {
-          mbar_wait(bar(B_OFULL + g * 2 + (j & 1)), o_cnt[j & 1] & 1);
-          ++o_cnt[j & 1];
+          mbar_wait(bar(B_OFULL + g * 2 + (j & 1)), (o_par >> (j & 1)) & 1);
+          o_par ^= 1u << (j & 1);
           fence_after();
           float part[DK];
           tmem_ld32(tm_o(g, j & 1) + lane_addr, part);
@@ -549,7 +561,8 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
                                void* out, int64_t ldo, int64_t sbo, const float* relbias, int max_rel,
                                const int32_t* kv_len, const int32_t* q_len, const int32_t* order, cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
-  if (dk != DK || Tk > MAX_TILES * KT || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
+  if (dk != DK || Tk > MAX_TK || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
+  if (mask_bits && Tk > 512) return CN_ERR_UNSUPPORTED;  // bit-packed per-row masks: 16 words per row
   if (mask && mi != 0) return CN_ERR_UNSUPPORTED;      // per-row byte masks go through cn_pack_mask_bits + *_bits
   const bool q_bcast = sbq == 0;
   // TMA: 16-byte aligned bases and pitches; 16-byte vector stores of the output rows
@@ -570,21 +583,29 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len; p.order = order;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+    const int sm = (int)SMEM_BYTES;
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (cudaFuncSetAttribute(attention_tc_kernel<false, false, false>, at, sm) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<false, false, true>, at, sm) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<true, false, false>, at, sm) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<true, false, true>, at, sm) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<false, true, false>, at, sm) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t items = B * h;
+  const int64_t items = B * h * ((Tq + 2 * QT - 1) / (2 * QT));          // (utterance, head, query-tile pair)
   const unsigned grid = (unsigned)(items < sms ? items : sms);           // persistent: one CTA per SM
   if (relbias && mask_bits) return CN_ERR_UNSUPPORTED;
-  if (relbias) attention_tc_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
-  else if (mask_bits) attention_tc_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
-  else attention_tc_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(mq, mk, mv, p);
+  const bool ring = Tk > MAX_TILES * KT;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (relbias && ring) attention_tc_kernel<true, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  else if (relbias) attention_tc_kernel<true, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  else if (mask_bits) attention_tc_kernel<false, true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  else if (ring) attention_tc_kernel<false, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  else attention_tc_kernel<false, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -286,7 +286,7 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
         assert t.stride(-1) == 1
     if q.dtype == torch.bfloat16:
         key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
-        if dk == 64 and Tk <= 512 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
+        if dk == 64 and Tk <= (2048 if key_mask else 512) and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
                 (rel is None or (n_head <= 8 and rel[3] <= 64 and key_mask)):
             return _attention_bf16(q, k, v, mask, n_head, rel)      # rel: q must already hold q + pos_bias_u
         if rel is not None and key_mask:

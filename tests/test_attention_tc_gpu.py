@@ -25,7 +25,8 @@ def ref_attention(q, k, v, mask, h):
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, d)
 
 
-@pytest.mark.parametrize("B,Tq,Tk,h", [(2, 128, 128, 1), (3, 100, 77, 2), (2, 390, 500, 8), (1, 7, 512, 4), (2, 257, 129, 2)])
+@pytest.mark.parametrize("B,Tq,Tk,h", [(2, 128, 128, 1), (3, 100, 77, 2), (2, 390, 500, 8), (1, 7, 512, 4), (2, 257, 129, 2),
+                                       (2, 300, 875, 2), (1, 520, 2048, 1), (3, 40, 1300, 4)])
 def test_attention_tc(B, Tq, Tk, h):
     d = 64 * h
     torch.manual_seed(Tq * 7 + Tk)
@@ -34,7 +35,7 @@ def test_attention_tc(B, Tq, Tk, h):
     key_mask = (torch.arange(Tk)[None] < lens[:, None]).unsqueeze(1)
     full = torch.rand(B, Tq, Tk) < 0.3
     full[:, Tq // 2:] = False                                  # fully masked rows -> uniform over all keys
-    for mask in (None, key_mask, full):
+    for mask in (None, key_mask) + ((full,) if Tk <= 512 else ()):      # per-row masks: bit-packed, Tk <= 512
         got = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV) if mask is not None else None, h)
         assert got.dtype == torch.bfloat16
         want = ref_attention(q.float(), k.float(), v.float(), mask, h)
@@ -83,15 +84,17 @@ def test_rel_attention_tc(B, U, h, m):
     assert rel(got.float(), want) < 3e-2
 
 
-def test_attention_tc_length_hints():
+@pytest.mark.parametrize("Tq,Tk,klen,qlen", [(400, 500, [500, 130, 257, 1], [400, 0, 129, 300]),
+                                             (600, 1500, [1500, 640, 513, 1100], [600, 10, 300, 513])])
+def test_attention_tc_length_hints(Tq, Tk, klen, qlen):
     """kv_len / q_len hints: skipped key tiles carry exactly zero weight, unneeded rows are zero-filled,
-    needed rows are unchanged."""
-    B, Tq, Tk, h = 4, 400, 500, 2
+    needed rows are unchanged (also when the K/V tiles stream through the ring, Tk > 512)."""
+    B, h = 4, 2
     d = 64 * h
     torch.manual_seed(3)
     q, k, v = (torch.randn(B, n, d).bfloat16().to(DEV) for n in (Tq, Tk, Tk))
-    klen = torch.tensor([500, 130, 257, 1])
-    qlen = torch.tensor([400, 0, 129, 300])
+    klen = torch.tensor(klen)
+    qlen = torch.tensor(qlen)
     mask = (torch.arange(Tk)[None] < klen[:, None]).unsqueeze(1).to(DEV)
     plain = ops.attention(q, k, v, mask, h).float()
     ops.attach_length_hints(mask, kv_len=klen.to(DEV), q_len=qlen.to(DEV))

@@ -46,6 +46,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// wait with a suspend-time hint: the single-lane producer / MMA warps share their schedulers with softmax
+// warps, so they should sleep in hardware rather than spin through issue slots
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (!ok && ++spins > 100000000u) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), (i == B_PREADY || i == B_PREADY + 1) ? 128 : 1);
+    for (int i = 0; i < N_BARS; ++i) mbar_init(bar(i), (i == B_PREADY || i == B_PREADY + 1) ? 4 : 1);   // one arrival per softmax warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -198,14 +211,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         if (2 * pr0 >= nq) continue;                            // nothing to compute for this item
         auto load_k = [&](int j) {
           const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
-          mbar_wait(bar(B_KFREE + sl), ((k_fill >> sl) & 1) ^ 1);
+          mbar_wait_sleepy(bar(B_KFREE + sl), ((k_fill >> sl) & 1) ^ 1);
           mbar_expect_tx(bar(B_KFULL + sl), KT * DK * 2);
           tma_load_3d(&map_k, bar(B_KFULL + sl), sbase + OFF_K + sl * 16384, hh * DK, j * KT, b);
           k_fill ^= 1u << sl;
         };
         auto load_v = [&](int j) {
           const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
-          mbar_wait(bar(B_VFREE + sl), ((v_fill >> sl) & 1) ^ 1);
+          mbar_wait_sleepy(bar(B_VFREE + sl), ((v_fill >> sl) & 1) ^ 1);
           mbar_expect_tx(bar(B_VFULL + sl), KT * DK * 2);
           tma_load_3d(&map_v, bar(B_VFULL + sl), sbase + OFF_V + sl * 16384, hh * DK, j * KT, b);
           v_fill ^= 1u << sl;
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           for (int g = 0; g < 2; ++g) {
             const int qt = 2 * pr + g;
             if (qt >= nq) continue;
-            mbar_wait(bar(B_QFREE + g), (q_cnt[g] & 1) ^ 1);
+            mbar_wait_sleepy(bar(B_QFREE + g), (q_cnt[g] & 1) ^ 1);
             mbar_expect_tx(bar(B_QFULL + g), QT * DK * 2);
             tma_load_3d(&map_q, bar(B_QFULL + g), sbase + OFF_Q + g * 16384, hh * DK, qt * QT, p.q_bcast ? 0 : b);
             ++q_cnt[g];
@@ -244,27 +257,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           const bool has[2] = {2 * pr < nq, 2 * pr + 1 < nq};
           const bool last_pair = true;                          // one pair per item: K/V are released at its end
           const int last_g = has[1] ? 1 : 0;
-          auto issue_s = [&](int g, int j) {
+          auto issue_s = [&](int g, int j, bool last_user) {     // last_user: the other group already issued S(j)
             const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
-            if (j == 0) mbar_wait(bar(B_QFULL + g), q_cnt[g] & 1);
-            mbar_wait(bar(B_KFULL + sl), (k_seen >> sl) & 1);
+            if (j == 0) mbar_wait_sleepy(bar(B_QFULL + g), q_cnt[g] & 1);
+            mbar_wait_sleepy(bar(B_KFULL + sl), (k_seen >> sl) & 1);
             fence_after();
             const uint64_t dq = desc_kmajor(sbase + OFF_Q + g * 16384), dkk = desc_kmajor(sbase + OFF_K + sl * 16384);
 #pragma unroll
             for (int k = 0; k < DK / 16; ++k) umma(tm_s(g), dq + (uint64_t)(k * 2), dkk + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
             tcgen05_commit(bar(B_SFULL + g));
             if (j == n_tiles - 1) { tcgen05_commit(bar(B_QFREE + g)); ++q_cnt[g]; }   // Q tile no longer needed
-            if (last_pair && g == last_g) { tcgen05_commit(bar(B_KFREE + sl)); k_seen ^= 1u << sl; }   // K_j consumed
+            if (last_pair && last_user) { tcgen05_commit(bar(B_KFREE + sl)); k_seen ^= 1u << sl; }   // K_j consumed
           };
           for (int g = 0; g < 2; ++g)
-            if (has[g]) issue_s(g, 0);
+            if (has[g]) issue_s(g, 0, g == last_g);
           for (int j = 0; j < n_tiles; ++j) {
             for (int g = 0; g < 2; ++g) {
               if (!has[g]) continue;
-              mbar_wait(bar(B_PREADY + g), p_cnt[g] & 1);       // P_g(j) written, S_g(j) consumed
+              mbar_wait_sleepy(bar(B_PREADY + g), p_cnt[g] & 1);       // P_g(j) written, S_g(j) consumed
               ++p_cnt[g];
+              // S_g(j+1) goes to the tensor pipe BEFORE P_g(j) V_j: the group's next softmax is the critical
+              // path, O_g(j) is only folded after that softmax
+              const bool last_user = g == last_g;
+              if (j + 1 < n_tiles) issue_s(g, j + 1, last_user);
               const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
-              mbar_wait(bar(B_VFULL + sl), (v_seen >> sl) & 1);
+              mbar_wait_sleepy(bar(B_VFULL + sl), (v_seen >> sl) & 1);
               fence_after();
               const uint64_t dv = desc_mnmajor(sbase + OFF_V + sl * 16384);
 #pragma unroll
@@ -274,8 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
               }
               tcgen05_commit(bar(B_PFREE + g));
               tcgen05_commit(bar(B_OFULL + g * 2 + (j & 1)));
-              if (last_pair && g == last_g) { tcgen05_commit(bar(B_VFREE + sl)); v_seen ^= 1u << sl; }
-              if (j + 1 < n_tiles) issue_s(g, j + 1);           // S_g(j+1) while group g folds O_g(j-1)
+              if (last_pair && last_user) { tcgen05_commit(bar(B_VFREE + sl)); v_seen ^= 1u << sl; }
             }
           }
         }
@@ -473,7 +489,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
           fence_before();                                                  // S_g fully read before it is handed back
-          mbar_arrive(bar(B_PREADY + g));
+          __syncwarp();                                                    // every lane's P writes + fences precede the arrival
+          if (lane == 0) mbar_arrive(bar(B_PREADY + g));
           if (j > 0) fold(j - 1, 1.f);                                     // O_g(j-1) while PV_g(j) / S_g(j+1) run
           l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
           m_run = m_new;

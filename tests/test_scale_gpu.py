@@ -91,3 +91,38 @@ def test_random_attention_shapes():
         s = (qh @ kh.transpose(-1, -2) / 8.0).masked_fill(mask.unsqueeze(1) == 0, float(torch.finfo(torch.float32).min))
         want = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, d)
         assert ((got.double() - want).abs().max() / want.abs().max()).item() < 2e-2, (B, h, Tq, Tk)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,lens", [(1, 5, [5]), (1, 1, [1]), (2, 33, [33, 2]), (3, 130, [130, 129, 1]), (2, 700, [700, 300])])
+def test_decode_edge_shapes(precision, B, T, lens):
+    """Single utterances, one-frame inputs, lengths around the 32/128 tile edges and utterances longer than
+    the 512 frames the K/V tiles of the tensor-core attention keep resident: the decode runs in both
+    precision modes, and in the parity mode the hypotheses equal the oracle port's."""
+    args = _args(N_mix_dec=2)
+    torch.manual_seed(13)
+    model = make_model(16, args)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    model.set_precision(precision)
+    try:
+        g = torch.Generator().manual_seed(T)
+        enc_h = torch.randn(B, T, 256, generator=g)
+        lens_t = torch.tensor(lens)
+        mask = (torch.arange(T)[None] < lens_t[:, None]).unsqueeze(1)
+        ratio = (lens_t.float() + 0.5) / T
+        with torch.no_grad():
+            for graphs in (False, True):
+                model.use_cuda_graphs = graphs
+                out, _ = model.decode_from_encoder(enc_h.to(DEV), mask.to(DEV), ratio.to(DEV), VOCAB, args)
+                hyps = [o[0]["hyp"] for o in out]
+                assert len(hyps) == B and all(h[0] == 1 for h in hyps)
+                assert all(np.isfinite(o[0]["score"]) for o in out)
+                if precision == "fp32":
+                    want = O.decode_from_encoder(enc_h, mask, (ratio * T).long(), sd, SimpleNamespace(**vars(args)))
+                    top2 = want["att_out"].topk(2, -1)[0]
+                    if bool(((top2[..., 0] - top2[..., 1]) > 1e-4).all()):
+                        assert hyps == want["hyps"], (B, T, graphs)
+                    assert np.array_equal(np.asarray([len(h) for h in hyps]), np.asarray([len(h) for h in want["hyps"]]))
+    finally:
+        model.set_precision("fp32")

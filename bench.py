@@ -342,7 +342,10 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     model.train()
     model.zero_dropout()
     params = [p for n, p in model.named_parameters() if not n.startswith(("src_embed.", "encoder."))]
-    buckets = sharding.GradientBuckets(params, comm_dtype=torch.bfloat16, hooks=not graphed) if world > 1 else None
+    # eager: bucketed bf16 all_reduce overlapped with backward through hooks; graph replay: gradients are views
+    # of one flat buffer that is reduced in place after the replay
+    buckets = sharding.GradientBuckets(params, comm_dtype=torch.bfloat16) if (world > 1 and not graphed) else None
+    flat = None
 
     def fwd_bwd():
         out = model.train_forward_from_encoder(enc_h, x_mask, ratio, labels, sizes, args)
@@ -366,22 +369,23 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     if graphed:
         # the training forward has no host synchronisation (ymax comes from the label tensor's shape), so
         # forward + backward are captured once and replayed: gradients live in the graph's memory pool
-        for p in params:
-            p.grad = None
         enc_h.grad = None
+        flat = sharding.FlatGradients(params)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
+            flat.zero()
             static_loss = fwd_bwd()
 
     def one():
         if graphed:
             graph.replay()
+            flat.all_reduce()
             res = static_loss
         else:
             res = eager()
-        if buckets is not None:
-            buckets.finish()
+            if buckets is not None:
+                buckets.finish()
         return res
 
     for _ in range(2):
@@ -396,14 +400,15 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        buckets.remove()
+        if buckets is not None:
+            buckets.remove()
     ms = float(t[0]) / iters
     n_par = sum(p.numel() for p in params)
     model.eval()
     for p in params:
         p.grad = None
     return {"workload": f"cfg5 (post-encoder path): base model, {B} x {frames_in / 100:.0f} s per GPU, T={T}, {L} labels/utt, "
-                        f"fwd + bwd" + (" + bf16 gradient all_reduce" if world > 1 else ""),
+                        f"fwd + bwd" + (" + gradient all_reduce (one flat fp32 buffer)" if world > 1 else ""),
             "ms_per_step": ms, "utt_per_s": B * world / (ms / 1e3), "loss": float(loss.detach()),
             "params_in_step": n_par, "precision": args_precision(model), "cuda_graph": graphed}
 

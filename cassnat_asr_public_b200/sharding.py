@@ -159,3 +159,32 @@ class GradientBuckets:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+
+class FlatGradients:
+    """Gradients of all parameters as views of ONE flat fp32 buffer, so that the data-parallel exchange is a
+    single in-place all_reduce with no gather/scatter copies.  Meant for the graph-replayed training step:
+    the buffer is static memory, backward accumulates into the views (`p.grad` stays defined), `zero()` and
+    the backward are captured, `all_reduce()` runs after the replay."""
+
+    def __init__(self, params, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.attach()
+
+    def attach(self):
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world)

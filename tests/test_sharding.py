@@ -104,3 +104,40 @@ def test_gradient_buckets_two_ranks_gloo():
         local1, avg1 = results[1][step]
         for a, b, m0, m1 in zip(local0, local1, avg0, avg1):
             assert np.allclose(m0, (a + b) / 2, rtol=1e-6) and np.allclose(m1, m0)
+
+
+def _flat_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    flat = sharding.FlatGradients(net.parameters())
+    res = []
+    for step in range(2):
+        flat.zero()
+        net(torch.full((3, 6), float(rank + 1 + step))).square().sum().backward()
+        assert all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())     # still views of the buffer
+        local = [p.grad.clone().numpy() for p in net.parameters()]
+        flat.all_reduce()
+        res.append((local, [p.grad.clone().numpy() for p in net.parameters()]))
+    out_q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_flat_gradients_two_ranks_gloo():
+    import numpy as np
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flat_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        (l0, a0), (l1, a1) = results[0][step], results[1][step]
+        for x, y, m0, m1 in zip(l0, l1, a0, a1):
+            assert np.allclose(m0, (x + y) / 2, rtol=1e-6) and np.allclose(m0, m1)

@@ -310,6 +310,7 @@ def run_ours(a, w):
     if world == 1 and not a.no_sampled and a.workload == "cfg3":
         model.use_cuda_graphs = not a.no_graphs
         line["speechlike_decode"] = speechlike_decode(model, args, w, dev_in, B, dev)
+        line["features_decode"] = features_decode(model, args, w, dev, B)
         line["sampled_decode"] = sampled_decode(model, w, dev)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
@@ -458,6 +459,43 @@ def speechlike_decode(model, args, w, dev_in, B, dev, iters=20, target=0.15):
     return {"workload": f"cfg3 model and inputs, CTC blank bias +{hi:.2f} so that tokens/frames = {r:.3f}",
             "ms_per_step": ms, "utt_per_s": B / (ms / 1e3), "tokens_U_mean": sum(toks) / len(toks), "tokens_U_max": max(toks),
             "note": "no L2 flush between steps; everything else as the headline run"}
+
+
+def features_decode(model, args, w, dev, B, iters=5):
+    """SURVEY §8f-1 (first 'next' row): the whole `beam_decode(src, ...)` call from 80-dim fbank features —
+    conv front-end (direct conv1 + implicit-GEMM conv2 on tcgen05), 12-layer encoder on the same kernels as the
+    decoder blocks, then the accelerated path.  CUDA events around each part, wall clock around the call."""
+    Tin = w["frames_in"]
+    g = torch.Generator().manual_seed(99)
+    src = torch.randn(B, Tin, 80, generator=g)
+    lens = torch.randint(int(0.6 * Tin), Tin + 1, (B,), generator=g)
+    lens[0] = Tin
+    for b in range(B):
+        src[b, lens[b]:] = 0
+    mask = (torch.arange(Tin)[None] < lens[:, None]).unsqueeze(1)
+    src, mask, ratio = src.to(dev), mask.to(dev), (lens.float() / Tin).to(dev)
+    with torch.no_grad():
+        for _ in range(2):
+            out, _ = model.beam_decode(src, mask, ratio, VOCAB, args)
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        x, xm = model.src_embed(src, mask)
+        e[1].record()
+        enc_h = model.encoder(x, xm)
+        e[2].record()
+        model.decode_from_encoder(enc_h, xm, ratio, VOCAB, args)
+        e[3].record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            out, _ = model.beam_decode(src, mask, ratio, VOCAB, args)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / iters
+    return {"workload": f"cfg3 from features: {B} x {w['audio_s']:.0f} s of 80-dim fbank -> hypotheses (front-end + 12-layer "
+                        f"encoder + post-encoder path)", "ms_per_step": dt * 1e3, "utt_per_s": B / dt,
+            "rtf": dt / (B * w["audio_s"]), "front_end_ms": e[0].elapsed_time(e[1]), "encoder_ms": e[1].elapsed_time(e[2]),
+            "post_encoder_ms": e[2].elapsed_time(e[3]), "tokens_U_mean": sum(len(o[0]["hyp"]) - 1 for o in out) / B}
 
 
 class StandInRanker(torch.nn.Module):

@@ -53,6 +53,7 @@ SIGNATURES = {
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "cn_conv_frontend_bf16": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "cn_pack_mask_bits": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "cn_trigger_mask_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "cn_attention_bf16_bits": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
@@ -115,7 +116,7 @@ LAUNCHES = {"cn_row_stats": 1, "cn_bestpath_collapse": 1, "cn_bestpath_from_logp
             "cn_layernorm": 1, "cn_attention_f32": 1, "cn_segment_attention_f32": 3,
             "cn_glu_dwconv_groupnorm_act": 2, "cn_gemm_bf16_rowstats": 2, "cn_rel_attention_bf16": 2,
             "cn_act_bwd_colsum": 2, "cn_layernorm_bwd": 3, "cn_label_smoothing": 3, "cn_ctc_loss": 4,
-            "cn_glu_dwconv_groupnorm_act_bwd": 7}
+            "cn_glu_dwconv_groupnorm_act_bwd": 7, "cn_conv_frontend_bf16": 2}
 launch_count = 0          # running total of our kernel launches (bench.py reads and resets it)
 _profile = None           # list of (name, start_event, end_event, work) while profiling
 PROFILE_SHAPES = False     # tag GEMM records with their shape (diagnostics)

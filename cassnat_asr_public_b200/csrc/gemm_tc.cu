@@ -516,6 +516,266 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
 #undef CN_TC_DISPATCH
 }
 
+// ================================================================ conv front-end (fast mode)
+// ConvEmbedding's two 3x3 / stride-2 / pad-1 convolutions (src/models/modules/embedding.py:103-119) with
+// channels-last bf16 activations:
+//   conv1 (1 -> C channels): direct, memory-bound (its output is the large tensor);
+//   conv2 (C -> C): implicit GEMM on tcgen05.  M = (utterance, 32 output frames, 4 output bins) = 128 rows,
+//   K = (tap, input channel) = 9*C, N = C.  The A tile of one (tap, 64-channel) k-block is ONE 4-D TMA box over
+//   the [B, T1, F1, C] input with traversal strides (1, 2, 2, 1): the stride-2 sampling and the zero padding
+//   (out-of-bounds fill) are done by the TMA unit, no im2col buffer exists.
+namespace {
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+constexpr int CV_TT = 32, CV_FT = 4;      // output frames x output bins per 128-row tile
+
+struct ConvArgs {
+  const float* bias; __nv_bfloat16* out;  // out [B, T2, F2, C] channels-last
+  int B, T2, F2, C;                       // C = input = output channels
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) conv2_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_w, ConvArgs cv) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tt = (cv.T2 + CV_TT - 1) / CV_TT, ft = (cv.F2 + CV_FT - 1) / CV_FT;
+  const int tiles_n = cv.C / BN, tiles_m = cv.B * tt * ft;
+  const int n_tiles = tiles_m * tiles_n;
+  const int cblk = cv.C / BK, k_blocks = 9 * cblk;
+  auto decode = [&](int tile, int& b, int& t0, int& f0, int& n0) {
+    const int mt = tile / tiles_n;
+    n0 = (tile % tiles_n) * BN;
+    f0 = (mt % ft) * CV_FT;
+    t0 = ((mt / ft) % tt) * CV_TT;
+    b = mt / (ft * tt);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int b, t0, f0, n0;
+        decode(tile, b, t0, f0, n0);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          const int tap = kb / cblk, c0 = (kb % cblk) * BK;
+          const int dt = tap / 3, df = tap % 3;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          // input frame 2*t + dt - 1, input bin 2*f + df - 1 (pad 1): negative / past-the-end coordinates read zeros
+          tma_load_4d(&map_a, &full[stage], sa, c0, 2 * f0 + df - 1, 2 * t0 + dt - 1, b);
+          tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)((k * UK * 2) >> 4), db + (uint64_t)((k * UK * 2) >> 4), idesc, (kb | k) ? 1u : 0u);
+          tcgen05_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // epilogue: thread = one output position (TMEM lane r -> frame t0 + r/4, bin f0 + r%4); bias + ReLU, bf16,
+    // 64 contiguous bytes per 32-column chunk into the channels-last output
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, t0, f0, n0;
+      decode(tile, b, t0, f0, n0);
+      const int t = t0 + (r >> 2), f = f0 + (r & 3);
+      const bool ok = t < cv.T2 && f < cv.F2;
+      __nv_bfloat16* orow = cv.out + (((int64_t)b * cv.T2 + t) * cv.F2 + f) * cv.C + n0;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, v);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x0 = fmaxf(__uint_as_float(v[j + 2 * q]) + __ldg(cv.bias + n0 + c0 + j + 2 * q), 0.f);
+              const float x1 = fmaxf(__uint_as_float(v[j + 2 * q + 1]) + __ldg(cv.bias + n0 + c0 + j + 2 * q + 1), 0.f);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+              pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// conv1: x f32 [B, Tin, Fin] (one input channel) -> y bf16 [B, T1, F1, C] = relu(conv3x3 s2 p1).
+// A warp produces 256 channels of one output position per step: lane = 8 channels whose 72 weights + 8 biases
+// stay in registers, the 9 input taps are warp-uniform (broadcast) loads, the store is one coalesced 512-byte
+// row segment.  Two positions per iteration for memory-level parallelism.  Bound: the 2*B*T1*F1*C output bytes.
+__global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restrict__ x, int64_t sbx, int64_t stx,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           int Tin, int Fin, int T1, int F1, int C, int64_t n_pos,
+                                                           __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto taps = [&](int64_t pos, float (&in)[9]) {
+    const int f = (int)(pos % F1), t = (int)((pos / F1) % T1);
+    const int64_t b = pos / ((int64_t)F1 * T1);
+#pragma unroll
+    for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+      for (int df = 0; df < 3; ++df) {
+        const int ti = 2 * t + dt - 1, fi = 2 * f + df - 1;
+        in[dt * 3 + df] = (ti >= 0 && ti < Tin && fi >= 0 && fi < Fin) ? __ldg(x + b * sbx + (int64_t)ti * stx + fi) : 0.f;
+      }
+  };
+  for (int c0 = lane * 8; c0 < C; c0 += 256) {
+    float wr[8][9], br[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      br[q] = bias[c0 + q];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wr[q][k] = w[(c0 + q) * 9 + k];
+    }
+    auto emit = [&](int64_t pos, const float (&in)[9]) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float a0 = br[2 * q], a1 = br[2 * q + 1];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          a0 = fmaf(in[k], wr[2 * q][k], a0);
+          a1 = fmaf(in[k], wr[2 * q + 1][k], a1);
+        }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+        pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(y + pos * C + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    };
+    int64_t pos = warp_g;
+    for (; pos + n_warps < n_pos; pos += 2 * n_warps) {
+      float ia[9], ib[9];
+      taps(pos, ia);
+      taps(pos + n_warps, ib);
+      emit(pos, ia);
+      emit(pos + n_warps, ib);
+    }
+    if (pos < n_pos) {
+      float ia[9];
+      taps(pos, ia);
+      emit(pos, ia);
+    }
+  }
+}
+
+bool make_map_conv(CUtensorMap* map, const void* base, int64_t B, int64_t T1, int64_t F1, int64_t C) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F1, (cuuint64_t)T1, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)F1 * C * 2, (cuuint64_t)T1 * F1 * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, 2 * CV_FT, 2 * CV_TT, 1};       // traversed extent; every 2nd bin / frame is taken
+  cuuint32_t estr[4] = {1, 2, 2, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+extern "C" int cn_conv_frontend_bf16(const float* x, int64_t sbx, int64_t stx, int64_t B, int64_t Tin, int64_t Fin,
+                                     const float* w1, const float* b1, const void* w2_taps, const float* b2, int64_t C,
+                                     void* mid, void* out, cn_stream_t stream_) {
+  if (!x || !w1 || !b1 || !w2_taps || !b2 || !mid || !out || B < 0 || Tin <= 0 || Fin <= 0 || C <= 0) return CN_ERR_BAD_ARG;
+  if (C % 256 != 0 || C > 1024 || (reinterpret_cast<uintptr_t>(mid) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(w2_taps) & 15))
+    return CN_ERR_UNSUPPORTED;
+  if (B == 0) return CN_OK;
+  const int64_t T1 = (Tin - 1) / 2 + 1, F1 = (Fin - 1) / 2 + 1, T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  {
+    const int64_t n_pos = B * T1 * F1;
+    int64_t blocks = (n_pos + 7) / 8;                      // 8 warps per block, one position per warp step
+    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+    conv1_direct_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, sbx, stx, w1, b1, (int)Tin, (int)Fin, (int)T1, (int)F1, (int)C,
+                                                                  n_pos, (__nv_bfloat16*)mid);
+    CN_CHECK_LAUNCH();
+  }
+  CUtensorMap ma, mw;
+  if (!make_map_conv(&ma, mid, B, T1, F1, C) || !make_map(&mw, w2_taps, C, 9 * C, 9 * C, 256)) return CN_ERR_DEVICE;
+  ConvArgs cv;
+  cv.bias = b2; cv.out = (__nv_bfloat16*)out; cv.B = (int)B; cv.T2 = (int)T2; cv.F2 = (int)F2; cv.C = (int)C;
+  constexpr uint32_t smem2 = 1024 + STAGES * (BM * BK * 2 + 256 * BK * 2) + 256;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv2_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+      return CN_ERR_LAUNCH;
+    configured = true;
+  }
+  const int64_t tiles = B * ((T2 + CV_TT - 1) / CV_TT) * ((F2 + CV_FT - 1) / CV_FT) * (C / 256);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  conv2_igemm_kernel<256><<<grid, THREADS, smem2, stream>>>(ma, mw, cv);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
 // ---------------------------------------------------------------- fused head + row statistics
 namespace {
 __global__ void __launch_bounds__(256) merge_row_parts_kernel(const float* __restrict__ pmax, const int32_t* __restrict__ pidx,

@@ -280,8 +280,28 @@ class ConvEmbedding(nn.Module):
         self.pos_enc = pos_enc
 
     def forward(self, x, mask):
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 like the reference CPU path
-            x = self.conv(x.unsqueeze(1))
+        if ops.is_bf16() and not torch.is_grad_enabled() and self.d_model % 256 == 0:
+            # fast mode: direct conv1 + implicit-GEMM conv2 on tcgen05, channels-last bf16 [B,T2,F2,C]; the output
+            # projection consumes that layout with its weight columns permuted from (c, f) to (f, c) order
+            conv = self.conv
+            y = ops.conv_frontend(x, conv[0].weight, conv[0].bias, conv[2].weight, conv[2].bias)
+            b, t, f, c = y.shape
+            w = self.linear_out.weight
+            key = ("linear_out_fc", id(w))
+            stamp = (w.data_ptr(), w._version)
+            hit = ops._BF16_WEIGHTS.get(key)
+            if hit is None or hit[0] != stamp:
+                with torch.no_grad():
+                    wp = w.detach().view(-1, c, f).transpose(1, 2).reshape(-1, f * c).contiguous()
+                    hit = (stamp, ops.cast_bf16(wp), w)
+                ops._BF16_WEIGHTS[key] = hit
+            x = ops.linear_bf16(y.view(b, t, f * c), hit[1], self.linear_out.bias, alpha=math.sqrt(self.d_model))
+            x = self.pos_enc(x)
+            mask = mask[:, :, ::2][:, :, ::2] if mask.size(1) == 1 else mask[:, ::2, ::2][:, ::2, ::2]
+            return x, mask
+        else:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 like the reference CPU path
+                x = self.conv(x.unsqueeze(1))
         b, c, t, f = x.size()
         x = ops.linear(x.transpose(1, 2).contiguous().view(b, t, c * f), self.linear_out.weight, self.linear_out.bias,
                        alpha=math.sqrt(self.d_model))

@@ -484,6 +484,30 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
     return out
 
 
+def conv_frontend(x, w1, b1, w2, b2):
+    """relu(conv2(relu(conv1(x)))) of ConvEmbedding (embedding.py:103-104): x f32 [B,Tin,F] ->
+    bf16 [B, T2, F2, C] channels-last (fast mode; conv2 = implicit GEMM on tcgen05)."""
+    require_cuda(x, w1, w2)
+    B, Tin, Fin = x.shape
+    C = w1.shape[0]
+    T1, F1 = (Tin - 1) // 2 + 1, (Fin - 1) // 2 + 1
+    T2, F2 = (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
+    xc = x if (x.stride(-1) == 1 and x.dtype == torch.float32) else x.float().contiguous()
+    key = ("conv2_taps", id(w2))
+    stamp = (w2.data_ptr(), w2._version)
+    hit = _BF16_WEIGHTS.get(key)
+    if hit is None or hit[0] != stamp:                 # [C_out, C_in, 3, 3] -> [C_out, (dt, df, c_in)] bf16
+        with torch.no_grad():
+            hit = (stamp, cast_bf16(w2.detach().permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()), w2)
+        _BF16_WEIGHTS[key] = hit
+    mid = torch.empty(B, T1, F1, C, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(B, T2, F2, C, dtype=torch.bfloat16, device=x.device)
+    call("cn_conv_frontend_bf16", ptr(xc), xc.stride(0), xc.stride(1), B, Tin, Fin, ptr(w1.detach().reshape(C, 9).contiguous()),
+         ptr(b1), ptr(hit[1]), ptr(b2), C, ptr(mid), ptr(out), stream(),
+         work=dict(flops=2.0 * B * T2 * F2 * C * 9 * C + 18.0 * B * T1 * F1 * C, bytes=2.0 * B * C * (2 * T1 * F1 + T2 * F2)))
+    return out
+
+
 # ----------------------------------------------------------------------------- K10 CTC loss
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, want_grad=True, grad_out=1.0):
     """CTC loss of cassnat.py:232 — torch.nn.CTCLoss(reduction='mean', zero_infinity=True) — on

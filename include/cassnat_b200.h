@@ -244,6 +244,17 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak, float* lse,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* Fast mode, encoder front-end (upstream of the accelerated path): the two 3x3 / stride-2 / pad-1
+ * convolutions + ReLU of ConvEmbedding with channels-last bf16 activations.
+ *   replaces: ConvEmbedding.conv                              src/models/modules/embedding.py:103-104,114-116
+ * x f32 [B,Tin,Fin] (batch / frame pitches sbx, stx); w1 f32 [C,9], b1 [C]; w2_taps bf16 [C, 9*C] with
+ * k = (3*dt+df)*C + c_in; b2 f32 [C]; mid bf16 [B,T1,F1,C] (scratch), out bf16 [B,T2,F2,C],
+ * T1 = (Tin-1)/2+1, F1 = (Fin-1)/2+1, T2 = (T1-1)/2+1, F2 = (F1-1)/2+1.  conv2 is an implicit GEMM on tcgen05
+ * whose A tiles are 4-D TMA boxes with traversal stride 2 (no im2col buffer).  C % 256 == 0. */
+int cn_conv_frontend_bf16(const float* x, int64_t sbx, int64_t stx, int64_t B, int64_t Tin, int64_t Fin,
+                          const float* w1, const float* b1, const void* w2_taps, const float* b2, int64_t C,
+                          void* mid, void* out, cn_stream_t stream);
+
 /* Fast mode, per-row masks: the mask arrives bit-packed, bits[b][i][w] (16 uint32 words per query row,
  * bit (t&31) of word (t>>5) = keep(i,t)); cn_attention_bf16 itself only takes key masks (mi == 0).
  *   cn_pack_mask_bits      u8 [B,Tq,Tk] (strides mb, mi) -> bits        (dense masks: src_trigger, unimask)

@@ -311,6 +311,7 @@ def run_ours(a, w):
         model.use_cuda_graphs = not a.no_graphs
         line["speechlike_decode"] = speechlike_decode(model, args, w, dev_in, B, dev)
         line["features_decode"] = features_decode(model, args, w, dev, B)
+        line["conformer_decode"] = conformer_decode(w, dev_in, B, dev, a.precision, not a.no_graphs)
         line["sampled_decode"] = sampled_decode(model, w, dev)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
@@ -496,6 +497,32 @@ def features_decode(model, args, w, dev, B, iters=5):
                         f"encoder + post-encoder path)", "ms_per_step": dt * 1e3, "utt_per_s": B / dt,
             "rtf": dt / (B * w["audio_s"]), "front_end_ms": e[0].elapsed_time(e[1]), "encoder_ms": e[1].elapsed_time(e[2]),
             "post_encoder_ms": e[2].elapsed_time(e[3]), "tokens_U_mean": sum(len(o[0]["hyp"]) - 1 for o in out) / B}
+
+
+def conformer_decode(w, dev_in, B, dev, precision, graphs, iters=10):
+    """The same workload on the conformer block family (use_conv_dec / relative positions: the reference's shipped
+    YAML default): relative-position attention on tcgen05, conv module, macaron half-step FFNs."""
+    from cassnat_asr_public_b200.cassnat import make_model
+    args = model_args(w, use_conv_dec=True, use_conv_enc=True, pos_type="relative", precision=precision)
+    torch.manual_seed(1234)
+    model = make_model(80, args).to(dev).eval()
+    model.set_precision(precision)
+    model.use_cuda_graphs = graphs
+    enc_h, mask, ratio = dev_in
+    with torch.no_grad():
+        for _ in range(3):
+            out, _ = model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out, _ = model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    toks = [len(o[0]["hyp"]) - 1 for o in out]
+    return {"workload": "cfg3 shapes, conformer decoder family (1+1+6 layers, kernel 3, max relative length 8)",
+            "ms_per_step": ms, "utt_per_s": B / (ms / 1e3), "tokens_U_mean": sum(toks) / len(toks), "tokens_U_max": max(toks)}
 
 
 class StandInRanker(torch.nn.Module):

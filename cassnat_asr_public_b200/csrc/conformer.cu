@@ -67,24 +67,130 @@ __global__ void __launch_bounds__(CC) glu_dwconv_kernel(const TIn* __restrict__ 
   }
 }
 
-// pass 2: GroupNorm(1,C) affine + activation; fp32 in place, or bf16 into out_bf16 (next GEMM's operand)
-__global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ z, const double* __restrict__ partial,
-                                                            int nblk, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float eps, int act, int L,
-                                                            int C, __nv_bfloat16* __restrict__ out_bf16) {
-  const int b = blockIdx.y;
+// pass 1, two adjacent channels per thread (C even): 4-byte bf16x2 / 8-byte float2 loads, float2 stores
+__device__ __forceinline__ float2 ld2_as_f32(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2_as_f32(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename TIn>
+__global__ void __launch_bounds__(CC) glu_dwconv2_kernel(const TIn* __restrict__ y, int64_t ldy, int64_t sby,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int L, int C, int ksz, float* __restrict__ z,
+                                                         double* __restrict__ partial) {
+  extern __shared__ float g[];                      // [(TL + ksz - 1)][2 * CC]
+  const int b = blockIdx.y, l0 = blockIdx.x * TL, pad = (ksz - 1) / 2;
+  const int rows = TL + ksz - 1;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 2 * CC) {
+    const int c = c0 + 2 * threadIdx.x;
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float2 a[8], gt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int l = l0 - pad + r0 + k;
+        const bool ok = c < C && r0 + k < rows && l >= 0 && l < L;
+        const TIn* row = y + (int64_t)b * sby + (int64_t)(ok ? l : 0) * ldy;
+        a[k] = ok ? ld2_as_f32(row + c) : make_float2(0.f, 0.f);
+        gt[k] = ok ? ld2_as_f32(row + C + c) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (r0 + k < rows) {
+          g[(r0 + k) * 2 * CC + 2 * threadIdx.x] = a[k].x * (1.f / (1.f + __expf(-gt[k].x)));
+          g[(r0 + k) * 2 * CC + 2 * threadIdx.x + 1] = a[k].y * (1.f / (1.f + __expf(-gt[k].y)));
+        }
+    }
+    if (c < C) {
+      const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+      for (int i = 0; i < TL && l0 + i < L; ++i) {
+        float a0 = b0, a1 = b1;
+        for (int k = 0; k < ksz; ++k) {
+          a0 = fmaf(w[c * ksz + k], g[(i + k) * 2 * CC + 2 * threadIdx.x], a0);
+          a1 = fmaf(w[(c + 1) * ksz + k], g[(i + k) * 2 * CC + 2 * threadIdx.x + 1], a1);
+        }
+        *reinterpret_cast<float2*>(z + ((int64_t)b * L + (l0 + i)) * C + c) = make_float2(a0, a1);
+        s1 += a0 + a1;
+        s2 = fmaf(a0, a0, fmaf(a1, a1, s2));
+      }
+    }
+  }
+  __shared__ double red[2][CC / 32];
+  double d1 = s1, d2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d1; red[1][threadIdx.x >> 5] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < CC / 32; ++i) { t1 += red[0][i]; t2 += red[1][i]; }
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 0] = t1;
+    partial[((int64_t)b * gridDim.x + blockIdx.x) * 2 + 1] = t2;
+  }
+}
+
+// pass 1b: per-utterance mean / rstd from the double partials (one warp per utterance); keeps the fp64 divide and
+// square root out of the elementwise pass
+__global__ void __launch_bounds__(32) gn_finalize_kernel(const double* __restrict__ partial, int nblk, int L, int C, float eps,
+                                                         float* __restrict__ stats) {
+  const int b = blockIdx.x;
   double t1 = 0, t2 = 0;
-  for (int i = 0; i < nblk; ++i) { t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1]; }
-  const double n = (double)L * C;
-  const double mean = t1 / n;
-  double var = t2 / n - mean * mean;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
-  const int64_t total = (int64_t)L * C;
+  for (int i = threadIdx.x; i < nblk; i += 32) { t1 += partial[((int64_t)b * nblk + i) * 2]; t2 += partial[((int64_t)b * nblk + i) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o); }
+  if (threadIdx.x == 0) {
+    const double n = (double)L * C;
+    const double mean = t1 / n;
+    double var = t2 / n - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * b] = (float)mean;
+    stats[2 * b + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// pass 2: GroupNorm(1,C) affine + activation, 4 channels per thread; fp32 in place, or bf16 into out_bf16
+__global__ void __launch_bounds__(256) groupnorm_act_kernel(float* __restrict__ z, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int act, int L, int C, __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.y;
+  const float mu = stats[2 * b], rstd = stats[2 * b + 1];
+  const int total4 = (L * C) >> 2, c4 = C >> 2;
+  float4* zb = reinterpret_cast<float4*>(z + (int64_t)b * L * C);
+  uint2* ob = out_bf16 ? reinterpret_cast<uint2*>(out_bf16 + (int64_t)b * L * C) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const int c = (i % c4) << 2;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+    float4 v = zb[i];
+    v.x = (v.x - mu) * rstd * g.x + bt.x; v.y = (v.y - mu) * rstd * g.y + bt.y;
+    v.z = (v.z - mu) * rstd * g.z + bt.z; v.w = (v.w - mu) * rstd * g.w + bt.w;
+    if (act == CN_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    else if (act == CN_ACT_SWISH) {
+      v.x = v.x / (1.f + __expf(-v.x)); v.y = v.y / (1.f + __expf(-v.y));
+      v.z = v.z / (1.f + __expf(-v.z)); v.w = v.w / (1.f + __expf(-v.w));
+    }
+    if (ob) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      ob[i] = pk;
+    } else {
+      zb[i] = v;
+    }
+  }
+}
+// scalar tail version for C % 4 != 0
+__global__ void __launch_bounds__(256) groupnorm_act_scalar_kernel(float* __restrict__ z, const float* __restrict__ stats,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   int act, int L, int C, __nv_bfloat16* __restrict__ out_bf16) {
+  const int b = blockIdx.y;
+  const float mu = stats[2 * b], rstd = stats[2 * b + 1];
+  const int total = L * C;
   float* zb = z + (int64_t)b * total;
   __nv_bfloat16* ob = out_bf16 ? out_bf16 + (int64_t)b * total : nullptr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C;
     float v = (zb[i] - mu) * rstd * gamma[c] + beta[c];
     if (act == CN_ACT_RELU) v = fmaxf(v, 0.f);
     else if (act == CN_ACT_SWISH) v = v / (1.f + __expf(-v));
@@ -219,7 +325,10 @@ __global__ void __launch_bounds__(CC) dwconv_glu_bwd_kernel(const TIn* __restric
 // per-function maximum, so it is always set to the ceiling, never to the size of one call
 bool set_smem_limits() {
   const int fwd = (TL + 62) * CC * (int)sizeof(float), bwd = 2 * fwd;
-  return cudaFuncSetAttribute(glu_dwconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd) == cudaSuccess &&
+  const int fwd2 = (TL + 30) * 2 * CC * (int)sizeof(float);            // pair kernel: ksz <= 31
+  return cudaFuncSetAttribute(glu_dwconv2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2) == cudaSuccess &&
+         cudaFuncSetAttribute(glu_dwconv2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2) == cudaSuccess &&
+         cudaFuncSetAttribute(glu_dwconv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd) == cudaSuccess &&
          cudaFuncSetAttribute(glu_dwconv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd) == cudaSuccess &&
          cudaFuncSetAttribute(dwconv_glu_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd) == cudaSuccess &&
          cudaFuncSetAttribute(dwconv_glu_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd) == cudaSuccess;
@@ -289,7 +398,7 @@ extern "C" int cn_glu_dwconv_groupnorm_act_bwd(const void* y, int y_is_bf16, int
 }
 
 extern "C" int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L) {
-  return B * ((L + TL - 1) / TL) * 2 * (int64_t)sizeof(double);
+  return B * ((L + TL - 1) / TL) * 2 * (int64_t)sizeof(double) + B * 2 * (int64_t)sizeof(float) + 64;
 }
 
 extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t ldy, int64_t sby,
@@ -305,17 +414,36 @@ extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t
   const int nblk = (int)((L + TL - 1) / TL);
   const size_t smem = (size_t)(TL + ksz - 1) * CC * sizeof(float);
   if (!set_smem_limits()) return CN_ERR_LAUNCH;
-  if (y_is_bf16)
+  const bool pair = (C & 1) == 0 && (ldy & 1) == 0 && (sby & 1) == 0 && ksz <= 31 &&
+                    (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  if (pair && y_is_bf16)
+    glu_dwconv2_kernel<__nv_bfloat16><<<dim3(nblk, (unsigned)B), CC, 2 * smem, stream>>>(
+        (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, (int)ksz, out, (double*)workspace);
+  else if (pair)
+    glu_dwconv2_kernel<float><<<dim3(nblk, (unsigned)B), CC, 2 * smem, stream>>>((const float*)y, ldy, sby, dw_weight, dw_bias,
+                                                                               (int)L, (int)C, (int)ksz, out, (double*)workspace);
+  else if (y_is_bf16)
     glu_dwconv_kernel<__nv_bfloat16><<<dim3(nblk, (unsigned)B), CC, smem, stream>>>(
         (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, (int)ksz, out, (double*)workspace);
   else
     glu_dwconv_kernel<float><<<dim3(nblk, (unsigned)B), CC, smem, stream>>>((const float*)y, ldy, sby, dw_weight, dw_bias,
                                                                           (int)L, (int)C, (int)ksz, out, (double*)workspace);
   CN_CHECK_LAUNCH();
-  int gx = (int)((L * C + 255) / 256);
-  if (gx > 148 * 4) gx = 148 * 4;
-  groupnorm_act_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(out, (const double*)workspace, nblk, gamma, beta, eps,
-                                                                  act, (int)L, (int)C, (__nv_bfloat16*)out_bf16);
+  if (L * C > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  float* stats = reinterpret_cast<float*>((char*)workspace + (int64_t)B * nblk * 2 * sizeof(double));
+  gn_finalize_kernel<<<(unsigned)B, 32, 0, stream>>>((const double*)workspace, nblk, (int)L, (int)C, eps, stats);
+  CN_CHECK_LAUNCH();
+  const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0;
+  const int64_t work = vec ? (L * C) / 4 : L * C;
+  int gx = (int)((work + 255) / 256);
+  if (gx > 148 * 2) gx = 148 * 2;
+  if (vec)
+    groupnorm_act_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(out, stats, gamma, beta, act, (int)L, (int)C,
+                                                                    (__nv_bfloat16*)out_bf16);
+  else
+    groupnorm_act_scalar_kernel<<<dim3(gx, (unsigned)B), 256, 0, stream>>>(out, stats, gamma, beta, act, (int)L, (int)C,
+                                                                           (__nv_bfloat16*)out_bf16);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

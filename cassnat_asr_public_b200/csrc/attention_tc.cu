@@ -382,43 +382,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             else if (p.mask) keep = kbits[(k0 + c) >> 5];                 // key mask: shared by all rows
             else keep = 0xffffffffu;
           };
-          auto add_rel = [&](float* t, int c) {
+          // relative term of a 32-key chunk: away from the diagonal every key of the chunk clamps to the same
+          // table entry, which is returned as ONE offset (folded into the max / the exp argument for free);
+          // only chunks that straddle the +-max_rel band gather per element
+          auto rel_off = [&](float* t, int c) -> float {
             const int d_lo = k0 + c - qi;                                   // j - i of the chunk's first key
-            if (d_lo + 31 <= -p.max_rel) {
+            // warp-uniform decisions (votes): the per-element gather below is only ever executed by warps that
+            // actually touch the band; its clamped lookup is valid for every lane of such a warp
+            if (__all_sync(0xffffffffu, d_lo + 31 <= -p.max_rel)) return rel_left;
+            if (__all_sync(0xffffffffu, d_lo >= p.max_rel)) return rel_right;
 #pragma unroll
-              for (int q = 0; q < 32; ++q) t[q] += rel_left;
-            } else if (d_lo >= p.max_rel) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) t[q] += rel_right;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                int r = d_lo + q;
-                r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
-                t[q] += __ldg(rb + r + p.max_rel);
-              }
+            for (int q = 0; q < 32; ++q) {
+              int r = d_lo + q;
+              r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
+              t[q] += __ldg(rb + r + p.max_rel);
             }
+            return 0.f;
           };
           // ---- sweep 1: row max (four independent chains; masked chunks take the slow path)
           float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
           auto sweep_max = [&](float* t, int c) {
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
-            if (REL) { add_rel(t, c); any_keep = any_keep || ((keep & valid) != 0u); }
+            float off = 0.f;
+            if (REL) { off = rel_off(t, c); any_keep = any_keep || ((keep & valid) != 0u); }
             if (BITS && uniform_row) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) t[q] = 0.f;                     // equal scores
             }
             if ((keep & valid) == 0xffffffffu) {
+              if (REL) {
+                float cm[4] = {t[0], t[1], t[2], t[3]};
 #pragma unroll
-              for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
+                for (int q = 4; q < 32; ++q) cm[q & 3] = fmaxf(cm[q & 3], t[q]);
+                mxv[0] = fmaxf(mxv[0], fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + off);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
+              }
             } else if (BITS && (keep & valid) == 0u) {
               // no weight in this chunk
             } else {
               float mm = -INFINITY;
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
-                float v = t[q] * scale;
+                float v = (REL ? t[q] + off : t[q]) * scale;
                 v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
                 v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
                 mm = fmaxf(mm, v);
@@ -444,15 +452,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           auto sweep_exp = [&](float* t, int c) {
             uint32_t keep, valid;
             chunk_bits(c, keep, valid);
-            if (REL) add_rel(t, c);
+            float off = 0.f;
+            if (REL) off = rel_off(t, c);
             if (BITS && uniform_row) {
 #pragma unroll
               for (int q = 0; q < 32; ++q) t[q] = 0.f;
             }
             if ((keep & valid) == 0xffffffffu) {
+              const float addend = REL ? fmaf(off, scale, -m_new) : -m_new;
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
-                t[q] = ex2(fmaf(t[q], scale, -m_new));
+                t[q] = ex2(fmaf(t[q], scale, addend));
                 lsv[q & 3] += t[q];
               }
             } else if (BITS && (keep & valid) == 0u) {
@@ -461,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             } else {
 #pragma unroll
               for (int q = 0; q < 32; ++q) {
-                float v = t[q] * scale;
+                float v = (REL ? t[q] + off : t[q]) * scale;
                 v = ((keep >> q) & 1u) ? v : CN_F32_MIN;
                 v = ((valid >> q) & 1u) ? v : -INFINITY;
                 t[q] = ex2(v - m_new);
@@ -552,21 +562,46 @@ bool make_map3(CUtensorMap* map, const void* base, int64_t B, int64_t T, int64_t
 }
 
 // (q_i + v_h) . P[r, h, :] for every query row and the 2m+1 clamped offsets; Q holds q + u_h.
-__global__ void __launch_bounds__(256) rel_bias_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, int64_t sbq,
+// Thread = one (row, head): its 64 query values stay in registers, the head's P rows are shared-memory
+// broadcasts (all lanes of a warp read the same address).
+__global__ void __launch_bounds__(128) rel_bias_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, int64_t sbq,
                                                        const float* __restrict__ rel_pos, const float* __restrict__ rel_u,
-                                                       const float* __restrict__ rel_v, int h, int Tq, int nrel,
+                                                       const float* __restrict__ rel_v, int B, int h, int Tq, int nrel,
                                                        float* __restrict__ out) {
-  const int i = blockIdx.x, b = blockIdx.y, hh = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (hh >= h) return;
-  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(Q + (int64_t)b * sbq + (int64_t)i * ldq + hh * 64 + lane * 2);
-  const float2 u = *reinterpret_cast<const float2*>(rel_u + hh * 64 + lane * 2);
-  const float2 v = *reinterpret_cast<const float2*>(rel_v + hh * 64 + lane * 2);
-  const float qx = __bfloat162float(q2.x) + (v.x - u.x), qy = __bfloat162float(q2.y) + (v.y - u.y);
+  extern __shared__ float ps[];                      // [nrel][64] rows of this head, then (v - u)[64]
+  const int hh = blockIdx.y;
+  for (int i = threadIdx.x; i < nrel * 64; i += blockDim.x) ps[i] = rel_pos[(int64_t)(i >> 6) * h * 64 + hh * 64 + (i & 63)];
+  float* du = ps + nrel * 64;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) du[i] = rel_v[hh * 64 + i] - rel_u[hh * 64 + i];
+  __syncthreads();
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (int64_t)B * Tq) return;
+  const int64_t b = row / Tq;
+  const int i = (int)(row % Tq);
+  const uint4* src = reinterpret_cast<const uint4*>(Q + b * sbq + (int64_t)i * ldq + hh * 64);
+  float q[64];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 raw = src[c];
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h2[e]);
+      q[c * 8 + 2 * e] = f.x + du[c * 8 + 2 * e];
+      q[c * 8 + 2 * e + 1] = f.y + du[c * 8 + 2 * e + 1];
+    }
+  }
   float* o = out + (((int64_t)b * h + hh) * Tq + i) * nrel;
   for (int r = 0; r < nrel; ++r) {
-    const float2 pr = *reinterpret_cast<const float2*>(rel_pos + (int64_t)r * h * 64 + hh * 64 + lane * 2);
-    const float s = cn_warp_sum(fmaf(qx, pr.x, qy * pr.y));
-    if (lane == 0) o[r] = s;
+    const float4* pr = reinterpret_cast<const float4*>(ps + r * 64);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 pv = pr[c];
+      a0 = fmaf(q[4 * c], pv.x, a0); a1 = fmaf(q[4 * c + 1], pv.y, a1);
+      a2 = fmaf(q[4 * c + 2], pv.z, a2); a3 = fmaf(q[4 * c + 3], pv.w, a3);
+    }
+    o[r] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -660,8 +695,10 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
   if (workspace_bytes < cn_rel_attention_workspace_bytes(B, h, Tq, max_rel)) return CN_ERR_WORKSPACE;
   if (B == 0 || Tq == 0) return CN_OK;
   float* relbias = (float*)workspace;
-  rel_bias_kernel<<<dim3((unsigned)Tq, (unsigned)B), (unsigned)(32 * h), 0, (cudaStream_t)stream_>>>(
-      (const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)h, (int)Tq, (int)(2 * max_rel + 1), relbias);
+  const int nrel = (int)(2 * max_rel + 1);
+  rel_bias_kernel<<<dim3((unsigned)((B * Tq + 127) / 128), (unsigned)h), 128, (size_t)(nrel + 1) * 64 * sizeof(float),
+                    (cudaStream_t)stream_>>>((const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)B, (int)h,
+                                             (int)Tq, nrel, relbias);
   CN_CHECK_LAUNCH();
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
                              relbias, (int)max_rel, kv_len, nullptr, nullptr, stream_);

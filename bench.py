@@ -313,6 +313,7 @@ def run_ours(a, w):
         line["features_decode"] = features_decode(model, args, w, dev, B)
         line["conformer_decode"] = conformer_decode(w, dev_in, B, dev, a.precision, not a.no_graphs)
         line["sampled_decode"] = sampled_decode(model, w, dev)
+        line["sampled_decode_lm"] = sampled_decode(model, w, dev, iters=3, real_lm=True)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
         torch.cuda.empty_cache()
@@ -542,13 +543,19 @@ class StandInRanker(torch.nn.Module):
         return torch.log_softmax(x @ self.out, -1)
 
 
-def sampled_decode(model, w, dev, B=32, S=10, iters=5):
+def sampled_decode(model, w, dev, B=32, S=10, iters=5, real_lm=False):
     """BASELINE configs[3] / SURVEY cfg4: decode with S=10 sampled alignments per utterance (threshold 0.9,
     host-drawn select bits as cassnat.py:373) + ranker rescoring (K11), batch 32 -> effective batch 320."""
     args = model_args(w, sample_num=S, threshold=0.9, rank_model="lm")
     enc_h, mask, ratio, lens = synth_encoder_output(w, B, 777)
     enc_h, mask, ratio = enc_h.to(dev), mask.to(dev), ratio.to(dev)
     ranker = StandInRanker(5000).to(dev)
+    if real_lm:
+        # the reference's ranker: TransformerLM of conf/lm.yaml (16 x 512, d_ff 2048, 8 heads; vocabulary widened to
+        # the ASR model's 5000 so that every id is in range), random init, on this package's kernels
+        from cassnat_asr_public_b200 import lm as LM
+        torch.manual_seed(4321)
+        ranker = LM.make_model(SimpleNamespace(n_head=8, d_model=512, d_ff=2048, dropout=0.0, vocab_size=5000, N=16)).to(dev).eval()
 
     def once():
         with torch.no_grad():
@@ -563,17 +570,24 @@ def sampled_decode(model, w, dev, B=32, S=10, iters=5):
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / iters * 1e3
     U = max(len(o[0]["hyp"]) - 1 for o in out)
-    ids = torch.randint(0, 5000, (B * S, U), device=dev)
+    ids = torch.randint(1, 5000, (B * S, U), device=dev)
+    lm_mask = torch.tril(torch.ones(U, U, dtype=torch.bool, device=dev)).unsqueeze(0).expand(B * S, U, U).contiguous()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(iters):
-        ranker(ids, None)
+    with torch.no_grad():
+        for _ in range(iters):
+            if real_lm:
+                ranker.score_tokens(ids, lm_mask, ids)
+            else:
+                ranker(ids, None)
     torch.cuda.synchronize()
     rk = (time.perf_counter() - t0) / iters * 1e3
+    what = ("TransformerLM 16 x 512 (conf/lm.yaml shape) on this package's kernels, fused target log-prob head" if real_lm
+            else "stand-in ranker (stock torch, not part of the path)")
     return {"workload": f"cfg4: base model, {B} utterances x {S} sampled alignments (threshold 0.9) + rescoring, T={enc_h.size(1)}, "
                         f"tokens_U_max={U}", "ms_per_step": ms, "utt_per_s": B / (ms / 1e3),
-            "alignments_per_s": B * S / (ms / 1e3), "stand_in_ranker_ms": rk,
-            "note": "wall clock incl. the host RNG draw, the stand-in ranker (stock torch, not part of the path) and the hypothesis read-back"}
+            "alignments_per_s": B * S / (ms / 1e3), "ranker": what, "ranker_ms": rk,
+            "note": "wall clock incl. the host RNG draw, the ranker and the hypothesis read-back"}
 
 
 def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):

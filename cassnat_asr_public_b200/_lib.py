@@ -43,7 +43,7 @@ SIGNATURES = {
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
     "cn_gemm_rowstats_workspace_bytes": (_i64, [_i64, _i64]),
-    "cn_gemm_bf16_rowstats": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cn_gemm_bf16_rowstats": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cn_rel_attention_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "cn_rel_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                      _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),

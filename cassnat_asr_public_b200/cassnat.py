@@ -370,8 +370,24 @@ class CassNAT(nn.Module):
         ids64 = ids.long()
         lm_in = torch.cat([torch.full((B * S, 1), sos, dtype=torch.long, device=ids.device), ids64[:, :-1]], 1)
         causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=ids.device)).unsqueeze(0)
-        lm_out = lm_model(lm_in, (tgt_mask & causal).long())
-        if lm_out.is_cuda and lm_out.dtype == torch.float32 and lm_out.stride(-1) == 1 and S <= 32:
+        lm_mask = tgt_mask & causal
+        if hasattr(lm_model, "score_tokens") and S <= 32:
+            # this package's LM mirror: log p(id) per position straight from the fused head epilogue (fast mode),
+            # the [B*S,U,V] tensor is never materialised; K11 then runs on the [B*S,U] scores (V = 1, id 0)
+            sc = lm_model.score_tokens(lm_in, lm_mask, ids).float().contiguous()
+            from ._lib import call, ptr, stream
+            mean = torch.empty(B * S, dtype=torch.float32, device=ids.device)
+            best = torch.empty(B, dtype=torch.int64, device=ids.device)
+            zero_ids = torch.zeros(B * S, ymax, dtype=torch.int32, device=ids.device)
+            call("cn_rescore_select", ptr(sc), sc.stride(0), 1, ptr(zero_ids), ptr(tgt_mask.reshape(B * S, ymax).contiguous()),
+                 B, S, ymax, ptr(mean), ptr(best), stream())
+            best = best.unsqueeze(1)
+            lm_out = None
+        else:
+            lm_out = lm_model(lm_in, lm_mask.long())
+        if lm_out is None:
+            pass
+        elif lm_out.is_cuda and lm_out.dtype == torch.float32 and lm_out.stride(-1) == 1 and S <= 32:
             from ._lib import call, ptr, stream                                            # K11
             mean = torch.empty(B * S, dtype=torch.float32, device=ids.device)
             best = torch.empty(B, dtype=torch.int64, device=ids.device)

@@ -117,6 +117,7 @@ struct Epilogue {
   float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
   // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
   float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
+  const int32_t* st_target; float* st_target_logit;    // optional: the logit of one given column per row
 };
 
 template <int ACT>
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
         const int row = m0 + quarter * 32 + lane;
         float m1 = -INFINITY, m2 = -INFINITY, ssum = 0.f;
         int i1 = 0x7fffffff, i2 = 0x7fffffff;
+        const int tgt = (ep.st_target && row < M) ? ep.st_target[row] : -1;
 #pragma unroll 1
         for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
           const int col0 = n0 + c0;
@@ -252,6 +254,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j >= N) x[j] = -INFINITY;
+          }
+          if (tgt >= col0 && tgt < col0 + 32) {                 // exactly one (tile, half, chunk) owns the target column
+            float tl = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tl = (col0 + j == tgt) ? x[j] : tl;
+            ep.st_target_logit[row] = tl;
           }
           if (ep.st_idx2) {
 #pragma unroll
@@ -498,6 +506,7 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
+  ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
 #define CN_TC_DISPATCH(BN_)                                                                              \
@@ -815,9 +824,10 @@ extern "C" int64_t cn_gemm_rowstats_workspace_bytes(int64_t M, int64_t N) {
 
 extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                                      float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
-                                     float* peak, float* lse, void* workspace, int64_t workspace_bytes,
-                                     cn_stream_t stream_) {
+                                     float* peak, float* lse, const int32_t* target, float* target_logit,
+                                     void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
   if (!A || !W || !top1 || !workspace || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K) return CN_ERR_BAD_ARG;
+  if ((target == nullptr) != (target_logit == nullptr)) return CN_ERR_BAD_ARG;
   if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return CN_ERR_UNSUPPORTED;
   if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
@@ -836,6 +846,7 @@ extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, 
   ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0;
   ep.st_max = pmax; ep.st_idx = pidx; ep.st_sum = psum; ep.st_max2 = top2 ? pmax2 : nullptr;
   ep.st_idx2 = top2 ? pidx2 : nullptr; ep.n_parts = parts;
+  ep.st_target = target; ep.st_target_logit = target_logit;
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = launch_tc<256, CN_ACT_NONE, false, true>(ma, mw, ep, (int)M, (int)N, (int)K, stream);
   if (rc != CN_OK) return rc;

@@ -460,8 +460,14 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
     if m is not None and mi != 0:                    # per-row mask: bit-pack it for the tensor-core kernel
         if rel is not None:
             raise RuntimeError("bf16 relative attention takes key masks only")
-        bits = torch.empty(B, Tq, 16, dtype=torch.int32, device=q.device)
-        call("cn_pack_mask_bits", ptr(m), mb, mi, B, Tq, Tk, ptr(bits), stream(), work=dict(bytes=float(B * Tq * (Tk + 64))))
+        bits = getattr(mask, "_cn_bits", None)           # packed once per mask tensor (every layer reuses it)
+        if bits is None or bits.shape[:2] != (B, Tq):
+            bits = torch.empty(B, Tq, 16, dtype=torch.int32, device=q.device)
+            call("cn_pack_mask_bits", ptr(m), mb, mi, B, Tq, Tk, ptr(bits), stream(), work=dict(bytes=float(B * Tq * (Tk + 64))))
+            try:
+                mask._cn_bits = bits
+            except AttributeError:
+                pass
         call("cn_attention_bf16_bits", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
              ptr(v), v.stride(1), v.stride(0), ptr(bits), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1),
              out.stride(0), None, None, stream(),
@@ -534,7 +540,7 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, want_gr
     return loss[0], nll, grad
 
 
-def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False):
+def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False, target=None):
     """K1/K9 fused (fast mode): argmax / runner-up / max / log-sum-exp of every row of
     alpha * (x @ weight.T + bias) straight out of the tcgen05 GEMM's epilogue; the logits are never
     written.  Returns the same dict as row_stats."""
@@ -550,10 +556,15 @@ def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False):
            "lse": torch.empty(M, dtype=torch.float32, device=dev)}
     if top2:
         out["top2"] = torch.empty(M, dtype=torch.int32, device=dev)
+    tgt = None
+    if target is not None:                 # also return z[row, target[row]] (0 where the id is outside [0, N))
+        tgt = target.reshape(-1).to(torch.int32).contiguous()
+        out["target_logit"] = torch.zeros(M, dtype=torch.float32, device=dev)
     ws_bytes = _lib.load().cn_gemm_rowstats_workspace_bytes(M, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("cn_gemm_bf16_rowstats", ptr(x2), x2.stride(0), ptr(wb), wb.stride(0), ptr(bias), float(alpha), M, N, K,
-         ptr(out["top1"]), ptr(out.get("top2")), ptr(out["peak"]), ptr(out["lse"]), ptr(ws), ws_bytes, stream(),
+         ptr(out["top1"]), ptr(out.get("top2")), ptr(out["peak"]), ptr(out["lse"]), ptr(tgt), ptr(out.get("target_logit")),
+         ptr(ws), ws_bytes, stream(),
          work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K)),
          tag=(f"cn_gemm_bf16_rowstats[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
     lead = x.shape[:-1]

@@ -242,6 +242,9 @@ int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, 
 int64_t cn_gemm_rowstats_workspace_bytes(int64_t M, int64_t N);
 int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha,
                           int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak, float* lse,
+                          const int32_t* target /* i32 [M] or NULL: one column per row (ids outside [0,N) are ignored) */,
+                          float* target_logit   /* f32 [M]: z[row, target[row]]; log-prob = target_logit - lse
+                                                   (rescoring, src/models/cassnat.py:517: gather(lm_out, att_pred)) */,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
 /* Fast mode, encoder front-end (upstream of the accelerated path): the two 3x3 / stride-2 / pad-1

@@ -376,3 +376,14 @@ def train_forward_from_encoder(enc_h, x_mask, src_size_frames, tgt_label, label_
     loss = cfg.ctc_alpha * ctc_loss + cfg.att_alpha * att_loss
     return dict(ctc_out=ctc_out, att_out=att_out, loss=loss, ctc_loss=ctc_loss, att_loss=att_loss,
                 aligned=aligned, trigger=trig, ac_embed=ac, pred_embed=pred, dec_h=dec_h)
+
+
+# --------------------------------------------------------------------- LM ranker
+def lm_forward(ids, mask, sd, n_head):
+    """TransformerLM.forward (src/models/lm.py:52-56): TextEmbedding (embedding.py:71-78) + absolute positional
+    encoding (embedding.py:29-31) -> transformer_blocks.Encoder (:51-71, same layer as the FaNAT encoder) ->
+    Generator (lm.py:35-43).  ids int64 [N,U], mask [N,U,U] -> log-probabilities [N,U,V]."""
+    w = sd["text_embed.0.lut.weight"]
+    d = w.shape[1]
+    x = w[ids] * math.sqrt(d) + sinusoid_table(d)[: ids.shape[1]].unsqueeze(0)
+    return generator(trf_encoder(x, mask, sd, n_head), sd, "out_generator")

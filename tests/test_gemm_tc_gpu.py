@@ -69,11 +69,17 @@ def test_fused_head_rowstats(M, N, K):
     nbytes = _lib.load().cn_gemm_rowstats_workspace_bytes(M, N)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     call("cn_gemm_bf16_rowstats", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), 1.0, M, N, K, ptr(got["top1"]),
-         ptr(got["top2"]), ptr(got["peak"]), ptr(got["lse"]), ptr(ws), nbytes, stream())
+         ptr(got["top2"]), ptr(got["peak"]), ptr(got["lse"]), None, None, ptr(ws), nbytes, stream())
     assert torch.equal(got["top1"], want["top1"]) and torch.equal(got["top2"], want["top2"])
     assert torch.equal(got["peak"], want["peak"])
     assert (got["lse"] - want["lse"]).abs().max().item() < 1e-4
     # and without the runner-up (the greedy decode configuration)
     call("cn_gemm_bf16_rowstats", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), 1.0, M, N, K, ptr(got["top1"]),
-         None, ptr(got["peak"]), ptr(got["lse"]), ptr(ws), nbytes, stream())
+         None, ptr(got["peak"]), ptr(got["lse"]), None, None, ptr(ws), nbytes, stream())
     assert torch.equal(got["top1"], want["top1"]) and (got["lse"] - want["lse"]).abs().max().item() < 1e-4
+    # the logit of a given column per row (rescoring: log p(id) = target_logit - lse), ids outside [0,N) -> 0
+    tgt = torch.randint(0, N, (M,), device=DEV, dtype=torch.int32)
+    tgt[::7] = -1
+    st = ops.head_rowstats(x, w, b, target=tgt)
+    ref = logits.gather(1, tgt.clamp(min=0).long().unsqueeze(1)).squeeze(1).masked_fill(tgt < 0, 0.0)
+    assert torch.equal(st["target_logit"], ref)

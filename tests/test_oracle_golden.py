@@ -117,3 +117,12 @@ def test_train_port_gradients(blocks_golden):
         assert np.abs(got.numpy() - want).max() / scale < 2e-4, (name, key)
         checked += 1
     assert checked > 100
+
+
+def test_lm_port():
+    """Oracle port of the LM ranker == the unmodified reference's TransformerLM (tests/golden/lm.npz)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm.npz"))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    with torch.no_grad():
+        got = O.lm_forward(torch.from_numpy(z["ids"]), torch.from_numpy(z["mask"]), sd, int(z["args"][0]))
+    assert _rel(got, z["lm_out"]) < 2e-5

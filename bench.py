@@ -577,7 +577,7 @@ def sampled_decode(model, w, dev, B=32, S=10, iters=5, real_lm=False):
     with torch.no_grad():
         for _ in range(iters):
             if real_lm:
-                ranker.score_tokens(ids, lm_mask, ids)
+                ranker.score_tokens(ids, lm_mask, ids, causal=True)
             else:
                 ranker(ids, None)
     torch.cuda.synchronize()

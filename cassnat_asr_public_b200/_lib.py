@@ -57,7 +57,7 @@ SIGNATURES = {
     "cn_pack_mask_bits": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "cn_trigger_mask_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "cn_attention_bf16_bits": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64,
-                                      _vp, _i64, _i64, _vp, _vp, _vp]),
+                                      _vp, _i64, _i64, _vp, _vp, _int, _vp]),
     "cn_gemm_f32_strided": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                    _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
     "cn_colsum_workspace_bytes": (_i64, [_i64, _i64]),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "cn_layernorm_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "cn_attn_softmax_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
     "cn_label_smoothing": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _f32, _f32, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "cn_gemm_bf16_mn": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_transpose_bf16": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _vp]),
     "cn_rel_bias_add": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp]),
     "cn_rel_bucket": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),

@@ -374,7 +374,7 @@ class CassNAT(nn.Module):
         if hasattr(lm_model, "score_tokens") and S <= 32:
             # this package's LM mirror: log p(id) per position straight from the fused head epilogue (fast mode),
             # the [B*S,U,V] tensor is never materialised; K11 then runs on the [B*S,U] scores (V = 1, id 0)
-            sc = lm_model.score_tokens(lm_in, lm_mask, ids).float().contiguous()
+            sc = lm_model.score_tokens(lm_in, lm_mask, ids, causal=True).float().contiguous()
             from ._lib import call, ptr, stream
             mean = torch.empty(B * S, dtype=torch.float32, device=ids.device)
             best = torch.empty(B, dtype=torch.int64, device=ids.device)

@@ -132,6 +132,7 @@ struct AttnTcArgs {
   // optional processing order: utterance order[i] is the i-th to be scheduled (heaviest first), so that the
   // static round-robin over the persistent CTAs hands every CTA a similar amount of work
   const int32_t* order;
+  int causal;                               // hint: key j > query i is masked for every row -> tiles above the diagonal are skipped
 };
 
 // Persistent, ping-pong design (v2):
@@ -164,10 +165,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   const int n_tiles_max = (p.Tk + KT - 1) / KT;        // key tiles (<= 4)
   const int nq_max = (p.Tq + QT - 1) / QT;             // query tiles
   // per-item tile counts; every role evaluates the same expressions, so they stay in lock step
-  auto tiles_of = [&](int b, int& n_tiles, int& nq) {
+  auto tiles_of = [&](int b, int pr, int& n_tiles, int& nq) {
     n_tiles = n_tiles_max;
+    if (p.causal) n_tiles = min(n_tiles, 2 * pr + 2);   // rows of pair pr end at query 256*pr+255: keys beyond are masked
     nq = nq_max;
-    if (p.kv_len) { int t = (min(max(p.kv_len[b], 1), p.Tk) + KT - 1) / KT; n_tiles = min(max(t, 1), n_tiles_max); }
+    if (p.kv_len) { int t = (min(max(p.kv_len[b], 1), p.Tk) + KT - 1) / KT; n_tiles = min(max(t, 1), n_tiles); }
     if (p.q_len) { int t = (min(max(p.q_len[b], 0), p.Tq) + QT - 1) / QT; nq = min(t, nq_max); }
   };
   // work item = (utterance, head, pair of 128-query tiles): finer than (utterance, head) so that the tail of
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         int b, hh, pr0;
         decode_item(item, b, hh, pr0);
         int n_tiles, nq;
-        tiles_of(b, n_tiles, nq);
+        tiles_of(b, pr0, n_tiles, nq);
         if (2 * pr0 >= nq) continue;                            // nothing to compute for this item
         auto load_k = [&](int j) {
           const int sl = RING ? j % MAX_TILES : j;          // RING: Tk > 512 streams through the slots
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         int b_, hh_, pr;
         decode_item(item, b_, hh_, pr);
         int n_tiles, nq;
-        tiles_of(b_, n_tiles, nq);
+        tiles_of(b_, pr, n_tiles, nq);
         if (2 * pr >= nq) continue;
         {
           const bool has[2] = {2 * pr < nq, 2 * pr + 1 < nq};
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       int b, hh, pr0;
       decode_item(item, b, hh, pr0);
       int n_tiles, nq;
-      tiles_of(b, n_tiles, nq);
+      tiles_of(b, pr0, n_tiles, nq);
       if (2 * pr0 >= nq && !(pr0 == 0 && nq < nq_max)) continue;
       if (p.mask && 2 * pr0 < nq) {
         // key-mask bits of this utterance (one private copy per group)
@@ -611,7 +613,8 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                const uint32_t* mask_bits, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                                void* out, int64_t ldo, int64_t sbo, const float* relbias, int max_rel,
-                               const int32_t* kv_len, const int32_t* q_len, const int32_t* order, cn_stream_t stream_) {
+                               const int32_t* kv_len, const int32_t* q_len, const int32_t* order, int causal,
+                               cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   if (dk != DK || Tk > MAX_TK || h > 65535 || B > 65535) return CN_ERR_UNSUPPORTED;
   if (mask_bits && Tk > 512) return CN_ERR_UNSUPPORTED;  // bit-packed per-row masks: 16 words per row
@@ -632,7 +635,7 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   p.mask = mask_bits ? nullptr : mask; p.mb = mb; p.mask_bits = mask_bits; p.q_bcast = q_bcast ? 1 : 0;
   p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
-  p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len; p.order = order;
+  p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len; p.order = order; p.causal = causal;
   static bool configured = false;
   if (!configured) {
     const int sm = (int)SMEM_BYTES;
@@ -668,16 +671,16 @@ extern "C" int cn_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const 
                                  int64_t sbo, const int32_t* kv_len, const int32_t* q_len, const int32_t* order,
                                  cn_stream_t stream_) {
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             nullptr, 0, kv_len, q_len, order, stream_);
+                             nullptr, 0, kv_len, q_len, order, 0, stream_);
 }
 
 extern "C" int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                       const void* V, int64_t ldv, int64_t sbv, const uint32_t* mask_bits, int64_t B,
                                       int64_t h, int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo, int64_t sbo,
-                                      const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream_) {
+                                      const int32_t* kv_len, const int32_t* q_len, int causal_hint, cn_stream_t stream_) {
   if (!mask_bits) return CN_ERR_BAD_ARG;
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, nullptr, 0, 0, mask_bits, B, h, Tq, Tk, dk, out, ldo,
-                             sbo, nullptr, 0, kv_len, q_len, nullptr, stream_);
+                             sbo, nullptr, 0, kv_len, q_len, nullptr, causal_hint ? 1 : 0, stream_);
 }
 
 extern "C" int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel) {
@@ -701,5 +704,5 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
                                              (int)Tq, nrel, relbias);
   CN_CHECK_LAUNCH();
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             relbias, (int)max_rel, kv_len, nullptr, nullptr, stream_);
+                             relbias, (int)max_rel, kv_len, nullptr, nullptr, 0, stream_);
 }

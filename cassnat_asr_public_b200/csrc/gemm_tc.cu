@@ -105,9 +105,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
-// both K-major (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// bit 15 / 16 = A / B is MN-major (0 = K-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// MN-major, 128-byte-swizzled operand: the tile is a row of [64 contraction rows x 64 MN elements] blocks (one TMA
+// box each, 8 KB apart = leading byte offset), 8-row groups of a block 1024 B apart (stride byte offset).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 struct Epilogue {
@@ -127,7 +139,7 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-template <int BN, int ACT, bool RES, bool STATS>
+template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K) {
@@ -174,8 +186,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * STAGE_BYTES;
           mbar_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(&map_a, &full[stage], sa, kb * BK, m0);
-          tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kb * BK, n0);
+          // K-major operand: one [rows x 64 k] box.  MN-major operand (the global tensor is [contraction, MN]
+          // row-major, used as is by the backward GEMMs): one [64 k x 64 mn] box per 64 MN elements.
+          if (!A_MN) tma_load_2d(&map_a, &full[stage], sa, kb * BK, m0);
+          else
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(&map_a, &full[stage], sa + i * 8192, m0 + i * 64, kb * BK);
+          if (!B_MN) tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kb * BK, n0);
+          else
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&map_w, &full[stage], sa + A_BYTES + i * 8192, n0 + i * 64, kb * BK);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);             // epilogue drained this accumulator
@@ -193,13 +211,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           mbar_wait(&full[stage], phase);                       // TMA bytes have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+          const uint64_t da = A_MN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+          const uint64_t db = B_MN ? make_smem_desc_mn(sa + A_BYTES) : make_smem_desc(sa + A_BYTES);
+          // advancing 16 contraction steps: +32 bytes inside the swizzle atom (K-major) / +16 rows of 128 B (MN-major)
+          constexpr uint32_t ka = A_MN ? (UK * 128) >> 4 : (UK * 2) >> 4, kw = B_MN ? (UK * 128) >> 4 : (UK * 2) >> 4;
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // advancing K inside the swizzle atom = +32 bytes on the (pre-swizzle) start address
-            umma_bf16(tmem_d, da + (uint64_t)((k * UK * 2) >> 4), db + (uint64_t)((k * UK * 2) >> 4), idesc,
-                      (kb | k) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(k * ka), db + (uint64_t)(k * kw), idesc, (kb | k) ? 1u : 0u);
           tcgen05_commit(&empty[stage]);                        // frees the smem slot when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -466,19 +484,19 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int ACT, bool RES, bool STATS = false>
+template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES, STATS><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
@@ -523,6 +541,54 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   if (bn == 256) CN_TC_DISPATCH(256);
   CN_TC_DISPATCH(128);
 #undef CN_TC_DISPATCH
+}
+
+// ---------------------------------------------------------------- backward GEMMs without transposed copies
+// C[M,N] = op(A) op(W)^T with either operand given in its "contraction-major" storage:
+//   a_mn = 0: A is [M, K] (row pitch lda)        a_mn = 1: A is [K, M] (row pitch lda)  -> C = A^T ...
+//   w_mn = 0: W is [N, K] (row pitch ldw)        w_mn = 1: W is [K, N] (row pitch ldw)
+// dX = dY W      -> A = dY [M,N'] (a_mn 0), W = weight [N',K'] stored [contraction, out] (w_mn 1)
+// dW = dY^T X    -> A = dY [M',N] stored [contraction, rows] (a_mn 1), W = X [M',K] (w_mn 1)
+namespace {
+bool make_map_mn(CUtensorMap* map, const void* base, int64_t kc, int64_t mn, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)kc};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, int w_mn, float* out_f32,
+                               void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K, cn_stream_t stream_) {
+  if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || ldc < N) return CN_ERR_BAD_ARG;
+  if (lda < (a_mn ? M : K) || ldw < (w_mn ? N : K)) return CN_ERR_BAD_ARG;
+  if (!w_mn) return CN_ERR_UNSUPPORTED;                        // (K-major W: cn_gemm_bf16 covers it when a_mn == 0)
+  if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return CN_ERR_UNSUPPORTED;
+  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
+  if (M == 0 || N == 0) return CN_OK;
+  const int bn = N > 128 ? 256 : 128;
+  CUtensorMap ma, mw;
+  const bool ok_a = a_mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BM);
+  if (!ok_a || !make_map_mn(&mw, W, K, N, ldw)) return CN_ERR_DEVICE;
+  Epilogue ep;
+  ep.bias = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = 1.f; ep.act = CN_ACT_NONE;
+  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
+  ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
+  ep.st_target = nullptr; ep.st_target_logit = nullptr;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int m = (int)M, n = (int)N, k = (int)K;
+  if (a_mn) {
+    if (bn == 256) return launch_tc<256, CN_ACT_NONE, false, false, true, true>(ma, mw, ep, m, n, k, stream);
+    return launch_tc<128, CN_ACT_NONE, false, false, true, true>(ma, mw, ep, m, n, k, stream);
+  }
+  if (bn == 256) return launch_tc<256, CN_ACT_NONE, false, false, false, true>(ma, mw, ep, m, n, k, stream);
+  return launch_tc<128, CN_ACT_NONE, false, false, false, true>(ma, mw, ep, m, n, k, stream);
 }
 
 // ================================================================ conv front-end (fast mode)
@@ -684,19 +750,9 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
                                                            int Tin, int Fin, int T1, int F1, int C, int64_t n_pos,
                                                            __nv_bfloat16* __restrict__ y) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  auto taps = [&](int64_t pos, float (&in)[9]) {
-    const int f = (int)(pos % F1), t = (int)((pos / F1) % T1);
-    const int64_t b = pos / ((int64_t)F1 * T1);
-#pragma unroll
-    for (int dt = 0; dt < 3; ++dt)
-#pragma unroll
-      for (int df = 0; df < 3; ++df) {
-        const int ti = 2 * t + dt - 1, fi = 2 * f + df - 1;
-        in[dt * 3 + df] = (ti >= 0 && ti < Tin && fi >= 0 && fi < Fin) ? __ldg(x + b * sbx + (int64_t)ti * stx + fi) : 0.f;
-      }
-  };
+  const int warp_g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int n_rows = (int)(n_pos / F1);                    // (utterance, output frame) rows; one warp walks a row's bins
   for (int c0 = lane * 8; c0 < C; c0 += 256) {
     float wr[8][9], br[8];
 #pragma unroll
@@ -705,33 +761,46 @@ __global__ void __launch_bounds__(256) conv1_direct_kernel(const float* __restri
 #pragma unroll
       for (int k = 0; k < 9; ++k) wr[q][k] = w[(c0 + q) * 9 + k];
     }
-    auto emit = [&](int64_t pos, const float (&in)[9]) {
-      uint32_t pk[4];
+    for (int row = warp_g; row < n_rows; row += n_warps) {
+      const int b = row / T1, t = row - b * T1;
+      const float* xb = x + (int64_t)b * sbx;
+      const float* xr[3];
+      bool okr[3];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float a0 = br[2 * q], a1 = br[2 * q + 1];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          a0 = fmaf(in[k], wr[2 * q][k], a0);
-          a1 = fmaf(in[k], wr[2 * q + 1][k], a1);
-        }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
-        pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int dt = 0; dt < 3; ++dt) {
+        const int ti = 2 * t + dt - 1;
+        okr[dt] = ti >= 0 && ti < Tin;
+        xr[dt] = xb + (int64_t)(okr[dt] ? ti : 0) * stx;
       }
-      *reinterpret_cast<uint4*>(y + pos * C + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    };
-    int64_t pos = warp_g;
-    for (; pos + n_warps < n_pos; pos += 2 * n_warps) {
-      float ia[9], ib[9];
-      taps(pos, ia);
-      taps(pos + n_warps, ib);
-      emit(pos, ia);
-      emit(pos + n_warps, ib);
-    }
-    if (pos < n_pos) {
-      float ia[9];
-      taps(pos, ia);
-      emit(pos, ia);
+      __nv_bfloat16* yrow = y + (int64_t)row * F1 * C + c0;
+      // sliding window over the bins: the tap column 2f+1 of bin f is the column 2(f+1)-1 of bin f+1
+      float prev[3];
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) prev[dt] = 0.f;       // column -1 (left padding)
+      for (int f = 0; f < F1; ++f) {
+        float in[9];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          const int f1 = 2 * f, f2 = 2 * f + 1;
+          in[dt * 3 + 0] = prev[dt];
+          in[dt * 3 + 1] = (okr[dt] && f1 < Fin) ? __ldg(xr[dt] + f1) : 0.f;
+          in[dt * 3 + 2] = (okr[dt] && f2 < Fin) ? __ldg(xr[dt] + f2) : 0.f;
+          prev[dt] = in[dt * 3 + 2];
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float a0 = br[2 * q], a1 = br[2 * q + 1];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            a0 = fmaf(in[k], wr[2 * q][k], a0);
+            a1 = fmaf(in[k], wr[2 * q + 1][k], a1);
+          }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+          pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(yrow + (int64_t)f * C) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
     }
   }
 }
@@ -761,7 +830,7 @@ extern "C" int cn_conv_frontend_bf16(const float* x, int64_t sbx, int64_t stx, i
   cudaStream_t stream = (cudaStream_t)stream_;
   {
     const int64_t n_pos = B * T1 * F1;
-    int64_t blocks = (n_pos + 7) / 8;                      // 8 warps per block, one position per warp step
+    int64_t blocks = (B * T1 + 7) / 8;                     // 8 warps per block, one (utterance, frame) row per warp step
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
     conv1_direct_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, sbx, stx, w1, b1, (int)Tin, (int)Fin, (int)T1, (int)F1, (int)C,
                                                                   n_pos, (__nv_bfloat16*)mid);

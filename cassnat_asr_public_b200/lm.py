@@ -42,15 +42,19 @@ class TransformerLM(nn.Module):
         ops.set_precision(mode)
         return self
 
-    def _hidden(self, tgt, tgt_mask):
+    def _hidden(self, tgt, tgt_mask, causal=False):
+        if causal and ops.is_bf16():
+            ops.mark_causal(tgt_mask)
         return self.encoder(self.text_embed(tgt), tgt_mask)
 
     def forward(self, tgt, tgt_mask):
         return self.out_generator(self._hidden(tgt, tgt_mask))
 
-    def score_tokens(self, tgt, tgt_mask, ids):
-        """log p(ids[n,u] | tgt[n,:u+1]) for every position: [N,U] f32 (what cassnat.py:517 gathers)."""
-        h = self._hidden(tgt, tgt_mask)
+    def score_tokens(self, tgt, tgt_mask, ids, causal=False):
+        """log p(ids[n,u] | tgt[n,:u+1]) for every position: [N,U] f32 (what cassnat.py:517 gathers).
+        causal=True promises tgt_mask is zero above the diagonal (mask & tril), which lets the fast-mode attention
+        skip those key tiles."""
+        h = self._hidden(tgt, tgt_mask, causal)
         gen = self.out_generator
         if ops.is_bf16() and not gen.add_norm and h.shape[-1] % 8 == 0:
             st = ops.head_rowstats(h, gen.proj.weight, gen.proj.bias, target=ids)

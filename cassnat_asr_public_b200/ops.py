@@ -407,6 +407,13 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     return o32 if o32 is not None else o16
 
 
+def mark_causal(mask):
+    """Tags a [B,U,U] mask whose entries above the diagonal are all zero (mask & tril): the tcgen05 attention then
+    skips the key tiles above the diagonal (the mask bits are still applied inside the diagonal tiles)."""
+    mask._cn_causal = True
+    return mask
+
+
 def attach_length_hints(mask, kv_len=None, q_len=None):
     """Tags a KEY mask ([B,1,Tk], prefix-shaped or not) with per-utterance hints for the tcgen05
     attention: kv_len[b] = (index of the last unmasked key) + 1, q_len[b] = number of leading query
@@ -444,7 +451,7 @@ def _segment_attention_bf16(q_rows, k, v, seg, ylens, src_mask, src_size, left, 
         q_rows = q_rows.contiguous()
     call("cn_attention_bf16_bits", ptr(q_rows), q_rows.stride(0), 0, ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(bits), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
-         ptr(kv_len), ptr(q_len), stream(), work=dict(flops=4.0 * B * U * T * d, bytes=2.0 * B * d * (2 * T + U)))
+         ptr(kv_len), ptr(q_len), 0, stream(), work=dict(flops=4.0 * B * U * T * d, bytes=2.0 * B * d * (2 * T + U)))
     return out
 
 
@@ -470,7 +477,7 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
                 pass
         call("cn_attention_bf16_bits", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
              ptr(v), v.stride(1), v.stride(0), ptr(bits), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1),
-             out.stride(0), None, None, stream(),
+             out.stride(0), None, None, int(bool(getattr(mask, "_cn_causal", False)) and Tq == Tk), stream(),
              work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
         return out
     if rel is not None:

@@ -273,7 +273,10 @@ int cn_trigger_mask_bits(const int32_t* seg, const int64_t* ylens, const uint8_t
 int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                            const void* V, int64_t ldv, int64_t sbv, const uint32_t* mask_bits, int64_t B, int64_t h,
                            int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo, int64_t sbo,
-                           const int32_t* kv_len, const int32_t* q_len, cn_stream_t stream);
+                           const int32_t* kv_len, const int32_t* q_len,
+                           int causal_hint /* 1: the mask is zero for every key j > query i (LM ranker): key tiles above
+                                              the diagonal are not computed; the bits are still applied inside */,
+                           cn_stream_t stream);
 
 /* Fast mode: relative-position (Transformer-XL style) self-attention on tcgen05.
  *   replaces (fast mode): RelMultiHeadedAttention.forward      src/models/modules/attention.py:104-143
@@ -365,6 +368,16 @@ int cn_glu_dwconv_groupnorm_act_bwd(const void* y, int y_is_bf16, int64_t ldy, i
                                     int64_t B, int64_t L, int64_t C, int64_t ksz, const float* dout, float* dy,
                                     float* d_dw_weight, float* d_dw_bias, float* dgamma, float* dbeta,
                                     void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
+/* Backward GEMMs on tcgen05 without transposed copies: C[M,N] = op(A) op(W)^T, bf16 operands, fp32 accumulate.
+ *   a_mn = 0: A is [M,K] row-major (pitch lda);  a_mn = 1: A is stored [K,M] (the contraction index is the row)
+ *   w_mn = 1: W is stored [K,N] (required);      K-major W with a_mn = 0 is cn_gemm_bf16.
+ * The MN-major operands are fed to the MMA as they are (TMA boxes of 64 contraction rows x 64 elements, MN-major
+ * shared-memory descriptors):  dX = dY W -> (A = dY, a_mn 0; W = weight [out,in], w_mn 1);
+ *                              dW = dY^T X -> (A = dY, a_mn 1; W = X, w_mn 1).
+ *   replaces: autograd of F.linear                            src/models/modules/positionff.py:15-16 etc. */
+int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, int w_mn, float* out_f32,
+                    void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K, cn_stream_t stream);
 
 /* out(bf16)[C, ldo] = in^T, in [R,C] f32 or bf16 with row stride ldi: operand staging of the
  * tensor-core backward GEMMs (dX = dY W needs W^T rows, dW = dY^T X needs dY^T and X^T rows). */

@@ -151,3 +151,21 @@ def test_segment_attention_tc_matches_fp32_segment_kernel(left, right):
     for bi in range(B):
         n = int(q_len[bi])
         assert torch.equal(hinted[bi, :n], got[bi, :n])
+
+
+def test_attention_tc_causal_hint():
+    """Causal per-row mask (LM ranker): with the causal hint the key tiles above the diagonal are skipped and the
+    result is unchanged."""
+    B, U, h = 3, 500, 2
+    d = 64 * h
+    torch.manual_seed(8)
+    q, k, v = (torch.randn(B, U, d).bfloat16().to(DEV) for _ in range(3))
+    lens = torch.tensor([500, 257, 130])
+    key = (torch.arange(U)[None] < lens[:, None]).unsqueeze(1)
+    mask = (key & torch.tril(torch.ones(U, U, dtype=torch.bool)).unsqueeze(0)).to(DEV)
+    plain = ops.attention(q, k, v, mask, h).float()
+    hinted = ops.attention(q, k, v, ops.mark_causal(mask.clone()), h).float()
+    valid = mask.any(-1)                                                   # rows with at least one key
+    assert torch.equal(plain[valid], hinted[valid])
+    want = ref_attention(q.float().cpu(), k.float().cpu(), v.float().cpu(), mask.cpu(), h)
+    assert rel(plain.cpu()[valid.cpu()], want[valid.cpu()]) < 2e-2

@@ -83,3 +83,20 @@ def test_fused_head_rowstats(M, N, K):
     st = ops.head_rowstats(x, w, b, target=tgt)
     ref = logits.gather(1, tgt.clamp(min=0).long().unsqueeze(1)).squeeze(1).masked_fill(tgt < 0, 0.0)
     assert torch.equal(st["target_logit"], ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (1312, 512, 2048), (1000, 72, 520), (5000, 512, 1312)])
+def test_gemm_mn_major_operands(M, N, K):
+    """cn_gemm_bf16_mn: the backward GEMMs with operands in contraction-major storage (no transposed copies):
+    C = A W with W stored [K,N] (dX = dY W), and C = A^T W with A stored [K,M], W stored [K,N] (dW = dY^T X)."""
+    from cassnat_asr_public_b200._lib import call, ptr, stream
+    torch.manual_seed(M + N + K)
+    pad = lambda n: (n + 7) // 8 * 8
+    a = torch.randn(M, pad(K)).bfloat16().to(DEV)[:, :K]              # [M,K] K-major, padded pitch
+    at = torch.randn(K, pad(M)).bfloat16().to(DEV)[:, :M]             # [K,M] contraction-major
+    w = (torch.randn(K, pad(N)) / K ** 0.5).bfloat16().to(DEV)[:, :N]  # [K,N] contraction-major
+    for a_mn, A in ((0, a), (1, at)):
+        out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+        call("cn_gemm_bf16_mn", ptr(A), A.stride(0), a_mn, ptr(w), w.stride(0), 1, ptr(out), None, N, M, N, K, stream())
+        ref = (A.double().t() if a_mn else A.double()) @ w.double()
+        assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5, (a_mn, M, N, K)

@@ -37,6 +37,7 @@ def test_lm_matches_reference(precision, tol):
             got = model(ids, mask).float().cpu()
             tgt = torch.roll(ids, -1, 1)
             sc = model.score_tokens(ids, mask, tgt).float().cpu()
+            sc_causal = model.score_tokens(ids, mask.clone(), tgt, causal=True).float().cpu()   # tile-skipping hint
     finally:
         ops.set_precision("fp32")
     valid = torch.from_numpy(z["mask"]).diagonal(dim1=1, dim2=2)            # positions that can see themselves
@@ -44,5 +45,6 @@ def test_lm_matches_reference(precision, tol):
         assert ((got - want).abs().max() / want.abs().max()).item() < tol
     else:
         assert (got - want)[valid].abs().max().item() < 0.05
+    assert torch.equal(sc[valid], sc_causal[valid])
     ref_sc = want.gather(-1, tgt.cpu().unsqueeze(-1)).squeeze(-1)
     assert (sc - ref_sc)[valid].abs().max().item() < (1e-3 if tol is not None else 0.05)

@@ -81,6 +81,19 @@ def act_forward(x, act, out_bf16=False):
     return y
 
 
+USE_MN_GEMM = True      # backward GEMMs read dY / X / W in place (MN-major tcgen05 operands) instead of transposed copies
+
+
+def gemm_bf16_mn(A, a_mn, W, M, N, K, out_dtype):
+    """out[M,N] = op(A) @ W with W stored [K,N]; a_mn: A stored [K,M] (contraction-major) instead of [M,K]."""
+    o32 = torch.empty(M, N, dtype=torch.float32, device=A.device) if out_dtype == torch.float32 else None
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=A.device) if out_dtype == torch.bfloat16 else None
+    call("cn_gemm_bf16_mn", ptr(A), A.stride(0), int(a_mn), ptr(W), W.stride(0), 1, ptr(o32), ptr(o16), N, M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (4.0 if o32 is not None else 2.0)),
+         tag=(f"cn_gemm_bf16_mn[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+    return o32 if o32 is not None else o16
+
+
 # =============================================================================== linear
 class Linear(torch.autograd.Function):
     """residual + alpha * act(x W^T + b)  (ops.linear); dX = dpre W, dW = dpre^T X, db = colsum(dpre),
@@ -138,7 +151,14 @@ class Linear(torch.autograd.Function):
             dpre, db = gy2, None
         x2 = x.reshape(-1, K)
         dx = dw = None
-        if ctx.tc and N % 8 == 0:
+        if ctx.tc and N % 8 == 0 and USE_MN_GEMM:
+            d16 = ops.cast_bf16(dpre)                                              # [M,N], read in place by both GEMMs
+            if needs[0]:
+                dx = gemm_bf16_mn(d16, False, ctx.wb, M, K, N, ctx.x_dtype)        # dY [M,N] x W [N,K] (contraction-major)
+            if needs[1]:
+                xb = x2 if x2.is_contiguous() else x2.contiguous()
+                dw = gemm_bf16_mn(d16, True, xb, N, K, M, torch.float32)           # dY^T x X, both contraction-major
+        elif ctx.tc and N % 8 == 0:
             d16 = ops.cast_bf16(dpre)
             if needs[0]:
                 wt = transpose_bf16(ctx.wb)                                        # [K, Npad]

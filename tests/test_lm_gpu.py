@@ -48,3 +48,52 @@ def test_lm_matches_reference(precision, tol):
     assert torch.equal(sc[valid], sc_causal[valid])
     ref_sc = want.gather(-1, tgt.cpu().unsqueeze(-1)).squeeze(-1)
     assert (sc - ref_sc)[valid].abs().max().item() < (1e-3 if tol is not None else 0.05)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampled_decode_with_lm_mirror_matches_generic_ranker_path(precision):
+    """Sampled-alignment decode (cassnat.py:499-561) with the LM mirror as ranker: the fused `score_tokens` branch of
+    `_rescore` picks the same samples and returns the same hypotheses as the generic branch that materialises the
+    [B*S,U,V] log-probabilities of the same LM."""
+    from cassnat_asr_public_b200.cassnat import make_model
+    a = dict(use_conv_enc=False, use_conv_dec=False, model_type="transformer", pos_type="absolute", n_head=2, d_model=128,
+             d_encff=256, d_decff=256, d_ff=256, dropout=0.0, N_enc=1, N_extra=1, N_self_dec=1, N_mix_dec=2, vocab_size=60,
+             interctc_alpha=0, interce_alpha=0, interctc_layer=0, interce_layer=0, padding_idx=0, label_smooth=0.1,
+             share_ff=False, enc_max_relative_len=20, enc_kernel_size=7, dec_max_relative_len=8, dec_kernel_size=3,
+             use_trigger=True, use_best_path=False, sample_topk=0, ctc_alpha=0.5, att_alpha=1.0, save_embedding=False,
+             use_unimask=False, src_trigger=False, left_trigger=0, right_trigger=0, test_hitrate=False, sample_num=4,
+             decode_type="att_only", threshold=0.9, rank_model="lm", lm_weight=0, beam_width=1, length_penalty=0, use_gpu=True)
+    args = SimpleNamespace(**a)
+    torch.manual_seed(3)
+    model = make_model(16, args).to(DEV).eval()
+    _, lm = _load()
+
+    class Plain(torch.nn.Module):                      # same LM without the fused entry point
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, ids, mask):
+            return self.inner(ids, mask)
+
+    g = torch.Generator().manual_seed(9)
+    B, T = 3, 40
+    enc_h = torch.randn(B, T, 128, generator=g).to(DEV)
+    lens = torch.tensor([40, 25, 33])
+    mask = (torch.arange(T)[None] < lens[:, None]).unsqueeze(1).to(DEV)
+    ratio = ((lens.float() + 0.5) / T).to(DEV)
+    vocab = SimpleNamespace(word2index={"sos": 1, "eos": 2, "blank": 0})
+    model.set_precision(precision)
+    try:
+        outs = []
+        for ranker in (lm, Plain(lm)):
+            torch.manual_seed(555)                         # same host-drawn select bits (cassnat.py:373)
+            with torch.no_grad():
+                out, _, keep = model.decode_from_encoder(enc_h, mask, ratio, vocab, args, lm_model=ranker, return_intermediates=True)
+            outs.append(([o[0]["hyp"] for o in out], keep["best_sample"].cpu().tolist()))
+    finally:
+        model.set_precision("fp32")
+    if precision == "fp32":
+        assert outs[0] == outs[1]
+    else:               # bf16: the two heads round differently (fused epilogue vs materialised logits); near-ties may flip
+        assert len(outs[0][0]) == B and len(outs[1][0]) == B

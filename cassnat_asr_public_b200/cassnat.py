@@ -11,7 +11,6 @@ the extractor), the MAD memory K/V projections of all layers are one GEMM, and t
 """
 import copy
 import math
-from types import SimpleNamespace
 
 import torch
 import torch.nn as nn

@@ -1,14 +1,17 @@
 // bf16 tensor-core GEMM for sm_100a: C[M,N] = residual + alpha * act(A[M,K] * W[N,K]^T + bias)
 //
 //   * persistent, one CTA per SM, warp-specialised (1 TMA producer lane, 1 MMA issuer lane,
-//     4 epilogue warps);
+//     8 epilogue warps);
 //   * operands: bf16, both K-major, staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
 //     4-stage shared-memory ring guarded by mbarriers;
 //   * math: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, fp32 accumulators in
 //     TMEM, two accumulator stages (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 //     tile i+1;
-//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation / scale /
-//     residual in registers -> fp32 and/or bf16 rows straight to global memory.
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> XOR-swizzled shared-memory transpose -> bias /
+//     activation / scale / residual -> coalesced fp32 and/or bf16 rows; or (STATS) per-row argmax / runner-up /
+//     log-sum-exp / target logit without writing the matrix;
+//   * operands may also be MN-major (backward GEMMs), and the same mainloop runs the front-end's 3x3 stride-2
+//     convolution as an implicit GEMM (4-D strided TMA boxes).
 //
 // Replaces (fast mode) the nn.Linear / Conv1d(k=1) / Generator.proj call sites of
 // src/models/modules/{attention,positionff,conformer_related}.py and src/models/cassnat.py:105,113.

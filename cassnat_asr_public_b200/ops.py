@@ -3,7 +3,6 @@ allocates outputs with torch and calls one entry point of the C ABI (include/cas
 Signatures and return conventions follow the reference methods they stand in for
 (src/models/cassnat.py:259-418); every operator raises if its input is not on a CUDA device.
 """
-import math
 
 import torch
 

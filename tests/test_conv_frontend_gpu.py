@@ -1,7 +1,6 @@
 """GPU: the fast-mode encoder front-end (direct conv1 + implicit-GEMM conv2 on tcgen05 with 4-D strided TMA
 boxes, channels-last bf16) against torch's fp32 convolutions (src/models/modules/embedding.py:103-119).
 Stated bf16 tolerance: 2e-2 of the output's max."""
-import math
 
 import pytest
 import torch

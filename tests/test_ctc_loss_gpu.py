@@ -1,7 +1,6 @@
 """GPU: K10 CTC loss forward-backward against torch.nn.functional.ctc_loss (the arithmetic the
 reference calls, cassnat.py:126,232) evaluated on CPU in float64, compared at the logits level.
 Tolerance: rel 1e-3 (north_star) — observed ~1e-5."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -419,8 +419,10 @@ class CassNAT(nn.Module):
         are the log-probabilities the caller decodes for WER and carry no gradient of their own.
         Under torch.no_grad() the same values are produced without a tape, and
         `self.last_ctc_grad` = ctc_alpha * d ctc_loss / d ctc logits (K10) is kept for inspection."""
-        enc_h, x_mask = self.encode(src, src_mask)
-        return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args)
+        x, x_mask = self.src_embed(src, src_mask)
+        enc = self.encoder(x, x_mask, args.interctc_alpha, args.interctc_layer)         # :139-143
+        enc_h, inter_h = enc if args.interctc_alpha > 0 else (enc, None)                  # :151
+        return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=inter_h)
 
     def zero_dropout(self):
         """The kernels implement no dropout; training runs with every dropout probability at 0.
@@ -431,13 +433,21 @@ class CassNAT(nn.Module):
                 m.p_drop = 0.0
         return self
 
-    def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args):
+    def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=None):
         """Post-encoder part of CassNAT.forward (cassnat.py:148-257): CTC posteriors, Viterbi forced
-        alignment, trigger segments, extractor -> SAD -> MAD -> log-probs, CTC + label-smoothing loss."""
-        if not args.use_trigger or args.use_best_path or args.interctc_alpha > 0 or args.interce_alpha > 0:
-            raise NotImplementedError("only the shipped training configuration is provided: use_trigger, Viterbi "
-                                      "alignment, no intermediate CTC/CE losses (use_best_path is broken upstream)")
+        alignment, trigger segments, extractor -> SAD -> MAD -> log-probs, CTC + label-smoothing loss, plus the
+        optional intermediate losses: interctc on `inter_h` (the encoder tap, :151-153,236-239) and interce on the
+        SAD (selfce) or MAD (mixce) tap (:194-197,216-221,253-255)."""
+        if not args.use_trigger or args.use_best_path:
+            raise NotImplementedError("training needs use_trigger with the Viterbi alignment (use_best_path is broken "
+                                      "upstream: cassnat.py:168,246)")
         assert args.ctc_alpha > 0
+        selfce, mixce = getattr(args, "selfce_alpha", 0), getattr(args, "mixce_alpha", 0)
+        if args.interctc_alpha > 0 and inter_h is None:
+            raise ValueError("interctc_alpha > 0 needs the encoder's intermediate output (inter_h)")
+        if selfce > 0 and not self._conformer_dec:
+            raise NotImplementedError("selfce with the transformer decoder: the reference hands the MAD a 1-tuple there "
+                                      "(cassnat.py:196) and fails")
         B, T, d = enc_h.shape
         dev = enc_h.device
         blank = args.padding_idx
@@ -461,11 +471,23 @@ class CassNAT(nn.Module):
                                                   args.left_trigger, args.right_trigger, True)[0]
         tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)             # :185-187 (K5)
         ac_embed = self.acembed_extractor.forward_segments(self._pe_rows(enc_h, ymax), mem, seg_ctx, dense_trigger)
-        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
-        if args.use_unimask:
-            raise NotImplementedError("use_unimask in training")
+        inter_tap = None
+        if selfce > 0:                                                                  # :193-197 (conformer: (x, pos, tap))
+            sad = self.embed_mapper(ac_embed, tgt_mask, selfce, args.interce_layer)
+            pred_embed, inter_tap = sad[:-1], sad[-1]
+        else:
+            pred_embed = self.embed_mapper(ac_embed, tgt_mask)
+        dec_in, dec_mask = pred_embed, tgt_mask
+        if args.use_unimask:                                                            # :205-208
+            if isinstance(pred_embed, tuple):
+                raise NotImplementedError("use_unimask with the conformer decoder raises in the reference (cassnat.py:206)")
+            dec_in = torch.cat([torch.zeros_like(pred_embed[:, :1]), pred_embed[:, :-1]], 1)
+            dec_mask = tgt_mask & torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=dev)).unsqueeze(0)
         mem_mask = dense_trigger() if args.src_trigger else x_mask
-        dec_h = self.decoder(pred_embed, mem, mem_mask, tgt_mask)
+        if mixce > 0:                                                                   # :216-221
+            dec_h, inter_tap = self.decoder(dec_in, mem, mem_mask, dec_mask, mixce, args.interce_layer)
+        else:
+            dec_h = self.decoder(dec_in, mem, mem_mask, dec_mask)
         if taped:
             z = self.att_generator.logits(dec_h)                                        # :226 + :248
             att_out, att_loss = grad.LabelSmoothingFromLogits.apply(z.reshape(-1, z.size(-1)), tgt_label.reshape(-1),
@@ -479,6 +501,24 @@ class CassNAT(nn.Module):
             att_loss = label_smoothing_loss(att_out.view(-1, att_out.size(-1)), tgt_label.reshape(-1),
                                             args.vocab_size, args.padding_idx, args.label_smooth)   # :248
         loss = args.ctc_alpha * ctc_loss + args.att_alpha * att_loss
+        if args.interctc_alpha > 0:                                                     # :236-239
+            if taped:
+                _, ic_loss = grad.CtcFromLogits.apply(self.interctc_generator.logits(inter_h), tgt_label, frames,
+                                                      label_sizes, blank)
+            else:
+                ic_loss = ops.ctc_loss(self.interctc_generator(inter_h), tgt_label, frames, label_sizes, blank,
+                                       want_grad=False)[0]
+            loss = loss + args.interctc_alpha * ic_loss
+        if args.interce_alpha > 0:                                                      # :253-255
+            if taped:
+                zi = self.interce_generator.logits(inter_tap)
+                _, ie_loss = grad.LabelSmoothingFromLogits.apply(zi.reshape(-1, zi.size(-1)), tgt_label.reshape(-1),
+                                                                 args.padding_idx, args.label_smooth)
+            else:
+                io = self.interce_generator(inter_tap)
+                ie_loss = label_smoothing_loss(io.view(-1, io.size(-1)), tgt_label.reshape(-1), args.vocab_size,
+                                               args.padding_idx, args.label_smooth)
+            loss = loss + args.interce_alpha * ie_loss
         return ctc_out, att_out, loss, ctc_loss, att_loss
 
 

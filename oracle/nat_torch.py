@@ -167,21 +167,28 @@ def trf_extractor(pe_rows, mem, trigger, sd, h, pfx="acembed_extractor"):
     return x
 
 
-def trf_sad(x, tgt_mask, sd, h, pfx="embed_mapper"):
+def trf_sad(x, tgt_mask, sd, h, pfx="embed_mapper", tap=None):
     for i in range(_n_layers(sd, pfx)):
         x = trf_self_layer(x, tgt_mask, sd, f"{pfx}.layers.{i}", h)
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return x
 
 
-def trf_mad(x, mem, src_mask, tgt_mask, sd, h, pfx="decoder"):
+def trf_mad(x, mem, src_mask, tgt_mask, sd, h, pfx="decoder", tap=None):
     for i in range(_n_layers(sd, pfx)):
         x = trf_mix_layer(x, mem, src_mask, tgt_mask, sd, f"{pfx}.layers.{i}", h)
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return layer_norm(x, sd, pfx + ".norm")
 
 
-def trf_encoder(x, mask, sd, h, pfx="encoder"):
+def trf_encoder(x, mask, sd, h, pfx="encoder", tap=None):
+    """tap = [layer, None]: tap[1] receives the (un-normalised) output of that layer (interctc, fanat_blocks.py:92-96)."""
     for i in range(_n_layers(sd, pfx)):
         x = trf_self_layer(x, mask, sd, f"{pfx}.layers.{i}", h)
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return layer_norm(x, sd, pfx + ".norm")
 
 
@@ -208,21 +215,27 @@ def con_extractor(pe_rows, mem, trigger, sd, h, max_rel, pfx="acembed_extractor"
     return x, pos
 
 
-def con_sad(x, pos, tgt_mask, sd, h, pfx="embed_mapper"):
+def con_sad(x, pos, tgt_mask, sd, h, pfx="embed_mapper", tap=None):
     for i in range(_n_layers(sd, pfx)):
         x = con_self_layer(x, tgt_mask, pos, sd, f"{pfx}.layers.{i}", h)
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return x, pos
 
 
-def con_mad(x, pos, mem, src_mask, tgt_mask, sd, h, pfx="decoder"):
+def con_mad(x, pos, mem, src_mask, tgt_mask, sd, h, pfx="decoder", tap=None):
     for i in range(_n_layers(sd, pfx)):
         x = con_self_layer(x, tgt_mask, pos, sd, f"{pfx}.layers.{i}", h, with_src=(mem, src_mask))
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return layer_norm(x, sd, pfx + ".norm")
 
 
-def con_encoder(x, pos, mask, sd, h, pfx="encoder"):
+def con_encoder(x, pos, mask, sd, h, pfx="encoder", tap=None):
     for i in range(_n_layers(sd, pfx)):
         x = con_self_layer(x, mask, pos, sd, f"{pfx}.layers.{i}", h)
+        if tap is not None and i == tap[0] - 1:
+            tap[1] = x
     return layer_norm(x, sd, pfx + ".norm")
 
 
@@ -242,17 +255,19 @@ def conv_embedding(src, src_mask, sd, cfg, pfx="src_embed"):
     return x + sinusoid_table(d)[:t].unsqueeze(0), mask
 
 
-def encode(src, src_mask, sd, cfg):
+def encode(src, src_mask, sd, cfg, tap=None):
     x, mask = conv_embedding(src, src_mask, sd, cfg)
     if cfg.use_conv_enc:
-        return con_encoder(x[0], x[1], mask, sd, cfg.n_head), mask
-    return trf_encoder(x, mask, sd, cfg.n_head), mask
+        return con_encoder(x[0], x[1], mask, sd, cfg.n_head, tap=tap), mask
+    return trf_encoder(x, mask, sd, cfg.n_head, tap=tap), mask
 
 
 # ----------------------------------------------------------------- the conditioned path
-def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg):
+def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg, taps=None):
     """cassnat.py:481-497 (== :191-226): PE queries -> extractor -> SAD -> MAD -> log-probs.
-    Returns (att_out, ac_embed, pred_embed, dec_h)."""
+    Returns (att_out, ac_embed, pred_embed, dec_h).  taps = {"sad": [layer, None], "mad": [layer, None]} collect
+    the intermediate hidden states of the interce losses (cassnat.py:194-197,216-221)."""
+    taps = taps or {}
     bs, _, d = enc_h.shape
     h = cfg.n_head
     pe = sinusoid_table(d).unsqueeze(0).repeat(bs, 1, 1)[:, :ymax, :]
@@ -271,14 +286,14 @@ def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg):
 
     if cfg.use_conv_dec:
         ac, pos = con_extractor(pe, enc_h, trigger, sd, h, cfg.dec_max_relative_len)
-        pred, pos = con_sad(ac, pos, tgt_mask, sd, h)
+        pred, pos = con_sad(ac, pos, tgt_mask, sd, h, tap=taps.get("sad"))
         dec_in, dec_mask = unimask(pred)
-        dec_h = con_mad(dec_in, pos, enc_h, mem_mask, dec_mask, sd, h)
+        dec_h = con_mad(dec_in, pos, enc_h, mem_mask, dec_mask, sd, h, tap=taps.get("mad"))
     else:
         ac = trf_extractor(pe, enc_h, trigger, sd, h)
-        pred = trf_sad(ac, tgt_mask, sd, h)
+        pred = trf_sad(ac, tgt_mask, sd, h, tap=taps.get("sad"))
         dec_in, dec_mask = unimask(pred)
-        dec_h = trf_mad(dec_in, enc_h, mem_mask, dec_mask, sd, h)
+        dec_h = trf_mad(dec_in, enc_h, mem_mask, dec_mask, sd, h, tap=taps.get("mad"))
     return generator(dec_h, sd, "att_generator"), ac, pred, dec_h
 
 
@@ -359,23 +374,47 @@ def label_smoothing_loss(logp, target, V, padding_idx, smoothing):
     return kl.masked_fill(~keep.unsqueeze(1), 0).sum() / keep.sum().item()
 
 
-def train_forward_from_encoder(enc_h, x_mask, src_size_frames, tgt_label, label_sizes, sd, cfg, t_sample=None):
-    """Post-encoder part of CassNAT.forward (cassnat.py:148-257) with use_trigger=True,
-    use_best_path=False, no intermediate losses."""
+def generator_norm(x, sd, pfx):
+    """Generator(add_norm=True) (cassnat.py:101-113): LayerNorm, projection, log-softmax."""
+    return F.log_softmax(linear(layer_norm(x, sd, pfx + ".norm"), sd, pfx + ".proj"), dim=-1)
+
+
+def train_forward_from_encoder(enc_h, x_mask, src_size_frames, tgt_label, label_sizes, sd, cfg, t_sample=None, inter_h=None):
+    """Post-encoder part of CassNAT.forward (cassnat.py:148-257) with use_trigger=True, use_best_path=False.
+    Intermediate losses: interctc_alpha > 0 takes `inter_h` (the encoder tap, :151-153,236-239); interce_alpha > 0
+    taps the SAD (selfce, :194-197) or the MAD (mixce, :216-221) after make_model's split of interce_layer (:73-83)."""
     ctc_out = generator(enc_h, sd, "ctc_generator")
     aligned, ylen, ymax = A.viterbi_align(ctc_out.detach().numpy(), x_mask.numpy(), src_size_frames.numpy(),
                                           tgt_label[:, :-1].numpy(), label_sizes.numpy(), cfg.padding_idx, t_sample)
     trig, ylen1, ymax1 = A.align_to_mask(aligned, ylen, ymax, x_mask.numpy(), src_size_frames.numpy(), cfg.padding_idx)
     trig = A.expand_trigger_mask(trig, cfg.left_trigger, cfg.right_trigger) & (x_mask.numpy() != 0)
     tgt_mask = torch.from_numpy(A.target_length_mask(ylen1, ymax1))
-    att_out, ac, pred, dec_h = decoder_stack(enc_h, torch.from_numpy(trig), x_mask, tgt_mask, ymax1, sd, cfg)
+    taps = {}
+    selfce, mixce = getattr(cfg, "selfce_alpha", 0), getattr(cfg, "mixce_alpha", 0)
+    if selfce > 0:
+        taps["sad"] = [cfg.interce_layer, None]
+    if mixce > 0:
+        taps["mad"] = [cfg.interce_layer, None]
+    att_out, ac, pred, dec_h = decoder_stack(enc_h, torch.from_numpy(trig), x_mask, tgt_mask, ymax1, sd, cfg, taps)
     ctc_loss = F.ctc_loss(ctc_out.transpose(0, 1), tgt_label, src_size_frames, label_sizes,
                           blank=0, reduction="mean", zero_infinity=True)
     att_loss = label_smoothing_loss(att_out.reshape(-1, att_out.size(-1)), tgt_label.reshape(-1),
                                     cfg.vocab_size, cfg.padding_idx, cfg.label_smooth)
     loss = cfg.ctc_alpha * ctc_loss + cfg.att_alpha * att_loss
+    extra = {}
+    if getattr(cfg, "interctc_alpha", 0) > 0:
+        ic = generator_norm(inter_h, sd, "interctc_generator")
+        extra["interctc_loss"] = F.ctc_loss(ic.transpose(0, 1), tgt_label, src_size_frames, label_sizes,
+                                            blank=0, reduction="mean", zero_infinity=True)
+        loss = loss + cfg.interctc_alpha * extra["interctc_loss"]
+    if getattr(cfg, "interce_alpha", 0) > 0:
+        tap = taps["sad"][1] if selfce > 0 else taps["mad"][1]
+        ie = generator_norm(tap, sd, "interce_generator")
+        extra["interce_loss"] = label_smoothing_loss(ie.reshape(-1, ie.size(-1)), tgt_label.reshape(-1), cfg.vocab_size,
+                                                     cfg.padding_idx, cfg.label_smooth)
+        loss = loss + cfg.interce_alpha * extra["interce_loss"]
     return dict(ctc_out=ctc_out, att_out=att_out, loss=loss, ctc_loss=ctc_loss, att_loss=att_loss,
-                aligned=aligned, trigger=trig, ac_embed=ac, pred_embed=pred, dec_h=dec_h)
+                aligned=aligned, trigger=trig, ac_embed=ac, pred_embed=pred, dec_h=dec_h, **extra)
 
 
 # --------------------------------------------------------------------- LM ranker (SURVEY §8f-3)

@@ -299,3 +299,46 @@ def test_whole_model_backward_vs_reference(name, precision, tol, loss_tol):
     cos = float(torch.dot(mine, ref) / (mine.norm() * ref.norm()))
     assert cos > (0.999999 if precision == "fp32" else 0.998), cos
     model.set_precision("fp32")
+
+
+INTER_CASES = [("trf", "interctc_mixce"), ("trf", "unimask"), ("con", "interctc_selfce"), ("con", "mixce")]
+
+
+@pytest.mark.parametrize("fam,case", INTER_CASES)
+def test_training_call_intermediate_losses_and_unimask(fam, case):
+    """CassNAT.forward with interctc / interce (self- and mix-decoder taps) and use_unimask against the unmodified
+    reference (tests/golden/inter.npz): log-probabilities and losses rel 1e-4, gradients of the generator and
+    LayerNorm parameters rel 1e-3 (fp32 mode)."""
+    import json
+    z = np.load(os.path.join(GOLDEN, "inter.npz"))
+    pre = f"{fam}::{case}::"
+    cfg = json.loads(bytes(z[pre + "cfg_json"]).decode())
+    args = SimpleNamespace(**cfg)
+    build_args = SimpleNamespace(**{**cfg, "interctc_alpha": 0.3, "interce_alpha": 0.2, "interce_layer": 3})
+    model = make_model(16, build_args)                       # built with both intermediate generators, like the fixture
+    sd = {k[len(fam) + 6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{fam}::sd::")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith("pos_enc.pe") for k in missing), (missing, unexpected)
+    model = model.to(DEV).train().zero_dropout()
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    labels, sizes = torch.from_numpy(z["labels"]).to(DEV), torch.from_numpy(z["label_sizes"]).to(DEV)
+    ctc_out, att_out, loss, ctc_loss, att_loss = model(src, mask, size, labels, sizes, args)
+    assert rel(ctc_out, z[pre + "ctc_out"]) < 1e-4 and rel(att_out, z[pre + "att_out"]) < 1e-4
+    want = z[pre + "losses"]
+    for got, w in zip((loss, ctc_loss, att_loss), want):
+        assert abs(float(got.detach()) - float(w)) < 1e-4 * max(1.0, abs(float(w)))
+    loss.backward()
+    params = dict(model.named_parameters())
+    n = 0
+    for key in z.files:
+        if key.startswith(pre + "grad::"):
+            g = z[key]
+            if np.abs(g).max() < 1e-7:
+                continue
+            assert rel(params[key[len(pre) + 6:]].grad, g) < 1e-3, key
+            n += 1
+    assert n > 20
+    # and the same values without a tape
+    with torch.no_grad():
+        out = model(src, mask, size, labels, sizes, args)
+    assert abs(float(out[2]) - float(want[0])) < 1e-4 * max(1.0, abs(float(want[0])))

@@ -126,3 +126,23 @@ def test_lm_port():
     with torch.no_grad():
         got = O.lm_forward(torch.from_numpy(z["ids"]), torch.from_numpy(z["mask"]), sd, int(z["args"][0]))
     assert _rel(got, z["lm_out"]) < 2e-5
+
+
+def test_train_port_intermediate_losses():
+    """Oracle port of the training call with interctc / interce / use_unimask == the unmodified reference
+    (tests/golden/inter.npz)."""
+    import json
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "inter.npz"))
+    src, mask, size = (torch.from_numpy(z[k]) for k in ("src", "src_mask", "src_size"))
+    labels, sizes = torch.from_numpy(z["labels"]), torch.from_numpy(z["label_sizes"])
+    for fam, case in (("trf", "interctc_mixce"), ("trf", "unimask"), ("con", "interctc_selfce"), ("con", "mixce")):
+        pre = f"{fam}::{case}::"
+        cfg = SimpleNamespace(**json.loads(bytes(z[pre + "cfg_json"]).decode()))
+        sd = {k[len(fam) + 6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{fam}::sd::")}
+        tap = [cfg.interctc_layer, None] if cfg.interctc_alpha > 0 else None
+        with torch.no_grad():
+            enc_h, x_mask = O.encode(src, mask, sd, cfg, tap=tap)
+            o = O.train_forward_from_encoder(enc_h, x_mask, (size * enc_h.size(1)).long(), labels, sizes, sd, cfg,
+                                             inter_h=tap[1] if tap else None)
+        assert _rel(o["ctc_out"], z[pre + "ctc_out"]) < 2e-5 and _rel(o["att_out"], z[pre + "att_out"]) < 2e-5, (fam, case)
+        assert abs(float(o["loss"]) - float(z[pre + "losses"][0])) < 1e-4 * abs(float(z[pre + "losses"][0])), (fam, case)

@@ -175,8 +175,9 @@ class CassNAT(nn.Module):
         if args.lm_weight > 0 or args.beam_width != 1:
             raise NotImplementedError("token-level LM fusion / beam_width > 1 (cassnat.py:600-636) is outside the "
                                       "single-step path this package accelerates")
-        if getattr(args, "test_hitrate", False):
-            raise NotImplementedError("test_hitrate diagnostic (cassnat.py:438-462) is not provided")
+        hitrate = bool(getattr(args, "test_hitrate", False)) and args.use_trigger
+        if hitrate and enc_h.size(0) != 1:
+            raise ValueError("test_hitrate works on one utterance at a time (cassnat.py:459 calls .item() on a [B] tensor)")
         sos, blank = vocab.word2index["sos"], vocab.word2index["blank"]
         B, T, d = enc_h.shape
         dev = enc_h.device
@@ -197,6 +198,16 @@ class CassNAT(nn.Module):
         else:
             st = self.ctc_generator.greedy(enc_h, want_top2=S > 1)
             aligned, ylen, ymax = self._collapse(st, mask2, B, T, S, blank, args.threshold if S > 1 else 0.9)
+        if hitrate:                                                                    # :438-439, :453-462
+            # trigger hit rate of the best-path alignment against the forced alignment of the reference labels
+            oracle_al, _, _ = ops.viterbi_align(self.ctc_generator(enc_h), src_mask, frames, labels[:, 1:-1].to(dev),
+                                                label_sizes.to(dev), blank, 0)
+            if S < 2:
+                a, o = aligned != 0, oracle_al != 0
+                args.total += int(o.sum().item())
+                args.num_correct += int(((a == o) & (a | o)).sum().item())
+                args.length_total += 1
+                args.length_correct += int(a.sum().item() == o.sum().item())
         if S > 1:                                                                      # :441-445
             rep = lambda x: x.repeat_interleave(S, 0)
             enc_h, src_mask, mask2, frames = rep(enc_h), rep(src_mask), rep(mask2), rep(frames)

@@ -199,3 +199,37 @@ def test_cuda_graph_replay_matches_eager(blocks_golden):
         model.use_cuda_graphs = False
     if max(len(o[0]["hyp"]) for o in ref) == max(len(o[0]["hyp"]) for o in out):     # same ymax -> same graph
         assert [o[0]["hyp"] for o in got] == [o[0]["hyp"] for o in ref]
+
+
+def test_hitrate_diagnostic(blocks_golden):
+    """args.test_hitrate (cassnat.py:438-462): trigger hit-rate counters of the best-path alignment against the
+    forced alignment of the labels, one utterance per call, compared with the same counts from the oracle."""
+    import oracle.align_np as A
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg, test_hitrate=True)
+    args.total = args.num_correct = args.length_total = args.length_correct = 0
+    enc_h = torch.from_numpy(z["greedy::enc_h"])
+    src_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2]
+    size = torch.from_numpy(z["src_size"])
+    labels = torch.from_numpy(z["train::labels"])
+    labels = torch.cat([torch.ones(labels.size(0), 1, dtype=torch.long), labels], 1)      # [sos, tokens..., eos]
+    sizes = torch.from_numpy(z["train::label_sizes"])
+    want = dict(total=0, num_correct=0, length_total=0, length_correct=0)
+    T = enc_h.size(1)
+    for b in range(enc_h.size(0)):
+        sl = slice(b, b + 1)
+        with torch.no_grad():
+            model.decode_from_encoder(enc_h[sl].to(DEV), src_mask[sl].to(DEV), size[sl].to(DEV), VOCAB, args,
+                                      labels=labels[sl], label_sizes=sizes[sl])
+        lp = z["greedy::ctc_out"][sl]
+        frames = (size[sl] * T).long().numpy()
+        al, _, _ = A.best_path_align(lp, src_mask[sl].numpy(), 0)
+        n = int(sizes[b])
+        oa, _, _ = A.viterbi_align(lp, src_mask[sl].numpy(), frames, labels[sl, 1:1 + n].numpy(), sizes[sl].numpy(), 0, None)
+        a, o = al != 0, oa != 0
+        want["total"] += int(o.sum())
+        want["num_correct"] += int(((a == o) & (a | o)).sum())
+        want["length_total"] += 1
+        want["length_correct"] += int(a.sum() == o.sum())
+    got = {k: getattr(args, k) for k in want}
+    assert got == want, (got, want)

@@ -285,8 +285,8 @@ def run_ours(a, w):
     roof["avg_launch_ms"] = d["ms"] / d["calls"]
     roof["share_of_step"] = d["ms"] / sum(v["ms"] for v in prof.values())
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        roof["traffic"] = json.load(open(tpath)).get(name)
+    if os.path.exists(tpath) and a.workload == "cfg3" and a.precision == "bf16" and B == w["batch"]:
+        roof["traffic"] = json.load(open(tpath)).get(name)      # ncu capture of exactly this workload (profiles/)
     h2d = sum(t.numel() * t.element_size() for t in host)
     ymax = max(len(h) - 1 for h in hyps[:B])
     d2h = B * ymax * (4 + 8) + B * 8 + 4          # ids i32 + logp f64 + ylen i64 + the ymax scalar

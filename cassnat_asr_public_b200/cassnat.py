@@ -172,9 +172,7 @@ class CassNAT(nn.Module):
                             label_sizes=None, return_intermediates=False):
         """Everything CassNAT.beam_decode does after the encoder (cassnat.py:433-637).
         src_size is the length RATIO tensor the reference takes (frames = (ratio*T).long(), :436)."""
-        if args.lm_weight > 0 or args.beam_width != 1:
-            raise NotImplementedError("token-level LM fusion / beam_width > 1 (cassnat.py:600-636) is outside the "
-                                      "single-step path this package accelerates")
+        beam = args.lm_weight > 0 or args.beam_width != 1        # cassnat.py:600-636: per-position top-k (+ token-level LM)
         hitrate = bool(getattr(args, "test_hitrate", False)) and args.use_trigger
         if hitrate and enc_h.size(0) != 1:
             raise ValueError("test_hitrate works on one utterance at a time (cassnat.py:459 calls .item() on a [B] tensor)")
@@ -214,7 +212,9 @@ class CassNAT(nn.Module):
         BS = B * S
 
         # ---- K4..K9: segments -> extractor -> SAD -> MAD -> head (optionally replayed as a CUDA graph)
-        graphable = (self.use_cuda_graphs and args.use_trigger and S == 1 and not args.use_unimask and
+        if beam and S > 1:
+            raise NotImplementedError("beam_width > 1 / lm_weight > 0 together with sampled alignments")
+        graphable = (self.use_cuda_graphs and args.use_trigger and S == 1 and not args.use_unimask and not beam and
                      not args.src_trigger and not getattr(args, "save_embedding", False) and not return_intermediates)
         if graphable:
             ids, logp, ylen, ymax = self._stage_b_graphed(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
@@ -229,6 +229,9 @@ class CassNAT(nn.Module):
         if S > 1:
             ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
             keep["best_sample"] = best
+        if beam:
+            out = self._assemble_beam(self.att_generator(dec_h).float(), ylen, ymax, args, lm_model, sos)
+            return (out, args, keep) if return_intermediates else (out, args)
         # ---- hypothesis assembly (cassnat.py:574-637 for beam_width 1): one D2H copy
         # one device->host transfer: [ids | logp bits | ylen] packed into a pinned int32 buffer
         U_ = ids.shape[1]
@@ -252,6 +255,51 @@ class CassNAT(nn.Module):
         if return_intermediates:
             return out, args, keep
         return out, args
+
+    def _assemble_beam(self, att_out, ylen, ymax, args, lm_model, sos):
+        """cassnat.py:574-637 for beam_width > 1 and / or lm_weight > 0: every kept hypothesis is extended by the
+        top-`beam_width` tokens of its position (plus lm_weight times the LM's next-token log-probabilities of the
+        hypothesis prefix), then the best `beam_width` by score + length penalty survive.  Positions i > ylen[b] leave
+        utterance b untouched.  Without LM fusion the top-k of all positions is taken in one pass and read back once."""
+        B, U, _ = att_out.shape
+        dev = att_out.device
+        k, lw, pad = int(args.beam_width), float(args.lm_weight), args.padding_idx
+        lp = getattr(args, "length_penalty", None)
+        key = (lambda x: x["score"] + (len(x["hyp"]) - 1) * lp) if lp is not None else (lambda x: x["score"])
+        ylen_h = ylen.tolist()
+        ys0 = torch.ones(1, 1).fill_(sos).long()
+        if getattr(args, "use_gpu", False):
+            ys0 = ys0.to(dev)
+        tops = [[{"ys": ys0, "score": 0.0, "hyp": [sos]}] for _ in range(B)]
+        if lw <= 0:
+            sc_all, idx_all = att_out.topk(k, -1)
+            sc_all, idx_all = sc_all.cpu().numpy(), idx_all.cpu().numpy()
+        for i in range(ymax):
+            active = [(b, seq) for b in range(B) for seq in tops[b] if i <= ylen_h[b]]
+            if not active:
+                break
+            if lw > 0:
+                rows = torch.cat([att_out[b, i:i + 1] for b, _ in active], 0)
+                ysb = torch.cat([seq["ys"].to(dev) for _, seq in active], 0)
+                n = ysb.size(-1)
+                m = (ysb != pad).unsqueeze(1) & torch.tril(torch.ones(n, n, dtype=torch.bool, device=dev)).unsqueeze(0)
+                rows = rows + lw * lm_model(ysb, m)[:, -1, :].float()
+                sc, idx = rows.topk(k, -1)
+                sc, idx = sc.tolist(), idx.tolist()
+            s_idx = -1
+            for b in range(B):
+                if i > ylen_h[b]:
+                    continue
+                cand = []
+                for seq in tops[b]:
+                    s_idx += 1
+                    for j in range(k):
+                        tok, ts = (idx[s_idx][j], sc[s_idx][j]) if lw > 0 else (int(idx_all[b, i, j]), float(sc_all[b, i, j]))
+                        ys = torch.cat([seq["ys"], torch.tensor([[tok]], dtype=torch.long, device=seq["ys"].device)], -1) \
+                            if lw > 0 else seq["ys"]
+                        cand.append({"ys": ys, "score": seq["score"] + ts, "hyp": seq["hyp"] + [tok]})
+                tops[b] = sorted(cand, key=key, reverse=True)[:k]
+        return tops
 
     def _stage_b(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank):
         """cassnat.py:465-497 after the alignment: no host synchronisation in here (CUDA-graph safe)."""

@@ -313,6 +313,49 @@ def pick_hypotheses(att_out, ylen, ymax, sos=1):
     return hyps, scores
 
 
+def beam_assemble(att_out, ylen, ymax, cfg, lm_model=None, sos=1):
+    """cassnat.py:574-637 in full: per-position top-`beam_width` extension of every kept hypothesis, optional
+    token-level LM fusion (the LM scores the hypothesis prefix, :600-606), sort by score + length penalty (:633-635).
+    Positions i > ylen[b] leave the hypotheses of utterance b untouched.  Returns (hyps, scores) per utterance/beam."""
+    bs = att_out.size(0)
+    ys0 = torch.ones(1, 1).fill_(sos).long()
+    tops = [[{"ys": ys0, "score": 0.0, "hyp": [sos]}] for _ in range(bs)]
+    for i in range(ymax):
+        all_seqs, ys, att_prob = [], [], []
+        for b in range(bs):
+            all_seqs.append([])
+            for seq in tops[b]:
+                if i > int(ylen[b]):
+                    all_seqs[b].append(seq)
+                    continue
+                att_prob.append(att_out[b, i:i + 1, :])
+                if cfg.lm_weight > 0:
+                    ys.append(seq["ys"])
+        if not att_prob:
+            break
+        local = torch.cat(att_prob, 0)
+        if cfg.lm_weight > 0:
+            ysb = torch.cat(ys, 0)
+            n = ysb.size(-1)
+            m = (ysb != cfg.padding_idx).unsqueeze(1) & torch.tril(torch.ones(n, n, dtype=torch.uint8)).unsqueeze(0).bool()
+            local = local + cfg.lm_weight * lm_model(ysb, m)[:, -1, :]
+        sc, idx = torch.topk(local, cfg.beam_width, dim=-1)
+        s_idx = -1
+        for b in range(bs):
+            for seq in tops[b]:
+                if i > int(ylen[b]):
+                    continue
+                s_idx += 1
+                for j in range(cfg.beam_width):
+                    tok = idx[s_idx][j]
+                    nys = torch.cat([seq["ys"], tok.view(-1, 1)], -1) if cfg.lm_weight > 0 else seq["ys"]
+                    all_seqs[b].append({"ys": nys, "score": seq["score"] + sc[s_idx][j].item(), "hyp": seq["hyp"] + [tok.item()]})
+            key = (lambda x: x["score"] + (len(x["hyp"]) - 1) * cfg.length_penalty) if cfg.length_penalty is not None \
+                else (lambda x: x["score"])
+            tops[b] = sorted(all_seqs[b], key=key, reverse=True)[:cfg.beam_width]
+    return [[s["hyp"] for s in t] for t in tops], [[s["score"] for s in t] for t in tops]
+
+
 def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, lm_model=None):
     """Post-encoder part of CassNAT.beam_decode (cassnat.py:433-637), greedy pick.
     src_size_frames: int64 [B] == (ratio * T).long() of :436.
@@ -353,6 +396,8 @@ def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, 
         out.update(best_sample=best.squeeze(1), lm_score=mean, att_out_best=att_out)
     hyps, scores = pick_hypotheses(att_out, ylen_t, ymax1)
     out.update(hyps=hyps, scores=scores)
+    if getattr(cfg, "beam_width", 1) > 1 or getattr(cfg, "lm_weight", 0) > 0:
+        out["beam_hyps"], out["beam_scores"] = beam_assemble(att_out, ylen_t, ymax1, cfg, lm_model)
     return out
 
 

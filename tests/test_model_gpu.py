@@ -233,3 +233,49 @@ def test_hitrate_diagnostic(blocks_golden):
         want["length_correct"] += int(a.sum() == o.sum())
     got = {k: getattr(args, k) for k in want}
     assert got == want, (got, want)
+
+
+class _TinyLM(torch.nn.Module):
+    """Same stand-in ranker as tests/golden/make_golden_blocks.py (CPU generator, seed 7)."""
+
+    def __init__(self, V, seed=7):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.emb = torch.nn.Parameter(torch.randn(V, 16, generator=g), requires_grad=False)
+        self.out = torch.nn.Parameter(torch.randn(16, V, generator=g), requires_grad=False)
+
+    def forward(self, ids, mask):
+        x = self.emb[ids]
+        m = (mask != 0).float()
+        ctx = torch.matmul(m / m.sum(-1, keepdim=True).clamp(min=1), x)
+        return torch.log_softmax(ctx @ self.out, -1)
+
+
+@pytest.mark.parametrize("case", ["beam3", "beam2_lm"])
+def test_beam_width_and_lm_fusion_vs_reference(case):
+    """Hypothesis assembly with beam_width > 1 and token-level LM fusion (cassnat.py:574-637) against the unmodified
+    reference (tests/golden/beam.npz, generated on the blocks_trf fixture): every beam's hypothesis identical,
+    scores within 1e-4."""
+    import os
+    from conftest import load_blocks
+    z, sd, cfg = load_blocks("trf")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam.npz"))
+    bw, lw, lp = g[case + "::flags"]
+    model, args = build(sd, cfg, beam_width=int(bw), lm_weight=float(lw), length_penalty=float(lp))
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    lm = _TinyLM(args.vocab_size).to(DEV)
+    out, _ = model.beam_decode(src, mask, size, VOCAB, args, lm_model=lm)
+    flat, lens, nb, score = (g[case + "::" + k] for k in ("hyp_flat", "hyp_len", "n_beams", "score"))
+    want, o, i = [], 0, 0
+    for n in nb:
+        beams = []
+        for _ in range(int(n)):
+            beams.append((flat[o:o + lens[i]].tolist(), float(score[i])))
+            o += int(lens[i])
+            i += 1
+        want.append(beams)
+    assert [len(b) for b in out] == [len(b) for b in want]
+    for got_b, want_b in zip(out, want):
+        for seq, (hyp, sc) in zip(got_b, want_b):
+            assert seq["hyp"] == hyp
+            assert abs(seq["score"] - sc) < 1e-4 * max(1.0, abs(sc))

@@ -146,3 +146,31 @@ def test_train_port_intermediate_losses():
                                              inter_h=tap[1] if tap else None)
         assert _rel(o["ctc_out"], z[pre + "ctc_out"]) < 2e-5 and _rel(o["att_out"], z[pre + "att_out"]) < 2e-5, (fam, case)
         assert abs(float(o["loss"]) - float(z[pre + "losses"][0])) < 1e-4 * abs(float(z[pre + "losses"][0])), (fam, case)
+
+
+def test_beam_assembly_port():
+    """Oracle restatement of the beam / LM-fusion hypothesis assembly (cassnat.py:574-637) == the unmodified
+    reference (tests/golden/beam.npz on the blocks_trf fixture)."""
+    from conftest import load_blocks
+    z, sd, cfg = load_blocks("trf")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "beam.npz"))
+
+    class TinyLM(torch.nn.Module):
+        def __init__(self, V, seed=7):
+            super().__init__()
+            gen = torch.Generator().manual_seed(seed)
+            self.emb, self.out = torch.randn(V, 16, generator=gen), torch.randn(16, V, generator=gen)
+
+        def forward(self, ids, mask):
+            m = (mask != 0).float()
+            return torch.log_softmax(torch.matmul(m / m.sum(-1, keepdim=True).clamp(min=1), self.emb[ids]) @ self.out, -1)
+
+    src, mask, size = (torch.from_numpy(z[k]) for k in ("src", "src_mask", "src_size"))
+    for case in ("beam3", "beam2_lm"):
+        bw, lw, lp = g[case + "::flags"]
+        c = SimpleNamespace(**{**vars(cfg), "beam_width": int(bw), "lm_weight": float(lw), "length_penalty": float(lp)})
+        with torch.no_grad():
+            o = O.beam_decode(src, mask, size, sd, c, None, TinyLM(c.vocab_size))
+        flat = [t for beams in o["beam_hyps"] for h in beams for t in h]
+        assert flat == g[case + "::hyp_flat"].tolist(), case
+        assert np.allclose(np.asarray(sum(o["beam_scores"], [])), g[case + "::score"], rtol=1e-5, atol=1e-5), case

@@ -244,7 +244,11 @@ def run_ours(a, w):
     sync_all()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allt = torch.empty(world, 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t.unsqueeze(0))
+        per_rank = [round(v / a.steps, 4) for v in allt[:, 0].tolist()]      # device ms/step of every rank (diagnostic)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = t.tolist()
     training = None
@@ -303,6 +307,8 @@ def run_ours(a, w):
                             **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] else
                                {"GBps": round(v["bytes"] / v["ms"] / 1e6, 1)})}
                         for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]["ms"])}}
+    if per_rank is not None:
+        line["ms_per_step_by_rank"] = per_rank
     if training is not None:
         line["training_step"] = training
     if world == 1 and not a.no_cpu_baseline:

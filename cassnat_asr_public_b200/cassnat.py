@@ -359,16 +359,29 @@ class CassNAT(nn.Module):
         return st["top1"], st["logp"], ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask
 
     use_cuda_graphs = False          # opt-in: replay the sync-free part of the decode as a CUDA graph
+    graph_bucket = 0                 # opt-in: token-axis bucket size for graph reuse across batches (0 = exact length)
     _GRAPH_CACHE_SIZE = 4
 
     def _stage_b_graphed(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank):
         """Same as _stage_b, captured once per (batch, frames, tokens, precision) shape and replayed:
         ~150 kernel launches become one graph launch.  The first call of a shape runs eagerly (it also
         warms the weight caches) and captures for the following calls."""
+        # The graph is specialised on the token-axis length.  With `model.graph_bucket = n` (> 1, transformer family:
+        # token rows are independent of the padded length) the length is rounded up to a multiple of n — extra rows are
+        # masked and never read — so that batches with similar lengths share one graph; the conformer family
+        # normalises over the padded slab (conformer_related.py:36-40) and always keeps the exact length.
+        ymax_true = int(ymax)
+        bucket = int(getattr(self, "graph_bucket", 0))
+        if bucket > 1 and not self._conformer_dec:
+            padded = -(-(ymax_true + 1) // bucket) * bucket
+            if ymax_true + 1 <= 512:
+                padded = min(padded, 512)                      # stay inside the resident-K/V attention variant
+            ymax = padded - 1
         key = (tuple(enc_h.shape), str(enc_h.dtype), int(ymax), ops.get_precision(), int(args.left_trigger),
                int(args.right_trigger), int(blank), str(src_mask.dtype))
         cache = self.__dict__.setdefault("_graphs", {})
         hit = cache.get(key)
+        fix = lambda r: (r[0], r[1], r[2], ymax_true + 1)      # the pick loop needs the true (max ylens) + 1
         if hit is None:
             out = self._stage_b(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
             statics = [t.clone() for t in (enc_h, src_mask, frames, aligned, ylen)]
@@ -383,14 +396,14 @@ class CassNAT(nn.Module):
             if len(cache) >= self._GRAPH_CACHE_SIZE:
                 cache.pop(next(iter(cache)))
             cache[key] = (graph, statics, res[:4], n_kernels)
-            return out[:4]
+            return fix(out[:4])
         graph, statics, res, n_kernels = hit
         for dst, src in zip(statics, (enc_h, src_mask, frames, aligned, ylen)):
             dst.copy_(src, non_blocking=True)
         graph.replay()
         from . import _lib
         _lib.launch_count += n_kernels
-        return res
+        return fix(res)
 
     def _pinned(self, shape):
         """Reusable pinned int32 staging buffer for the hypothesis read-back."""

@@ -279,3 +279,28 @@ def test_beam_width_and_lm_fusion_vs_reference(case):
         for seq, (hyp, sc) in zip(got_b, want_b):
             assert seq["hyp"] == hyp
             assert abs(seq["score"] - sc) < 1e-4 * max(1.0, abs(sc))
+
+
+def test_cuda_graph_length_buckets(blocks_golden):
+    """model.graph_bucket: batches whose token-axis lengths fall into the same bucket replay ONE graph (transformer
+    family) and return the same hypotheses as eager launches; the conformer family keeps exact lengths."""
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    enc_h = torch.from_numpy(z["greedy::enc_h"]).to(DEV)
+    src_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2].to(DEV)
+    size = torch.from_numpy(z["src_size"]).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    variants = [enc_h, enc_h + 0.3 * torch.randn(enc_h.shape, device=DEV, generator=g),
+                enc_h + 0.6 * torch.randn(enc_h.shape, device=DEV, generator=g)]
+    with torch.no_grad():
+        model.use_cuda_graphs = False
+        eager = [[o[0]["hyp"] for o in model.decode_from_encoder(v, src_mask, size, VOCAB, args)[0]] for v in variants]
+        model.use_cuda_graphs, model.graph_bucket = True, 32
+        for rep in range(2):
+            got = [[o[0]["hyp"] for o in model.decode_from_encoder(v, src_mask, size, VOCAB, args)[0]] for v in variants]
+            assert got == eager, (name, rep)
+    lens = {max(len(h) for h in hyps) for hyps in eager}
+    if name == "trf":
+        assert len(model._graphs) == 1 or len(lens) == 1 or max(lens) - min(lens) >= 32
+    else:
+        assert len(model._graphs) == len(lens)

@@ -312,8 +312,6 @@ class CassNAT(nn.Module):
             _, ylen, ymax, seg = ops.align_to_mask(aligned, ylen, ymax, mask2, frames, blank, want_mask=False,
                                                    want_seg=True)
             seg_ctx = (seg, ylen - 1, mask2, frames, args.left_trigger, args.right_trigger)
-            if ops.is_bf16() and not self._conformer_dec and not args.use_unimask:
-                seg_ctx = seg_ctx + ((ylen + 1).clamp(max=ymax),)      # token rows the pick loop can read
             dense_trigger = lambda: ops.align_to_mask(aligned, ylen - 1, ymax - 1, mask2, frames, blank,
                                                       args.left_trigger, args.right_trigger, True)[0]
         else:                                                                          # :470-473
@@ -324,12 +322,26 @@ class CassNAT(nn.Module):
             # zero weight; in the transformer family token rows past ylen[b] (the pick loop reads rows
             # 0..ylen[b], cassnat.py:587) never influence a row that is read, so they are zero-filled.
             # The conformer family mixes rows (depthwise conv, GroupNorm over the padded slab): no q hint.
-            need_rows = None if self._conformer_dec else (ylen + 1).clamp(max=ymax)
-            ops.attach_length_hints(tgt_mask, kv_len=ylen.clamp(max=ymax), q_len=need_rows)
-            if not args.src_trigger:
-                valid = mask2 != 0
-                last_key = (valid * torch.arange(1, T + 1, device=dev)).amax(1)
-                src_mask = ops.attach_length_hints(src_mask.reshape(BS, 1, T), kv_len=last_key, q_len=need_rows)
+            if BS <= 1024:                  # one launch for every hint and both processing orders
+                h = ops.decode_hints(ylen, ymax, mask2, use_q=not self._conformer_dec)
+                need_rows = None if self._conformer_dec else h["need_rows"]
+                tgt_mask._cn_kv_len, tgt_mask._cn_order = h["kv_tgt"], h["order_tgt"]
+                if need_rows is not None:
+                    tgt_mask._cn_q_len = need_rows
+                if not args.src_trigger:
+                    src_mask = src_mask.reshape(BS, 1, T)
+                    src_mask._cn_kv_len, src_mask._cn_order = h["last_key"], h["order_src"]
+                    if need_rows is not None:
+                        src_mask._cn_q_len = need_rows
+            else:
+                need_rows = None if self._conformer_dec else (ylen + 1).clamp(max=ymax)
+                ops.attach_length_hints(tgt_mask, kv_len=ylen.clamp(max=ymax), q_len=need_rows)
+                if not args.src_trigger:
+                    valid = mask2 != 0
+                    last_key = (valid * torch.arange(1, T + 1, device=dev)).amax(1)
+                    src_mask = ops.attach_length_hints(src_mask.reshape(BS, 1, T), kv_len=last_key, q_len=need_rows)
+            if seg_ctx is not None and need_rows is not None:
+                seg_ctx = seg_ctx + (need_rows,)                       # extractor: token rows the pick loop can read
         # ---- K6: token acoustic extractor
         pe_rows = self._pe_rows(enc_h, ymax)
         if seg_ctx is not None:

@@ -384,6 +384,59 @@ __global__ void __launch_bounds__(256) pack_mask_bits_kernel(const uint8_t* __re
   }
 }
 
+// Length hints of one decode step for the tensor-core attention, in ONE launch (replaces ~25 tiny elementwise /
+// sort launches): rows the pick loop can read, last valid token / frame per utterance, and the heaviest-first
+// processing orders of the self- and the source-attention.  Single CTA, B <= 1024.
+__global__ void __launch_bounds__(1024) decode_hints_kernel(const int64_t* __restrict__ ylen, int ymax,
+                                                            const uint8_t* __restrict__ src_mask, int B, int T, int use_q,
+                                                            int32_t* __restrict__ need_rows, int32_t* __restrict__ kv_tgt,
+                                                            int32_t* __restrict__ last_key, int32_t* __restrict__ order_tgt,
+                                                            int32_t* __restrict__ order_src) {
+  __shared__ int key_t[1024], key_s[1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = warp; b < B; b += 32) {                 // last unmasked frame + 1 (scan backwards, 32 frames per step)
+    const uint8_t* m = src_mask + (int64_t)b * T;
+    int last = 0;
+    for (int t0 = ((T - 1) / 32) * 32; t0 >= 0; t0 -= 32) {
+      const int t = t0 + lane;
+      const uint32_t bits = __ballot_sync(0xffffffffu, t < T && m[t] != 0);
+      if (bits) { last = t0 + 32 - __clz(bits); break; }
+    }
+    if (lane == 0) {
+      const int yl = (int)ylen[b];
+      const int nr = min(yl + 1, ymax), kt = min(yl, ymax);
+      need_rows[b] = nr; kv_tgt[b] = kt; last_key[b] = last;
+      const int qt = use_q ? (nr + 127) / 128 : 1;
+      key_t[b] = ((kt + 127) / 128) * qt;
+      key_s[b] = ((last + 127) / 128) * qt;
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {    // stable descending rank by counting
+    int rt = 0, rs = 0;
+    const int kt = key_t[b], ks = key_s[b];
+    for (int j = 0; j < B; ++j) {
+      rt += (key_t[j] > kt) || (key_t[j] == kt && j < b);
+      rs += (key_s[j] > ks) || (key_s[j] == ks && j < b);
+    }
+    order_tgt[rt] = b;
+    order_src[rs] = b;
+  }
+}
+
+extern "C" int cn_decode_hints(const int64_t* ylen, int64_t ymax, const uint8_t* src_mask, int64_t B, int64_t T, int use_q,
+                               int32_t* need_rows, int32_t* kv_tgt, int32_t* last_key, int32_t* order_tgt,
+                               int32_t* order_src, cn_stream_t stream) {
+  if (!ylen || !src_mask || !need_rows || !kv_tgt || !last_key || !order_tgt || !order_src || B < 0 || T <= 0 || ymax < 0)
+    return CN_ERR_BAD_ARG;
+  if (B > 1024 || ymax > 0x7ffffff) return CN_ERR_UNSUPPORTED;
+  if (B == 0) return CN_OK;
+  decode_hints_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ylen, (int)ymax, src_mask, (int)B, (int)T, use_q, need_rows, kv_tgt,
+                                                          last_key, order_tgt, order_src);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
 extern "C" int cn_trigger_mask_bits(const int32_t* seg, const int64_t* ylens, const uint8_t* src_mask,
                                     const int64_t* src_size, int64_t B, int64_t T, int64_t n_rows, int left, int right,
                                     uint32_t* bits, cn_stream_t stream) {

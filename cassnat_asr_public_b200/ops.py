@@ -406,6 +406,17 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     return o32 if o32 is not None else o16
 
 
+def decode_hints(ylen, ymax, src_mask2, use_q=True):
+    """All length hints of a decode step in one launch -> dict(need_rows, kv_tgt, last_key, order_tgt, order_src)
+    of int32 [B] tensors (see cn_decode_hints)."""
+    B, T = src_mask2.shape
+    dev = src_mask2.device
+    buf = torch.empty(5, B, dtype=torch.int32, device=dev)
+    call("cn_decode_hints", ptr(_i64(ylen)), int(ymax), ptr(_u8(src_mask2, B, T)), B, T, int(bool(use_q)),
+         ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), ptr(buf[3]), ptr(buf[4]), stream())
+    return dict(need_rows=buf[0], kv_tgt=buf[1], last_key=buf[2], order_tgt=buf[3], order_src=buf[4])
+
+
 def mark_causal(mask):
     """Tags a [B,U,U] mask whose entries above the diagonal are all zero (mask & tril): the tcgen05 attention then
     skips the key tiles above the diagonal (the mask bits are still applied inside the diagonal tiles)."""

@@ -258,6 +258,16 @@ int cn_conv_frontend_bf16(const float* x, int64_t sbx, int64_t stx, int64_t B, i
                           const float* w1, const float* b1, const void* w2_taps, const float* b2, int64_t C,
                           void* mid, void* out, cn_stream_t stream);
 
+/* Length hints of one decode step for the tcgen05 attention in one launch (B <= 1024):
+ *   need_rows[b] = min(ylen[b]+1, ymax)   token rows the pick loop can read (cassnat.py:587)
+ *   kv_tgt[b]    = min(ylen[b], ymax)     valid tokens (keys of the self-attention)
+ *   last_key[b]  = 1 + last frame with src_mask != 0 (keys of the source attention)
+ *   order_tgt / order_src: utterances sorted by (key tiles) x (query tiles), heaviest first (stable);
+ *   use_q = 0 leaves the query tiles out (conformer family: every row is needed). */
+int cn_decode_hints(const int64_t* ylen, int64_t ymax, const uint8_t* src_mask, int64_t B, int64_t T, int use_q,
+                    int32_t* need_rows, int32_t* kv_tgt, int32_t* last_key, int32_t* order_tgt, int32_t* order_src,
+                    cn_stream_t stream);
+
 /* Fast mode, per-row masks: the mask arrives bit-packed, bits[b][i][w] (16 uint32 words per query row,
  * bit (t&31) of word (t>>5) = keep(i,t)); cn_attention_bf16 itself only takes key masks (mi == 0).
  *   cn_pack_mask_bits      u8 [B,Tq,Tk] (strides mb, mi) -> bits        (dense masks: src_trigger, unimask)

@@ -158,3 +158,26 @@ def test_cfg2_full_size_properties():
     assert np.array_equal(va[sl].cpu().numpy(), ova)
     oa, oyl, _ = A.best_path_align(lp[sl].cpu().numpy(), mask[sl].cpu().numpy(), 0)
     assert np.array_equal(a[sl].cpu().numpy(), oa) and np.array_equal(yl[sl].cpu().numpy(), oyl)
+
+
+def test_decode_hints_kernel():
+    """cn_decode_hints: rows needed, valid tokens, last valid frame and the heaviest-first (stable) orders, against
+    the same quantities computed with torch."""
+    g = torch.Generator().manual_seed(3)
+    for B, T, ymax, use_q in ((1, 5, 3, True), (64, 500, 501, True), (37, 130, 77, False), (300, 33, 20, True)):
+        ylen = torch.randint(1, ymax + 3, (B,), generator=g)
+        lens = torch.randint(0, T + 1, (B,), generator=g)
+        mask = torch.arange(T)[None] < lens[:, None]
+        if B > 2:
+            mask[1, :] = False                           # an utterance without any valid frame
+            mask[2, T // 2] = False                      # a hole inside the valid range
+        h = ops.decode_hints(ylen.to("cuda:0"), ymax, mask.to("cuda:0"), use_q=use_q)
+        need = (ylen + 1).clamp(max=ymax)
+        kv = ylen.clamp(max=ymax)
+        last = (mask * torch.arange(1, T + 1)).amax(1)
+        assert torch.equal(h["need_rows"].cpu().long(), need) and torch.equal(h["kv_tgt"].cpu().long(), kv)
+        assert torch.equal(h["last_key"].cpu().long(), last)
+        qt = (need + 127) // 128 if use_q else torch.ones_like(need)
+        for key, got in ((((kv + 127) // 128) * qt, h["order_tgt"]), (((last + 127) // 128) * qt, h["order_src"])):
+            want = torch.argsort(key, descending=True, stable=True)
+            assert torch.equal(got.cpu().long(), want)

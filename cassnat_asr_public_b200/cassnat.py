@@ -317,7 +317,7 @@ class CassNAT(nn.Module):
         else:                                                                          # :470-473
             seg_ctx = None
         tgt_mask = ops.tgt_length_mask(ylen, ymax, as_u8=True).unsqueeze(1)            # [BS,1,U]
-        if ops.is_bf16() and not args.use_unimask:
+        if ops.is_bf16() and not args.use_unimask and self.use_length_hints:
             # Length hints for the tcgen05 attention (exact): key tiles past the last valid key carry
             # zero weight; in the transformer family token rows past ylen[b] (the pick loop reads rows
             # 0..ylen[b], cassnat.py:587) never influence a row that is read, so they are zero-filled.
@@ -371,6 +371,7 @@ class CassNAT(nn.Module):
         return st["top1"], st["logp"], ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask
 
     use_cuda_graphs = False          # opt-in: replay the sync-free part of the decode as a CUDA graph
+    use_length_hints = True          # fast mode: skip attention tiles that cannot carry weight / are never read (exact)
     graph_bucket = 0                 # opt-in: token-axis bucket size for graph reuse across batches (0 = exact length)
     _GRAPH_CACHE_SIZE = 4
 

@@ -126,3 +126,34 @@ def test_decode_edge_shapes(precision, B, T, lens):
                     assert np.array_equal(np.asarray([len(h) for h in hyps]), np.asarray([len(h) for h in want["hyps"]]))
     finally:
         model.set_precision("fp32")
+
+
+def test_full_size_decode_invariants():
+    """BASELINE configs[2] at full size (base model, 64 x 500 frames, bf16 fast mode): the exact optimisations do not
+    change a single token — length hints / heaviest-first order on vs off, CUDA-graph replay vs eager launches — and
+    the bit-exact integer stage agrees with the oracle's collapse of the same argmax ids."""
+    import bench
+    w = bench.WORKLOADS["cfg3"]
+    args = bench.model_args(w)
+    torch.manual_seed(1234)
+    model = make_model(80, args).to(DEV).eval()
+    model.set_precision("bf16")
+    try:
+        enc_h, mask, ratio, lens = bench.synth_encoder_output(w, 64, 1234)
+        inp = [t.to(DEV) for t in (enc_h, mask, ratio)]
+        runs = {}
+        with torch.no_grad():
+            for name, hints, graphs in (("plain", False, False), ("hints", True, False), ("graph", True, True), ("graph2", True, True)):
+                model.use_length_hints, model.use_cuda_graphs = hints, graphs
+                out, _ = model.decode_from_encoder(*inp, bench.VOCAB, args)
+                runs[name] = [o[0]["hyp"] for o in out]
+        assert runs["plain"] == runs["hints"] == runs["graph"] == runs["graph2"]
+        assert all(h[0] == 1 and len(h) >= 2 for h in runs["plain"])
+        # hypothesis lengths follow the bit-exact integer stage: tokens kept = min(ylen + 1, ymax) with ylen = #segments + 1
+        with torch.no_grad():
+            model.use_cuda_graphs = False
+            _, _, keep = model.decode_from_encoder(*inp, bench.VOCAB, args, return_intermediates=True)
+        ylen, ymax = keep["ylen"].cpu(), keep["ymax"]
+        assert [len(h) - 1 for h in runs["plain"]] == [min(int(y) + 1, ymax) for y in ylen]
+    finally:
+        model.set_precision("fp32")

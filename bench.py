@@ -337,7 +337,7 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     time = max over ranks of the CUDA-event time of `iters` steps."""
     import torch.distributed as dist
 
-    from cassnat_asr_public_b200 import sharding
+    from cassnat_asr_public_b200 import ops, sharding
     T = (frames_in + 3) // 4
     g = torch.Generator().manual_seed(4321 + rank)
     enc_h = torch.randn(B, T, w["d_model"], generator=g).to(dev).requires_grad_(True)
@@ -419,12 +419,7 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     return {"workload": f"cfg5 (post-encoder path): base model, {B} x {frames_in / 100:.0f} s per GPU, T={T}, {L} labels/utt, "
                         f"fwd + bwd" + (" + gradient all_reduce (one flat fp32 buffer)" if world > 1 else ""),
             "ms_per_step": ms, "utt_per_s": B * world / (ms / 1e3), "loss": float(loss.detach()),
-            "params_in_step": n_par, "precision": args_precision(model), "cuda_graph": graphed}
-
-
-def args_precision(model):
-    from cassnat_asr_public_b200 import ops
-    return ops.get_precision()
+            "params_in_step": n_par, "precision": ops.get_precision(), "cuda_graph": graphed}
 
 
 def speechlike_decode(model, args, w, dev_in, B, dev, iters=20, target=0.15):

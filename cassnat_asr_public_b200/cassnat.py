@@ -184,7 +184,9 @@ class CassNAT(nn.Module):
         frames = (src_size.to(dev) * T).long()                                       # :436 / :471
         keep = {}
         if ops.is_bf16():
-            enc_h = ops.cast_bf16(enc_h)     # one bf16 copy feeds the CTC head and every K/V projection
+            # one bf16 copy feeds the CTC head and every K/V projection; with decision-safe heads (or in bf16x3 mode)
+            # it is the hi half of a split operand whose lo half the CTC head also reads
+            enc_h = ops.cast_bf16(enc_h, split=ops.SAFE_HEADS or ops.is_x3())
 
         # ---- K1 + K2: CTC head -> per-frame argmax/top-2 -> collapsed, shifted alignment
         if args.use_trigger and args.decode_type == "oracle_att":
@@ -390,20 +392,29 @@ class CassNAT(nn.Module):
             if ymax_true + 1 <= 512:
                 padded = min(padded, 512)                      # stay inside the resident-K/V attention variant
             ymax = padded - 1
-        key = (tuple(enc_h.shape), str(enc_h.dtype), int(ymax), ops.get_precision(), int(args.left_trigger),
-               int(args.right_trigger), int(blank), str(src_mask.dtype))
+        # A captured graph holds raw pointers to derived weight copies (bf16 casts, fused QKV / KV concatenations):
+        # every graph is dropped when any parameter was updated, replaced or moved since it was captured.
+        stamp = self._weight_stamp()
         cache = self.__dict__.setdefault("_graphs", {})
+        if self.__dict__.get("_graphs_stamp") != stamp:
+            cache.clear()
+            self.__dict__["_graphs_stamp"] = stamp
+        enc_full = ops.split_of(enc_h)                          # bf16x3 / safe heads: enc_h is the hi half of [hi | lo]
+        key = (tuple(enc_h.shape), str(enc_h.dtype), enc_full is not None, int(ymax), ops.get_precision(), ops.SAFE_HEADS,
+               int(args.left_trigger), int(args.right_trigger), int(blank), str(src_mask.dtype))
         hit = cache.get(key)
         fix = lambda r: (r[0], r[1], r[2], ymax_true + 1)      # the pick loop needs the true (max ylens) + 1
+        live = (enc_full if enc_full is not None else enc_h, src_mask, frames, aligned, ylen)
         if hit is None:
             out = self._stage_b(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
-            statics = [t.clone() for t in (enc_h, src_mask, frames, aligned, ylen)]
+            statics = [t.clone() for t in live]
+            s_enc = ops._hi_view(statics[0]) if enc_full is not None else statics[0]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             from . import _lib
             before = _lib.launch_count
             with torch.cuda.graph(graph):
-                res = self._stage_b(statics[0], statics[1], statics[2], statics[3], statics[4], ymax, args, blank)
+                res = self._stage_b(s_enc, statics[1], statics[2], statics[3], statics[4], ymax, args, blank)
             n_kernels = _lib.launch_count - before          # our kernels recorded into the graph
             _lib.launch_count = before                       # capture launched nothing
             if len(cache) >= self._GRAPH_CACHE_SIZE:
@@ -411,12 +422,20 @@ class CassNAT(nn.Module):
             cache[key] = (graph, statics, res[:4], n_kernels)
             return fix(out[:4])
         graph, statics, res, n_kernels = hit
-        for dst, src in zip(statics, (enc_h, src_mask, frames, aligned, ylen)):
+        for dst, src in zip(statics, live):
             dst.copy_(src, non_blocking=True)
         graph.replay()
         from . import _lib
         _lib.launch_count += n_kernels
         return fix(res)
+
+    def _weight_stamp(self):
+        """(storage address, version counter) of every parameter: changes on optimizer.step(), load_state_dict(),
+        .to(), .half() ... anything after which cached derived weights (and graphs that point at them) are stale."""
+        ps = self.__dict__.get("_stamp_params")
+        if ps is None or len(ps) != sum(1 for _ in self.parameters()):
+            ps = self.__dict__["_stamp_params"] = list(self.parameters())
+        return hash(tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps))
 
     def _pinned(self, shape):
         """Reusable pinned int32 staging buffer for the hypothesis read-back."""
@@ -475,8 +494,9 @@ class CassNAT(nn.Module):
             from ._lib import call, ptr, stream                                            # K11
             mean = torch.empty(B * S, dtype=torch.float32, device=ids.device)
             best = torch.empty(B, dtype=torch.int64, device=ids.device)
-            call("cn_rescore_select", ptr(lm_out), lm_out.stride(0), lm_out.stride(1), ptr(ids.contiguous()),
-                 ptr(tgt_mask.reshape(B * S, ymax).contiguous()), B, S, ymax, ptr(mean), ptr(best), stream())
+            ids_c, tm_c = ids.contiguous(), tgt_mask.reshape(B * S, ymax).contiguous()
+            call("cn_rescore_select", ptr(lm_out), lm_out.stride(0), lm_out.stride(1), ptr(ids_c),
+                 ptr(tm_c), B, S, ymax, ptr(mean), ptr(best), stream())
             best = best.unsqueeze(1)
         else:
             valid = tgt_mask.reshape(B, S, ymax) != 0

@@ -130,6 +130,7 @@ struct Epilogue {
   const float* residual; int64_t ldr; int64_t res_rows;
   float alpha; int act;
   float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
+  int64_t lo_off;        // != 0: out_bf16 is a split (bf16x3) operand, the rounding residue goes lo_off elements further
   // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
   float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
   const int32_t* st_target; float* st_target_logit;    // optional: the logit of one given column per row
@@ -145,7 +146,7 @@ __device__ __forceinline__ float act_fn(float v) {
 template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
-                                                                  Epilogue ep, int M, int N, int K) {
+                                                                  Epilogue ep, int M, int N, int K, int split) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;                    // two accumulator stages (power of two >= 32)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -159,7 +160,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
-  const int k_blocks = (K + BK - 1) / BK;
+  // split (bf16x3): both operands are stored [hi | lo] along the contraction axis (2K columns, K % BK == 0); the
+  // mainloop walks three parts of K/BK blocks each -- (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) -- into the same
+  // accumulator, i.e. a plain GEMM over a 3K-long contraction whose TMA coordinates are remapped per part
+  // split == 2: only W is split (A is a plain bf16 operand, e.g. an attention context): (A, W_hi), (A, W_lo)
+  const int k_part = (K + BK - 1) / BK;
+  const int k_blocks = split == 1 ? 3 * k_part : (split == 2 ? 2 * k_part : k_part);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -191,12 +197,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           // K-major operand: one [rows x 64 k] box.  MN-major operand (the global tensor is [contraction, MN]
           // row-major, used as is by the backward GEMMs): one [64 k x 64 mn] box per 64 MN elements.
-          if (!A_MN) tma_load_2d(&map_a, &full[stage], sa, kb * BK, m0);
+          int ka = kb, kw = kb;
+          if (split) {
+            const int part = kb / k_part, r = kb - part * k_part;
+            if (split == 1) {
+              ka = part == 1 ? k_part + r : r;                  // A: hi, lo, hi
+              kw = part == 2 ? k_part + r : r;                  // W: hi, hi, lo
+            } else {
+              ka = r;                                           // A: plain
+              kw = part == 1 ? k_part + r : r;                  // W: hi, lo
+            }
+          }
+          if (!A_MN) tma_load_2d(&map_a, &full[stage], sa, ka * BK, m0);
           else
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(&map_a, &full[stage], sa + i * 8192, m0 + i * 64, kb * BK);
-          if (!B_MN) tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kb * BK, n0);
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(&map_a, &full[stage], sa + i * 8192, m0 + i * 64, ka * BK);
+          if (!B_MN) tma_load_2d(&map_w, &full[stage], sa + A_BYTES, kw * BK, n0);
           else
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&map_w, &full[stage], sa + A_BYTES + i * 8192, n0 + i * 64, kb * BK);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&map_w, &full[stage], sa + A_BYTES + i * 8192, n0 + i * 64, kw * BK);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -403,6 +420,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
                 *reinterpret_cast<uint2*>(o) = pk;
+                if (ep.lo_off) {                               // rounding residue of a split (bf16x3) operand
+                  const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
+                  __nv_bfloat162 r0 = __floats2bfloat162_rn(x[it][0] - f0.x, x[it][1] - f0.y),
+                                 r1 = __floats2bfloat162_rn(x[it][2] - f1.x, x[it][3] - f1.y);
+                  pk.x = *reinterpret_cast<uint32_t*>(&r0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&r1);
+                  *reinterpret_cast<uint2*>(o + ep.lo_off) = pk;
+                }
               }
             }
           }
@@ -418,7 +443,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
                 float y = x[it][q];
                 if (ep.residual) y += ep.residual[rrow * ep.ldr + gcol + q];
                 if (ep.out_f32) ep.out_f32[(int64_t)grow * ep.ldc + gcol + q] = y;
-                if (ep.out_bf16) ep.out_bf16[(int64_t)grow * ep.ldc + gcol + q] = __float2bfloat16(y);
+                if (ep.out_bf16) {
+                  const __nv_bfloat16 yh = __float2bfloat16(y);
+                  ep.out_bf16[(int64_t)grow * ep.ldc + gcol + q] = yh;
+                  if (ep.lo_off) ep.out_bf16[(int64_t)grow * ep.ldc + gcol + q + ep.lo_off] = __float2bfloat16(y - __bfloat162float(yh));
+                }
               }
             }
           }
@@ -489,7 +518,7 @@ int sm_count() {
 
 template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
-              cudaStream_t stream) {
+              cudaStream_t stream, int split = 0) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
@@ -499,51 +528,70 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K);
+  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
 }  // namespace
 
-extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
-                            const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
-                            float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                            cn_stream_t stream_) {
-  if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || lda < K || ldw < K || ldc < N)
+static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                         const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                         float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                         int split, int out_split, cn_stream_t stream_) {
+  const int64_t kcols = split ? 2 * K : K, acols = split == 1 ? 2 * K : K;      // stored columns of W and A
+  if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || lda < acols || ldw < kcols || ldc < N)
     return CN_ERR_BAD_ARG;
   if (residual && ldr < N) return CN_ERR_BAD_ARG;
+  if (split && (K % BK)) return CN_ERR_UNSUPPORTED;            // the hi | lo boundary must fall on a k-block
+  if (out_split && (!out_bf16 || out_f32 || ldc < 2 * N || (N & 3))) return CN_ERR_BAD_ARG;
   // TMA needs 16-byte aligned bases and row pitches
   if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return CN_ERR_UNSUPPORTED;
-  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
+  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x3fffff00) return CN_ERR_UNSUPPORTED;
   if (M == 0 || N == 0) return CN_OK;
   // 128x256 tiles unless the problem is the HBM-bound d x d projection shape (N, K <= 512): there the
   // epilogue streams more bytes than the mainloop computes, and 128x128 tiles fill the last wave of the
   // 148 persistent CTAs better (measured on [32000x512x512]: 38.8 -> 34.9 us)
-  const int bn = (N > 128 && !(N <= 512 && K <= 512)) ? 256 : 128;
+  const int bn = (N > 128 && !(N <= 512 && K <= 512 && !split)) ? 256 : 128;
   CUtensorMap ma, mw;
-  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mw, W, N, K, ldw, bn)) return CN_ERR_DEVICE;
+  if (!make_map(&ma, A, M, acols, lda, BM) || !make_map(&mw, W, N, kcols, ldw, bn)) return CN_ERR_DEVICE;
   Epilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
-  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
+  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = out_split ? N : 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
-#define CN_TC_DISPATCH(BN_)                                                                              \
-  do {                                                                                                   \
-    if (residual) {                                                                                      \
-      if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, true>(ma, mw, ep, m, n, k, stream);    \
-      if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, true>(ma, mw, ep, m, n, k, stream);  \
-      return launch_tc<BN_, CN_ACT_NONE, true>(ma, mw, ep, m, n, k, stream);                            \
-    }                                                                                                    \
-    if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, false>(ma, mw, ep, m, n, k, stream);     \
-    if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, false>(ma, mw, ep, m, n, k, stream);   \
-    return launch_tc<BN_, CN_ACT_NONE, false>(ma, mw, ep, m, n, k, stream);                             \
+#define CN_TC_DISPATCH(BN_)                                                                                     \
+  do {                                                                                                          \
+    if (residual) {                                                                                             \
+      if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, true>(ma, mw, ep, m, n, k, stream, split);    \
+      if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, true>(ma, mw, ep, m, n, k, stream, split);  \
+      return launch_tc<BN_, CN_ACT_NONE, true>(ma, mw, ep, m, n, k, stream, split);                            \
+    }                                                                                                           \
+    if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, false>(ma, mw, ep, m, n, k, stream, split);     \
+    if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, false>(ma, mw, ep, m, n, k, stream, split);   \
+    return launch_tc<BN_, CN_ACT_NONE, false>(ma, mw, ep, m, n, k, stream, split);                             \
   } while (0)
   if (bn == 256) CN_TC_DISPATCH(256);
   CN_TC_DISPATCH(128);
 #undef CN_TC_DISPATCH
+}
+
+extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                            const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                            float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                            cn_stream_t stream_) {
+  return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, act, out_f32, out_bf16, ldc, M, N, K, 0, 0,
+                        stream_);
+}
+
+extern "C" int cn_gemm_bf16x3(const void* A, int64_t lda, int a_split, const void* W, int64_t ldw, const float* bias,
+                              const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                              float* out_f32, void* out_bf16, int out_split, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                              cn_stream_t stream_) {
+  return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, act, out_f32, out_bf16, ldc, M, N, K,
+                        a_split ? 1 : 2, out_split, stream_);
 }
 
 // ---------------------------------------------------------------- backward GEMMs without transposed copies
@@ -581,7 +629,7 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
   if (!ok_a || !make_map_mn(&mw, W, K, N, ldw)) return CN_ERR_DEVICE;
   Epilogue ep;
   ep.bias = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = 1.f; ep.act = CN_ACT_NONE;
-  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc;
+  ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -894,19 +942,21 @@ extern "C" int64_t cn_gemm_rowstats_workspace_bytes(int64_t M, int64_t N) {
   return M * parts * 5 * 4 + 256;
 }
 
-extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
-                                     float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
-                                     float* peak, float* lse, const int32_t* target, float* target_logit,
-                                     void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
-  if (!A || !W || !top1 || !workspace || M < 0 || N <= 0 || K <= 0 || lda < K || ldw < K) return CN_ERR_BAD_ARG;
+static int gemm_rowstats_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
+                             float* peak, float* lse, const int32_t* target, float* target_logit,
+                             void* workspace, int64_t workspace_bytes, int split, cn_stream_t stream_) {
+  const int64_t kcols = split ? 2 * K : K;
+  if (!A || !W || !top1 || !workspace || M < 0 || N <= 0 || K <= 0 || lda < kcols || ldw < kcols) return CN_ERR_BAD_ARG;
   if ((target == nullptr) != (target_logit == nullptr)) return CN_ERR_BAD_ARG;
+  if (split && (K % BK)) return CN_ERR_UNSUPPORTED;
   if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return CN_ERR_UNSUPPORTED;
   if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
   if (workspace_bytes < cn_gemm_rowstats_workspace_bytes(M, N)) return CN_ERR_WORKSPACE;
   if (M == 0) return CN_OK;
   CUtensorMap ma, mw;
-  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mw, W, N, K, ldw, 256)) return CN_ERR_DEVICE;
+  if (!make_map(&ma, A, M, kcols, lda, BM) || !make_map(&mw, W, N, kcols, ldw, 256)) return CN_ERR_DEVICE;
   const int parts = (int)(((N + 255) / 256) * 2);
   float* pmax = (float*)workspace;
   int32_t* pidx = (int32_t*)(pmax + M * parts);
@@ -915,17 +965,33 @@ extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, 
   int32_t* pidx2 = (int32_t*)(pmax2 + M * parts);
   Epilogue ep;
   ep.bias = bias; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = alpha; ep.act = CN_ACT_NONE;
-  ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0;
+  ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0; ep.lo_off = 0;
   ep.st_max = pmax; ep.st_idx = pidx; ep.st_sum = psum; ep.st_max2 = top2 ? pmax2 : nullptr;
   ep.st_idx2 = top2 ? pidx2 : nullptr; ep.n_parts = parts;
   ep.st_target = target; ep.st_target_logit = target_logit;
   cudaStream_t stream = (cudaStream_t)stream_;
-  int rc = launch_tc<256, CN_ACT_NONE, false, true>(ma, mw, ep, (int)M, (int)N, (int)K, stream);
+  int rc = launch_tc<256, CN_ACT_NONE, false, true>(ma, mw, ep, (int)M, (int)N, (int)K, stream, split);
   if (rc != CN_OK) return rc;
   merge_row_parts_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(pmax, pidx, psum, ep.st_max2, ep.st_idx2, parts, M,
                                                                           top1, top2, peak, lse);
   CN_CHECK_LAUNCH();
   return CN_OK;
+}
+
+extern "C" int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                     float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
+                                     float* peak, float* lse, const int32_t* target, float* target_logit,
+                                     void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
+  return gemm_rowstats_impl(A, lda, W, ldw, bias, alpha, M, N, K, top1, top2, peak, lse, target, target_logit, workspace,
+                            workspace_bytes, 0, stream_);
+}
+
+extern "C" int cn_gemm_bf16x3_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                       float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2,
+                                       float* peak, float* lse, const int32_t* target, float* target_logit,
+                                       void* workspace, int64_t workspace_bytes, cn_stream_t stream_) {
+  return gemm_rowstats_impl(A, lda, W, ldw, bias, alpha, M, N, K, top1, top2, peak, lse, target, target_logit, workspace,
+                            workspace_bytes, 1, stream_);
 }
 
 // f32 -> bf16 cast (operands of the tensor-core GEMM that arrive in fp32, e.g. enc_h)
@@ -939,6 +1005,39 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     pk.y = *reinterpret_cast<uint32_t*>(&hi);
     reinterpret_cast<uint2*>(y)[i] = pk;
   }
+}
+
+// f32 [rows, K] -> split bf16 operand [rows, 2K] = [hi | lo], hi = bf16(x), lo = bf16(x - hi): hi + lo carries 16
+// mantissa bits, which is what the bf16x3 GEMM consumes.  The hi half alone is the plain bf16 cast.
+__global__ void __launch_bounds__(256) cast_bf16_split_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                                              int64_t ldy, int64_t rows, int K4) {
+  const int64_t total = rows * K4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / K4;
+    const int c = (int)(i - r * K4) * 4;
+    const float4 v = cn_ld_stream_f32x4(reinterpret_cast<const float4*>(x + r * ldx + c));
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(y + r * ldy + c) = pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&l0); pk.y = *reinterpret_cast<uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(y + r * ldy + 4 * (int64_t)K4 + c) = pk;
+  }
+}
+
+extern "C" int cn_cast_bf16_split(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t K,
+                                  cn_stream_t stream_) {
+  if (!x || !y || rows < 0 || K <= 0 || (K & 3) || ldx < K || ldy < 2 * K || (ldx & 3) || (ldy & 3) ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
+    return CN_ERR_BAD_ARG;
+  if (rows == 0) return CN_OK;
+  int64_t blocks = (rows * (K / 4) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_bf16_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, ldx, (__nv_bfloat16*)y, ldy, rows, (int)(K / 4));
+  CN_CHECK_LAUNCH();
+  return CN_OK;
 }
 
 extern "C" int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream_) {

@@ -103,6 +103,7 @@ class Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, alpha, act, res_rows, out_bf16):
         swish = act == "swish"            # the backward needs the pre-activation: GEMM, then a separate activation
         assert not (swish and residual is not None)
+        assert not (act == "relu" and (residual is not None or alpha != 1.0)), "relu mask is taken from the output"
         ctx.tc = ops.is_bf16() and x.shape[-1] % 8 == 0
         ctx.alpha, ctx.act, ctx.res_rows = float(alpha), act, int(res_rows)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None

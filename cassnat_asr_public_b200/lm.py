@@ -57,7 +57,7 @@ class TransformerLM(nn.Module):
         h = self._hidden(tgt, tgt_mask, causal)
         gen = self.out_generator
         if ops.is_bf16() and not gen.add_norm and h.shape[-1] % 8 == 0:
-            st = ops.head_rowstats(h, gen.proj.weight, gen.proj.bias, target=ids)
+            st = ops.head_rowstats(h, gen.proj.weight, gen.proj.bias, target=ids, safe=False)   # a score, not a decision
             return (st["target_logit"].reshape(-1) - st["lse"].reshape(-1)).reshape(ids.shape)
         return gen(h).gather(-1, ids.long().unsqueeze(-1)).squeeze(-1)
 

@@ -85,7 +85,8 @@ class PositionwiseFeedForward(nn.Module):
         """w_2(act(w_1 x)); with `residual` the pre-norm residual add (and the conformer's 1/2
         scale) is fused into the second GEMM's epilogue."""
         _no_dropout(self, self.p_drop)
-        hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation), out_bf16=ops.is_bf16())
+        hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation), out_bf16=ops.is_bf16(),
+                         out_split=ops.is_x3())
         return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale)
 
 
@@ -258,7 +259,7 @@ class ConvModule(nn.Module):
         """x [B,L,C] -> [B,L,C]: pointwise conv (a GEMM over channels) + GLU, depthwise conv,
         GroupNorm(1,C) over the whole [C,L] slab of each utterance, Swish, pointwise conv."""
         C = x.size(-1)
-        fast = ops.is_bf16()
+        fast = ops.is_bf16() and not ops.is_x3()      # bf16x3: fp32 between the GEMMs and the conv core
         y = ops.linear(x, self.pointwise_conv1.weight.view(2 * C, C), self.pointwise_conv1.bias, out_bf16=fast)
         y = ops.glu_dwconv_groupnorm_act(y, self.depthwise_conv.weight, self.depthwise_conv.bias,
                                          self.norm.weight, self.norm.bias, self.norm.eps, _act_name(self.activation),

@@ -144,16 +144,22 @@ def tgt_length_mask(ylen, ymax, as_u8=False):
 
 
 # ----------------------------------------------------------------------------- fp32 blocks
-_PRECISION = "fp32"          # "fp32": FFMA GEMMs (parity mode) | "bf16": tcgen05 GEMMs, fp32 accumulate
+_PRECISION = "fp32"          # "fp32": FFMA GEMMs (parity mode) | "bf16" / "bf16x3": tcgen05 GEMMs, fp32 accumulate
+SAFE_HEADS = True            # bf16 mode: the two decision heads (K1 CTC argmax, K9 token pick) run as bf16x3
 _BF16_WEIGHTS = {}           # id(tensor) -> (version stamp, bf16 copy)
+WEIGHT_EPOCH = 0             # bumped whenever a derived weight copy is rebuilt (captured CUDA graphs key on it)
 
 
 def set_precision(mode):
-    """Selects the arithmetic of every linear layer on the path.  'fp32' is the parity mode
-    (bit-exact hypotheses vs the reference); 'bf16' feeds the 5th-gen tensor cores (bf16 operands,
-    fp32 accumulation in TMEM) under the stated bf16 tolerance."""
+    """Selects the arithmetic of every linear layer on the path.
+    'fp32'   parity mode: FFMA GEMMs, fp32 attention (bit-exact hypotheses vs the reference);
+    'bf16'   fast mode: bf16 operands on the 5th-gen tensor cores, fp32 accumulation in TMEM, under the stated bf16
+             tolerance -- except the two decision heads, which run as bf16x3 (SAFE_HEADS) so that a rounding flip of
+             an argmax cannot change the alignment or a token given the same head input;
+    'bf16x3' precise tensor-core mode: every GEMM operand is carried as a (hi, lo) bf16 pair and multiplied in three
+             passes (error ~2^-17); attention stays bf16."""
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
+    if mode not in ("fp32", "bf16", "bf16x3"):
         raise ValueError(mode)
     _PRECISION = mode
 
@@ -163,7 +169,28 @@ def get_precision():
 
 
 def is_bf16():
-    return _PRECISION == "bf16"
+    """True in both tensor-core modes (bf16 activations between kernels)."""
+    return _PRECISION != "fp32"
+
+
+def is_x3():
+    return _PRECISION == "bf16x3"
+
+
+def split_of(x):
+    """The [.., 2K] split twin ([hi | lo]) of a bf16 tensor produced as the hi half of a bf16x3 operand, or None."""
+    sp = getattr(x, "_cn_split", None)
+    if sp is not None and sp.data_ptr() == x.data_ptr() and sp.shape[-1] == 2 * x.shape[-1] and sp.shape[:-1] == x.shape[:-1]:
+        return sp
+    return None
+
+
+def _hi_view(full):
+    """[.., 2K] split operand -> its hi half [.., K] (a strided view) tagged with the full tensor."""
+    K = full.shape[-1] // 2
+    hi = full[..., :K]
+    hi._cn_split = full
+    return hi
 
 
 def bf16_weight(w):
@@ -176,9 +203,26 @@ def bf16_weight(w):
     stamp = (base.data_ptr(), base._version)
     hit = _BF16_WEIGHTS.get(key)
     if hit is None or hit[0] != stamp:
+        global WEIGHT_EPOCH
+        WEIGHT_EPOCH += 1
         with torch.no_grad():
             src = w.detach()
             hit = (stamp, cast_bf16(src if src.is_contiguous() else src.contiguous()), base)
+        _BF16_WEIGHTS[key] = hit
+    return hit[1]
+
+
+def bf16_weight_split(w):
+    """Split ([hi | lo], [N, 2K]) copy of a weight for the bf16x3 GEMM, cached like bf16_weight."""
+    base = w._base if w._base is not None else w
+    key = ("x3", id(base), w.storage_offset(), tuple(w.shape), tuple(w.stride()))
+    stamp = (base.data_ptr(), base._version)
+    hit = _BF16_WEIGHTS.get(key)
+    if hit is None or hit[0] != stamp:
+        global WEIGHT_EPOCH
+        WEIGHT_EPOCH += 1
+        with torch.no_grad():
+            hit = (stamp, cast_bf16_split(w.detach().float(), tag=False), base)
         _BF16_WEIGHTS[key] = hit
     return hit[1]
 
@@ -187,21 +231,25 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
-def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False):
+def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False, out_split=False):
     """residual + alpha * act(x @ weight.T + bias) over the last dim of x.
     fp32 mode: FFMA kernel on f32 operands.  bf16 mode: x (f32 or bf16) and the weight go through the
     tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains).
-    With grad mode on and an input requiring grad the call is recorded for backward (grad.Linear)."""
+    bf16x3 mode: three-pass split GEMM; out_split (with out_bf16) returns the hi half of a split operand for the
+    next GEMM.  With grad mode on and an input requiring grad the call is recorded for backward (grad.Linear)."""
     if _needs_grad(x, weight, bias, residual):
         from . import grad
         assert out is None
         return grad.Linear.apply(x, weight, bias, residual, alpha, act, res_rows, out_bf16)
-    return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16)
+    return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split)
 
 
-def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False):
+def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False,
+                   out_split=False):
     require_cuda(x, weight)
-    if _PRECISION == "bf16" and x.shape[-1] % 8 == 0:
+    if _PRECISION == "bf16x3" and x.shape[-1] % 64 == 0 and not torch.is_grad_enabled():
+        return linear_x3(x, weight, bias, residual, alpha, act, res_rows, out_bf16, out_split)
+    if _PRECISION != "fp32" and x.shape[-1] % 8 == 0:
         return linear_bf16(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, act, res_rows,
                            torch.bfloat16 if out_bf16 else torch.float32)
     if x.dtype != torch.float32:
@@ -241,6 +289,11 @@ def layer_norm_forward(x, a_2, b_2, eps=1e-6, bf16=False):
     x2 = x.reshape(-1, d)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
+    if bf16 and _PRECISION == "bf16x3" and d % 4 == 0 and not torch.is_grad_enabled():
+        full = torch.empty(*x.shape[:-1], 2 * d, dtype=torch.bfloat16, device=x.device)
+        call("cn_layernorm_bf16x2", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps), ptr(full), 2 * d,
+             stream(), work=dict(bytes=float(x2.shape[0] * d * 8)))
+        return _hi_view(full)
     out = torch.empty(x.shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
     o2 = out.reshape(-1, d)
     call("cn_layernorm", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps),
@@ -324,8 +377,9 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
     ws_bytes = _lib.load().cn_segment_attention_workspace_bytes(B, U, d)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=k.device)
     mask = _u8(src_mask, B, T)
+    yl64, sz64 = _i64(ylens), _i64(src_size)           # converted copies must outlive the call (no inline temporaries)
     call("cn_segment_attention_f32", ptr(q_rows), q_rows.stride(0), ptr(k), k.stride(1), k.stride(0),
-         ptr(v), v.stride(1), v.stride(0), ptr(seg), ptr(_i64(ylens)), ptr(mask), ptr(_i64(src_size)),
+         ptr(v), v.stride(1), v.stride(0), ptr(seg), ptr(yl64), ptr(mask), ptr(sz64),
          int(left > 0), int(right > 0), B, n_head, U, T, d // n_head, ptr(out), out.stride(1), out.stride(0),
          ptr(ws), ws_bytes, stream(), work=dict(flops=4.0 * B * T * d, bytes=4.0 * B * d * (3 * T + U)))
     return out
@@ -358,11 +412,68 @@ def glu_dwconv_groupnorm_act_forward(y, dw_weight, dw_bias, gamma, beta, eps, ac
 
 
 # ----------------------------------------------------------------------------- bf16 tensor-core path
-def cast_bf16(x):
-    """f32 -> bf16 copy (operands of the tensor-core GEMMs that arrive in fp32)."""
+def cast_bf16_split(x, tag=True):
+    """f32 [.., K] -> split bf16 operand [.., 2K] = [hi | lo] (see cn_gemm_bf16x3).  Returns the hi half (a strided
+    [.., K] view, usable wherever a plain bf16 tensor is) tagged with the full tensor; tag=False returns the full one."""
+    require_cuda(x)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16 or x2.dtype != torch.float32:
+        x2 = x2.float().contiguous()
+    full = torch.empty(*x.shape[:-1], 2 * K, dtype=torch.bfloat16, device=x.device)
+    call("cn_cast_bf16_split", ptr(x2), x2.stride(0), ptr(full), 2 * K, x2.shape[0], K, stream(),
+         work=dict(bytes=8.0 * x2.shape[0] * K))
+    return _hi_view(full) if tag else full
+
+
+def linear_x3(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out_bf16=False, out_split=False):
+    """bf16x3 GEMM: x is the hi half of a split operand (three passes), an f32 tensor (split here) or a plain bf16
+    tensor such as an attention context (two passes: only the weight is split)."""
+    K = x.shape[-1]
+    N = weight.shape[0]
+    w = bf16_weight_split(weight)
+    a_split = 1
+    if x.dtype == torch.bfloat16:
+        full = split_of(x)
+        if full is None:
+            a_split, full = 0, x
+    else:
+        full = cast_bf16_split(x, tag=False)
+    a2 = full.reshape(-1, full.shape[-1])
+    if a2.stride(-1) != 1 or a2.stride(0) % 8 or a2.data_ptr() % 16:
+        a2 = a2.contiguous()
+    M = a2.shape[0]
+    lead = x.shape[:-1]
+    dev = x.device
+    o32 = o16 = None
+    if out_bf16:
+        o16 = torch.empty(*lead, 2 * N if out_split else N, dtype=torch.bfloat16, device=dev)
+    else:
+        o32 = torch.empty(*lead, N, dtype=torch.float32, device=dev)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    split_out = bool(out_bf16 and out_split)
+    call("cn_gemm_bf16x3", ptr(a2), a2.stride(0), a_split, ptr(w), w.stride(0), ptr(bias), ptr(r2),
+         r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ACT[act], ptr(o32), ptr(o16), int(split_out),
+         2 * N if split_out else N, M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) * 2 + M * N * (4.0 if o32 is not None else 2.0)),
+         tag=(f"cn_gemm_bf16x3[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+    if o32 is not None:
+        return o32
+    return _hi_view(o16) if split_out else o16
+
+
+def cast_bf16(x, split=False):
+    """f32 -> bf16 copy (operands of the tensor-core GEMMs that arrive in fp32).  split=True also produces the lo
+    half (the returned tensor is the hi half of a split operand, see cast_bf16_split)."""
     require_cuda(x)
     if x.dtype == torch.bfloat16:
         return x
+    if split and not _needs_grad(x) and x.shape[-1] % 4 == 0:
+        return cast_bf16_split(x)
     if _needs_grad(x):
         from . import grad
         return grad.CastBf16.apply(x)
@@ -412,7 +523,8 @@ def decode_hints(ylen, ymax, src_mask2, use_q=True):
     B, T = src_mask2.shape
     dev = src_mask2.device
     buf = torch.empty(5, B, dtype=torch.int32, device=dev)
-    call("cn_decode_hints", ptr(_i64(ylen)), int(ymax), ptr(_u8(src_mask2, B, T)), B, T, int(bool(use_q)),
+    yl64, m8 = _i64(ylen), _u8(src_mask2, B, T)
+    call("cn_decode_hints", ptr(yl64), int(ymax), ptr(m8), B, T, int(bool(use_q)),
          ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), ptr(buf[3]), ptr(buf[4]), stream())
     return dict(need_rows=buf[0], kv_tgt=buf[1], last_key=buf[2], order_tgt=buf[3], order_src=buf[4])
 
@@ -449,7 +561,8 @@ def _segment_attention_bf16(q_rows, k, v, seg, ylens, src_mask, src_size, left, 
     B, T, _ = k.shape
     dev = k.device
     bits = torch.empty(B, U, 16, dtype=torch.int32, device=dev)
-    call("cn_trigger_mask_bits", ptr(seg), ptr(_i64(ylens)), ptr(_u8(src_mask, B, T)), ptr(_i64(src_size)), B, T, U,
+    yl64, m8, sz64 = _i64(ylens), _u8(src_mask, B, T), _i64(src_size)
+    call("cn_trigger_mask_bits", ptr(seg), ptr(yl64), ptr(m8), ptr(sz64), B, T, U,
          int(left > 0), int(right > 0), ptr(bits), stream(), work=dict(bytes=4.0 * B * T + 64.0 * B * U))
     out = torch.empty(B, U, d, dtype=torch.bfloat16, device=dev)
     # no kv_len hint: the first row past eos is fully masked and must stay uniform over ALL T frames
@@ -494,9 +607,10 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
         rp, ru, rv, mr = rel
         ws_bytes = _lib.load().cn_rel_attention_workspace_bytes(B, n_head, Tq, int(mr))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+        rp, ru, rv = rp.float().contiguous(), ru.contiguous(), rv.contiguous()
         call("cn_rel_attention_bf16", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
-             ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp.float().contiguous()), ptr(ru.contiguous()),
-             ptr(rv.contiguous()), int(mr), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1), out.stride(0),
+             ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp), ptr(ru),
+             ptr(rv), int(mr), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1), out.stride(0),
              ptr(ws), ws_bytes, ptr(kv_len), stream(),
              work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
         return out
@@ -557,14 +671,22 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, want_gr
     return loss[0], nll, grad
 
 
-def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False, target=None):
+def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False, target=None, safe=None):
     """K1/K9 fused (fast mode): argmax / runner-up / max / log-sum-exp of every row of
     alpha * (x @ weight.T + bias) straight out of the tcgen05 GEMM's epilogue; the logits are never
     written.  Returns the same dict as row_stats."""
     require_cuda(x, weight)
-    xb, wb = cast_bf16(x), bf16_weight(weight)
-    K, N = xb.shape[-1], wb.shape[0]
-    x2 = xb.reshape(-1, K)
+    K, N = x.shape[-1], weight.shape[0]
+    # safe (default: SAFE_HEADS): run the head as bf16x3 so that the argmax / runner-up are those of the fp32 logits
+    safe = (SAFE_HEADS if safe is None else safe) or _PRECISION == "bf16x3"
+    x3 = safe and K % 64 == 0 and (x.dtype != torch.bfloat16 or split_of(x) is not None)
+    if x3:                        # decision-safe head: split operands, three passes
+        full = split_of(x) if x.dtype == torch.bfloat16 else cast_bf16_split(x, tag=False)
+        wb = bf16_weight_split(weight)
+        x2 = full.reshape(-1, 2 * K)
+    else:
+        xb, wb = cast_bf16(x), bf16_weight(weight)
+        x2 = xb.reshape(-1, K)
     if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
         x2 = x2.contiguous()
     M = x2.shape[0]
@@ -579,10 +701,11 @@ def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False, target=None):
         out["target_logit"] = torch.zeros(M, dtype=torch.float32, device=dev)
     ws_bytes = _lib.load().cn_gemm_rowstats_workspace_bytes(M, N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    call("cn_gemm_bf16_rowstats", ptr(x2), x2.stride(0), ptr(wb), wb.stride(0), ptr(bias), float(alpha), M, N, K,
+    name = "cn_gemm_bf16x3_rowstats" if x3 else "cn_gemm_bf16_rowstats"
+    call(name, ptr(x2), x2.stride(0), ptr(wb), wb.stride(0), ptr(bias), float(alpha), M, N, K,
          ptr(out["top1"]), ptr(out.get("top2")), ptr(out["peak"]), ptr(out["lse"]), ptr(tgt), ptr(out.get("target_logit")),
          ptr(ws), ws_bytes, stream(),
-         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K)),
-         tag=(f"cn_gemm_bf16_rowstats[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) * (2 if x3 else 1)),
+         tag=(f"{name}[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
     lead = x.shape[:-1]
     return {k: v.reshape(lead) for k, v in out.items()}

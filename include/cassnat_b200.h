@@ -205,6 +205,26 @@ int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
 /* y(bf16) = x(f32), n elements (n % 4 == 0, 16-byte aligned x). */
 int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * bf16x3 ("split") arithmetic: fp32-grade products on the bf16 tensor cores.  A value v is carried as the pair
+ * hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits); a split operand matrix stores [hi | lo] along the contraction
+ * axis ([rows, 2K], row pitch ld).  The GEMM accumulates A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32 (TMEM): three
+ * passes of the same tcgen05 mainloop with remapped TMA coordinates; relative error ~2^-17 of |a||w| instead of
+ * 2^-9.  Used for the two decision heads (K1 CTC argmax -> alignment, K9 token pick: cassnat.py:367-389, :611),
+ * where a bf16 rounding flip would change integers, and for the whole path in the 'bf16x3' precision mode.
+ * K % 64 == 0.  a_split == 0: A is a plain bf16 [M,K] operand (an attention context), only W is split (two passes).
+ * out_split != 0: out_bf16 is itself written as a split operand [M, 2N] (ldc >= 2N, out_f32 NULL). */
+int cn_gemm_bf16x3(const void* A, int64_t lda, int a_split, const void* W_split, int64_t ldw, const float* bias,
+                   const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
+                   float* out_f32, void* out_bf16, int out_split, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                   cn_stream_t stream);
+/* x f32 [rows, K] (row pitch ldx) -> split operand bf16 [rows, 2K] (row pitch ldy); K % 4 == 0.  The hi half is
+ * the plain bf16 cast (single-pass GEMMs may read it in place with row pitch ldy). */
+int cn_cast_bf16_split(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t K, cn_stream_t stream);
+/* LayerNorm (as cn_layernorm) emitting the split operand bf16 [rows, 2d] (row pitch ldo). */
+int cn_layernorm_bf16x2(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
+                        float eps, void* out_split, int64_t ldo, cn_stream_t stream);
+
 /* Fast mode: masked multi-head attention on tcgen05 (bf16 Q/K/V in, bf16 context out, fp32 softmax).
  * Same semantics as cn_attention_f32 without the relative-position terms; d_k == 64, Tk <= 512,
  * row/batch pitches multiples of 8 elements and 16-byte aligned bases (TMA).
@@ -246,6 +266,12 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           float* target_logit   /* f32 [M]: z[row, target[row]]; log-prob = target_logit - lse
                                                    (rescoring, src/models/cassnat.py:517: gather(lm_out, att_pred)) */,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+/* The same head with split (bf16x3) operands A [M,2K], W [N,2K]: argmax / runner-up equal the fp32 result wherever
+ * the fp32 top-2 margin exceeds ~1e-4 of the logit scale (decision-safe heads of the fast mode). */
+int cn_gemm_bf16x3_rowstats(const void* A_split, int64_t lda, const void* W_split, int64_t ldw, const float* bias,
+                            float alpha, int64_t M, int64_t N, int64_t K, int32_t* top1, int32_t* top2, float* peak,
+                            float* lse, const int32_t* target, float* target_logit, void* workspace,
+                            int64_t workspace_bytes, cn_stream_t stream);
 
 /* Fast mode, encoder front-end (upstream of the accelerated path): the two 3x3 / stride-2 / pad-1
  * convolutions + ReLU of ConvEmbedding with channels-last bf16 activations.

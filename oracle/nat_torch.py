@@ -124,7 +124,7 @@ def sinusoid_table(d_model, max_len=5000):
 
 def rel_pos_embed(n, table, max_rel):
     """embedding.py:52-60: rows of the (2m+1)-row table for offsets -(n-1)..(n-1), clamped."""
-    r = torch.arange(-(n - 1), n).clamp(-max_rel, max_rel) + max_rel
+    r = torch.arange(-(n - 1), n, device=table.device).clamp(-max_rel, max_rel) + max_rel
     return table[r]
 
 
@@ -270,7 +270,7 @@ def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg, taps=None):
     taps = taps or {}
     bs, _, d = enc_h.shape
     h = cfg.n_head
-    pe = sinusoid_table(d).unsqueeze(0).repeat(bs, 1, 1)[:, :ymax, :]
+    pe = sinusoid_table(d).to(enc_h.device).unsqueeze(0).repeat(bs, 1, 1)[:, :ymax, :]
     mem_mask = trigger if cfg.src_trigger else src_mask
 
     def unimask(pred):
@@ -281,7 +281,7 @@ def decoder_stack(enc_h, trigger, src_mask, tgt_mask, ymax, sd, cfg, taps=None):
             raise AttributeError("use_unimask with the conformer decoder fails in the reference "
                                  "(cassnat.py:487 calls .size on the (x, pos_embed) tuple)")
         shifted = torch.cat([torch.zeros_like(pred[:, :1]), pred[:, :-1]], dim=1)
-        causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8)).unsqueeze(0)
+        causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=pred.device)).unsqueeze(0)
         return shifted, tgt_mask & causal.type_as(tgt_mask)
 
     if cfg.use_conv_dec:

@@ -100,3 +100,70 @@ def test_gemm_mn_major_operands(M, N, K):
         call("cn_gemm_bf16_mn", ptr(A), A.stride(0), a_mn, ptr(w), w.stride(0), 1, ptr(out), None, N, M, N, K, stream())
         ref = (A.double().t() if a_mn else A.double()) @ w.double()
         assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5, (a_mn, M, N, K)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 512, 512), (1000, 5000, 512), (513, 1536, 2048), (77, 120, 128)])
+def test_gemm_bf16x3(M, N, K):
+    """bf16x3 (split) GEMM: fp32 operands carried as (hi, lo) bf16 pairs, three tensor-core passes.  Against the
+    fp64 product of the fp32 operands the error is ~2^-17 of |a||w| (plain bf16: ~2^-9)."""
+    torch.manual_seed(M * 3 + N + K)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV)
+    r = torch.randn(M, N, device=DEV)
+    ref = x.double() @ w.double().t()
+    ops.set_precision("bf16x3")
+    try:
+        y = ops.linear(x, w)
+        assert y.dtype == torch.float32 and rel(y, ref) < 3e-5
+        y = ops.linear(x, w, b, r, 0.5, "relu")
+        assert rel(y, 0.5 * torch.relu(ref + b.double()) + r.double()) < 3e-5
+        # split output feeding the next GEMM: hi + lo reproduces the fp32 result to 2^-16
+        h = ops.linear(x, w, b, out_bf16=True, out_split=True)
+        full = ops.split_of(h)
+        assert full is not None and full.shape == (M, 2 * N)
+        assert rel(full[:, :N].float() + full[:, N:].float(), ref + b.double()) < 3e-5
+        w2 = torch.randn(64, N, device=DEV) / N ** 0.5
+        y2 = ops.linear(h, w2)
+        assert rel(y2, (ref + b.double()) @ w2.double().t()) < 5e-5
+        # plain bf16 A (an attention context): only the weight is split (two passes)
+        xb = x.bfloat16()
+        y3 = ops.linear(xb, w)
+        assert rel(y3, xb.double() @ w.double().t()) < 3e-5
+        # LayerNorm emitting the split operand
+        a2, b2 = torch.rand(K, device=DEV) + 0.5, torch.randn(K, device=DEV)
+        ln = ops.layer_norm(x, a2, b2, bf16=True)
+        lnf = ops.split_of(ln)
+        ops.set_precision("fp32")
+        want = ops.layer_norm(x, a2, b2)
+        assert rel(lnf[:, :K].float() + lnf[:, K:].float(), want) < 2e-5
+    finally:
+        ops.set_precision("fp32")
+    plain = ops.linear_bf16(x.bfloat16(), w.bfloat16())
+    assert rel(plain, ref) > 3e-4                                # plain bf16 operands are visibly coarser
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 5000, 512), (129, 120, 128), (1000, 4990, 256)])
+def test_decision_safe_head(M, N, K):
+    """K1/K9 as bf16x3: argmax and runner-up equal those of the fp32 logits wherever the fp32 top-2 (resp. 2-3)
+    margin exceeds 1e-4; peak / lse within 1e-4.  (cassnat.py:367-389 argmax -> alignment, :611 token pick.)"""
+    torch.manual_seed(M + N + 1)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV) * 0.1
+    z = (x.double() @ w.double().t() + b.double())
+    top = z.topk(3, -1)
+    ops.set_precision("bf16")
+    try:
+        st = ops.head_rowstats(x, w, b, top2=True)              # safe by default
+        assert st["top1"].dtype == torch.int32
+        clear1 = (top.values[:, 0] - top.values[:, 1]) > 1e-4
+        clear2 = clear1 & ((top.values[:, 1] - top.values[:, 2]) > 1e-4)
+        assert torch.equal(st["top1"].long()[clear1], top.indices[:, 0][clear1])
+        assert torch.equal(st["top2"].long()[clear2], top.indices[:, 1][clear2])
+        assert (st["peak"].double() - top.values[:, 0]).abs().max().item() < 1e-4
+        assert (st["lse"].double() - torch.logsumexp(z, -1)).abs().max().item() < 1e-4
+        plain = ops.head_rowstats(x, w, b, safe=False)
+        assert (plain["peak"].double() - top.values[:, 0]).abs().max().item() > 1e-4      # the bf16 head is coarser
+    finally:
+        ops.set_precision("fp32")

@@ -119,10 +119,13 @@ def test_sampled_decode_with_ranker(blocks_golden):
     assert [o[0]["hyp"] for o in out] == hyps_of(z, "sampled")
 
 
-def test_bf16_tensor_core_mode(blocks_golden):
-    """Fast mode (bf16 operands on tcgen05, fp32 accumulation).  Stated tolerance: embeddings within
-    rel 3e-2 of the fp32 reference (bf16 has 8 mantissa bits; ~20 GEMMs deep), log-probs within 0.05,
-    token ids equal wherever the reference's top-2 margin exceeds 0.1 nat."""
+@pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
+def test_bf16_tensor_core_mode(blocks_golden, mode):
+    """Fast mode (bf16 operands on tcgen05, fp32 accumulation) and the precise tensor-core mode (bf16x3 GEMMs).
+    The CTC head runs as bf16x3 in both (decision-safe heads), so the best-path alignment is the reference's, bit for
+    bit, in BOTH block families.  Stated tolerance after that: embeddings within rel 3e-2 (bf16) / 1e-2 (bf16x3: the
+    attention operands stay bf16) of the fp32 reference, log-probs within 0.05, token ids equal wherever the
+    reference's top-2 margin exceeds 0.1 nat."""
     from cassnat_asr_public_b200 import ops
     name, z, sd, cfg = blocks_golden
     model, args = build(sd, cfg)
@@ -130,19 +133,18 @@ def test_bf16_tensor_core_mode(blocks_golden):
     src_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2].to(DEV)
     size = torch.from_numpy(z["src_size"]).to(DEV)
     try:
-        model.set_precision("bf16")
+        model.set_precision(mode)
         with torch.no_grad():
             out, _, keep = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args, return_intermediates=True)
     finally:
         model.set_precision("fp32")
-    if not np.array_equal(keep["aligned"].cpu().numpy(), z["greedy::aligned"]):
-        pytest.skip("bf16 CTC head flipped a near-tie frame: alignment differs, tensors not comparable")
+    assert np.array_equal(keep["aligned"].cpu().numpy(), z["greedy::aligned"]), (name, mode)
     ylen = torch.from_numpy(z["greedy::ylen"])
     U = keep["dec_h"].shape[1]
     needed = torch.arange(U)[None, :] <= ylen[:, None]          # rows 0..ylen[b]: what the pick loop reads
     for key in ("ac_embed", "pred_embed", "dec_h"):
         got, want = keep[key].float().cpu()[needed], torch.from_numpy(z[f"greedy::{key}"])[needed]
-        assert rel(got, want) < 3e-2, (name, key)
+        assert rel(got, want) < (3e-2 if mode == "bf16" else 1e-2), (name, key, mode)
     att = torch.from_numpy(z["greedy::att_out"])
     top2 = att.topk(2, -1)[0]
     clear = ((top2[..., 0] - top2[..., 1]) > 0.1) & needed
@@ -304,3 +306,35 @@ def test_cuda_graph_length_buckets(blocks_golden):
         assert len(model._graphs) == 1 or len(lens) == 1 or max(lens) - min(lens) >= 32
     else:
         assert len(model._graphs) == len(lens)
+
+
+def test_cuda_graph_dropped_when_weights_change(blocks_golden):
+    """A captured graph holds raw pointers to derived weight copies (bf16 casts, fused QKV concatenations): after an
+    in-place parameter update or load_state_dict the cached graphs must be dropped, not replayed on stale weights."""
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    enc_h = torch.from_numpy(z["greedy::enc_h"]).to(DEV)
+    src_mask = torch.from_numpy(z["src_mask"])[:, :, ::2][:, :, ::2].to(DEV)
+    size = torch.from_numpy(z["src_size"]).to(DEV)
+    try:
+        model.set_precision("bf16")
+        with torch.no_grad():
+            model.use_cuda_graphs = True
+            for _ in range(2):
+                model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args)
+            assert len(model._graphs) == 1
+            # new weights for the output head and one FFN (what optimizer.step() / load_state_dict do)
+            g = torch.Generator(device=DEV).manual_seed(11)
+            model.att_generator.proj.weight.copy_(torch.randn(model.att_generator.proj.weight.shape, device=DEV, generator=g) * 0.2)
+            sd2 = {k: v.clone() for k, v in model.state_dict().items()}
+            k_ff = next(k for k in sd2 if k.endswith("feed_forward.w_1.weight") and k.startswith("decoder"))
+            sd2[k_ff] = sd2[k_ff] * -1.5
+            model.load_state_dict(sd2)
+            got, _ = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args)          # must re-capture
+            model.use_cuda_graphs = False
+            want, _ = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args)
+        assert [o[0]["hyp"] for o in got] == [o[0]["hyp"] for o in want]
+        assert [o[0]["score"] for o in got] == [o[0]["score"] for o in want]
+    finally:
+        model.use_cuda_graphs = False
+        model.set_precision("fp32")

@@ -328,27 +328,36 @@ def run_ours(a, w):
         line["strong_scaling"] = strong
     if training is not None:
         line["training_step"] = training
+    def leg(key, fn, *fa, **kw):
+        """Auxiliary measurement: a failure is recorded in the line instead of losing the headline numbers."""
+        try:
+            line[key] = fn(*fa, **kw)
+        except Exception as e:                                  # noqa: BLE001
+            line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
+
     if world == 1 and not a.no_parity and a.precision != "fp32":
         model.use_cuda_graphs = False
-        line["parity"] = parity_report(model, args, w, dev_in, a.precision)
-        line["fp32_parity_mode"] = line["parity"].pop("fp32_parity_mode")
+        leg("parity", parity_report, model, args, w, dev_in, a.precision)
+        if "fp32_parity_mode" in line["parity"]:
+            line["fp32_parity_mode"] = line["parity"].pop("fp32_parity_mode")
     if world == 1 and not a.no_eager:
-        line["gpu_eager_baseline"] = gpu_eager_baseline(model, args, dev_in, value, units / e2e_s)
+        leg("gpu_eager_baseline", gpu_eager_baseline, model, args, dev_in, value, units / e2e_s)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a, w, args)
     if world == 1 and a.workload == "cfg3" and not a.no_sampled:
-        line["cfg1_decode"] = small_decode(dev, a.precision, not a.no_graphs)
+        leg("cfg1_decode", small_decode, dev, a.precision, not a.no_graphs)
     if world == 1 and not a.no_sampled and a.workload == "cfg3":
         model.use_cuda_graphs = not a.no_graphs
-        line["speechlike_decode"] = speechlike_decode(model, args, w, dev_in, B, dev)
-        line["features_decode"] = features_decode(model, args, w, dev, B)
-        line["conformer_decode"] = conformer_decode(w, dev_in, B, dev, a.precision, not a.no_graphs)
-        line["sampled_decode"] = sampled_decode(model, w, dev)
-        line["sampled_decode_lm"] = sampled_decode(model, w, dev, iters=3, real_lm=True)
+        leg("speechlike_decode", speechlike_decode, model, args, w, dev_in, B, dev)
+        leg("features_decode", features_decode, model, args, w, dev, B)
+        leg("conformer_decode", conformer_decode, w, dev_in, B, dev, a.precision, not a.no_graphs)
+        leg("sampled_decode", sampled_decode, model, w, dev)
+        leg("sampled_decode_lm", sampled_decode, model, w, dev, iters=3, real_lm=True)
     if world == 1 and not a.no_lattice:
         del model, dev_in, flush
         torch.cuda.empty_cache()
-        line["alignment_lattice"] = alignment_lattice(dev, pk)
+        leg("alignment_lattice", alignment_lattice, dev, pk)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -433,10 +442,26 @@ def parity_report(model, args, w, dev_in, precision):
         with torch.no_grad():
             want = O.decode_from_encoder(enc_h[:n_oracle].cpu(), mask[:n_oracle].cpu(), frames[:n_oracle].cpu(), sd,
                                          SimpleNamespace(**{**vars(args), "use_gpu": False}))
-        # the oracle pads its sub-batch to its own ymax: compare the hypotheses (what the caller gets)
-        anchor = sum(int(a == b) for a, b in zip(ref_h[:n_oracle], want["hyps"]))
+        # the oracle pads its sub-batch to its own ymax: compare the hypotheses (what the caller gets), token by token
+        # with the oracle's own top-2 margin (fp32 summation order differs between FFMA tiles and the CPU BLAS, so
+        # tokens whose margin is inside fp32 round-off are undecidable)
+        omarg = want["att_out"].topk(2, -1)[0]
+        omarg = (omarg[..., 0] - omarg[..., 1])
+        n_tok = n_diff = n_diff_clear = 0
+        same_len = True
+        for b in range(n_oracle):
+            hw, hg = want["hyps"][b], ref_h[b]
+            same_len &= abs(len(hw) - len(hg)) <= 1     # min(ylen + 1, ymax): ymax is the sub-batch's own maximum
+            for i, (x, y) in enumerate(zip(hw[1:], hg[1:])):
+                n_tok += 1
+                if x != y:
+                    n_diff += 1
+                    n_diff_clear += int(float(omarg[b, i]) > 1e-4)
+        frac = lambda num, den: {"equal": int(num), "of": int(den), "rate": (float(num) / float(den)) if int(den) else None}
         rep = {"reference_mode": "this package's fp32 parity mode on the same inputs (cfg3 full size)",
-               "fp32_mode_vs_oracle_port": f"{anchor}/{n_oracle} hypotheses identical (first {n_oracle} utterances, CPU oracle)",
+               "fp32_mode_vs_oracle_port": {"utterances": n_oracle, "same_lengths": bool(same_len), "tokens": n_tok,
+                                            "tokens_differing": n_diff, "differing_with_oracle_margin_gt_1e-4": n_diff_clear,
+                                            "alignment_identical": bool((ref["aligned"][:n_oracle].cpu().numpy() == want["aligned"]).all())},
                "frames": int(valid.sum()), "token_rows_read": int(read.sum()), "utterances": B}
         variants = [(precision, True, precision + " (decision-safe heads: K1/K9 as bf16x3)")]
         if precision == "bf16":
@@ -444,20 +469,18 @@ def parity_report(model, args, w, dev_in, precision):
         for mode, safe, label in variants:
             hyp, got = run(mode, safe)
             same_al = got["aligned"] == ref["aligned"]
-            al_frames = float(same_al[valid].float().mean())
             utt_al = same_al.all(1)
-            a1 = (got["aligned"] != ref["aligned"])[valid]
-            r = {"alignment_frame_agreement": al_frames, "alignments_identical": f"{int(utt_al.sum())}/{B}",
-                 "alignment_frame_agreement_where_fp32_margin_gt_1e-4": float((~a1[m1 > 1e-4]).float().mean())}
+            r = {"alignment_frames": frac(same_al[valid].sum(), valid.sum()), "alignments_identical": f"{int(utt_al.sum())}/{B}",
+                 "alignment_frames_where_fp32_margin_gt_1e-4": frac(same_al[valid][m1 > 1e-4].sum(), (m1 > 1e-4).sum())}
             # tokens: only utterances whose alignment (hence token grid) is identical are comparable row by row
             if got["ids"].shape == ref["ids"].shape:
                 rows = read & utt_al[:, None]
                 eq = (got["ids"] == ref["ids"])
-                r["token_agreement"] = float(eq[rows].float().mean()) if int(rows.sum()) else None
+                r["tokens"] = frac(eq[rows].sum(), rows.sum())
                 for thr in (1e-4, 1e-3, 1e-2, 5e-2):
                     sel = rows & (m9 > thr)
-                    r[f"token_agreement_where_fp32_margin_gt_{thr:g}"] = float(eq[sel].float().mean()) if int(sel.sum()) else None
-                r["fraction_of_rows_with_margin_lt_1e-2"] = float((m9[rows] < 1e-2).float().mean()) if int(rows.sum()) else None
+                    r[f"tokens_where_fp32_margin_gt_{thr:g}"] = frac(eq[sel].sum(), sel.sum())
+                r["fraction_of_rows_with_margin_lt_1e-2"] = float((m9[rows] < 1e-2).double().mean()) if int(rows.sum()) else None
                 for key in ("ac_embed", "pred_embed", "dec_h"):
                     x, y = got[key].float()[rows], ref[key].float()[rows]
                     r[f"rel_err_{key}"] = float((x - y).norm() / y.norm())

@@ -21,8 +21,9 @@ def clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
 
-def _self_attention_block(x, norm, attn, mask, pos_embed=None):
-    """x + self_attn(norm(x)) with the residual fused into the output projection."""
+def _self_attention_block(x, norm, attn, mask, pos_embed=None, next_norm=None):
+    """x + self_attn(norm(x)) with the residual (and, in fast mode, the LayerNorm `next_norm` that consumes the
+    result next) fused into the output projection."""
     y = norm.for_gemm(x)
     if pos_embed is None:
         q, k, v = attn.project_qkv(y, out_bf16=ops.is_bf16())     # bf16 -> tcgen05 attention
@@ -37,18 +38,32 @@ def _self_attention_block(x, norm, attn, mask, pos_embed=None):
         else:
             q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
         ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m))
-    return attn.output(ctx, residual=x)
+    return attn.output(ctx, residual=x, next_ln=next_norm)
 
 
-def _src_attention_block(x, norm, attn, memory, mask, kv=None):
+def _src_attention_block(x, norm, attn, memory, mask, kv=None, next_norm=None):
     y = norm.for_gemm(x)
     q = attn.project_q(y, out_bf16=ops.is_bf16())
     k, v = kv if kv is not None else attn.project_kv(memory, out_bf16=ops.is_bf16())
-    return attn.output(ops.attention(q, k, v, mask, attn.h), residual=x)
+    return attn.output(ops.attention(q, k, v, mask, attn.h), residual=x, next_ln=next_norm)
 
 
-def _ffn_block(x, norm, ff, scale=1.0):
-    return ff(norm.for_gemm(x), residual=x, scale=scale)
+def _ffn_block(x, norm, ff, scale=1.0, next_norm=None):
+    return ff(norm.for_gemm(x), residual=x, scale=scale, next_ln=next_norm)
+
+
+def _first_norm(layer):
+    """The LayerNorm a layer applies to its input first (sublayer[0].norm / sublayer.norm), or None."""
+    sub = getattr(layer, "sublayer", None)
+    if sub is None:
+        return None
+    return sub[0].norm if isinstance(sub, nn.ModuleList) else sub.norm
+
+
+def _next_norms(layers, after=None):
+    """For every layer of a stack: the norm that consumes its output (the next layer's first norm; `after` for
+    the last layer: the stack's final norm or the first norm of whatever follows)."""
+    return [(_first_norm(layers[n + 1]) if n + 1 < len(layers) else after) for n in range(len(layers))]
 
 
 # =============================================================================== transformer family
@@ -62,9 +77,9 @@ class SelfAttLayer(nn.Module):
         self.sublayer = clones(SublayerConnection(size, dropout), 2)
         self.size = size
 
-    def forward(self, x, self_mask):
-        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask)
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward)
+    def forward(self, x, self_mask, next_norm=None):
+        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
+        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
 
 
 class SrcAttLayer(nn.Module):
@@ -77,11 +92,11 @@ class SrcAttLayer(nn.Module):
         self.sublayer = clones(SublayerConnection(size, dropout), 2)
         self.size = size
 
-    def forward(self, x, m, src_mask):
-        x = _src_attention_block(x, self.sublayer[0].norm, self.src_attn, m, src_mask)
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward)
+    def forward(self, x, m, src_mask, next_norm=None):
+        x = _src_attention_block(x, self.sublayer[0].norm, self.src_attn, m, src_mask, next_norm=self.sublayer[1].norm)
+        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
 
-    def forward_segments(self, pe_rows, m, seg_ctx, kv=None):
+    def forward_segments(self, pe_rows, m, seg_ctx, kv=None, next_norm=None):
         """Same result as forward(pe_rows repeated over the batch, m, trigger_mask) with the
         trigger mask given implicitly by `seg_ctx` = (seg, ylens, src_mask, src_size, left, right)."""
         attn = self.src_attn
@@ -89,8 +104,8 @@ class SrcAttLayer(nn.Module):
         q_rows = attn.project_q(self.sublayer[0].norm.for_gemm(pe_rows), out_bf16=fast)   # batch independent [U,d]
         k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
         ctx = ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h, q_len=seg_ctx[6] if len(seg_ctx) > 6 else None)
-        x = attn.output(ctx, residual=pe_rows, res_rows=pe_rows.size(0))
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward)
+        x = attn.output(ctx, residual=pe_rows, res_rows=pe_rows.size(0), next_ln=self.sublayer[1].norm)
+        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
 
 
 class MixAttLayer(nn.Module):
@@ -104,10 +119,10 @@ class MixAttLayer(nn.Module):
         self.feed_forward = feed_forward
         self.sublayer = clones(SublayerConnection(size, dropout), 3)
 
-    def forward(self, x, memory, src_mask, self_mask, kv=None):
-        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask)
-        x = _src_attention_block(x, self.sublayer[1].norm, self.src_attn, memory, src_mask, kv)
-        return _ffn_block(x, self.sublayer[2].norm, self.feed_forward)
+    def forward(self, x, memory, src_mask, self_mask, kv=None, next_norm=None):
+        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
+        x = _src_attention_block(x, self.sublayer[1].norm, self.src_attn, memory, src_mask, kv, next_norm=self.sublayer[2].norm)
+        return _ffn_block(x, self.sublayer[2].norm, self.feed_forward, next_norm=next_norm)
 
 
 class Encoder(nn.Module):
@@ -121,8 +136,9 @@ class Encoder(nn.Module):
 
     def forward(self, x, mask, interctc_alpha=0, interctc_layer=6):
         inter = None
+        nxt = _next_norms(self.layers)
         for n, layer in enumerate(self.layers):
-            x = layer(x, mask)
+            x = layer(x, mask, next_norm=nxt[n])
             if interctc_alpha > 0 and n == interctc_layer - 1:
                 inter = x
         return (self.norm(x), inter) if interctc_alpha > 0 else self.norm(x)
@@ -136,20 +152,23 @@ class AcEmbedExtractor(nn.Module):
         layer = SrcAttLayer(size, src_attn, feed_forward, dropout)
         self.layers = clones(layer, N)
 
-    def forward(self, x, memory, trigger_mask):
-        for layer in self.layers:
-            x = layer(x, memory, trigger_mask)
+    def forward(self, x, memory, trigger_mask, next_norm=None):
+        nxt = _next_norms(self.layers, next_norm)
+        for n, layer in enumerate(self.layers):
+            x = layer(x, memory, trigger_mask, next_norm=nxt[n])
         return x
 
-    def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None):
+    def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None, next_norm=None):
+        """next_norm: the LayerNorm of whatever consumes the embeddings next (the SAD's first pre-norm)."""
         if torch.is_grad_enabled() and (memory.requires_grad or any(p.requires_grad for p in self.parameters())):
             # training: dense trigger mask through the attention that has a backward
             return self.forward(pe_rows.unsqueeze(0).expand(memory.size(0), -1, -1), memory, dense_mask_fn())
-        x = self.layers[0].forward_segments(pe_rows, memory, seg_ctx)
+        nxt = _next_norms(self.layers, next_norm)
+        x = self.layers[0].forward_segments(pe_rows, memory, seg_ctx, next_norm=nxt[0])
         if len(self.layers) > 1:
             mask = dense_mask_fn()
-            for layer in self.layers[1:]:
-                x = layer(x, memory, mask)
+            for n, layer in enumerate(self.layers[1:], 1):
+                x = layer(x, memory, mask, next_norm=nxt[n])
         return x
 
 
@@ -161,10 +180,11 @@ class SelfAttDecoder(nn.Module):
         layer = SelfAttLayer(size, self_attn, feed_forward, dropout)
         self.layers = clones(layer, N)
 
-    def forward(self, x, mask, interce_alpha=0, interce_layer=4):
+    def forward(self, x, mask, interce_alpha=0, interce_layer=4, next_norm=None):
         inter = None
+        nxt = _next_norms(self.layers, next_norm)
         for n, layer in enumerate(self.layers):
-            x = layer(x, mask)
+            x = layer(x, mask, next_norm=nxt[n])
             if interce_alpha > 0 and n == interce_layer - 1:
                 inter = x
         return (x, inter) if interce_alpha > 0 else x
@@ -187,11 +207,12 @@ class MixAttDecoder(nn.Module):
     def forward(self, x, memory, src_mask, tgt_mask, interce_alpha=0, interce_layer=4):
         kvs = self.project_memory(memory)
         inter = None
+        nxt = _next_norms(self.layers)           # (the final norm stays a separate pass: it also feeds the fp32 API)
         for n, layer in enumerate(self.layers):
-            x = layer(x, memory, src_mask, tgt_mask, kvs[n])
+            x = layer(x, memory, src_mask, tgt_mask, kvs[n], next_norm=nxt[n])
             if interce_alpha > 0 and n == interce_layer - 1:
                 inter = x
-        return (self.norm(x), inter) if interce_alpha > 0 else self.norm(x)
+        return (self.norm.for_head(x), inter) if interce_alpha > 0 else self.norm.for_head(x)
 
 
 def _project_memory_all(dec, memory):
@@ -221,18 +242,20 @@ class ConSelfAttLayer(nn.Module):
         self.pos_type = pos_type
         self.ff_scale = ff_scale
 
-    def _conv(self, x):
-        return self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
+    def _conv(self, x, next_norm=None):
+        return self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x, next_ln=next_norm)
 
-    def forward(self, x, mask, pos_embed):
-        x = _ffn_block(x, self.sublayer[0].norm, self.feed_forward1, self.ff_scale)
+    def forward(self, x, mask, pos_embed, next_norm=None):
+        sl = self.sublayer
         if self.pos_type == "absolute":
-            x = self._conv(x)
-            x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, mask, None)
+            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
+            x = self._conv(x, sl[2].norm)
+            x = _self_attention_block(x, sl[2].norm, self.self_attn, mask, None, next_norm=sl[3].norm)
         else:
-            x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, mask, pos_embed)
-            x = self._conv(x)
-        return _ffn_block(x, self.sublayer[3].norm, self.feed_forward2, self.ff_scale)
+            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
+            x = _self_attention_block(x, sl[2].norm, self.self_attn, mask, pos_embed, next_norm=sl[1].norm)
+            x = self._conv(x, sl[3].norm)
+        return _ffn_block(x, sl[3].norm, self.feed_forward2, self.ff_scale, next_norm=next_norm)
 
 
 class ConSrcAttLayer(nn.Module):
@@ -248,25 +271,26 @@ class ConSrcAttLayer(nn.Module):
         self.pos_type = pos_type
         self.size = size
 
-    def _finish(self, ctx):
-        x = self.pos_enc(self.src_attn.output(ctx, scale=math.sqrt(self.size)))
+    def _finish(self, ctx, next_norm=None):
         if self.pos_type == "relative":
-            x, pos_embed = x
-            return _ffn_block(x, self.sublayer.norm, self.feed_forward), pos_embed
-        return _ffn_block(x, self.sublayer.norm, self.feed_forward)
+            # relative positions: pos_enc leaves x untouched, so the pre-norm of the FFN can ride on the projection
+            x, pos_embed = self.pos_enc(self.src_attn.output(ctx, scale=math.sqrt(self.size), next_ln=self.sublayer.norm))
+            return _ffn_block(x, self.sublayer.norm, self.feed_forward, next_norm=next_norm), pos_embed
+        x = self.pos_enc(self.src_attn.output(ctx, scale=math.sqrt(self.size)))
+        return _ffn_block(x, self.sublayer.norm, self.feed_forward, next_norm=next_norm)
 
-    def forward(self, x, m, src_mask):
+    def forward(self, x, m, src_mask, next_norm=None):
         attn = self.src_attn
         q = attn.project_q(x)
         k, v = attn.project_kv(m)
-        return self._finish(ops.attention(q, k, v, src_mask, attn.h))
+        return self._finish(ops.attention(q, k, v, src_mask, attn.h), next_norm)
 
-    def forward_segments(self, pe_rows, m, seg_ctx, kv=None):
+    def forward_segments(self, pe_rows, m, seg_ctx, kv=None, next_norm=None):
         attn = self.src_attn
         fast = ops.is_bf16() and attn.d_k == 64 and m.size(1) <= 512
         q_rows = attn.project_q(pe_rows, out_bf16=fast)
         k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
-        return self._finish(ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h))
+        return self._finish(ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h), next_norm)
 
 
 class ConMixAttLayer(nn.Module):
@@ -285,16 +309,18 @@ class ConMixAttLayer(nn.Module):
         self.pos_type = pos_type
         self.ff_scale = ff_scale
 
-    def forward(self, x, memory, src_mask, self_mask, pos_embed, kv=None):
-        x = _ffn_block(x, self.sublayer[0].norm, self.feed_forward1, self.ff_scale)
+    def forward(self, x, memory, src_mask, self_mask, pos_embed, kv=None, next_norm=None):
+        sl = self.sublayer
         if self.pos_type == "absolute":
-            x = self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
-            x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, self_mask, None)
+            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
+            x = self.conv_module(sl[1].norm.for_gemm(x), residual=x, next_ln=sl[2].norm)
+            x = _self_attention_block(x, sl[2].norm, self.self_attn, self_mask, None, next_norm=sl[3].norm)
         else:
-            x = _self_attention_block(x, self.sublayer[2].norm, self.self_attn, self_mask, pos_embed)
-            x = self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x)
-        x = _src_attention_block(x, self.sublayer[3].norm, self.src_attn, memory, src_mask, kv)
-        return _ffn_block(x, self.sublayer[4].norm, self.feed_forward2, self.ff_scale)
+            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
+            x = _self_attention_block(x, sl[2].norm, self.self_attn, self_mask, pos_embed, next_norm=sl[1].norm)
+            x = self.conv_module(sl[1].norm.for_gemm(x), residual=x, next_ln=sl[3].norm)
+        x = _src_attention_block(x, sl[3].norm, self.src_attn, memory, src_mask, kv, next_norm=sl[4].norm)
+        return _ffn_block(x, sl[4].norm, self.feed_forward2, self.ff_scale, next_norm=next_norm)
 
 
 def _split_pos(x, pos_type):
@@ -318,8 +344,9 @@ class ConEncoder(nn.Module):
     def forward(self, x, mask, interctc_alpha=0, interctc_layer=0):
         x, pos_embed = _split_pos(x, self.pos_type)
         inter = None
+        nxt = _next_norms(self.layers)
         for n, layer in enumerate(self.layers):
-            x = layer(x, mask, pos_embed)
+            x = layer(x, mask, pos_embed, next_norm=nxt[n])
             if interctc_alpha > 0 and n == interctc_layer - 1:
                 inter = x
         return (self.norm(x), inter) if interctc_alpha > 0 else self.norm(x)
@@ -334,15 +361,15 @@ class ConAcEmbedExtractor(nn.Module):
         self.layers = clones(layer, N)
         assert N == 1, "if more than 1 layer use, code needs to be modified"
 
-    def forward(self, x, memory, trigger_mask):
+    def forward(self, x, memory, trigger_mask, next_norm=None):
         for layer in self.layers:
-            x = layer(x, memory, trigger_mask)
+            x = layer(x, memory, trigger_mask, next_norm=next_norm)
         return x
 
-    def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None):
+    def forward_segments(self, pe_rows, memory, seg_ctx, dense_mask_fn=None, next_norm=None):
         if torch.is_grad_enabled() and (memory.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self.forward(pe_rows.unsqueeze(0).expand(memory.size(0), -1, -1), memory, dense_mask_fn())
-        return self.layers[0].forward_segments(pe_rows, memory, seg_ctx)
+        return self.layers[0].forward_segments(pe_rows, memory, seg_ctx, next_norm=next_norm)
 
 
 class ConSelfAttDecoder(nn.Module):
@@ -356,11 +383,12 @@ class ConSelfAttDecoder(nn.Module):
         self.layers = clones(layer, N)
         self.pos_type = pos_type
 
-    def forward(self, x, mask, interce_alpha=0, interce_layer=0):
+    def forward(self, x, mask, interce_alpha=0, interce_layer=0, next_norm=None):
         x, pos_embed = _split_pos(x, self.pos_type)
         inter = None
+        nxt = _next_norms(self.layers, next_norm)
         for n, layer in enumerate(self.layers):
-            x = layer(x, mask, pos_embed)
+            x = layer(x, mask, pos_embed, next_norm=nxt[n])
             if interce_alpha > 0 and n == interce_layer - 1:
                 inter = x
         return (x, pos_embed, inter) if interce_alpha > 0 else (x, pos_embed)
@@ -385,11 +413,12 @@ class ConMixAttDecoder(nn.Module):
         x, pos_embed = _split_pos(x, self.pos_type)
         kvs = self.project_memory(memory)
         inter = None
+        nxt = _next_norms(self.layers)
         for n, layer in enumerate(self.layers):
-            x = layer(x, memory, src_mask, tgt_mask, pos_embed, kvs[n])
+            x = layer(x, memory, src_mask, tgt_mask, pos_embed, kvs[n], next_norm=nxt[n])
             if interce_alpha > 0 and n == interce_layer - 1:
                 inter = x
-        out = self.norm(x)
+        out = self.norm.for_head(x)
         if interce_alpha > 0:
             return (out, inter) if is_last else (out, pos_embed, inter)
         return out if is_last else (out, pos_embed)

@@ -346,12 +346,16 @@ class CassNAT(nn.Module):
                 seg_ctx = seg_ctx + (need_rows,)                       # extractor: token rows the pick loop can read
         # ---- K6: token acoustic extractor
         pe_rows = self._pe_rows(enc_h, ymax)
+        # (fast mode: every residual GEMM also emits the LayerNorm its consumer applies first -- the stacks hand each
+        # other the norm that comes next; use_unimask shifts the SAD output, so no hand-over there)
+        sad_norm = BK._first_norm(self.embed_mapper.layers[0])
+        mad_norm = None if args.use_unimask else BK._first_norm(self.decoder.layers[0])
         if seg_ctx is not None:
-            ac_embed = self.acembed_extractor.forward_segments(pe_rows, enc_h, seg_ctx, dense_trigger)
+            ac_embed = self.acembed_extractor.forward_segments(pe_rows, enc_h, seg_ctx, dense_trigger, next_norm=sad_norm)
         else:
-            ac_embed = self.acembed_extractor(pe_rows.unsqueeze(0).repeat(BS, 1, 1), enc_h, src_mask)
+            ac_embed = self.acembed_extractor(pe_rows.unsqueeze(0).repeat(BS, 1, 1), enc_h, src_mask, next_norm=sad_norm)
         # ---- K7: SAD
-        pred_embed = self.embed_mapper(ac_embed, tgt_mask)
+        pred_embed = self.embed_mapper(ac_embed, tgt_mask, next_norm=mad_norm)
         if getattr(args, "save_embedding", False) and getattr(args, "sample_num", 0) <= 1:
             first = lambda x: x[0] if isinstance(x, tuple) else x
             args.ac_embed, args.pred_embed = first(ac_embed)[0].cpu(), first(pred_embed)[0].cpu()
@@ -433,9 +437,10 @@ class CassNAT(nn.Module):
         """(storage address, version counter) of every parameter: changes on optimizer.step(), load_state_dict(),
         .to(), .half() ... anything after which cached derived weights (and graphs that point at them) are stale."""
         ps = self.__dict__.get("_stamp_params")
-        if ps is None or len(ps) != sum(1 for _ in self.parameters()):
-            ps = self.__dict__["_stamp_params"] = list(self.parameters())
-        return hash(tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps))
+        if ps is None:                  # the parameters the captured stage reads (everything after the encoder)
+            ps = self.__dict__["_stamp_params"] = [p for n, p in self.named_parameters()
+                                                   if not n.startswith(("src_embed.", "encoder.", "ctc_generator."))]
+        return hash(tuple([p._version for p in ps] + [p.data_ptr() for p in ps]))
 
     def _pinned(self, shape):
         """Reusable pinned int32 staging buffer for the hypothesis read-back."""

@@ -131,6 +131,8 @@ struct Epilogue {
   float alpha; int act;
   float* out_f32; __nv_bfloat16* out_bf16; int64_t ldc;
   int64_t lo_off;        // != 0: out_bf16 is a split (bf16x3) operand, the rounding residue goes lo_off elements further
+  // LN mode: the LayerNorm that consumes the fp32 output (next sublayer's pre-norm) is applied by the same kernel
+  const float* ln_a; const float* ln_b; float ln_eps; __nv_bfloat16* ln_out; int64_t ld_ln;
   // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
   float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
   const int32_t* st_target; float* st_target_logit;    // optional: the logit of one given column per row
@@ -143,7 +145,7 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false>
+template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false, bool LN = false>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K, int split) {
@@ -166,6 +168,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   // split == 2: only W is split (A is a plain bf16 operand, e.g. an attention context): (A, W_hi), (A, W_lo)
   const int k_part = (K + BK - 1) / BK;
   const int k_blocks = split == 1 ? 3 * k_part : (split == 2 ? 2 * k_part : k_part);
+  // Tile schedule (every role walks the same list).  Default: tile = blockIdx + i * grid over the n-fastest tile
+  // index.  LN: a CTA owns whole 128-row blocks (all N tiles of a block back to back), because the fused LayerNorm
+  // needs the complete rows: the row statistics are accumulated across the block's N tiles by the same warps.
+  const int n_my = LN ? (((tiles_m - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * tiles_n)
+                      : ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+  auto tile_of = [&](int i) {
+    return LN ? ((int)blockIdx.x + (i / tiles_n) * (int)gridDim.x) * tiles_n + (i % tiles_n) : (int)blockIdx.x + i * (int)gridDim.x;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -189,7 +199,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int tile = tile_of(ti);
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0; ti < n_my; ++ti) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);             // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -260,7 +271,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       float* bias_s = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES + 256);       // [2][BN]
       const int tid_e = threadIdx.x - 64;
       uint32_t acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int tile = tile_of(ti);
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
         if (tid_e < BN) bias_s[acc * BN + tid_e] = (ep.bias && n0 + tid_e < N) ? ep.bias[n0 + tid_e] : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -338,7 +350,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     const int rr = lane >> 3, cc = (lane & 7) * 4;
     const bool vec_ok = ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0);
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    float ln_s1[8], ln_s2[8];            // LN: sum / sum of squares of this lane's columns of its 8 rows (all N tiles)
+#pragma unroll
+    for (int it = 0; it < 8; ++it) ln_s1[it] = ln_s2[it] = 0.f;
+    for (int ti = 0; ti < n_my; ++ti) {
+      const int tile = tile_of(ti);
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int row0 = m0 + quarter * 32 + rr;                  // first of the 8 rows (stride 4) this lane stores
       // Residual rows do not depend on the accumulator: fetch them one chunk ahead so their HBM
@@ -404,6 +420,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
               x[it][0] += res_cur[it].x; x[it][1] += res_cur[it].y; x[it][2] += res_cur[it].z; x[it][3] += res_cur[it].w;
             }
           }
+          if (LN) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              ln_s1[it] += (x[it][0] + x[it][1]) + (x[it][2] + x[it][3]);
+              ln_s2[it] = fmaf(x[it][0], x[it][0], fmaf(x[it][1], x[it][1], fmaf(x[it][2], x[it][2], fmaf(x[it][3], x[it][3], ln_s2[it]))));
+            }
+          }
           if (ep.out_f32) {
             float* o = ep.out_f32 + (int64_t)row0 * ep.ldc + gcol;
 #pragma unroll
@@ -462,6 +485,70 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (LN && (tile % tiles_n) == tiles_n - 1) {
+        // ---- fused LayerNorm of the 128 finished rows (modules/norm.py:15-18: unbiased std, eps added to std).
+        // Row totals: over this lane's columns (registers), over the 8 lanes that share a row (shuffles), over the
+        // two warps that share the lane quarter (staging buffer + a 64-thread named barrier).  The MMA warp is
+        // already filling the next block's accumulator while this runs.
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            ln_s1[it] += __shfl_xor_sync(0xffffffffu, ln_s1[it], o);
+            ln_s2[it] += __shfl_xor_sync(0xffffffffu, ln_s2[it], o);
+          }
+        }
+        if ((lane & 7) == 0) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(stg + (uint32_t)((it * 4 + rr) * 8)), "f"(ln_s1[it]), "f"(ln_s2[it]) : "memory");
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+        const uint32_t stg_peer = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)((warp - 2) ^ 4) * 4096u;
+        float mean[8], rinv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float a1, a2, b1, b2;
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a1), "=f"(a2) : "r"(stg + (uint32_t)((it * 4 + rr) * 8)));
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(b1), "=f"(b2) : "r"(stg_peer + (uint32_t)((it * 4 + rr) * 8)));
+          const float s1 = a1 + b1, s2 = a2 + b2;
+          mean[it] = s1 / (float)N;
+          const float var = fmaxf(s2 - s1 * mean[it], 0.f) / (float)(N - 1);
+          rinv[it] = 1.f / (sqrtf(var) + ep.ln_eps);
+          ln_s1[it] = ln_s2[it] = 0.f;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");     // both warps have read: staging is free again
+        // second pass over this lane's own outputs (just written: L2-resident; a thread sees its own stores)
+#pragma unroll 1
+        for (int nt = 0; nt < tiles_n; ++nt) {
+#pragma unroll 1
+          for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+            const int gcol = nt * BN + c0 + cc;
+            if (gcol + 3 >= N) continue;                             // (N % 4 == 0: a lane is inside or outside)
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(ep.ln_a + gcol));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(ep.ln_b + gcol));
+            float4 xv[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row0 + it * 4;
+              xv[it] = grow < M ? *reinterpret_cast<const float4*>(ep.out_f32 + (int64_t)grow * ep.ldc + gcol)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int grow = row0 + it * 4;
+              if (grow >= M) continue;
+              const float y0 = fmaf(ga.x * (xv[it].x - mean[it]), rinv[it], be.x), y1 = fmaf(ga.y * (xv[it].y - mean[it]), rinv[it], be.y);
+              const float y2 = fmaf(ga.z * (xv[it].z - mean[it]), rinv[it], be.z), y3 = fmaf(ga.w * (xv[it].w - mean[it]), rinv[it], be.w);
+              __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(ep.ln_out + (int64_t)grow * ep.ld_ln + gcol) = pk;
+            }
+          }
+        }
+      }
     }
     }  // !STATS
   }
@@ -516,28 +603,30 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false>
+template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false, bool LN = false>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream, int split = 0) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int tiles = LN ? (M + BM - 1) / BM : ((M + BM - 1) / BM) * ((N + BN - 1) / BN);     // LN: whole row blocks per CTA
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
+  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
 }  // namespace
 
+struct LnArgs { const float* a; const float* b; float eps; void* out; int64_t ld; };
+
 static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
                          float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                         int split, int out_split, cn_stream_t stream_) {
+                         int split, int out_split, cn_stream_t stream_, const LnArgs* ln = nullptr) {
   const int64_t kcols = split ? 2 * K : K, acols = split == 1 ? 2 * K : K;      // stored columns of W and A
   if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || lda < acols || ldw < kcols || ldc < N)
     return CN_ERR_BAD_ARG;
@@ -552,16 +641,36 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
   // 128x256 tiles unless the problem is the HBM-bound d x d projection shape (N, K <= 512): there the
   // epilogue streams more bytes than the mainloop computes, and 128x128 tiles fill the last wave of the
   // 148 persistent CTAs better (measured on [32000x512x512]: 38.8 -> 34.9 us)
-  const int bn = (N > 128 && !(N <= 512 && K <= 512 && !split)) ? 256 : 128;
+  int bn = (N > 128 && !(N <= 512 && K <= 512 && !split)) ? 256 : 128;
+  if (ln) {
+    // fused LayerNorm: a CTA owns complete rows as at most two N tiles; vector epilogue only
+    if (!ln->a || !ln->b || !ln->out || !out_f32 || out_bf16 || act != CN_ACT_NONE || ln->ld < N) return CN_ERR_BAD_ARG;
+    if (N > 512 || N < 2 || (N & 3) || (ldc & 3) || (ln->ld & 3) || (residual && (ldr & 3)) ||
+        (reinterpret_cast<uintptr_t>(out_f32) & 15) || (reinterpret_cast<uintptr_t>(ln->out) & 7) ||
+        (reinterpret_cast<uintptr_t>(ln->a) & 15) || (reinterpret_cast<uintptr_t>(ln->b) & 15) ||
+        (residual && (reinterpret_cast<uintptr_t>(residual) & 15)))
+      return CN_ERR_UNSUPPORTED;
+    bn = N > 256 ? 256 : 128;
+  }
   CUtensorMap ma, mw;
   if (!make_map(&ma, A, M, acols, lda, BM) || !make_map(&mw, W, N, kcols, ldw, bn)) return CN_ERR_DEVICE;
   Epilogue ep;
   ep.bias = bias; ep.residual = residual; ep.ldr = ldr; ep.res_rows = res_rows; ep.alpha = alpha; ep.act = act;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = out_split ? N : 0;
+  ep.ln_a = ln ? ln->a : nullptr; ep.ln_b = ln ? ln->b : nullptr; ep.ln_eps = ln ? ln->eps : 0.f;
+  ep.ln_out = ln ? (__nv_bfloat16*)ln->out : nullptr; ep.ld_ln = ln ? ln->ld : 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
+  if (ln) {
+    if (bn == 256) {
+      if (residual) return launch_tc<256, CN_ACT_NONE, true, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+      return launch_tc<256, CN_ACT_NONE, false, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+    }
+    if (residual) return launch_tc<128, CN_ACT_NONE, true, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+    return launch_tc<128, CN_ACT_NONE, false, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+  }
 #define CN_TC_DISPATCH(BN_)                                                                                     \
   do {                                                                                                          \
     if (residual) {                                                                                             \
@@ -584,6 +693,15 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                             cn_stream_t stream_) {
   return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, act, out_f32, out_bf16, ldc, M, N, K, 0, 0,
                         stream_);
+}
+
+extern "C" int cn_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                               const float* residual, int64_t ldr, int64_t res_rows, float alpha, float* out_f32,
+                               int64_t ldc, const float* ln_a, const float* ln_b, float ln_eps, void* ln_out,
+                               int64_t ld_ln, int64_t M, int64_t N, int64_t K, cn_stream_t stream_) {
+  LnArgs ln{ln_a, ln_b, ln_eps, ln_out, ld_ln};
+  return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, CN_ACT_NONE, out_f32, nullptr, ldc, M, N, K, 0, 0,
+                        stream_, &ln);
 }
 
 extern "C" int cn_gemm_bf16x3(const void* A, int64_t lda, int a_split, const void* W, int64_t ldw, const float* bias,
@@ -630,6 +748,7 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
   Epilogue ep;
   ep.bias = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = 1.f; ep.act = CN_ACT_NONE;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = 0;
+  ep.ln_a = nullptr; ep.ln_b = nullptr; ep.ln_eps = 0.f; ep.ln_out = nullptr; ep.ld_ln = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -966,6 +1085,7 @@ static int gemm_rowstats_impl(const void* A, int64_t lda, const void* W, int64_t
   Epilogue ep;
   ep.bias = bias; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = alpha; ep.act = CN_ACT_NONE;
   ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0; ep.lo_off = 0;
+  ep.ln_a = nullptr; ep.ln_b = nullptr; ep.ln_eps = 0.f; ep.ln_out = nullptr; ep.ld_ln = 0;
   ep.st_max = pmax; ep.st_idx = pidx; ep.st_sum = psum; ep.st_max2 = top2 ? pmax2 : nullptr;
   ep.st_idx2 = top2 ? pidx2 : nullptr; ep.n_parts = parts;
   ep.st_target = target; ep.st_target_logit = target_logit;

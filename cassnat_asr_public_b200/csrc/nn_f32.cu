@@ -128,7 +128,7 @@ extern "C" int cn_gemm_f32(const float* A, int64_t lda, const float* W, int64_t 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
                                                         const float* __restrict__ a, const float* __restrict__ b,
                                                         float eps, float* __restrict__ of32,
-                                                        __nv_bfloat16* __restrict__ obf, int64_t ldo, int64_t lo_off) {
+                                                        __nv_bfloat16* __restrict__ obf, int64_t ldo, int64_t ldob, int64_t lo_off) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (of32) of32[r * ldo + i] = y;
     if (obf) {
       const __nv_bfloat16 yh = __float2bfloat16(y);
-      obf[r * ldo + i] = yh;
-      if (lo_off) obf[r * ldo + lo_off + i] = __float2bfloat16(y - __bfloat162float(yh));   // split (bf16x3) operand
+      obf[r * ldob + i] = yh;
+      if (lo_off) obf[r * ldob + lo_off + i] = __float2bfloat16(y - __bfloat162float(yh));   // split (bf16x3) operand
     }
   }
 }
@@ -159,7 +159,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int64_t ldx,
                                                             const float* __restrict__ a, const float* __restrict__ b,
                                                             float eps, float* __restrict__ of32,
-                                                            __nv_bfloat16* __restrict__ obf, int64_t ldo, int64_t lo_off) {
+                                                            __nv_bfloat16* __restrict__ obf, int64_t ldo, int64_t ldob, int64_t lo_off) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -192,47 +192,50 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(obf + r * ldo + c) = pk;
+      *reinterpret_cast<uint2*>(obf + r * ldob + c) = pk;
       if (lo_off) {                                         // split (bf16x3) operand: rounding residue in the lo half
         const float2 f0 = __bfloat1622float2(lo), f1 = __bfloat1622float2(hi);
         __nv_bfloat162 r0 = __floats2bfloat162_rn(y.x - f0.x, y.y - f0.y), r1 = __floats2bfloat162_rn(y.z - f1.x, y.w - f1.y);
         pk.x = *reinterpret_cast<uint32_t*>(&r0);
         pk.y = *reinterpret_cast<uint32_t*>(&r1);
-        *reinterpret_cast<uint2*>(obf + r * ldo + lo_off + c) = pk;
+        *reinterpret_cast<uint2*>(obf + r * ldob + lo_off + c) = pk;
       }
     }
   }
 }
 
 static int layernorm_impl(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
-                          float eps, float* out_f32, void* out_bf16, int64_t ldo, int64_t lo_off, cn_stream_t stream_) {
-  if (!x || !a || !b || rows < 0 || d < 2 || ldx < d || ldo < d + lo_off || (!out_f32 && !out_bf16)) return CN_ERR_BAD_ARG;
+                          float eps, float* out_f32, void* out_bf16, int64_t ldo, int64_t ldob, int64_t lo_off,
+                          cn_stream_t stream_) {
+  if (!x || !a || !b || rows < 0 || d < 2 || ldx < d || (!out_f32 && !out_bf16)) return CN_ERR_BAD_ARG;
+  if ((out_f32 && ldo < d) || (out_bf16 && ldob < d + lo_off)) return CN_ERR_BAD_ARG;
   if (rows == 0) return CN_OK;
   const int64_t blocks = (rows + 7) / 8;
   cudaStream_t stream = (cudaStream_t)stream_;
   __nv_bfloat16* obf = (__nv_bfloat16*)out_bf16;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                          reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && (lo_off & 3) == 0;
-  if (aligned && d == 128) layernorm_vec_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, lo_off);
-  else if (aligned && d == 256) layernorm_vec_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, lo_off);
-  else if (aligned && d == 512) layernorm_vec_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, lo_off);
-  else if (aligned && d == 1024) layernorm_vec_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, lo_off);
-  else layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, (int)d, ldx, a, b, eps, out_f32, obf, ldo, lo_off);
+                       (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && (ldob & 3) == 0 && (lo_off & 3) == 0;
+  if (aligned && d == 128) layernorm_vec_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+  else if (aligned && d == 256) layernorm_vec_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+  else if (aligned && d == 512) layernorm_vec_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+  else if (aligned && d == 1024) layernorm_vec_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+  else layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, (int)d, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
 
 extern "C" int cn_layernorm(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
                             float eps, float* out_f32, void* out_bf16, int64_t ldo, cn_stream_t stream_) {
-  return layernorm_impl(x, rows, d, ldx, a, b, eps, out_f32, out_bf16, ldo, 0, stream_);
+  return layernorm_impl(x, rows, d, ldx, a, b, eps, out_f32, out_bf16, ldo, ldo, 0, stream_);
 }
 
 // LayerNorm emitting the split bf16 operand [rows, 2d] = [hi | lo] of the bf16x3 GEMM (see cn_gemm_bf16x3)
 extern "C" int cn_layernorm_bf16x2(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
-                                   float eps, void* out_split, int64_t ldo, cn_stream_t stream_) {
+                                   float eps, float* out_f32, int64_t ldo_f32, void* out_split, int64_t ldo,
+                                   cn_stream_t stream_) {
   if (!out_split) return CN_ERR_BAD_ARG;
-  return layernorm_impl(x, rows, d, ldx, a, b, eps, nullptr, out_split, ldo, d, stream_);
+  return layernorm_impl(x, rows, d, ldx, a, b, eps, out_f32, out_split, ldo_f32, ldo, d, stream_);
 }
 
 // ===================================================================== masked MHA (fp32)

@@ -189,7 +189,7 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, a_2, b_2, eps, bf16):
         with torch.no_grad():
-            y = ops.layer_norm_forward(x, a_2, b_2, eps, bf16)
+            y = ops.layer_norm_forward(x, a_2, b_2, eps, bf16, split_ok=False)     # training runs plain bf16 GEMMs
         ctx.eps = float(eps)
         ctx.save_for_backward(x, a_2)
         return y

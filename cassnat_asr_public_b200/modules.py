@@ -69,8 +69,19 @@ class LayerNorm(nn.Module):
         return ops.layer_norm(x, self.a_2, self.b_2, self.eps)
 
     def for_gemm(self, x):
-        """Same normalisation, emitted in the operand type of the next GEMM (bf16 in fast mode)."""
+        """Same normalisation, emitted in the operand type of the next GEMM (bf16 in fast mode).  When the kernel
+        that produced x already applied this norm in its epilogue (ops.linear(..., next_ln=self)) the result is
+        picked up instead of being recomputed."""
+        hit = getattr(x, "_cn_ln", None)
+        if hit is not None and hit[0] is self and ops.get_precision() == "bf16":
+            return hit[1]
         return ops.layer_norm(x, self.a_2, self.b_2, self.eps, bf16=ops.is_bf16())
+
+    def for_head(self, x):
+        """fp32 result (API contract) whose split bf16 twin for the decision-safe head comes from the same pass."""
+        if ops.is_bf16() and (ops.SAFE_HEADS or ops.is_x3()) and x.shape[-1] % 64 == 0 and not ops._needs_grad(x, self.a_2, self.b_2):
+            return ops.layer_norm_for_head(x, self.a_2, self.b_2, self.eps)
+        return self.forward(x)
 
 
 class PositionwiseFeedForward(nn.Module):
@@ -81,13 +92,13 @@ class PositionwiseFeedForward(nn.Module):
         self.p_drop = dropout
         self.activation = activation
 
-    def forward(self, x, residual=None, scale=1.0):
+    def forward(self, x, residual=None, scale=1.0, next_ln=None):
         """w_2(act(w_1 x)); with `residual` the pre-norm residual add (and the conformer's 1/2
-        scale) is fused into the second GEMM's epilogue."""
+        scale) is fused into the second GEMM's epilogue, and with `next_ln` the following LayerNorm too."""
         _no_dropout(self, self.p_drop)
         hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation), out_bf16=ops.is_bf16(),
                          out_split=ops.is_x3())
-        return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale)
+        return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale, next_ln=next_ln)
 
 
 class SublayerConnection(nn.Module):
@@ -132,9 +143,9 @@ class MultiHeadedAttention(nn.Module):
         d = self.h * self.d_k
         return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
 
-    def output(self, ctx, residual=None, scale=1.0, res_rows=0):
+    def output(self, ctx, residual=None, scale=1.0, res_rows=0, next_ln=None):
         return ops.linear(ctx, self.linears[3].weight, self.linears[3].bias, residual=residual, alpha=scale,
-                          res_rows=res_rows)
+                          res_rows=res_rows, next_ln=next_ln)
 
     def forward(self, query, key, value, mask=None, pos_embed=None):
         _no_dropout(self, self.p_drop)
@@ -255,7 +266,7 @@ class ConvModule(nn.Module):
         self.pointwise_conv2 = nn.Conv1d(channels, channels, kernel_size=1, stride=1, padding=0, bias=bias)
         self.activation = activation
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, next_ln=None):
         """x [B,L,C] -> [B,L,C]: pointwise conv (a GEMM over channels) + GLU, depthwise conv,
         GroupNorm(1,C) over the whole [C,L] slab of each utterance, Swish, pointwise conv."""
         C = x.size(-1)
@@ -264,7 +275,8 @@ class ConvModule(nn.Module):
         y = ops.glu_dwconv_groupnorm_act(y, self.depthwise_conv.weight, self.depthwise_conv.bias,
                                          self.norm.weight, self.norm.bias, self.norm.eps, _act_name(self.activation),
                                          out_bf16=fast)
-        return ops.linear(y, self.pointwise_conv2.weight.view(C, C), self.pointwise_conv2.bias, residual=residual)
+        return ops.linear(y, self.pointwise_conv2.weight.view(C, C), self.pointwise_conv2.bias, residual=residual,
+                          next_ln=next_ln)
 
 
 class ConvEmbedding(nn.Module):

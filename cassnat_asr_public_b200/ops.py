@@ -231,7 +231,8 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
-def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False, out_split=False):
+def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False, out_split=False,
+           next_ln=None):
     """residual + alpha * act(x @ weight.T + bias) over the last dim of x.
     fp32 mode: FFMA kernel on f32 operands.  bf16 mode: x (f32 or bf16) and the weight go through the
     tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains).
@@ -241,15 +242,25 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
         from . import grad
         assert out is None
         return grad.Linear.apply(x, weight, bias, residual, alpha, act, res_rows, out_bf16)
-    return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split)
+    return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split, next_ln)
+
+
+FUSE_LN = True       # fast mode: the LayerNorm that consumes a residual GEMM's output runs in that GEMM's epilogue
 
 
 def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False,
-                   out_split=False):
+                   out_split=False, next_ln=None):
+    """next_ln (fast mode): the LayerNorm module that will normalise this output next (the following sublayer's
+    pre-norm).  Its bf16 result is produced by the same kernel and attached to the returned tensor, where
+    LayerNorm.for_gemm finds it (cn_gemm_bf16_ln)."""
     require_cuda(x, weight)
-    if _PRECISION == "bf16x3" and x.shape[-1] % 64 == 0 and not torch.is_grad_enabled():
+    if _PRECISION == "bf16x3" and x.shape[-1] % 64 == 0:
         return linear_x3(x, weight, bias, residual, alpha, act, res_rows, out_bf16, out_split)
     if _PRECISION != "fp32" and x.shape[-1] % 8 == 0:
+        N = weight.shape[0]
+        if (FUSE_LN and next_ln is not None and _PRECISION == "bf16" and not out_bf16 and act is None and N <= 512 and
+                N % 4 == 0 and N >= 8):
+            return linear_bf16_ln(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, res_rows, next_ln)
         return linear_bf16(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, act, res_rows,
                            torch.bfloat16 if out_bf16 else torch.float32)
     if x.dtype != torch.float32:
@@ -283,22 +294,38 @@ def layer_norm(x, a_2, b_2, eps=1e-6, bf16=False):
     return layer_norm_forward(x, a_2, b_2, eps, bf16)
 
 
-def layer_norm_forward(x, a_2, b_2, eps=1e-6, bf16=False):
+def layer_norm_forward(x, a_2, b_2, eps=1e-6, bf16=False, split_ok=True):
     require_cuda(x)
     d = x.shape[-1]
     x2 = x.reshape(-1, d)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
-    if bf16 and _PRECISION == "bf16x3" and d % 4 == 0 and not torch.is_grad_enabled():
+    if bf16 and split_ok and _PRECISION == "bf16x3" and d % 4 == 0:
         full = torch.empty(*x.shape[:-1], 2 * d, dtype=torch.bfloat16, device=x.device)
-        call("cn_layernorm_bf16x2", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps), ptr(full), 2 * d,
-             stream(), work=dict(bytes=float(x2.shape[0] * d * 8)))
+        call("cn_layernorm_bf16x2", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps), None, 0, ptr(full),
+             2 * d, stream(), work=dict(bytes=float(x2.shape[0] * d * 8)))
         return _hi_view(full)
     out = torch.empty(x.shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
     o2 = out.reshape(-1, d)
     call("cn_layernorm", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps),
          None if bf16 else ptr(o2), ptr(o2) if bf16 else None, o2.stride(0), stream(),
          work=dict(bytes=float(x2.shape[0] * d * (4 + (2 if bf16 else 4)))))
+    return out
+
+
+def layer_norm_for_head(x, a_2, b_2, eps=1e-6):
+    """LayerNorm in fp32 (what the API returns) plus, in one pass, its split bf16 twin for a decision-safe head:
+    the f32 result carries `_cn_split16` = [.., 2d] bf16 [hi | lo], which head_rowstats consumes."""
+    require_cuda(x)
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    full = torch.empty(*x.shape[:-1], 2 * d, dtype=torch.bfloat16, device=x.device)
+    call("cn_layernorm_bf16x2", ptr(x2), x2.shape[0], d, x2.stride(0), ptr(a_2), ptr(b_2), float(eps), ptr(out), d, ptr(full),
+         2 * d, stream(), work=dict(bytes=float(x2.shape[0] * d * 12)))
+    out._cn_split16 = full
     return out
 
 
@@ -517,6 +544,32 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
     return o32 if o32 is not None else o16
 
 
+def linear_bf16_ln(x, weight_bf16, bias, residual, alpha, res_rows, ln):
+    """residual + alpha * (x W^T + bias) as fp32, plus ln(that) as bf16 from the same kernel; the bf16 tensor rides on
+    the fp32 one as `_cn_ln = (ln module, tensor)`."""
+    K = x.shape[-1]
+    N = weight_bf16.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    lead = x.shape[:-1]
+    o32 = torch.empty(*lead, N, dtype=torch.float32, device=x.device)
+    o16 = torch.empty(*lead, N, dtype=torch.bfloat16, device=x.device)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1 or r2.stride(0) % 4 or r2.data_ptr() % 16:
+            r2 = r2.contiguous()
+    call("cn_gemm_bf16_ln", ptr(x2), x2.stride(0), ptr(weight_bf16), weight_bf16.stride(0), ptr(bias), ptr(r2),
+         r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ptr(o32), N, ptr(ln.a_2), ptr(ln.b_2),
+         float(ln.eps), ptr(o16), N, M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (4.0 + 2.0 + (4.0 if r2 is not None else 0.0))),
+         tag=(f"cn_gemm_bf16_ln[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
+    o32._cn_ln = (ln, o16)
+    return o32
+
+
 def decode_hints(ylen, ymax, src_mask2, use_q=True):
     """All length hints of a decode step in one launch -> dict(need_rows, kv_tgt, last_key, order_tgt, order_src)
     of int32 [B] tensors (see cn_decode_hints)."""
@@ -681,7 +734,13 @@ def head_rowstats(x, weight, bias=None, alpha=1.0, top2=False, target=None, safe
     safe = (SAFE_HEADS if safe is None else safe) or _PRECISION == "bf16x3"
     x3 = safe and K % 64 == 0 and (x.dtype != torch.bfloat16 or split_of(x) is not None)
     if x3:                        # decision-safe head: split operands, three passes
-        full = split_of(x) if x.dtype == torch.bfloat16 else cast_bf16_split(x, tag=False)
+        twin = getattr(x, "_cn_split16", None)                  # produced together with x by layer_norm_for_head
+        if x.dtype == torch.bfloat16:
+            full = split_of(x)
+        elif twin is not None and twin.shape[:-1] == x.shape[:-1] and twin.shape[-1] == 2 * K:
+            full = twin
+        else:
+            full = cast_bf16_split(x, tag=False)
         wb = bf16_weight_split(weight)
         x2 = full.reshape(-1, 2 * K)
     else:

@@ -205,6 +205,18 @@ int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const f
 /* y(bf16) = x(f32), n elements (n % 4 == 0, 16-byte aligned x). */
 int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stream);
 
+/* The pre-norm residual step and the LayerNorm that consumes it, in one kernel:
+ *   x_new = residual + alpha * (A W^T + bias)      -> out_f32 [M,N]   (the fp32 residual stream)
+ *   ln_out = ln_a * (x_new - mean) / (std_unbiased + ln_eps) + ln_b   -> bf16 [M,N] (operand of the next GEMM)
+ *   replaces: SublayerConnection + the next sublayer's LayerNorm   src/models/modules/utils.py:25-32, norm.py:15-18
+ * A CTA owns complete 128-row blocks (its <= 2 column tiles back to back); the row statistics are accumulated in
+ * the epilogue, exchanged through shared memory, and the normalised copy is produced from the L2-hot fp32 rows
+ * while the tensor pipe already works on the next block.  N <= 512, N % 4 == 0, 16-byte aligned rows. */
+int cn_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                    const float* residual, int64_t ldr, int64_t res_rows, float alpha, float* out_f32, int64_t ldc,
+                    const float* ln_a, const float* ln_b, float ln_eps, void* ln_out, int64_t ld_ln,
+                    int64_t M, int64_t N, int64_t K, cn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * bf16x3 ("split") arithmetic: fp32-grade products on the bf16 tensor cores.  A value v is carried as the pair
  * hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits); a split operand matrix stores [hi | lo] along the contraction
@@ -221,9 +233,10 @@ int cn_gemm_bf16x3(const void* A, int64_t lda, int a_split, const void* W_split,
 /* x f32 [rows, K] (row pitch ldx) -> split operand bf16 [rows, 2K] (row pitch ldy); K % 4 == 0.  The hi half is
  * the plain bf16 cast (single-pass GEMMs may read it in place with row pitch ldy). */
 int cn_cast_bf16_split(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t K, cn_stream_t stream);
-/* LayerNorm (as cn_layernorm) emitting the split operand bf16 [rows, 2d] (row pitch ldo). */
+/* LayerNorm (as cn_layernorm) emitting the split operand bf16 [rows, 2d] (row pitch ldo) and, optionally, the fp32
+ * result as well (out_f32 may be NULL; row pitch ldo_f32): the decoder's final norm feeding the K9 head. */
 int cn_layernorm_bf16x2(const float* x, int64_t rows, int64_t d, int64_t ldx, const float* a, const float* b,
-                        float eps, void* out_split, int64_t ldo, cn_stream_t stream);
+                        float eps, float* out_f32, int64_t ldo_f32, void* out_split, int64_t ldo, cn_stream_t stream);
 
 /* Fast mode: masked multi-head attention on tcgen05 (bf16 Q/K/V in, bf16 context out, fp32 softmax).
  * Same semantics as cn_attention_f32 without the relative-position terms; d_k == 64, Tk <= 512,

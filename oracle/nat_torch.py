@@ -67,7 +67,9 @@ def mha(q_in, kv_in, mask, sd, pfx, h):
     v = _heads(linear(kv_in, sd, pfx + ".linears.2"), h)
     s = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.size(-1))
     if mask is not None:
-        s = s.masked_fill(mask.unsqueeze(1) == 0, F32_MIN)
+        # fp32: np.finfo(float32).min like the reference; under bf16 autocast (bench.py's GPU-eager comparator only)
+        # the fill must be representable in the score dtype
+        s = s.masked_fill(mask.unsqueeze(1) == 0, F32_MIN if s.dtype == torch.float32 else torch.finfo(s.dtype).min)
     p = F.softmax(s, dim=-1)
     ctx = torch.matmul(p, v).transpose(1, 2).contiguous().view(q_in.size(0), -1, q.size(-1) * h)
     return linear(ctx, sd, pfx + ".linears.3")

@@ -26,6 +26,8 @@ constexpr int BK = 64;           // bf16 elements per stage row = 128 bytes = on
 constexpr int UK = 16;           // K per tcgen05.mma for 16-bit inputs
 constexpr int STAGES = 4;
 constexpr int THREADS = 320;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..9: epilogue
+constexpr int EPI_WARP0 = 2;     // first epilogue warp
+constexpr int CONV_THREADS = 320;   // conv2_igemm_kernel keeps the compact layout (warps 2..9 epilogue)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -194,6 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // (setmaxnreg re-balancing between the single-lane roles and the epilogue warps was tried: ptxas then spills in
+  // every instantiation, with or without role-pure warpgroups; the epilogue stays inside the common 168 registers)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -256,20 +260,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // ===================== epilogue (warps 2..9) =====================
     // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the BN columns.
     // TMEM hands every thread one ROW (32 consecutive columns).  Writing rows straight to global
     // memory costs 32 L1 wavefronts per store instruction, so each warp transposes its 32x32 chunk
     // through a private padded smem buffer and stores 4 rows x 128 contiguous bytes per instruction.
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int quarter = warp & 3, half = (warp - EPI_WARP0) >> 2;
     if constexpr (STATS) {
       // Fused row statistics (K1/K9): every thread owns one output ROW of the tile (its TMEM lane) and
       // scans its half of the tile's columns: running (max, first index), runner-up and online
       // sum of exp.  Partials go to [row][part] arrays; a tiny second kernel merges the parts.
       // The logits themselves never leave the SM.
       float* bias_s = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES + 256);       // [2][BN]
-      const int tid_e = threadIdx.x - 64;
+      const int tid_e = threadIdx.x - EPI_WARP0 * 32;
       uint32_t acc = 0, acc_phase = 0;
       for (int ti = 0; ti < n_my; ++ti) {
         const int tile = tile_of(ti);
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
-    const uint32_t stg = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)(warp - 2) * 4096u;   // 32 x 32 fp32, XOR-swizzled 16-byte chunks
+    const uint32_t stg = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)(warp - EPI_WARP0) * 4096u;   // 32 x 32 fp32, XOR-swizzled 16-byte chunks
     const int rr = lane >> 3, cc = (lane & 7) * 4;
     const bool vec_ok = ((ep.ldc & 3) == 0) && (!ep.residual || (ep.ldr & 3) == 0);
     uint32_t acc = 0, acc_phase = 0;
@@ -359,6 +363,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       const int row0 = m0 + quarter * 32 + rr;                  // first of the 8 rows (stride 4) this lane stores
       // Residual rows do not depend on the accumulator: fetch them one chunk ahead so their HBM
       // latency hides behind the MMAs / the previous chunk instead of stalling the epilogue.
+      // (Measured alternatives, both slower: a continuous stream two chunks ahead across tile boundaries with the
+      // chunk loop unrolled, 35 -> 47 us on [32000x512x512]; setmaxnreg re-balancing, which makes ptxas spill.)
       auto load_res = [&](int c0, float4 (&r)[8]) {
         const int gc = n0 + c0 + cc;
         const bool ok = RES && ep.residual && vec_ok && gc + 3 < N;
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
             asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(stg + (uint32_t)((it * 4 + rr) * 8)), "f"(ln_s1[it]), "f"(ln_s2[it]) : "memory");
         }
         asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
-        const uint32_t stg_peer = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)((warp - 2) ^ 4) * 4096u;
+        const uint32_t stg_peer = smem_u32(tiles + STAGES * STAGE_BYTES + 256) + (uint32_t)((warp - EPI_WARP0) ^ 4) * 4096u;
         float mean[8], rinv[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -785,7 +791,7 @@ struct ConvArgs {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) conv2_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv2_igemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_w, ConvArgs cv) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -1019,7 +1025,7 @@ extern "C" int cn_conv_frontend_bf16(const float* x, int64_t sbx, int64_t stx, i
   }
   const int64_t tiles = B * ((T2 + CV_TT - 1) / CV_TT) * ((F2 + CV_FT - 1) / CV_FT) * (C / 256);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  conv2_igemm_kernel<256><<<grid, THREADS, smem2, stream>>>(ma, mw, cv);
+  conv2_igemm_kernel<256><<<grid, CONV_THREADS, smem2, stream>>>(ma, mw, cv);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -5,13 +5,14 @@
 // by all query tiles.  Two softmax warpgroups ping-pong on two query tiles (A/B) so that the
 // tensor pipe computes S_B while group A is in its softmax and vice versa:
 //   * S_g = Q_g K_j^T  (128 x 128 x 64, K-major operands) into TMEM;
-//   * the softmax group reads S_g with tcgen05.ld (32-column chunks, software pipelined), applies
+//   * the softmax group reads its S_g row ONCE (tcgen05.ld, 128 fp32 values per thread stay in registers), applies
 //     1/sqrt(d_k) and the mask with the reference's finfo.min semantics (fully masked rows stay
-//     uniform over all Tk keys, modules/attention.py:19-21), keeps a running max / sum and writes
-//     P_g as bf16 into shared memory in the K-major swizzled layout the next MMA reads;
-//   * O_g = P_g V_j (128 x 64 x 128; the V tile is used in place as an MN-major operand) into a
-//     double-buffered TMEM slot, folded into per-row fp32 registers with the online-softmax
-//     correction while the next MMAs run;
+//     uniform over all Tk keys, modules/attention.py:19-21), and writes P_g as packed bf16 back into TMEM
+//     (tcgen05.st): P never touches shared memory;
+//   * O_g += P_g V_j (128 x 64 x 128; A operand from TMEM, the V tile used in place as an MN-major shared-memory
+//     operand) accumulates in TMEM across the key tiles.  The running maximum is only advanced when a tile exceeds
+//     it by more than 2^8 (lazy rescale): then, and only then, a thread rescales its O row in TMEM; the exact
+//     normalisation by the row sum happens once, at the end;
 //   * a dedicated TMA warp runs ahead through the schedule (next Q tiles, next item's K/V as soon
 //     as the last MMA that reads a slot has retired).
 // Replaces (fast mode) attention() of src/models/modules/attention.py:13-24.
@@ -96,6 +97,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 32 consecutive 32-bit columns <- 32 registers per thread (thread i = TMEM lane base+i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* u) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+        "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]),
+        "r"(u[18]), "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]),
+        "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P, bf16 pairs packed along K in 32-bit columns) comes from TMEM
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -140,13 +162,14 @@ struct AttnTcArgs {
 //   warps 4-7  softmax group B (query tile 2p+1)          -> two softmax warps per scheduler
 //   warp 8     tcgen05.mma issuer (one lane)
 //   warp 9     TMA producer (one lane), runs ahead through the whole schedule
-// smem: Q_A | Q_B | K 4x16K | V 4x16K | P_A 32K | P_B 32K | barriers ; TMEM: S_A S_B O_A[2] O_B[2]
-constexpr uint32_t OFF_Q = 0, OFF_K = 2 * 16384, OFF_V = OFF_K + MAX_TILES * 16384, OFF_P = OFF_V + MAX_TILES * 16384,
-                   OFF_BAR = OFF_P + 2 * 32768, SMEM_BYTES = OFF_BAR + 1024 + 1024;   // barriers + key-mask words, alignment slack
+// smem: Q_A | Q_B | K 4x16K | V 4x16K | barriers ; TMEM: S_A S_B | O_A O_B | P_A P_B
+constexpr uint32_t OFF_Q = 0, OFF_K = 2 * 16384, OFF_V = OFF_K + MAX_TILES * 16384,
+                   OFF_BAR = OFF_V + MAX_TILES * 16384, SMEM_BYTES = OFF_BAR + 1024 + 1024;   // barriers + key-mask words, alignment slack
 constexpr int NTHREADS = 320;
 // barrier indices
 constexpr int B_QFULL = 0, B_QFREE = 2, B_KFULL = 4, B_VFULL = 8, B_KFREE = 12, B_VFREE = 16, B_SFULL = 20,
-              B_PREADY = 22, B_PFREE = 24, B_OFULL = 26, N_BARS = 30;
+              B_PREADY = 22, B_PFREE = 24, N_BARS = 26;
+constexpr float RESCALE_LOG2 = 8.f;     // the running maximum is advanced only when a tile exceeds it by 2^8
 
 template <bool REL, bool BITS, bool RING>
 __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_q,
@@ -195,9 +218,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
-  // TMEM columns: S_A 0..127 | S_B 128..255 | O_A[0] 256 | O_A[1] 320 | O_B[0] 384 | O_B[1] 448
+  // TMEM columns: S_A 0..127 | S_B 128..255 | O_A 256..319 | O_B 320..383 | P_A 384..447 | P_B 448..511 (bf16 pairs)
   auto tm_s = [&](int g) { return tmem + g * 128; };
-  auto tm_o = [&](int g, int buf) { return tmem + 256 + g * 128 + buf * 64; };
+  auto tm_o = [&](int g) { return tmem + 256 + g * 64; };
+  auto tm_p = [&](int g) { return tmem + 384 + g * 64; };
 
   if (warp == 9) {
     // ===================== TMA producer =====================
@@ -286,13 +310,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
               mbar_wait_sleepy(bar(B_VFULL + sl), (v_seen >> sl) & 1);
               fence_after();
               const uint64_t dv = desc_mnmajor(sbase + OFF_V + sl * 16384);
+              // O_g (+)= P_g V_j: P from TMEM (8 packed columns per 16 keys), accumulating over the key tiles
 #pragma unroll
-              for (int k = 0; k < KT / 16; ++k) {
-                const uint64_t dp = desc_kmajor(sbase + OFF_P + g * 32768 + (k >> 2) * 16384) + (uint64_t)((k & 3) * 2);
-                umma(tm_o(g, j & 1), dp, dv + (uint64_t)((k * 16 * 128) >> 4), idesc_o, k ? 1u : 0u);
-              }
-              tcgen05_commit(bar(B_PFREE + g));
-              tcgen05_commit(bar(B_OFULL + g * 2 + (j & 1)));
+              for (int k = 0; k < KT / 16; ++k)
+                umma_ts(tm_o(g), tm_p(g) + (uint32_t)(k * 8), dv + (uint64_t)((k * 16 * 128) >> 4), idesc_o, (j | k) ? 1u : 0u);
+              tcgen05_commit(bar(B_PFREE + g));                 // P_g consumed, O_g updated (the softmax group waits on it)
               if (last_pair && last_user) { tcgen05_commit(bar(B_VFREE + sl)); v_seen ^= 1u << sl; }
             }
           }
@@ -306,8 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float scale = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
     uint32_t* kbits = kbits_all + g * (MAX_TK / 32);
-    uint32_t s_cnt = 0, pf_cnt = 0, o_par = 0;              // o_par: phase bit of each of the two O buffers
-    uint8_t* pbase = smem + OFF_P + g * 32768 + row * 128;
+    uint32_t s_cnt = 0, pf_cnt = 0;                         // phases of S_full / P_free (one completion per key tile)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, hh, pr0;
       decode_item(item, b, hh, pr0);
@@ -333,194 +354,174 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           for (int d = 0; d < DK / 8; ++d) dst[d] = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      {
-        const int pr = pr0;
-        const int qt = 2 * pr + g;
-        if (qt >= nq) continue;
-        const int qi = qt * QT + row;
-        const uint32_t* brow = BITS ? p.mask_bits + ((int64_t)b * p.Tq + (qi < p.Tq ? qi : 0)) * 16 : nullptr;
-        // BITS: a row without any unmasked key is uniform over all Tk keys (scores all finfo.min,
-        // modules/attention.py:19-21) = softmax of equal scores; every other row gives masked keys exactly zero
-        // weight, so chunks without a kept key are skipped
-        bool uniform_row = false;
-        if (BITS) {
-          uint32_t any = 0;
-          for (int w = 0; w < (p.Tk + 31) >> 5; ++w) {
-            const int n = p.Tk - w * 32;
-            any |= __ldg(brow + w) & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
-          }
-          uniform_row = any == 0u;
+      const int qt = 2 * pr0 + g;
+      if (qt >= nq) continue;
+      const int qi = qt * QT + row;
+      const uint32_t* brow = BITS ? p.mask_bits + ((int64_t)b * p.Tq + (qi < p.Tq ? qi : 0)) * 16 : nullptr;
+      // BITS: a row without any unmasked key is uniform over all Tk keys (scores all finfo.min,
+      // modules/attention.py:19-21) = softmax of equal scores; every other row gives masked keys exactly zero
+      // weight, so chunks without a kept key cost nothing
+      bool uniform_row = false;
+      if (BITS) {
+        uint32_t any = 0;
+        for (int w = 0; w < (p.Tk + 31) >> 5; ++w) {
+          const int n = p.Tk - w * 32;
+          any |= __ldg(brow + w) & (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
         }
-        float o[DK];
+        uniform_row = any == 0u;
+      }
+      // m_run: the maximum the exponentials are taken against (log2 domain).  It lags the true running maximum by
+      // at most RESCALE_LOG2, so P stays below 2^8 and O / l_run need no per-tile correction.
+      float m_run = -INFINITY, l_run = 0.f;
+      // relative-position term (modules/attention.py:104-143): score += (q_i+v).P[clamp(j-i,-m,m)+m]
+      const int nrel = 2 * p.max_rel + 1;
+      const float* rb = REL ? p.relbias + (((int64_t)b * p.h + hh) * p.Tq + (qi < p.Tq ? qi : p.Tq - 1)) * nrel : nullptr;
+      const float rel_left = REL ? rb[0] : 0.f, rel_right = REL ? rb[nrel - 1] : 0.f;
+      bool any_keep = false;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(bar(B_SFULL + g), s_cnt & 1);
+        ++s_cnt;
+        fence_after();
+        const int k0 = j * KT;
+        const uint32_t s_addr = tm_s(g) + lane_addr;
+        float t[KT];                                               // this thread's score row of the tile
 #pragma unroll
-        for (int d = 0; d < DK; ++d) o[d] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-        // relative-position term (modules/attention.py:104-143): score += (q_i+v).P[clamp(j-i,-m,m)+m]
-        const int nrel = 2 * p.max_rel + 1;
-        const float* rb = REL ? p.relbias + (((int64_t)b * p.h + hh) * p.Tq + (qi < p.Tq ? qi : p.Tq - 1)) * nrel : nullptr;
-        const float rel_left = REL ? rb[0] : 0.f, rel_right = REL ? rb[nrel - 1] : 0.f;
-        bool any_keep = false;
-        auto fold = [&](int j, float extra) {
-          mbar_wait(bar(B_OFULL + g * 2 + (j & 1)), (o_par >> (j & 1)) & 1);
-          o_par ^= 1u << (j & 1);
-          fence_after();
-          float part[DK];
-          tmem_ld32(tm_o(g, j & 1) + lane_addr, part);
-          tmem_ld32(tm_o(g, j & 1) + lane_addr + 32, part + 32);
-          tmem_wait_ld();
+        for (int c = 0; c < KT; c += 32) tmem_ld32(s_addr + c, t + c);
+        tmem_wait_ld();
+        // ---- masks / relative term per 32-key chunk; afterwards either t holds raw scores (state RAW: the exponent is
+        // fma(t, scale, off*scale - m)) or, for chunks that needed per-element work, final log2-domain values (DONE)
+        float off[KT / 32];
+        uint32_t done = 0;                                         // bit c: chunk c holds final log2-domain values
+        float mx = -INFINITY;
 #pragma unroll
-          for (int d = 0; d < DK; ++d) o[d] = (o[d] * corr_prev + part[d]) * extra;
-        };
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(bar(B_SFULL + g), s_cnt & 1);
-          ++s_cnt;
-          fence_after();
-          const int k0 = j * KT;
-          const uint32_t s_addr = tm_s(g) + lane_addr;
-          auto chunk_bits = [&](int c, uint32_t& keep, uint32_t& valid) {
-            const int n = p.Tk - (k0 + c);
-            valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
-            if (BITS) keep = uniform_row ? 0xffffffffu : __ldg(brow + ((k0 + c) >> 5));   // per-row mask, bit-packed
-            else if (p.mask) keep = kbits[(k0 + c) >> 5];                 // key mask: shared by all rows
-            else keep = 0xffffffffu;
-          };
-          // relative term of a 32-key chunk: away from the diagonal every key of the chunk clamps to the same
-          // table entry, which is returned as ONE offset (folded into the max / the exp argument for free);
-          // only chunks that straddle the +-max_rel band gather per element
-          auto rel_off = [&](float* t, int c) -> float {
+        for (int ci = 0; ci < KT / 32; ++ci) {
+          float* tc = t + ci * 32;
+          const int c = ci * 32;
+          const int n = p.Tk - (k0 + c);
+          const uint32_t valid = n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+          uint32_t keep;
+          if (BITS) keep = uniform_row ? 0xffffffffu : __ldg(brow + ((k0 + c) >> 5));   // per-row mask, bit-packed
+          else if (p.mask) keep = kbits[(k0 + c) >> 5];                 // key mask: shared by all rows
+          else keep = 0xffffffffu;
+          off[ci] = 0.f;
+          if (REL) {
+            // away from the diagonal every key of the chunk clamps to the same table entry (ONE offset, folded into
+            // the exponent for free); only chunks that straddle the +-max_rel band gather per element
             const int d_lo = k0 + c - qi;                                   // j - i of the chunk's first key
-            // warp-uniform decisions (votes): the per-element gather below is only ever executed by warps that
-            // actually touch the band; its clamped lookup is valid for every lane of such a warp
-            if (__all_sync(0xffffffffu, d_lo + 31 <= -p.max_rel)) return rel_left;
-            if (__all_sync(0xffffffffu, d_lo >= p.max_rel)) return rel_right;
+            if (__all_sync(0xffffffffu, d_lo + 31 <= -p.max_rel)) off[ci] = rel_left;
+            else if (__all_sync(0xffffffffu, d_lo >= p.max_rel)) off[ci] = rel_right;
+            else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                int r = d_lo + q;
+                r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
+                tc[q] += __ldg(rb + r + p.max_rel);
+              }
+            }
+            any_keep = any_keep || ((keep & valid) != 0u);
+          }
+          if (BITS && uniform_row) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) tc[q] = 0.f;                      // equal scores
+          }
+          if ((keep & valid) == 0xffffffffu) {
+            float cm[4] = {tc[0], tc[1], tc[2], tc[3]};
+#pragma unroll
+            for (int q = 4; q < 32; ++q) cm[q & 3] = fmaxf(cm[q & 3], tc[q]);
+            mx = fmaxf(mx, (fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + off[ci]) * scale);   // scale > 0
+          } else if (BITS && (keep & valid) == 0u) {
+            done |= 1u << ci;                                             // no weight in this chunk
+#pragma unroll
+            for (int q = 0; q < 32; ++q) tc[q] = -INFINITY;
+          } else {
+            done |= 1u << ci;
+            float mm = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              int r = d_lo + q;
-              r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
-              t[q] += __ldg(rb + r + p.max_rel);
+              float v = (tc[q] + off[ci]) * scale;
+              v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
+              v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
+              tc[q] = v;
+              mm = fmaxf(mm, v);
             }
-            return 0.f;
-          };
-          // ---- sweep 1: row max (four independent chains; masked chunks take the slow path)
-          float mxv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mx_masked = -INFINITY;
-          auto sweep_max = [&](float* t, int c) {
-            uint32_t keep, valid;
-            chunk_bits(c, keep, valid);
-            float off = 0.f;
-            if (REL) { off = rel_off(t, c); any_keep = any_keep || ((keep & valid) != 0u); }
-            if (BITS && uniform_row) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) t[q] = 0.f;                     // equal scores
-            }
-            if ((keep & valid) == 0xffffffffu) {
-              if (REL) {
-                float cm[4] = {t[0], t[1], t[2], t[3]};
-#pragma unroll
-                for (int q = 4; q < 32; ++q) cm[q & 3] = fmaxf(cm[q & 3], t[q]);
-                mxv[0] = fmaxf(mxv[0], fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) + off);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) mxv[q & 3] = fmaxf(mxv[q & 3], t[q]);
-              }
-            } else if (BITS && (keep & valid) == 0u) {
-              // no weight in this chunk
-            } else {
-              float mm = -INFINITY;
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                float v = (REL ? t[q] + off : t[q]) * scale;
-                v = ((keep >> q) & 1u) ? v : CN_F32_MIN;                  // masked: finfo.min, like the reference
-                v = ((valid >> q) & 1u) ? v : -INFINITY;                  // beyond the key range: no weight at all
-                mm = fmaxf(mm, v);
-              }
-              mx_masked = fmaxf(mx_masked, mm);
-            }
-          };
-          float ta[32], tb[32];
-          tmem_ld32(s_addr, ta); tmem_wait_ld();
-#pragma unroll 1
-          for (int c = 0; c < KT; c += 64) {                              // software pipeline, 2 chunks / iteration
-            tmem_ld32(s_addr + c + 32, tb); sweep_max(ta, c); tmem_wait_ld();
-            tmem_ld32(s_addr + ((c + 64) & (KT - 1)), ta); sweep_max(tb, c + 32); tmem_wait_ld();   // wraps to chunk 0
+            mx = fmaxf(mx, mm);
           }
-          const float mx = fmaxf(fmaxf(fmaxf(mxv[0], mxv[1]), fmaxf(mxv[2], mxv[3])) * scale, mx_masked);   // scale > 0
-          const float m_new = fmaxf(m_run, mx);
-          // BITS: a row can have no unmasked key in the tiles seen so far (m_new still -inf): nothing to rescale
-          const float corr = (BITS && m_new == -INFINITY) ? 1.f : ex2(m_run - m_new);
-          float lsv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (pf_cnt > 0) mbar_wait(bar(B_PFREE + g), (pf_cnt - 1) & 1);   // previous PV finished reading P_g
-          ++pf_cnt;
-          // ---- sweep 2: exp, row sum, P (bf16) into the K-major swizzled layout of the PV MMA
-          auto sweep_exp = [&](float* t, int c) {
-            uint32_t keep, valid;
-            chunk_bits(c, keep, valid);
-            float off = 0.f;
-            if (REL) off = rel_off(t, c);
-            if (BITS && uniform_row) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) t[q] = 0.f;
-            }
-            if ((keep & valid) == 0xffffffffu) {
-              const float addend = REL ? fmaf(off, scale, -m_new) : -m_new;
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                t[q] = ex2(fmaf(t[q], scale, addend));
-                lsv[q & 3] += t[q];
-              }
-            } else if (BITS && (keep & valid) == 0u) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) t[q] = 0.f;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                float v = (REL ? t[q] + off : t[q]) * scale;
-                v = ((keep >> q) & 1u) ? v : CN_F32_MIN;
-                v = ((valid >> q) & 1u) ? v : -INFINITY;
-                t[q] = ex2(v - m_new);
-                lsv[q & 3] += t[q];
-              }
-            }
-#pragma unroll
-            for (int gq = 0; gq < 32; gq += 8) {
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(t[gq], t[gq + 1]), b1 = __floats2bfloat162_rn(t[gq + 2], t[gq + 3]),
-                             b2 = __floats2bfloat162_rn(t[gq + 4], t[gq + 5]), b3 = __floats2bfloat162_rn(t[gq + 6], t[gq + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-              pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-              const int col = c + gq;
-              const int atom = col >> 6, chunk = (col & 63) >> 3;         // 64-key swizzle atoms, 16-byte chunks
-              *reinterpret_cast<uint4*>(pbase + atom * 16384 + ((chunk ^ (row & 7)) << 4)) = pk;
-            }
-          };
-#pragma unroll 1
-          for (int c = 0; c < KT; c += 64) {                              // ta holds chunk c on entry
-            tmem_ld32(s_addr + c + 32, tb); sweep_exp(ta, c); tmem_wait_ld();
-            if (c + 64 < KT) tmem_ld32(s_addr + c + 64, ta);
-            sweep_exp(tb, c + 32);
-            tmem_wait_ld();
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA
-          fence_before();                                                  // S_g fully read before it is handed back
-          __syncwarp();                                                    // every lane's P writes + fences precede the arrival
-          if (lane == 0) mbar_arrive(bar(B_PREADY + g));
-          if (j > 0) fold(j - 1, 1.f);                                     // O_g(j-1) while PV_g(j) / S_g(j+1) run
-          l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
-          m_run = m_new;
-          corr_prev = corr;
-          fence_before();
         }
-        fold(n_tiles - 1, (REL && !any_keep) ? 0.f : 1.f / l_run);      // REL: masked probabilities are re-zeroed
+        // ---- lazy running maximum
+        float corr = 1.f;
+        bool rescale = false;
+        if (mx > m_run + RESCALE_LOG2 || (m_run == -INFINITY && mx > -INFINITY)) {
+          if (m_run != -INFINITY && j > 0) { rescale = true; corr = ex2(m_run - mx); }
+          m_run = mx;
+        }
+        const float m_use = m_run == -INFINITY ? 0.f : m_run;      // a row with no weight so far: exponentials are 0
+        // ---- exponentials, row sum, P as packed bf16 pairs (two keys per 32-bit TMEM column)
+        float lsv[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[KT / 2];
+#pragma unroll
+        for (int ci = 0; ci < KT / 32; ++ci) {
+          float* tc = t + ci * 32;
+          if (!((done >> ci) & 1u)) {                                // raw scores: scale, offset and maximum in one FFMA
+            const float addend = fmaf(off[ci], scale, -m_use);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) tc[q] = fmaf(tc[q], scale, addend);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) tc[q] -= m_use;
+          }
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const float e0 = ex2(tc[q]), e1 = ex2(tc[q + 1]);
+            lsv[(q >> 1) & 3] += e0 + e1;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+            pk[(ci * 32 + q) >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+        // ---- P_g / O_g are free once PV(j-1) has retired
+        if (j > 0) {
+          mbar_wait(bar(B_PFREE + g), pf_cnt & 1);
+          ++pf_cnt;
+          fence_after();
+          if (__any_sync(0xffffffffu, rescale)) {                  // rare: this warp's rows advance their maximum
+            float o[DK];
+            tmem_ld32(tm_o(g) + lane_addr, o);
+            tmem_ld32(tm_o(g) + lane_addr + 32, o + 32);
+            tmem_wait_ld();
+#pragma unroll
+            for (int d = 0; d < DK; ++d) o[d] *= corr;
+            tmem_st32(tm_o(g) + lane_addr, reinterpret_cast<uint32_t*>(o));
+            tmem_st32(tm_o(g) + lane_addr + 32, reinterpret_cast<uint32_t*>(o) + 32);
+          }
+        }
+        tmem_st32(tm_p(g) + lane_addr, pk);
+        tmem_st32(tm_p(g) + lane_addr + 32, pk + 32);
+        tmem_wait_st();
+        fence_before();                                                  // S_g read, P_g (and O_g) written: hand over
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_PREADY + g));
+        l_run = l_run * corr + ((lsv[0] + lsv[1]) + (lsv[2] + lsv[3]));
+      }
+      // ---- epilogue of the query tile: O_g / l once the last PV has retired
+      mbar_wait(bar(B_PFREE + g), pf_cnt & 1);
+      ++pf_cnt;
+      fence_after();
+      {
+        float o[DK];
+        tmem_ld32(tm_o(g) + lane_addr, o);
+        tmem_ld32(tm_o(g) + lane_addr + 32, o + 32);
+        tmem_wait_ld();
         fence_before();
+        const float inv = (REL && !any_keep) ? 0.f : 1.f / l_run;      // REL: masked probabilities are re-zeroed
         if (qi < p.Tq) {
           __nv_bfloat16* dst = p.out + (int64_t)b * p.sbo + (int64_t)qi * p.ldo + hh * DK;
 #pragma unroll
           for (int d = 0; d < DK; d += 8) {
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(o[d], o[d + 1]), b1 = __floats2bfloat162_rn(o[d + 2], o[d + 3]),
-                           b2 = __floats2bfloat162_rn(o[d + 4], o[d + 5]), b3 = __floats2bfloat162_rn(o[d + 6], o[d + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-            *reinterpret_cast<uint4*>(dst + d) = pk;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(o[d] * inv, o[d + 1] * inv), b1 = __floats2bfloat162_rn(o[d + 2] * inv, o[d + 3] * inv),
+                           b2 = __floats2bfloat162_rn(o[d + 4] * inv, o[d + 5] * inv), b3 = __floats2bfloat162_rn(o[d + 6] * inv, o[d + 7] * inv);
+            uint4 w4;
+            w4.x = *reinterpret_cast<uint32_t*>(&b0); w4.y = *reinterpret_cast<uint32_t*>(&b1);
+            w4.z = *reinterpret_cast<uint32_t*>(&b2); w4.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(dst + d) = w4;
           }
         }
       }

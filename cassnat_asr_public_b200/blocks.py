@@ -14,42 +14,54 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import LayerNorm, SublayerConnection
+from .modules import LayerNorm, SublayerConnection, _p
 
 
 def clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
 
-def _self_attention_block(x, norm, attn, mask, pos_embed=None, next_norm=None):
+def _residual(sub, x, branch, scale=1.0, next_norm=None, **kw):
+    """x + scale * dropout(branch(...)) of SublayerConnection (modules/utils.py:32).  Without active dropout the add (and
+    the next LayerNorm) is fused into the branch's last GEMM; with dropout the branch output is dropped first."""
+    p = _p(sub)
+    if p > 0:
+        return x + scale * ops.dropout(branch(residual=None, scale=1.0, **kw), p)
+    return branch(residual=x, scale=scale, next_ln=next_norm, **kw)
+
+
+def _self_attention_block(x, sub, attn, mask, pos_embed=None, next_norm=None):
     """x + self_attn(norm(x)) with the residual (and, in fast mode, the LayerNorm `next_norm` that consumes the
-    result next) fused into the output projection."""
+    result next) fused into the output projection.  sub: the SublayerConnection (norm + dropout probability)."""
+    norm = sub.norm
     y = norm.for_gemm(x)
     if pos_embed is None:
-        q, k, v = attn.project_qkv(y, out_bf16=ops.is_bf16())     # bf16 -> tcgen05 attention
-        ctx = ops.attention(q, k, v, mask, attn.h)
+        q, k, v = attn.project_qkv(y, out_bf16=ops.attn_bf16())   # bf16 -> tcgen05 attention
+        ctx = ops.attention(q, k, v, mask, attn.h, p_drop=_p(attn))
     else:
         from .modules import distinct_rel_rows
         table, m = distinct_rel_rows(pos_embed, x.size(1))
-        fast = ops.is_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= 64
+        fast = ops.attn_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= 64
         rel_pos = ops.linear(table, attn.linear_pos.weight)
         if torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad):
             q, k, v = attn.project_qkv(y, out_bf16=fast)           # training: raw q, grad.RelAttention adds u
         else:
             q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
-        ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m))
-    return attn.output(ctx, residual=x, next_ln=next_norm)
+        ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m), p_drop=_p(attn))
+    return _residual(sub, x, lambda **kw: attn.output(ctx, **kw), next_norm=next_norm)
 
 
-def _src_attention_block(x, norm, attn, memory, mask, kv=None, next_norm=None):
-    y = norm.for_gemm(x)
-    q = attn.project_q(y, out_bf16=ops.is_bf16())
-    k, v = kv if kv is not None else attn.project_kv(memory, out_bf16=ops.is_bf16())
-    return attn.output(ops.attention(q, k, v, mask, attn.h), residual=x, next_ln=next_norm)
+def _src_attention_block(x, sub, attn, memory, mask, kv=None, next_norm=None):
+    y = sub.norm.for_gemm(x)
+    q = attn.project_q(y, out_bf16=ops.attn_bf16())
+    k, v = kv if kv is not None else attn.project_kv(memory, out_bf16=ops.attn_bf16())
+    ctx = ops.attention(q, k, v, mask, attn.h, p_drop=_p(attn))
+    return _residual(sub, x, lambda **kw: attn.output(ctx, **kw), next_norm=next_norm)
 
 
-def _ffn_block(x, norm, ff, scale=1.0, next_norm=None):
-    return ff(norm.for_gemm(x), residual=x, scale=scale, next_ln=next_norm)
+def _ffn_block(x, sub, ff, scale=1.0, next_norm=None):
+    y = sub.norm.for_gemm(x)
+    return _residual(sub, x, lambda **kw: ff(y, **kw), scale=scale, next_norm=next_norm)
 
 
 def _first_norm(layer):
@@ -78,8 +90,8 @@ class SelfAttLayer(nn.Module):
         self.size = size
 
     def forward(self, x, self_mask, next_norm=None):
-        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
+        x = _self_attention_block(x, self.sublayer[0], self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
+        return _ffn_block(x, self.sublayer[1], self.feed_forward, next_norm=next_norm)
 
 
 class SrcAttLayer(nn.Module):
@@ -93,19 +105,19 @@ class SrcAttLayer(nn.Module):
         self.size = size
 
     def forward(self, x, m, src_mask, next_norm=None):
-        x = _src_attention_block(x, self.sublayer[0].norm, self.src_attn, m, src_mask, next_norm=self.sublayer[1].norm)
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
+        x = _src_attention_block(x, self.sublayer[0], self.src_attn, m, src_mask, next_norm=self.sublayer[1].norm)
+        return _ffn_block(x, self.sublayer[1], self.feed_forward, next_norm=next_norm)
 
     def forward_segments(self, pe_rows, m, seg_ctx, kv=None, next_norm=None):
         """Same result as forward(pe_rows repeated over the batch, m, trigger_mask) with the
         trigger mask given implicitly by `seg_ctx` = (seg, ylens, src_mask, src_size, left, right)."""
         attn = self.src_attn
-        fast = ops.is_bf16() and attn.d_k == 64 and m.size(1) <= 512                # tcgen05 attention, mask fused
+        fast = ops.attn_bf16() and attn.d_k == 64 and m.size(1) <= 512              # tcgen05 attention, mask fused
         q_rows = attn.project_q(self.sublayer[0].norm.for_gemm(pe_rows), out_bf16=fast)   # batch independent [U,d]
         k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
         ctx = ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h, q_len=seg_ctx[6] if len(seg_ctx) > 6 else None)
         x = attn.output(ctx, residual=pe_rows, res_rows=pe_rows.size(0), next_ln=self.sublayer[1].norm)
-        return _ffn_block(x, self.sublayer[1].norm, self.feed_forward, next_norm=next_norm)
+        return _ffn_block(x, self.sublayer[1], self.feed_forward, next_norm=next_norm)
 
 
 class MixAttLayer(nn.Module):
@@ -120,9 +132,9 @@ class MixAttLayer(nn.Module):
         self.sublayer = clones(SublayerConnection(size, dropout), 3)
 
     def forward(self, x, memory, src_mask, self_mask, kv=None, next_norm=None):
-        x = _self_attention_block(x, self.sublayer[0].norm, self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
-        x = _src_attention_block(x, self.sublayer[1].norm, self.src_attn, memory, src_mask, kv, next_norm=self.sublayer[2].norm)
-        return _ffn_block(x, self.sublayer[2].norm, self.feed_forward, next_norm=next_norm)
+        x = _self_attention_block(x, self.sublayer[0], self.self_attn, self_mask, next_norm=self.sublayer[1].norm)
+        x = _src_attention_block(x, self.sublayer[1], self.src_attn, memory, src_mask, kv, next_norm=self.sublayer[2].norm)
+        return _ffn_block(x, self.sublayer[2], self.feed_forward, next_norm=next_norm)
 
 
 class Encoder(nn.Module):
@@ -220,7 +232,7 @@ def _project_memory_all(dec, memory):
     attns = [layer.src_attn for layer in dec.layers]
     w = _cat_cached(dec, "kv_all_w", [t for a in attns for t in (a.linears[1].weight, a.linears[2].weight)])
     b = _cat_cached(dec, "kv_all_b", [t for a in attns for t in (a.linears[1].bias, a.linears[2].bias)])
-    kv = ops.linear(memory, w, b, out_bf16=ops.is_bf16())                      # [B,T,2d*N]
+    kv = ops.linear(memory, w, b, out_bf16=ops.attn_bf16())                    # [B,T,2d*N]
     d = memory.size(-1)
     return [(kv[..., 2 * i * d:(2 * i + 1) * d], kv[..., (2 * i + 1) * d:(2 * i + 2) * d]) for i in range(len(attns))]
 
@@ -243,19 +255,20 @@ class ConSelfAttLayer(nn.Module):
         self.ff_scale = ff_scale
 
     def _conv(self, x, next_norm=None):
-        return self.conv_module(self.sublayer[1].norm.for_gemm(x), residual=x, next_ln=next_norm)
+        y = self.sublayer[1].norm.for_gemm(x)
+        return _residual(self.sublayer[1], x, lambda scale=1.0, **kw: self.conv_module(y, **kw), next_norm=next_norm)
 
     def forward(self, x, mask, pos_embed, next_norm=None):
         sl = self.sublayer
         if self.pos_type == "absolute":
-            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
+            x = _ffn_block(x, sl[0], self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
             x = self._conv(x, sl[2].norm)
-            x = _self_attention_block(x, sl[2].norm, self.self_attn, mask, None, next_norm=sl[3].norm)
+            x = _self_attention_block(x, sl[2], self.self_attn, mask, None, next_norm=sl[3].norm)
         else:
-            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
-            x = _self_attention_block(x, sl[2].norm, self.self_attn, mask, pos_embed, next_norm=sl[1].norm)
+            x = _ffn_block(x, sl[0], self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
+            x = _self_attention_block(x, sl[2], self.self_attn, mask, pos_embed, next_norm=sl[1].norm)
             x = self._conv(x, sl[3].norm)
-        return _ffn_block(x, sl[3].norm, self.feed_forward2, self.ff_scale, next_norm=next_norm)
+        return _ffn_block(x, sl[3], self.feed_forward2, self.ff_scale, next_norm=next_norm)
 
 
 class ConSrcAttLayer(nn.Module):
@@ -275,9 +288,9 @@ class ConSrcAttLayer(nn.Module):
         if self.pos_type == "relative":
             # relative positions: pos_enc leaves x untouched, so the pre-norm of the FFN can ride on the projection
             x, pos_embed = self.pos_enc(self.src_attn.output(ctx, scale=math.sqrt(self.size), next_ln=self.sublayer.norm))
-            return _ffn_block(x, self.sublayer.norm, self.feed_forward, next_norm=next_norm), pos_embed
+            return _ffn_block(x, self.sublayer, self.feed_forward, next_norm=next_norm), pos_embed
         x = self.pos_enc(self.src_attn.output(ctx, scale=math.sqrt(self.size)))
-        return _ffn_block(x, self.sublayer.norm, self.feed_forward, next_norm=next_norm)
+        return _ffn_block(x, self.sublayer, self.feed_forward, next_norm=next_norm)
 
     def forward(self, x, m, src_mask, next_norm=None):
         attn = self.src_attn
@@ -287,7 +300,7 @@ class ConSrcAttLayer(nn.Module):
 
     def forward_segments(self, pe_rows, m, seg_ctx, kv=None, next_norm=None):
         attn = self.src_attn
-        fast = ops.is_bf16() and attn.d_k == 64 and m.size(1) <= 512
+        fast = ops.attn_bf16() and attn.d_k == 64 and m.size(1) <= 512
         q_rows = attn.project_q(pe_rows, out_bf16=fast)
         k, v = kv if kv is not None else attn.project_kv(m, out_bf16=fast)
         return self._finish(ops.segment_attention(q_rows, k, v, *seg_ctx[:6], attn.h), next_norm)
@@ -309,18 +322,20 @@ class ConMixAttLayer(nn.Module):
         self.pos_type = pos_type
         self.ff_scale = ff_scale
 
+    _conv = ConSelfAttLayer._conv
+
     def forward(self, x, memory, src_mask, self_mask, pos_embed, kv=None, next_norm=None):
         sl = self.sublayer
         if self.pos_type == "absolute":
-            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
-            x = self.conv_module(sl[1].norm.for_gemm(x), residual=x, next_ln=sl[2].norm)
-            x = _self_attention_block(x, sl[2].norm, self.self_attn, self_mask, None, next_norm=sl[3].norm)
+            x = _ffn_block(x, sl[0], self.feed_forward1, self.ff_scale, next_norm=sl[1].norm)
+            x = self._conv(x, sl[2].norm)
+            x = _self_attention_block(x, sl[2], self.self_attn, self_mask, None, next_norm=sl[3].norm)
         else:
-            x = _ffn_block(x, sl[0].norm, self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
-            x = _self_attention_block(x, sl[2].norm, self.self_attn, self_mask, pos_embed, next_norm=sl[1].norm)
-            x = self.conv_module(sl[1].norm.for_gemm(x), residual=x, next_ln=sl[3].norm)
-        x = _src_attention_block(x, sl[3].norm, self.src_attn, memory, src_mask, kv, next_norm=sl[4].norm)
-        return _ffn_block(x, sl[4].norm, self.feed_forward2, self.ff_scale, next_norm=next_norm)
+            x = _ffn_block(x, sl[0], self.feed_forward1, self.ff_scale, next_norm=sl[2].norm)
+            x = _self_attention_block(x, sl[2], self.self_attn, self_mask, pos_embed, next_norm=sl[1].norm)
+            x = self._conv(x, sl[3].norm)
+        x = _src_attention_block(x, sl[3], self.src_attn, memory, src_mask, kv, next_norm=sl[4].norm)
+        return _ffn_block(x, sl[4], self.feed_forward2, self.ff_scale, next_norm=next_norm)
 
 
 def _split_pos(x, pos_type):

@@ -529,21 +529,24 @@ class CassNAT(nn.Module):
         are the log-probabilities the caller decodes for WER and carry no gradient of their own.
         Under torch.no_grad() the same values are produced without a tape, and
         `self.last_ctc_grad` = ctc_alpha * d ctc_loss / d ctc logits (K10) is kept for inspection."""
+        ops.dropout_begin_step()
         x, x_mask = self.src_embed(src, src_mask)
         enc = self.encoder(x, x_mask, args.interctc_alpha, args.interctc_layer)         # :139-143
         enc_h, inter_h = enc if args.interctc_alpha > 0 else (enc, None)                  # :151
-        return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=inter_h)
+        return self.train_forward_from_encoder(enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=inter_h,
+                                               _begin_step=False)
 
     def zero_dropout(self):
-        """The kernels implement no dropout; training runs with every dropout probability at 0.
-        (The reference's transformer-family make_model hard-codes 0.1 for the encoder's attention
-        dropout whatever args.dropout says, so even its dropout=0 configuration is random there.)"""
+        """Sets every dropout probability to 0 (deterministic training step, e.g. for gradient parity tests: the
+        reference's transformer-family make_model hard-codes 0.1 for the encoder's attention dropout whatever
+        args.dropout says, so even its dropout=0 configuration is random there).  With p > 0 the modules apply the
+        stateless-mask dropout of ops.dropout wherever the reference applies nn.Dropout."""
         for m in self.modules():
             if hasattr(m, "p_drop"):
                 m.p_drop = 0.0
         return self
 
-    def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=None):
+    def train_forward_from_encoder(self, enc_h, x_mask, src_size, tgt_label, label_sizes, args, inter_h=None, _begin_step=True):
         """Post-encoder part of CassNAT.forward (cassnat.py:148-257): CTC posteriors, Viterbi forced
         alignment, trigger segments, extractor -> SAD -> MAD -> log-probs, CTC + label-smoothing loss, plus the
         optional intermediate losses: interctc on `inter_h` (the encoder tap, :151-153,236-239) and interce on the
@@ -551,6 +554,8 @@ class CassNAT(nn.Module):
         if not args.use_trigger or args.use_best_path:
             raise NotImplementedError("training needs use_trigger with the Viterbi alignment (use_best_path is broken "
                                       "upstream: cassnat.py:168,246)")
+        if _begin_step:
+            ops.dropout_begin_step()                 # (CassNAT.forward starts the step before the encoder runs)
         assert args.ctc_alpha > 0
         selfce, mixce = getattr(args, "selfce_alpha", 0), getattr(args, "mixce_alpha", 0)
         if args.interctc_alpha > 0 and inter_h is None:

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(float* __restrict
   const int i = (int)(row % Tq);
   const int64_t b = row / ((int64_t)Tq * h);
   float* s = S + row * Tk;
-  float* g = dP + row * Tk;
+  float* g = dP ? dP + row * Tk : nullptr;                  // NULL: forward only (P in place)
   const uint8_t* mk = mask ? mask + b * mb + (int64_t)i * mi : nullptr;
   float mx = -INFINITY;
   int any = 0;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(float* __restrict
   any = __any_sync(0xffffffffu, any);
   if (!any) {
     const float u = zero_masked ? 0.f : 1.f / Tk;
-    for (int j = lane; j < Tk; j += 32) { s[j] = u; g[j] = 0.f; }
+    for (int j = lane; j < Tk; j += 32) { s[j] = u; if (g) g[j] = 0.f; }
     return;
   }
   float sum = 0.f;
@@ -203,10 +203,38 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(float* __restrict
   for (int j = lane; j < Tk; j += 32) {
     const float p = s[j] * inv;
     s[j] = p;
-    dot += p * g[j];
+    if (g) dot += p * g[j];
   }
+  if (!g) return;
   dot = cn_warp_sum(dot);
   for (int j = lane; j < Tk; j += 32) g[j] = s[j] * (g[j] - dot);
+}
+
+// ===================================================================== dropout (training)
+// nn.Dropout of the reference (modules/utils.py:32 residual branches, attention.py:22-23 attention probabilities,
+// positionff.py:16 FFN hidden, embedding.py:31,60 positional encodings).  The keep mask is a pure function of
+// (seed, site, element index) -- a counter-based hash, no state -- so the backward pass regenerates it instead of
+// storing it, the seed can live in device memory (a CUDA-graph-replayed step advances it without re-capture), and a
+// test can obtain the very mask the kernels used.
+__device__ __forceinline__ uint32_t cn_fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool cn_dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t threshold) {
+  uint32_t h = cn_fmix32((uint32_t)idx * 0x9E3779B1u ^ (uint32_t)seed);
+  h = cn_fmix32(h ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u + site * 0xC2B2AE3Du + (uint32_t)(seed >> 32)));
+  return h >= threshold;                                   // P(keep) = 1 - threshold / 2^32
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dropout_kernel(const TI* __restrict__ x, TO* __restrict__ out, int64_t n, uint32_t threshold,
+                                                      float inv_keep, const int64_t* __restrict__ seed_dev, uint64_t seed,
+                                                      uint32_t site) {
+  const uint64_t sd = seed_dev ? (uint64_t)seed_dev[0] : seed;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = cn_dropout_keep(sd, site, (uint64_t)i, threshold) ? (float)x[i] * inv_keep : 0.f;
+    out[i] = (TO)v;
+  }
 }
 
 // ===================================================================== label smoothing loss
@@ -449,9 +477,31 @@ extern "C" int cn_layernorm_bwd(const float* x, int64_t ldx, const float* dy, in
   return CN_OK;
 }
 
+extern "C" int cn_dropout(const void* x, int x_is_bf16, void* out, int out_is_bf16, int64_t n, float p, const int64_t* seed_dev,
+                          int64_t seed, int64_t site, cn_stream_t stream) {
+  if (!x || !out || n < 0 || !(p >= 0.f) || p >= 1.f) return CN_ERR_BAD_ARG;
+  if (n == 0) return CN_OK;
+  const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
+  const float inv_keep = 1.f / (1.f - p);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = (unsigned)blocks;
+  if (x_is_bf16 && out_is_bf16)
+    dropout_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
+  else if (x_is_bf16)
+    dropout_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
+  else if (out_is_bf16)
+    dropout_kernel<<<g, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
+  else
+    dropout_kernel<<<g, 256, 0, st>>>((const float*)x, (float*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
 extern "C" int cn_attn_softmax_bwd(float* S, float* dP, const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t h,
                                    int64_t Tq, int64_t Tk, int zero_masked, cn_stream_t stream) {
-  if (!S || !dP || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
+  if (!S || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
   const int64_t rows = B * h * Tq;
   if (rows == 0) return CN_OK;
   if ((rows + 7) / 8 > 0x7fffffff) return CN_ERR_UNSUPPORTED;

@@ -213,6 +213,28 @@ class LayerNormFn(torch.autograd.Function):
         return dx, da, db, None, None
 
 
+# =============================================================================== dropout
+class Dropout(torch.autograd.Function):
+    """y = x * mask / (1 - p); the mask is regenerated from (seed, site) in backward, never stored."""
+
+    @staticmethod
+    def forward(ctx, x, p, site):
+        ctx.p, ctx.site = p, site
+        return ops.dropout_forward(x, p, site)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.dropout_forward(gy, ctx.p, ctx.site), None, None
+
+
+def _attn_probs_dropped(S, mask, B, h, Tq, Tk, zero_masked, p, site):
+    """In place on the scaled scores S [B,h,Tq,Tk]: softmax with the reference's masking, then dropout."""
+    m, mb, mi = ops._mask_strides(mask, B, Tq, Tk)
+    call("cn_attn_softmax_bwd", ptr(S), None, ptr(m), mb, mi, B, h, Tq, Tk, int(zero_masked), stream(),
+         work=dict(bytes=8.0 * B * h * Tq * Tk))
+    return ops.dropout_forward(S, p, site, inplace=True)
+
+
 # =============================================================================== attention
 class Attention(torch.autograd.Function):
     """Masked multi-head attention (ops.attention, plain variant).  Backward recomputes the
@@ -220,10 +242,26 @@ class Attention(torch.autograd.Function):
     dV = P^T dO, dQ = dS K/sqrt(dk), dK = dS^T Q/sqrt(dk) as batched strided GEMMs."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, n_head):
+    def forward(ctx, q, k, v, mask, n_head, p=0.0, site=0):
         with torch.no_grad():
-            out = ops.attention_forward(q, k, v, mask, n_head)
-        ctx.n_head = n_head
+            if p > 0.0:
+                # dropout on the probabilities (attention.py:22-23): materialised scores, P, dropout, P V
+                B, Tq, d = q.shape
+                Tk, dk = k.shape[1], d // n_head
+                f = lambda t: t if t.dtype == torch.float32 else t.float()
+                qf, kf, vf = f(q), f(k), f(v)
+                S = torch.empty(B, n_head, Tq, Tk, dtype=torch.float32, device=q.device)
+                st = lambda t: (t.stride(0), dk, t.stride(1), 1)
+                gemm_strided(qf, st(qf), kf, st(kf), S, (n_head * Tq * Tk, Tq * Tk, Tk), B, n_head, Tq, Tk, dk, alpha=1.0 / dk ** 0.5)
+                _attn_probs_dropped(S, mask, B, n_head, Tq, Tk, 0, p, site)
+                out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
+                gemm_strided(S, (n_head * Tq * Tk, Tq * Tk, Tk, 1), vf, (vf.stride(0), dk, 1, vf.stride(1)), out, (Tq * d, dk, d),
+                             B, n_head, Tq, dk, Tk)
+                if q.dtype != torch.float32:
+                    out = out.to(q.dtype)
+            else:
+                out = ops.attention_forward(q, k, v, mask, n_head)
+        ctx.n_head, ctx.p, ctx.site = n_head, p, site
         ctx.mask = mask
         ctx.save_for_backward(q, k, v)
         return out
@@ -247,9 +285,13 @@ class Attention(torch.autograd.Function):
         st = lambda t: (t.stride(0), dk, t.stride(1), 1)                 # (batch, head, row, feature)
         gemm_strided(qf, st(qf), kf, st(kf), S, sz, B, h, Tq, Tk, dk, alpha=scale)
         gemm_strided(gf, st(gf), vf, st(vf), dP, sz, B, h, Tq, Tk, dk)
+        if ctx.p > 0.0:
+            ops.dropout_forward(dP, ctx.p, ctx.site, inplace=True)          # d(dropped P) -> dP through the same mask
         m, mb, mi = ops._mask_strides(ctx.mask, B, Tq, Tk)
         call("cn_attn_softmax_bwd", ptr(S), ptr(dP), ptr(m), mb, mi, B, h, Tq, Tk, 0, stream(),
              work=dict(bytes=16.0 * B * h * Tq * Tk))
+        if ctx.p > 0.0:
+            ops.dropout_forward(S, ctx.p, ctx.site, inplace=True)           # dV needs the dropped probabilities
         dq = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
         dk_ = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
         dv = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
@@ -260,7 +302,7 @@ class Attention(torch.autograd.Function):
         gemm_strided(dP, P_n, kf, tr(kf), dq, (Tq * d, dk, d), B, h, Tq, dk, Tk, alpha=scale)
         gemm_strided(dP, P_t, qf, tr(qf), dk_, (Tk * d, dk, d), B, h, Tk, dk, Tq, alpha=scale)
         c = lambda g, ref: g if ref.dtype == torch.float32 else g.to(ref.dtype)
-        return c(dq, q), c(dk_, k), c(dv, v), None, None
+        return c(dq, q), c(dk_, k), c(dv, v), None, None, None, None
 
 
 class RelAttention(torch.autograd.Function):
@@ -270,18 +312,39 @@ class RelAttention(torch.autograd.Function):
     then d(q+v) = G P and dP = G^T (q+v) as strided GEMMs."""
 
     @staticmethod
-    def forward(ctx, q, k, v, rel_pos, bias_u, bias_v, mask, n_head, m):
+    def forward(ctx, q, k, v, rel_pos, bias_u, bias_v, mask, n_head, m, p=0.0, site=0):
         with torch.no_grad():
             key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
             fast = (q.dtype == torch.bfloat16 and key_mask and q.shape[-1] // n_head == 64 and k.shape[1] <= 512
                     and n_head <= 8 and m <= 64)
-            if fast:                           # tcgen05 kernel takes q + u as its Q operand
+            if p > 0.0:
+                # dropout on the probabilities (attention.py:140-141): materialised scores incl. the relative term
+                B, Tq, d = q.shape
+                Tk, dk, R = k.shape[1], d // n_head, 2 * int(m) + 1
+                f = lambda t: t if t.dtype == torch.float32 else t.float()
+                qf, kf, vf = f(q), f(k), f(v)
+                Pm = f(rel_pos).contiguous()
+                qu, qv = qf + bias_u.reshape(1, 1, -1), qf + bias_v.reshape(1, 1, -1)
+                sc = 1.0 / dk ** 0.5
+                S = torch.empty(B, n_head, Tq, Tk, dtype=torch.float32, device=q.device)
+                Tb = torch.empty(B, n_head, Tq, R, dtype=torch.float32, device=q.device)
+                st = lambda t: (t.stride(0), dk, t.stride(1), 1)
+                gemm_strided(qu, st(qu), kf, st(kf), S, (n_head * Tq * Tk, Tq * Tk, Tk), B, n_head, Tq, Tk, dk, alpha=sc)
+                gemm_strided(qv, st(qv), Pm, (0, dk, d, 1), Tb, (n_head * Tq * R, Tq * R, R), B, n_head, Tq, R, dk)
+                call("cn_rel_bias_add", ptr(S), ptr(Tb), B * n_head, Tq, Tk, int(m), sc, stream(), work=dict(bytes=8.0 * B * n_head * Tq * Tk))
+                _attn_probs_dropped(S, mask, B, n_head, Tq, Tk, 1, p, site)
+                out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
+                gemm_strided(S, (n_head * Tq * Tk, Tq * Tk, Tk, 1), vf, (vf.stride(0), dk, 1, vf.stride(1)), out, (Tq * d, dk, d),
+                             B, n_head, Tq, dk, Tk)
+                if q.dtype != torch.float32:
+                    out = out.to(q.dtype)
+            elif fast:                         # tcgen05 kernel takes q + u as its Q operand
                 qu = (q.float() + bias_u.reshape(1, 1, -1)).to(torch.bfloat16)
                 out = ops.attention_forward(qu, k, v, mask, n_head, (rel_pos, bias_u, bias_v, m))
             else:
                 out = ops.attention_forward(q.float(), k.float(), v.float(), mask, n_head, (rel_pos, bias_u, bias_v, m))
                 out = out.to(q.dtype)
-        ctx.n_head, ctx.m, ctx.mask = n_head, int(m), mask
+        ctx.n_head, ctx.m, ctx.mask, ctx.p, ctx.site = n_head, int(m), mask, p, site
         ctx.save_for_backward(q, k, v, rel_pos, bias_u, bias_v)
         return out
 
@@ -313,9 +376,13 @@ class RelAttention(torch.autograd.Function):
         gemm_strided(qv, st(qv), P, (0, dk, d, 1), Tb, (h * Tq * R, Tq * R, R), B, h, Tq, R, dk)
         call("cn_rel_bias_add", ptr(S), ptr(Tb), Z, Tq, Tk, m, scale, stream(), work=dict(bytes=8.0 * Z * Tq * Tk))
         gemm_strided(gf, st(gf), vf, st(vf), dP, sz, B, h, Tq, Tk, dk)
+        if ctx.p > 0.0:
+            ops.dropout_forward(dP, ctx.p, ctx.site, inplace=True)
         mk, mb, mi = ops._mask_strides(ctx.mask, B, Tq, Tk)
         call("cn_attn_softmax_bwd", ptr(S), ptr(dP), ptr(mk), mb, mi, B, h, Tq, Tk, 1, stream(),
              work=dict(bytes=16.0 * Z * Tq * Tk))
+        if ctx.p > 0.0:
+            ops.dropout_forward(S, ctx.p, ctx.site, inplace=True)
         dqu = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
         dqv = torch.empty(B, Tq, d, dtype=torch.float32, device=dev)
         dk_ = torch.empty(B, Tk, d, dtype=torch.float32, device=dev)
@@ -335,7 +402,7 @@ class RelAttention(torch.autograd.Function):
         dq = dqu + dqv
         c = lambda g, ref: g if ref.dtype == torch.float32 else g.to(ref.dtype)
         return (c(dq, q), c(dk_, k), c(dv, v), c(dPb.sum(0), rel_pos), du.view_as(bias_u), dvb.view_as(bias_v),
-                None, None, None)
+                None, None, None, None, None)
 
 
 # =============================================================================== conformer conv module core

@@ -11,8 +11,8 @@ Reference interfaces mirrored (paths relative to /root/reference/src/models/modu
   ConvModule, Swish             conformer_related.py:10-44
   PositionalEncoding, RelativePositionalEncoding, ConvEmbedding   embedding.py:10-124
 
-Inference only for now: modules raise in training mode with dropout > 0 (the kernels have no
-dropout), and tensors must live on a CUDA device (no CPU fallback).
+Dropout (training mode, p > 0) is applied where the reference applies nn.Dropout, with a stateless counter-hash mask
+(ops.dropout / cn_dropout); tensors must live on a CUDA device (no CPU fallback).
 """
 import math
 
@@ -36,9 +36,9 @@ def _cat_cached(owner, key, tensors, dim=0):
     return hit[1]
 
 
-def _no_dropout(mod, p):
-    if mod.training and p > 0:
-        raise NotImplementedError("cassnat_asr_public_b200 kernels implement no dropout: call .eval() or use dropout=0")
+def _p(mod):
+    """Active dropout probability of a module: its p_drop in training mode, else 0."""
+    return float(mod.p_drop) if (mod.training and mod.p_drop > 0) else 0.0
 
 
 class Swish(nn.Module):
@@ -95,9 +95,9 @@ class PositionwiseFeedForward(nn.Module):
     def forward(self, x, residual=None, scale=1.0, next_ln=None):
         """w_2(act(w_1 x)); with `residual` the pre-norm residual add (and the conformer's 1/2
         scale) is fused into the second GEMM's epilogue, and with `next_ln` the following LayerNorm too."""
-        _no_dropout(self, self.p_drop)
         hid = ops.linear(x, self.w_1.weight, self.w_1.bias, act=_act_name(self.activation), out_bf16=ops.is_bf16(),
                          out_split=ops.is_x3())
+        hid = ops.dropout(hid, _p(self))                                    # positionff.py:16
         return ops.linear(hid, self.w_2.weight, self.w_2.bias, residual=residual, alpha=scale, next_ln=next_ln)
 
 
@@ -108,9 +108,8 @@ class SublayerConnection(nn.Module):
         self.p_drop = dropout
 
     def forward(self, x, sublayer, scale=1.0, has_cache=False):
-        _no_dropout(self, self.p_drop)
         residual = x[:, -1:, :] if has_cache else x
-        y = sublayer(self.norm(x))
+        y = ops.dropout(sublayer(self.norm(x)), _p(self))                   # utils.py:32
         return residual + scale * y
 
 
@@ -148,7 +147,6 @@ class MultiHeadedAttention(nn.Module):
                           res_rows=res_rows, next_ln=next_ln)
 
     def forward(self, query, key, value, mask=None, pos_embed=None):
-        _no_dropout(self, self.p_drop)
         if query is key and key is value:
             q, k, v = self.project_qkv(query)
         elif key is value:
@@ -158,7 +156,7 @@ class MultiHeadedAttention(nn.Module):
             q = self.project_q(query)
             k = ops.linear(key, self.linears[1].weight, self.linears[1].bias)
             v = ops.linear(value, self.linears[2].weight, self.linears[2].bias)
-        return self.output(ops.attention(q, k, v, mask, self.h))
+        return self.output(ops.attention(q, k, v, mask, self.h, p_drop=_p(self)))
 
 
 class RelMultiHeadedAttention(nn.Module):
@@ -193,14 +191,13 @@ class RelMultiHeadedAttention(nn.Module):
         """pos_embed: [2L-1, d] rows of the clamped relative-position table (what
         RelativePositionalEncoding returns).  Only 2m+1 of them are distinct; the kernel works on
         those, recovered from the first, middle-run and last rows."""
-        _no_dropout(self, self.p_drop)
         assert query is key and key is value, "relative attention is self-attention in CASS-NAT"
         L = query.size(1)
         assert pos_embed.size(0) == 2 * L - 1
         table, m = distinct_rel_rows(pos_embed, L)
         rel_pos = ops.linear(table, self.linear_pos.weight)
         q, k, v = self.project_qkv(query)
-        ctx = ops.attention(q, k, v, mask, self.h, (rel_pos, self.pos_bias_u, self.pos_bias_v, m))
+        ctx = ops.attention(q, k, v, mask, self.h, (rel_pos, self.pos_bias_u, self.pos_bias_v, m), p_drop=_p(self))
         return self.output(ctx)
 
 
@@ -230,10 +227,13 @@ class RelativePositionalEncoding(nn.Module):
         self.d_model = d_model
 
     def forward(self, x):
-        _no_dropout(self, self.p_drop)
         L, m = x.size(1), self.max_relative_len
         idx = torch.arange(-(L - 1), L, device=x.device).clamp(-m, m) + m
         pos = self.embedding.weight.detach()[idx]
+        if _p(self) > 0:
+            # embedding.py:60: independent dropout on x and on every row of the expanded table -- rows of clamped
+            # offsets are no longer identical, so the (2m+1)-row shortcut below does not apply
+            return (ops.dropout(x, _p(self)), ops.dropout(pos, _p(self)))
         mm = min(m, L - 1)
         pos._cn_table = (self.embedding.weight.detach()[m - mm:m + mm + 1].contiguous(), mm)
         return (x, pos)
@@ -252,8 +252,7 @@ class PositionalEncoding(nn.Module):
         self.register_buffer("pe", pe.unsqueeze(0))
 
     def forward(self, x):
-        _no_dropout(self, self.p_drop)
-        return x + self.pe[:, :x.size(1)]
+        return ops.dropout(x + self.pe[:, :x.size(1)], _p(self))            # embedding.py:30-31
 
 
 class ConvModule(nn.Module):

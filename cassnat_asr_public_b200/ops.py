@@ -157,7 +157,7 @@ def set_precision(mode):
              tolerance -- except the two decision heads, which run as bf16x3 (SAFE_HEADS) so that a rounding flip of
              an argmax cannot change the alignment or a token given the same head input;
     'bf16x3' precise tensor-core mode: every GEMM operand is carried as a (hi, lo) bf16 pair and multiplied in three
-             passes (error ~2^-17); attention stays bf16."""
+             passes (error ~2^-17); attention runs on the fp32 kernel (X3_FP32_ATTENTION) or, optionally, in bf16."""
     global _PRECISION
     if mode not in ("fp32", "bf16", "bf16x3"):
         raise ValueError(mode)
@@ -175,6 +175,15 @@ def is_bf16():
 
 def is_x3():
     return _PRECISION == "bf16x3"
+
+
+X3_FP32_ATTENTION = True     # bf16x3 mode: Q/K/V stay fp32 and the attention runs on the fp32 kernel, so that no bf16
+#                              rounding is left anywhere on the path (the GEMMs are the 3-pass tensor-core ones)
+
+
+def attn_bf16():
+    """True when Q/K/V are produced in bf16 for the tcgen05 attention kernel."""
+    return _PRECISION == "bf16" or (_PRECISION == "bf16x3" and not X3_FP32_ATTENTION)
 
 
 def split_of(x):
@@ -345,17 +354,69 @@ def _mask_strides(mask, B, Tq, Tk):
     return m, m.stride(0), (0 if m.shape[1] == 1 else m.stride(1))
 
 
-def attention(q, k, v, mask, n_head, rel=None, out=None):
+# ----------------------------------------------------------------------------- dropout (training)
+DROPOUT_SEED = 0             # host seed, used when DROPOUT_SEED_DEV is None
+DROPOUT_SEED_DEV = None      # optional int64 [1] device tensor: a CUDA-graph-replayed training step advances it in-graph
+_dropout_site = 0            # running id of the dropout call sites of one step (every site draws an independent mask)
+
+
+def dropout_begin_step(seed=None):
+    """Call at the start of every training forward: resets the call-site counter (so that forward and its recorded
+    backward agree on the site ids) and optionally sets the host seed of the step."""
+    global _dropout_site, DROPOUT_SEED
+    _dropout_site = 0
+    if seed is not None:
+        DROPOUT_SEED = int(seed)
+
+
+def _next_site():
+    global _dropout_site
+    _dropout_site += 1
+    return _dropout_site
+
+
+def dropout_forward(x, p, site, inplace=False):
+    """x * keep / (1 - p) with the stateless keep mask of (seed, site, element index) (cn_dropout)."""
+    require_cuda(x)
+    xc = x if x.is_contiguous() else x.contiguous()
+    if xc.dtype not in (torch.float32, torch.bfloat16):
+        xc = xc.float()
+    out = xc if (inplace and xc is x) else torch.empty_like(xc)
+    call("cn_dropout", ptr(xc), int(xc.dtype == torch.bfloat16), ptr(out), int(out.dtype == torch.bfloat16), xc.numel(),
+         float(p), ptr(DROPOUT_SEED_DEV), int(DROPOUT_SEED), int(site), stream(),
+         work=dict(bytes=2.0 * xc.numel() * xc.element_size()))
+    return out
+
+
+def dropout_mask(shape, p, site, device):
+    """The multiplicative mask (0 or 1/(1-p)) the kernels use for `site` under the current seed (tests)."""
+    return dropout_forward(torch.ones(shape, dtype=torch.float32, device=device), p, site)
+
+
+def dropout(x, p, training=True):
+    """nn.Dropout of the reference's modules; identity in eval mode or at p = 0."""
+    if not training or p <= 0.0:
+        return x
+    site = _next_site()
+    if _needs_grad(x):
+        from . import grad
+        return grad.Dropout.apply(x, float(p), site)
+    return dropout_forward(x, p, site)
+
+
+def attention(q, k, v, mask, n_head, rel=None, out=None, p_drop=0.0):
     """Masked multi-head attention on projected q [B,Tq,d], k/v [B,Tk,d] (views with a row stride
     are fine, e.g. slices of a fused QKV buffer).  mask: [B,1,Tk] or [B,Tq,Tk], 0 = masked.
     rel = (rel_pos [2m+1,d], pos_bias_u [h,dk], pos_bias_v [h,dk], m) selects the relative-position
-    variant (modules/attention.py:104-143)."""
-    if _needs_grad(q, k, v) or (rel is not None and _needs_grad(rel[0], rel[1], rel[2])):
+    variant (modules/attention.py:104-143).  p_drop > 0 (training): dropout on the attention probabilities
+    (attention.py:22-23,140-141) through the materialised path of grad.py."""
+    site = _next_site() if p_drop > 0.0 else 0
+    if p_drop > 0.0 or _needs_grad(q, k, v) or (rel is not None and _needs_grad(rel[0], rel[1], rel[2])):
         from . import grad
         assert out is None
         if rel is not None:
-            return grad.RelAttention.apply(q, k, v, rel[0], rel[1], rel[2], mask, n_head, rel[3])
-        return grad.Attention.apply(q, k, v, mask, n_head)
+            return grad.RelAttention.apply(q, k, v, rel[0], rel[1], rel[2], mask, n_head, rel[3], float(p_drop), site)
+        return grad.Attention.apply(q, k, v, mask, n_head, float(p_drop), site)
     return attention_forward(q, k, v, mask, n_head, rel, out)
 
 

@@ -384,9 +384,20 @@ int cn_layernorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy,
 /* Softmax backward of masked attention, in place: S [B,h,Tq,Tk] (scaled raw scores) <- probabilities
  * as the forward used them; dP [B,h,Tq,Tk] (= dO V^T) <- gradient at the scaled scores.  Fully masked
  * rows: uniform probabilities and zero score gradient (attention.py:19-21); zero_masked = 1 applies the
- * relative variant's re-zeroing (attention.py:138).  mask as in cn_attention_f32. */
+ * relative variant's re-zeroing (attention.py:138).  mask as in cn_attention_f32.  dP may be NULL: forward only
+ * (the materialised attention of the training path with dropout on the probabilities). */
 int cn_attn_softmax_bwd(float* S, float* dP, const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t h,
                         int64_t Tq, int64_t Tk, int zero_masked, cn_stream_t stream);
+
+/* Dropout (training): out[i] = keep(i) ? x[i] / (1 - p) : 0 with keep a counter-based hash of (seed, site, i):
+ * stateless, so the backward pass regenerates the mask from the same (seed, site) instead of storing it.
+ *   replaces: nn.Dropout                 src/models/modules/utils.py:21,32; attention.py:22-23,140-141;
+ *                                        positionff.py:12,16; embedding.py:17,31,49,60
+ * x / out f32 or bf16 (flags), n elements, in place allowed.  seed_dev (i64 [1], may be NULL) overrides `seed`: a
+ * step captured in a CUDA graph advances the device-side seed between replays.  site: a distinct id per dropout
+ * call site of a step. */
+int cn_dropout(const void* x, int x_is_bf16, void* out, int out_is_bf16, int64_t n, float p, const int64_t* seed_dev,
+               int64_t seed, int64_t site, cn_stream_t stream);
 
 /* Label-smoothing KL loss over log-softmax rows and its gradient at the logits:
  *   loss = sum_{rows with target != pad} KL(w || p) / #such rows,  w = (1-s) one-hot + s/(V-1) elsewhere

@@ -579,12 +579,14 @@ def small_decode(dev, precision, graphs, iters=50):
             "note": "no L2 flush between steps (the working set is smaller than L2 anyway)"}
 
 
-def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32, frames_in=1000, L=40, iters=10):
-    """SURVEY §8 cfg5 on the post-encoder path: forward (CTC head, Viterbi forced alignment, trigger
-    segments, extractor -> SAD -> MAD -> head, CTC + label-smoothing loss), loss.backward() on the
-    package's backward kernels (gradient returned at enc_h for the encoder) and, for N > 1, the bucketed
-    bf16 gradient all_reduce overlapped with backward.  Runs on every rank (it contains the collective);
-    time = max over ranks of the CUDA-event time of `iters` steps."""
+def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32, frames_in=1000, L=40, iters=10, dropout=0.1):
+    """SURVEY §8 cfg5 on the post-encoder path: forward (CTC head, Viterbi forced alignment, trigger segments,
+    extractor -> SAD -> MAD -> head, CTC + label-smoothing loss) and loss.backward() on the package's backward kernels
+    (gradient returned at enc_h for the encoder), with the reference's training dropout (conf/cassnat_train.yaml:11:
+    0.1; stateless masks, the step's seed lives on the device and is advanced inside the graph).  N > 1: the gradients
+    are views of one flat buffer whose bf16 buckets are all_reduced from post-accumulate hooks, i.e. overlapped with
+    the rest of backward; zero + forward + backward + exchange are captured as ONE CUDA graph.  Runs on every rank;
+    time = max over ranks of the CUDA-event time of `iters` steps.  Also reports the dropout-free step."""
     import torch.distributed as dist
 
     from cassnat_asr_public_b200 import ops, sharding
@@ -599,76 +601,84 @@ def training_step(model, args, w, dev, rank, world, sync_all, graphed=True, B=32
     labels[:, L] = 2
     labels, sizes = labels.to(dev), torch.full((B,), L, dtype=torch.int64, device=dev)
     model.train()
-    model.zero_dropout()
     params = [p for n, p in model.named_parameters() if not n.startswith(("src_embed.", "encoder."))]
-    # eager: bucketed bf16 all_reduce overlapped with backward through hooks; graph replay: gradients are views
-    # of one flat buffer that is reduced in place after the replay
-    buckets = sharding.GradientBuckets(params, comm_dtype=torch.bfloat16) if (world > 1 and not graphed) else None
-    flat = None
+    n_par = sum(p.numel() for p in params)
+    seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
-    def fwd_bwd():
-        out = model.train_forward_from_encoder(enc_h, x_mask, ratio, labels, sizes, args)
-        out[2].backward()
-        return out[2]
+    def set_dropout(p):
+        for m in model.modules():
+            if hasattr(m, "p_drop"):
+                m.p_drop = p
 
-    def eager():
+    def measure(p_drop):
+        set_dropout(p_drop)
+        ops.DROPOUT_SEED_DEV = seed_dev
+        flat = sharding.OverlappedFlatGradients(params, comm_dtype=torch.bfloat16)
+
+        def fwd_bwd():
+            seed_dev.add_(1)                               # a fresh mask every step, also under graph replay
+            flat.zero()
+            out = model.train_forward_from_encoder(enc_h, x_mask, ratio, labels, sizes, args)
+            out[2].backward()
+            flat.finish()                                  # waits for the bucket all_reduces launched during backward
+            return out[2]
+
+        # warm-up on a side stream (PyTorch's whole-step capture recipe: the gradient accumulators of the leaves
+        # must not be tied to the legacy default stream when backward is captured)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                enc_h.grad = None
+                loss = fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = None
+        if graphed:
+            # the training forward has no host synchronisation (ymax comes from the label tensor's shape), so the
+            # whole step is captured once and replayed: gradients live in the flat buffer (static memory)
+            enc_h.grad = None
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd()
+
+        def one():
+            if graph is not None:
+                graph.replay()
+                return static_loss
+            enc_h.grad = None
+            return fwd_bwd()
+
+        for _ in range(2):
+            loss = one()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            loss = one()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        flat.remove()
+        ops.DROPOUT_SEED_DEV = None
         for p in params:
             p.grad = None
-        enc_h.grad = None
-        return fwd_bwd()
+        return float(t[0]) / iters, float(loss.detach())
 
-    # warm-up on a side stream (PyTorch's whole-step capture recipe: the gradient accumulators of the leaves
-    # must not be tied to the legacy default stream when backward is captured)
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            loss = eager()
-    torch.cuda.current_stream().wait_stream(side)
-    if graphed:
-        # the training forward has no host synchronisation (ymax comes from the label tensor's shape), so
-        # forward + backward are captured once and replayed: gradients live in the graph's memory pool
-        enc_h.grad = None
-        flat = sharding.FlatGradients(params)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            flat.zero()
-            static_loss = fwd_bwd()
-
-    def one():
-        if graphed:
-            graph.replay()
-            flat.all_reduce()
-            res = static_loss
-        else:
-            res = eager()
-            if buckets is not None:
-                buckets.finish()
-        return res
-
-    for _ in range(2):
-        loss = one()
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        loss = one()
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if buckets is not None:
-            buckets.remove()
-    ms = float(t[0]) / iters
-    n_par = sum(p.numel() for p in params)
-    model.eval()
-    for p in params:
-        p.grad = None
+    try:
+        ms, loss = measure(dropout)
+        ms0, loss0 = measure(0.0)
+    finally:
+        set_dropout(0.0)
+        model.eval()
+        ops.DROPOUT_SEED_DEV = None
     return {"workload": f"cfg5 (post-encoder path): base model, {B} x {frames_in / 100:.0f} s per GPU, T={T}, {L} labels/utt, "
-                        f"fwd + bwd" + (" + gradient all_reduce (one flat fp32 buffer)" if world > 1 else ""),
-            "ms_per_step": ms, "utt_per_s": B * world / (ms / 1e3), "loss": float(loss.detach()),
+                        f"fwd + bwd, dropout {dropout}" + (", bf16 bucketed gradient all_reduce overlapped with backward (in-graph)"
+                                                         if world > 1 else ""),
+            "ms_per_step": ms, "utt_per_s": B * world / (ms / 1e3), "loss": loss,
+            "no_dropout": {"ms_per_step": ms0, "utt_per_s": B * world / (ms0 / 1e3), "loss": loss0},
             "params_in_step": n_par, "precision": ops.get_precision(), "cuda_graph": graphed}
 
 

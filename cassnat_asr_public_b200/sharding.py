@@ -116,13 +116,20 @@ class GradientBuckets:
         self.reset()
 
     def reset(self):
+        """Call before every backward whose gradients are to be exchanged (finish() does it for the next step).  With
+        gradient accumulation (cassnat_task.py:290-292) call `reset()` + `finish()` around the LAST micro-batch only
+        and keep `hooks_enabled = False` for the earlier ones, the equivalent of DDP's no_sync()."""
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
 
+    hooks_enabled = True
+
     def _ready(self, p):
+        if not self.hooks_enabled:
+            return
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
-        if self._pending[i] == 0:
+        if self._pending[i] == 0 and self._work[i] is None:
             self._launch(i)
 
     def _launch(self, i):
@@ -141,10 +148,8 @@ class GradientBuckets:
         if self.world == 1:
             return
         for i, b in enumerate(self.buckets):
-            if self._work[i] is None:              # parameters that received no gradient this step
-                if all(p.grad is None for p in b):
-                    continue
-                for p in b:
+            if self._work[i] is None:              # parameters that received no gradient this step: every rank still
+                for p in b:                        # launches the bucket (zeros), so the collectives always match up
                     if p.grad is None:
                         p.grad = torch.zeros_like(p)
                 self._launch(i)
@@ -188,3 +193,82 @@ class FlatGradients:
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.div_(self.world)
+
+
+class OverlappedFlatGradients(FlatGradients):
+    """FlatGradients whose exchange overlaps backward: the parameters are laid out in reverse registration order (the
+    order backward produces their gradients) and cut into contiguous buckets of the flat buffer; a post-accumulate
+    hook launches a bucket's all_reduce (NCCL's own stream, async) as soon as its last gradient is complete, while
+    the rest of backward keeps running.  comm_dtype=torch.bfloat16 sends bf16 on NVLink (half the bytes; fp32 master
+    gradients restored, averaged, on the way back).  Everything -- hooks, casts, collectives, the final wait -- is
+    stream work, so a whole step (zero(), forward, backward, finish()) can be captured in ONE CUDA graph and replayed:
+    the all_reduces then overlap the replayed backward as well.
+    Reference: DistributedDataParallel's bucketed gradient all_reduce (src/tasks/base_task.py:82-83)."""
+
+    def __init__(self, params, group=None, bucket_bytes=16 << 20, comm_dtype=torch.bfloat16):
+        ordered = [p for p in reversed(list(params)) if p.requires_grad]
+        super().__init__(ordered, group)
+        self.comm_dtype = comm_dtype
+        self.bounds, lo, o = [], 0, 0                       # element ranges [lo, hi) of the buckets in the flat buffer
+        esize = torch.empty(0, dtype=comm_dtype).element_size()
+        self._bucket_of = {}
+        for p in self.params:
+            self._bucket_of[id(p)] = len(self.bounds)
+            o += p.numel()
+            if (o - lo) * esize >= bucket_bytes:
+                self.bounds.append((lo, o))
+                lo = o
+        if o > lo:
+            self.bounds.append((lo, o))
+        self._count = [0] * len(self.bounds)
+        for p in self.params:
+            self._count[self._bucket_of[id(p)]] += 1
+        self.comm = None if comm_dtype == torch.float32 else torch.empty(self.flat.numel(), dtype=comm_dtype, device=self.flat.device)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._ready) for p in self.params] if self.world > 1 else []
+        self.hooks_enabled = True
+        self.begin()
+
+    def begin(self):
+        """Before every backward that is to be exchanged (zero() calls it)."""
+        self._pending = list(self._count)
+        self._work = [None] * len(self.bounds)
+
+    def zero(self):
+        self.flat.zero_()
+        self.begin()
+
+    def _ready(self, p):
+        if not self.hooks_enabled:
+            return
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0 and self._work[i] is None:
+            self._launch(i)
+
+    def _launch(self, i):
+        lo, hi = self.bounds[i]
+        buf = self.flat[lo:hi]
+        if self.comm is not None:
+            buf = self.comm[lo:hi]
+            buf.copy_(self.flat[lo:hi])
+        self._work[i] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """After backward: launches what no hook launched (same decision on every rank), waits, averages."""
+        if self.world == 1:
+            return
+        for i, (lo, hi) in enumerate(self.bounds):
+            if self._work[i] is None:
+                self._launch(i)
+        for i, (lo, hi) in enumerate(self.bounds):
+            self._work[i].wait()
+            if self.comm is not None:
+                self.flat[lo:hi].copy_(self.comm[lo:hi])
+        self.flat.div_(self.world)
+
+    all_reduce = finish
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

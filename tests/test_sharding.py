@@ -141,3 +141,69 @@ def test_flat_gradients_two_ranks_gloo():
         (l0, a0), (l1, a1) = results[0][step], results[1][step]
         for x, y, m0, m1 in zip(l0, l1, a0, a1):
             assert np.allclose(m0, (x + y) / 2, rtol=1e-6) and np.allclose(m0, m1)
+
+
+def _overlap_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 2))
+    unused = torch.nn.Linear(3, 3)                                         # parameters no backward ever reaches
+    params = list(net.parameters()) + list(unused.parameters())
+    res = []
+
+    def local_grads(inputs):
+        """This rank's own gradients, computed without any exchange (buckets reduced during backward already hold
+        the sum by the time backward returns, so p.grad cannot be read for that)."""
+        gs = torch.autograd.grad(sum(net(x).square().sum() for x in inputs), list(net.parameters()))
+        return [g.numpy() for g in gs] + [torch.zeros_like(p).numpy() for p in unused.parameters()]
+
+    for comm in (torch.float32, torch.bfloat16):
+        og = sharding.OverlappedFlatGradients(params, bucket_bytes=48, comm_dtype=comm)     # several tiny buckets
+        assert len(og.bounds) >= 3
+        for step in range(2):
+            x = torch.full((3, 6), float(rank + 1 + step))
+            local = local_grads([x])
+            og.zero()
+            net(x).square().sum().backward()
+            launched = sum(w is not None for w in og._work)                # hooks fired during backward
+            og.finish()
+            res.append((str(comm), launched, local, [p.grad.clone().numpy() for p in params]))
+        # gradient accumulation: first micro-batch without exchange (hooks off), second one exchanges the sum
+        xs = [torch.full((3, 6), float(rank + 1)), torch.full((3, 6), float(rank + 2))]
+        local = local_grads(xs)
+        og.zero()
+        og.hooks_enabled = False
+        net(xs[0]).square().sum().backward()
+        og.hooks_enabled = True
+        og.begin()
+        net(xs[1]).square().sum().backward()
+        og.finish()
+        res.append((str(comm) + "/accum", 0, local, [p.grad.clone().numpy() for p in params]))
+        og.remove()
+    out_q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_overlapped_flat_gradients_two_ranks_gloo():
+    """Bucketed all_reduce launched from post-accumulate hooks over slices of ONE flat buffer (fp32 and bf16 on the
+    wire), incl. parameters that never receive a gradient and a gradient-accumulation step."""
+    import numpy as np
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for (tag, launched, l0, a0), (_, _, l1, a1) in zip(results[0], results[1]):
+        tol = 1e-6 if "float32" in tag else 2e-2
+        if "accum" not in tag:
+            assert launched >= 2, tag                       # at least the early buckets went out during backward
+        for x, y, m0, m1 in zip(l0, l1, a0, a1):
+            assert np.allclose(m0, (x + y) / 2, rtol=tol, atol=tol * (np.abs(x).max() + 1e-6)), tag
+            assert np.array_equal(m0, m1)

@@ -873,9 +873,13 @@ def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
         ops.align_to_mask(a, yl, ym, mask, xl, 0)
         va, _, _ = ops.viterbi_align(lp, mask, xl, ys, yls, 0)
         ops.align_to_mask(va, yls, U, mask, xl, 0)
+        emis = ops.gather_emissions(lp, ys, 0)
+        ca, _, _ = ops.viterbi_align_compact(emis, V, mask, xl, ys, yls, 0)
+        return va, ca
 
     for _ in range(2):
-        once()
+        va, ca = once()
+    same = bool(torch.equal(va, ca))
     _lib.start_profile()
     for _ in range(iters):
         once()
@@ -884,10 +888,16 @@ def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
     S = 2 * U + 1
     lattice = B * T * S * 5 + B * T * 9
     vit, bp = ms["cn_viterbi_align"], ms["cn_bestpath_from_logp"]
+    vc, ge = ms["cn_viterbi_align_compact"], ms["cn_gather_emissions"]
     return {"workload": f"cfg2: B={B} T={T} V={V} U={U} planted posteriors ({4 * B * T * V / 1e9:.2f} GB f32)",
             "viterbi_ms": vit, "viterbi_utt_per_s": B / (vit / 1e3),
             "viterbi_lattice_GBps": lattice / (vit / 1e3) / 1e9, "viterbi_lattice_frac_of_hbm": lattice / (vit / 1e3) / 1e9 / pk["hbm"],
             "viterbi_note": "emission gather touches one 64-B DRAM atom per (frame, label): see DESIGN.md §4",
+            "viterbi_compact_ms": vc, "viterbi_compact_lattice_GBps": lattice / (vc / 1e3) / 1e9,
+            "viterbi_compact_lattice_frac_of_hbm": lattice / (vc / 1e3) / 1e9 / pk["hbm"],
+            "gather_emissions_ms": ge, "compact_alignments_identical": same,
+            "viterbi_compact_note": "the same DP on compact [B,T,U+1] emissions (gathered once by cn_gather_emissions; shareable "
+                                    "with the CTC loss): 4(U+1) coalesced bytes per frame instead of a 64-B atom per value",
             "bestpath_ms": bp, "bestpath_GBps": 4.0 * B * T * V / (bp / 1e3) / 1e9,
             "bestpath_frac_of_hbm": 4.0 * B * T * V / (bp / 1e3) / 1e9 / pk["hbm"],
             "align_to_mask_ms": ms["cn_align_to_mask"],

@@ -27,6 +27,9 @@ SIGNATURES = {
     "cn_viterbi_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_viterbi_align": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64,
                                 _vp, _vp, _i64, _vp]),
+    "cn_gather_emissions": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "cn_viterbi_align_compact": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64,
+                                        _vp, _vp, _i64, _vp]),
     "cn_align_to_mask": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "cn_expand_trigger_mask": (_int, [_vp, _i64, _i64, _i64, _int, _int, _vp, _vp]),
     "cn_tgt_length_mask": (_int, [_vp, _i64, _i64, _vp, _vp, _vp]),

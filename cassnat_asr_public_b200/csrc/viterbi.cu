@@ -17,11 +17,13 @@ constexpr int kBtBytes = 8192;       // back-trace staging bytes (fits inside th
 
 struct VitArgs {
   const float* logp; int64_t sb, st;
+  const float* emis; int64_t eb, et;   // compact emissions [B,T,U+1] (slot 0 = blank, slot u = label u) instead of logp
   const uint8_t* src_mask; const int64_t* src_size;
   const int64_t* ys; int64_t ys_stride; const int64_t* ylens;
   int T, U, V; int64_t blank;
   const int32_t* t_sample; int n_sample;
   int64_t* aligned; uint32_t* bp;
+  int n_sm;                            // SM count: co-resident CTAs put their DP warp on different schedulers
 };
 
 template <int SPL>
@@ -36,13 +38,17 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
   __shared__ int samp[16];
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // The DP is one serial warp per utterance.  CTAs are handed out one per SM and then wrap around, so the k-th CTA
+  // of an SM runs its DP on warp k (scheduler k): two co-resident utterances never share an issue port.
+  const int dp_warp = ((int)blockIdx.x / p.n_sm) & 3;
   const int T = p.T, U = p.U;
   const int S = 2 * U + 1;
   int xb = (int)p.src_size[b];
   xb = xb < 0 ? 0 : (xb > T ? T : xb);
   const int ylen_b = (int)p.ylens[b];
   const int path_len = 2 * ylen_b + 1;
-  const float* logp_b = p.logp + (int64_t)b * p.sb;
+  const float* logp_b = p.emis ? p.emis + (int64_t)b * p.eb : p.logp + (int64_t)b * p.sb;
+  const int64_t row_pitch = p.emis ? p.et : p.st;
   const uint8_t* mask_b = p.src_mask + (int64_t)b * T;
   uint32_t* bp_b = p.bp + (int64_t)b * T * NWORD * 32;
 
@@ -54,19 +60,22 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
   if (tid < 16) samp[tid] = (tid < p.n_sample) ? p.t_sample[tid] : -1;
   __syncthreads();
 
-  auto fill = [&](int chunk, int buf, int first_warp, int n_warps) {
+  auto fill = [&](int chunk, int buf, bool all_warps) {
     const int t0 = chunk * kFrames;
     const int nf = min(kFrames, xb - t0);
     float* e = emis + buf * kFrames * EW;
-    for (int f = warp - first_warp; f < nf; f += n_warps) {
+    const int n_warps = all_warps ? kThreads / 32 : kThreads / 32 - 1;
+    const int fw = all_warps ? warp : (warp < dp_warp ? warp : warp - 1);     // rank among the filling warps
+    for (int f = fw; f < nf; f += n_warps) {
       const bool valid = mask_b[t0 + f] != 0;
-      const float* row = logp_b + (int64_t)(t0 + f) * p.st;
+      const float* row = logp_b + (int64_t)(t0 + f) * row_pitch;
       for (int u0 = 0; u0 < EW; u0 += 32 * 8) {
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int u = u0 + k * 32 + lane;
-          v[k] = (u <= U) ? (valid ? cn_ld_stream_f32(row + cols[u]) : CN_LOGZERO) : 0.f;
+          // compact emissions: slot u of the row, coalesced; posteriors: the label's vocabulary column (a gather)
+          v[k] = (u <= U) ? (valid ? cn_ld_stream_f32(row + (p.emis ? u : cols[u])) : CN_LOGZERO) : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
   // ---- DP warp state
   float a[SPL];
   uint32_t skip_ok = 0, inside = 0;
-  if (warp == 0) {
+  if (warp == dp_warp) {
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = lane * SPL + j;
@@ -94,11 +103,11 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
   }
 
   const int n_chunks = (xb + kFrames - 1) / kFrames;
-  if (n_chunks > 0) fill(0, 0, 0, kThreads / 32);
+  if (n_chunks > 0) fill(0, 0, true);
   __syncthreads();
 
   for (int c = 0; c < n_chunks; ++c) {
-    if (warp == 0) {
+    if (warp == dp_warp) {
       const int t0 = c * kFrames;
       const int nf = min(kFrames, xb - t0);
       const float* e = emis + (c & 1) * kFrames * EW;
@@ -148,13 +157,13 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
         for (int w = 0; w < NWORD; ++w) bp_b[((int64_t)t * NWORD + w) * 32 + lane] = words[w];
       }
     } else if (c + 1 < n_chunks) {
-      fill(c + 1, (c + 1) & 1, 1, kThreads / 32 - 1);
+      fill(c + 1, (c + 1) & 1, false);
     }
     __syncthreads();
   }
 
   // ---- termination (cassnat.py:337-339): strict '>' between the last two path states at t = xb
-  if (warp == 0) {
+  if (warp == dp_warp) {
 #pragma unroll
     for (int j = 0; j < SPL; ++j) fin[lane * SPL + j] = a[j];
   }
@@ -252,9 +261,94 @@ extern "C" int cn_viterbi_align(const float* logp, int64_t B, int64_t T, int64_t
   if (workspace_bytes < cn_viterbi_workspace_bytes(B, T, U)) return CN_ERR_WORKSPACE;
   if (B == 0) return CN_OK;
   VitArgs p;
+  p.emis = nullptr; p.eb = 0; p.et = 0;
   p.logp = logp; p.sb = sb; p.st = st; p.src_mask = src_mask; p.src_size = src_size;
   p.ys = ys; p.ys_stride = ys_stride; p.ylens = ylens; p.T = (int)T; p.U = (int)U; p.V = (int)V; p.blank = blank;
   p.t_sample = t_sample; p.n_sample = (int)n_sample; p.aligned = aligned; p.bp = (uint32_t*)workspace;
+  { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); p.n_sm = n > 0 ? n : 148; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (spl_for(U)) {
+    case 2: return launch<2>(p, B, stream);
+    case 4: return launch<4>(p, B, stream);
+    case 6: return launch<6>(p, B, stream);
+    case 8: return launch<8>(p, B, stream);
+    case 10: return launch<10>(p, B, stream);
+    case 12: return launch<12>(p, B, stream);
+    case 14: return launch<14>(p, B, stream);
+    case 16: return launch<16>(p, B, stream);
+    case 20: return launch<20>(p, B, stream);
+    case 24: return launch<24>(p, B, stream);
+    case 28: return launch<28>(p, B, stream);
+    case 32: return launch<32>(p, B, stream);
+    default: return CN_ERR_UNSUPPORTED;
+  }
+}
+
+// ---------------------------------------------------------------- compact emissions
+// The forced alignment only ever looks at U+1 of the V posteriors of a frame.  With dumped posteriors the gather is
+// the cost (one 64-byte DRAM atom per 4-byte value); when the caller can hand over (or produce once and share with
+// the CTC loss) the compact [B,T,U+1] emissions, the dynamic program reads 4*(U+1) coalesced bytes per frame.
+namespace {
+__global__ void __launch_bounds__(256) gather_emissions_kernel(const float* __restrict__ logp, int64_t sb, int64_t st, int T, int V,
+                                                               const int64_t* __restrict__ ys, int64_t ys_stride, int U, int64_t blank,
+                                                               float* __restrict__ emis) {
+  extern __shared__ int gcols[];                               // [U+1] vocabulary column per slot
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  for (int u = threadIdx.x; u <= U; u += 256) {
+    int64_t col = u == 0 ? blank : ys[(int64_t)b * ys_stride + (u - 1)];
+    gcols[u] = (int)(col < 0 ? 0 : (col >= V ? V - 1 : col));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = warp; f < 32 && t0 + f < T; f += 8) {           // a warp per frame, 4 frames per warp
+    const float* row = logp + (int64_t)b * sb + (int64_t)(t0 + f) * st;
+    float* out = emis + ((int64_t)b * T + t0 + f) * (U + 1);
+    for (int u0 = 0; u0 <= U; u0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = u0 + k * 32 + lane;
+        v[k] = u <= U ? cn_ld_stream_f32(row + gcols[u]) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = u0 + k * 32 + lane;
+        if (u <= U) out[u] = v[k];
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cn_gather_emissions(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* ys,
+                                   int64_t U, int64_t ys_stride, int64_t blank, float* emis, cn_stream_t stream_) {
+  if (!logp || !ys || !emis || B < 0 || T <= 0 || V <= 0 || U < 1 || ys_stride < U) return CN_ERR_BAD_ARG;
+  if (B > 65535 || U > 8191) return CN_ERR_UNSUPPORTED;
+  if (B == 0) return CN_OK;
+  dim3 grid((unsigned)((T + 31) / 32), (unsigned)B);
+  gather_emissions_kernel<<<grid, 256, (size_t)(U + 1) * sizeof(int), (cudaStream_t)stream_>>>(logp, sb, st, (int)T, (int)V, ys, ys_stride,
+                                                                                             (int)U, blank, emis);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+extern "C" int cn_viterbi_align_compact(const float* emis, int64_t B, int64_t T, int64_t V, int64_t eb, int64_t et,
+                                        const uint8_t* src_mask, const int64_t* src_size, const int64_t* ys, int64_t U,
+                                        int64_t ys_stride, const int64_t* ylens, int64_t blank, const int32_t* t_sample,
+                                        int64_t n_sample, int64_t* aligned, void* workspace, int64_t workspace_bytes,
+                                        cn_stream_t stream_) {
+  if (!emis || !src_mask || !src_size || !ys || !ylens || !aligned || !workspace) return CN_ERR_BAD_ARG;
+  if (B < 0 || T <= 0 || V <= 0 || ys_stride < U || n_sample < 0 || et < U + 1) return CN_ERR_BAD_ARG;
+  if (U < 1 || U > 511 || T > 65535 || n_sample > 16) return CN_ERR_UNSUPPORTED;
+  if (n_sample > 0 && !t_sample) return CN_ERR_BAD_ARG;
+  if (workspace_bytes < cn_viterbi_workspace_bytes(B, T, U)) return CN_ERR_WORKSPACE;
+  if (B == 0) return CN_OK;
+  VitArgs p;
+  p.emis = emis; p.eb = eb; p.et = et;
+  p.logp = nullptr; p.sb = 0; p.st = 0; p.src_mask = src_mask; p.src_size = src_size;
+  p.ys = ys; p.ys_stride = ys_stride; p.ylens = ylens; p.T = (int)T; p.U = (int)U; p.V = (int)V; p.blank = blank;
+  p.t_sample = t_sample; p.n_sample = (int)n_sample; p.aligned = aligned; p.bp = (uint32_t*)workspace;
+  { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); p.n_sm = n > 0 ? n : 148; }
   cudaStream_t stream = (cudaStream_t)stream_;
   switch (spl_for(U)) {
     case 2: return launch<2>(p, B, stream);

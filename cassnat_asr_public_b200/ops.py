@@ -100,6 +100,44 @@ def viterbi_align(ctc_out, src_mask, src_size, ys, ylens, blank, sample_topk=0):
     return aligned, ylens, U
 
 
+def gather_emissions(ctc_out, ys, blank):
+    """The U+1 posteriors per frame the forced alignment (and the CTC loss) look at: emis[b,t,0] = ctc_out[b,t,blank],
+    emis[b,t,u] = ctc_out[b,t,ys[b,u-1]] -> f32 [B,T,U+1] (cn_gather_emissions)."""
+    require_cuda(ctc_out)
+    B, T, V = ctc_out.shape
+    U = ys.size(1)
+    lp = ctc_out if ctc_out.stride(-1) == 1 else ctc_out.contiguous()
+    ys64 = _i64(ys)
+    emis = torch.empty(B, T, U + 1, dtype=torch.float32, device=ctc_out.device)
+    call("cn_gather_emissions", ptr(lp), B, T, V, lp.stride(0), lp.stride(1), ptr(ys64), U, ys64.stride(0), int(blank), ptr(emis),
+         stream(), work=dict(bytes=4.0 * B * T * (U + 1) * 2))
+    return emis
+
+
+def viterbi_align_compact(emis, vocab_size, src_mask, src_size, ys, ylens, blank, sample_topk=0):
+    """CassNAT.viterbi_align on compact emissions [B,T,U+1] (see gather_emissions): the same dynamic program, the same
+    alignments bit for bit, without touching the [B,T,V] posteriors.  -> (aligned_seq_shift i64 [B,T], ylens, U)."""
+    require_cuda(emis)
+    B, T, U1 = emis.shape
+    U = ys.size(1)
+    assert U1 == U + 1 and emis.stride(-1) == 1
+    dev = emis.device
+    t_sample, n_sample = None, 0
+    if sample_topk > 1:
+        t_sample = torch.randint(1, T, (1, sample_topk)).to(torch.int32).reshape(-1).to(dev)     # cassnat.py:312
+        n_sample = int(sample_topk)
+    mask = _u8(src_mask, B, T)
+    ys64, yl64, sz64 = _i64(ys), _i64(ylens), _i64(src_size)
+    aligned = torch.empty(B, T, dtype=torch.int64, device=dev)
+    ws_bytes = _lib.load().cn_viterbi_workspace_bytes(B, T, U)
+    if ws_bytes < 0:
+        raise RuntimeError(f"viterbi_align: unsupported label length U={U} (1..511)")
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    call("cn_viterbi_align_compact", ptr(emis), B, T, int(vocab_size), emis.stride(0), emis.stride(1), ptr(mask), ptr(sz64), ptr(ys64),
+         U, ys64.stride(0), ptr(yl64), int(blank), ptr(t_sample), n_sample, ptr(aligned), ptr(ws), ws_bytes, stream())
+    return aligned, ylens, U
+
+
 def align_to_mask(aligned_seq_shift, ylens, ymax, src_mask, src_size, blank, left=0, right=0, and_src_mask=False,
                   want_mask=True, want_seg=False):
     """CassNAT.align_to_mask (cassnat.py:355-365) -> (bool [B,ymax+1,T], ylens+1, ymax+1).

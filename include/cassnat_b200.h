@@ -99,6 +99,22 @@ int cn_viterbi_align(const float* logp, int64_t B, int64_t T, int64_t V, int64_t
                      int64_t blank, const int32_t* t_sample, int64_t n_sample,
                      int64_t* aligned, void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* K3 on compact emissions.  The forced alignment reads only U+1 of the V posteriors of a frame; with the dumped
+ * [B,T,V] tensor that gather costs a 64-byte DRAM atom per 4-byte value (cfg2: 3.7 GB moved for 0.2 GB used).
+ * cn_gather_emissions extracts emis[b,t,0] = logp[b,t,blank], emis[b,t,u] = logp[b,t,ys[b,u-1]] (u = 1..U) once --
+ * fully parallel, and shareable with the CTC loss, which needs the same values -- and cn_viterbi_align_compact runs
+ * the identical dynamic program (same kernel, bit-identical alignments) on 4*(U+1) coalesced bytes per frame.
+ *   replaces: the emission indexing of CassNAT.viterbi_align      src/models/cassnat.py:296-331
+ * emis f32 [B,T,U+1] (batch / frame pitches eb, et); the other arguments as cn_viterbi_align (V: vocabulary size,
+ * used to clamp label ids exactly as there). */
+int cn_gather_emissions(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st, const int64_t* ys,
+                        int64_t U, int64_t ys_stride, int64_t blank, float* emis, cn_stream_t stream);
+int cn_viterbi_align_compact(const float* emis, int64_t B, int64_t T, int64_t V, int64_t eb, int64_t et,
+                             const uint8_t* src_mask, const int64_t* src_size, const int64_t* ys, int64_t U,
+                             int64_t ys_stride, const int64_t* ylens, int64_t blank, const int32_t* t_sample,
+                             int64_t n_sample, int64_t* aligned, void* workspace, int64_t workspace_bytes,
+                             cn_stream_t stream);
+
 /* K4/K5  alignment -> per-token trigger mask (+ optional +-1 frame dilation and src_mask AND).
  *   replaces: CassNAT.align_to_mask                          src/models/cassnat.py:355-365
  *             CassNAT.expand_trigger_mask + "& src_mask"     src/models/cassnat.py:259-270,:175,:468

@@ -54,6 +54,15 @@ def test_golden_cases(align_golden):
         torch.manual_seed(2000 + c + 1)
         vs, _, _ = ops.viterbi_align(lp, mask, xl, ys, yls, 0, 4)
         assert np.array_equal(vs.cpu().numpy(), g[p + "vits_aligned"]), p
+        # the same alignments from the compact emissions [B,T,U+1] (gathered once, coalesced DP reads)
+        emis = ops.gather_emissions(lp, ys, 0)
+        want_e = torch.cat([lp[:, :, :1], torch.gather(lp, 2, ys.clamp(0, lp.shape[2] - 1).unsqueeze(1).expand(-1, T, -1))], 2)
+        assert torch.equal(emis, want_e), p
+        ca, _, _ = ops.viterbi_align_compact(emis, lp.shape[2], mask, xl, ys, yls, 0)
+        assert np.array_equal(ca.cpu().numpy(), g[p + "vit_aligned"]), p
+        torch.manual_seed(2000 + c + 1)
+        cs, _, _ = ops.viterbi_align_compact(emis, lp.shape[2], mask, xl, ys, yls, 0, 4)
+        assert np.array_equal(cs.cpu().numpy(), g[p + "vits_aligned"]), p
         for tag, (al, yin, ymx) in {"bp": (a, yl, ym), "vit": (va, yls, vym)}.items():
             tm, tyl, tym = ops.align_to_mask(al, yin, ymx, mask, xl, 0)
             assert np.array_equal(tm.cpu().numpy(), unpack(g[p + tag + "_trigger"], T)), (p, tag)
@@ -97,6 +106,8 @@ def test_random_vs_oracle(B, T, V, U, peak):
     va, _, _ = ops.viterbi_align(cu(lp), cu(mask), cu(xl), cu(ys), cu(yls), 0)
     ova, _, _ = A.viterbi_align(lp, mask, xl, ys, yls, 0)
     assert np.array_equal(va.cpu().numpy(), ova)
+    ca, _, _ = ops.viterbi_align_compact(ops.gather_emissions(cu(lp), cu(ys), 0), V, cu(mask), cu(xl), cu(ys), cu(yls), 0)
+    assert np.array_equal(ca.cpu().numpy(), ova)
     for (al, yin, ymx) in ((oa, oyl, oym), (ova, yls, U)):
         for (l, r) in [(0, 0), (1, 1)]:
             tm, tyl, tym, seg = ops.align_to_mask(cu(al), cu(yin), ymx, cu(mask), cu(xl), 0, l, r, True, want_seg=True)

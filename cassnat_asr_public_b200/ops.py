@@ -292,6 +292,7 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
     return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split, next_ln)
 
 
+FUSE_LN_MAX_ROWS = 0      # (automatic use below this many rows: measured slower at cfg1 too, 0.967 vs 0.939 ms/step -> off)
 FUSE_LN = False      # opt-in: the LayerNorm that consumes a residual GEMM's output runs in that GEMM's epilogue
 #                      (cn_gemm_bf16_ln).  Measured on B200 at [32000x512x512]: 69 us fused vs 35 + 23 us for the GEMM and
 #                      the stand-alone LayerNorm -- the epilogue warps are latency-bound, the second pass over the
@@ -308,8 +309,9 @@ def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res
         return linear_x3(x, weight, bias, residual, alpha, act, res_rows, out_bf16, out_split)
     if _PRECISION != "fp32" and x.shape[-1] % 8 == 0:
         N = weight.shape[0]
-        if (FUSE_LN and next_ln is not None and _PRECISION == "bf16" and not out_bf16 and act is None and N <= 512 and
-                N % 4 == 0 and N >= 8):
+        rows = x.numel() // x.shape[-1]
+        if ((FUSE_LN or rows <= FUSE_LN_MAX_ROWS) and next_ln is not None and _PRECISION == "bf16" and not out_bf16 and
+                act is None and N <= 512 and N % 4 == 0 and N >= 8):
             return linear_bf16_ln(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, res_rows, next_ln)
         return linear_bf16(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, act, res_rows,
                            torch.bfloat16 if out_bf16 else torch.float32)

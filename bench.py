@@ -465,7 +465,8 @@ def parity_report(model, args, w, dev_in, precision):
                "frames": int(valid.sum()), "token_rows_read": int(read.sum()), "utterances": B}
         variants = [(precision, True, precision + " (decision-safe heads: K1/K9 as bf16x3)")]
         if precision == "bf16":
-            variants += [("bf16", False, "bf16 with plain bf16 heads"), ("bf16x3", True, "bf16x3 (all GEMMs three-pass, bf16 attention)")]
+            variants += [("bf16", False, "bf16 with plain bf16 heads"),
+                         ("bf16x3", True, "bf16x3 (all GEMMs three-pass on tcgen05, fp32 attention)")]
         for mode, safe, label in variants:
             hyp, got = run(mode, safe)
             same_al = got["aligned"] == ref["aligned"]
@@ -485,6 +486,15 @@ def parity_report(model, args, w, dev_in, precision):
                     x, y = got[key].float()[rows], ref[key].float()[rows]
                     r[f"rel_err_{key}"] = float((x - y).norm() / y.norm())
             r["hypotheses_identical"] = f"{sum(int(a == b) for a, b in zip(hyp, ref_h))}/{B}"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.no_grad():
+                for _ in range(3):
+                    model.decode_from_encoder(enc_h, mask, ratio, VOCAB, args)
+            e1.record()
+            torch.cuda.synchronize()
+            r["ms_per_step_eager"] = e0.elapsed_time(e1) / 3
+            r["utt_per_s_eager"] = B / (r["ms_per_step_eager"] / 1e3)
             rep[label] = r
         rep["fp32_parity_mode"] = {"ms_per_step": fp32_ms, "utt_per_s": B / (fp32_ms / 1e3),
                                    "note": "FFMA GEMMs + fp32 attention; hypotheses identical to the reference on every golden fixture"}

@@ -45,6 +45,9 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _i64, _vp]),
     "cn_gemm_bf16": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16": (_int, [_vp, _vp, _i64, _vp]),
+    "cn_gemm_rowpart_count": (_i64, [_i64, _i64]),
+    "cn_gemm_bf16_rowpart": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "cn_gemm_bf16_folded": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_gemm_bf16_ln": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _i64, _vp, _vp, _f32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_gemm_bf16x3": (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _int, _i64, _i64, _i64, _i64, _vp]),
     "cn_cast_bf16_split": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),

@@ -135,6 +135,13 @@ struct Epilogue {
   int64_t lo_off;        // != 0: out_bf16 is a split (bf16x3) operand, the rounding residue goes lo_off elements further
   // LN mode: the LayerNorm that consumes the fp32 output (next sublayer's pre-norm) is applied by the same kernel
   const float* ln_a; const float* ln_b; float ln_eps; __nv_bfloat16* ln_out; int64_t ld_ln;
+  // LayerNorm folding (fast mode), producer side (LNM_PART): besides the fp32 rows (and their raw bf16 copy) the
+  // epilogue emits per-row partial sums (sum, sum of squares) of its 128-column halves: part [M][n_parts] float2.
+  // Consumer side (LNM_FOLD): A is the RAW bf16 row, W already carries the LayerNorm gain, and the epilogue applies
+  //   y = rinv_m * (acc - mean_m * c_n) + bias'_n      (c_n = sum_k W'_nk, bias' = bias + W b)
+  // i.e. LayerNorm(x) W^T without a LayerNorm kernel or a normalised copy of x ever existing.
+  float* part; int n_rowparts;                             // producer: output; consumer: input (stats of ITS rows)
+  const float* fold_c; float fold_eps; int fold_d;         // consumer: column sums of the folded weight, eps, row width
   // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
   float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
   const int32_t* st_target; float* st_target_logit;    // optional: the logit of one given column per row
@@ -147,10 +154,13 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false, bool LN = false>
+constexpr int LNM_NONE = 0, LNM_FUSED = 1, LNM_PART = 2, LNM_FOLD = 3;
+
+template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false, int LNM = LNM_NONE>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   Epilogue ep, int M, int N, int K, int split) {
+  constexpr bool LN = LNM == LNM_FUSED;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;                    // two accumulator stages (power of two >= 32)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -381,6 +391,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       };
       float4 res_cur[8], res_next[8];
       if (RES) load_res(half * (BN / 2), res_cur);
+      float f_mean[8], f_rinv[8];                               // LNM_FOLD: LayerNorm statistics of this lane's 8 rows
+      if (LNM == LNM_FOLD) {
+        // lane l finalises row (quarter*32 + l) from the producer's partial sums, then the 8 rows a lane stores
+        // (rows rr + 4*it of the quarter) are fetched by shuffle
+        const int myrow = m0 + quarter * 32 + lane;
+        float s1 = 0.f, s2 = 0.f;
+        if (myrow < M) {
+          const float2* pp = reinterpret_cast<const float2*>(ep.part) + (int64_t)myrow * ep.n_rowparts;
+          for (int q = 0; q < ep.n_rowparts; ++q) { const float2 v2 = __ldg(pp + q); s1 += v2.x; s2 += v2.y; }
+        }
+        const float mean = s1 / (float)ep.fold_d;
+        const float var = fmaxf(s2 - s1 * mean, 0.f) / (float)(ep.fold_d - 1);
+        const float rinv = 1.f / (sqrtf(var) + ep.fold_eps);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          f_mean[it] = __shfl_sync(0xffffffffu, mean, it * 4 + rr);
+          f_rinv[it] = __shfl_sync(0xffffffffu, rinv, it * 4 + rr);
+        }
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -412,6 +441,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                        : "=f"(x[it][0]), "=f"(x[it][1]), "=f"(x[it][2]), "=f"(x[it][3])
                        : "r"(stg + (uint32_t)((it * 4 + rr) * 128 + ((((lane & 7)) ^ ((it * 4 + rr) & 7)) << 4))));
+        if (LNM == LNM_FOLD) {
+          const float4 c4 = gcol + 3 < N ? __ldg(reinterpret_cast<const float4*>(ep.fold_c + gcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            x[it][0] = f_rinv[it] * fmaf(-f_mean[it], c4.x, x[it][0]);
+            x[it][1] = f_rinv[it] * fmaf(-f_mean[it], c4.y, x[it][1]);
+            x[it][2] = f_rinv[it] * fmaf(-f_mean[it], c4.z, x[it][2]);
+            x[it][3] = f_rinv[it] * fmaf(-f_mean[it], c4.w, x[it][3]);
+          }
+        }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           x[it][0] = act_fn<ACT>(x[it][0] + bz.x) * ep.alpha;
@@ -426,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
               x[it][0] += res_cur[it].x; x[it][1] += res_cur[it].y; x[it][2] += res_cur[it].z; x[it][3] += res_cur[it].w;
             }
           }
-          if (LN) {
+          if (LN || LNM == LNM_PART) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               ln_s1[it] += (x[it][0] + x[it][1]) + (x[it][2] + x[it][3]);
@@ -491,6 +530,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (LNM == LNM_PART) {
+        // row partial sums of this warp's 128-column half of the tile -> part[row][tile_n * 2 + half]
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            ln_s1[it] += __shfl_xor_sync(0xffffffffu, ln_s1[it], o);
+            ln_s2[it] += __shfl_xor_sync(0xffffffffu, ln_s2[it], o);
+          }
+          if ((lane & 7) == 0 && row0 + it * 4 < M)
+            reinterpret_cast<float2*>(ep.part)[(int64_t)(row0 + it * 4) * ep.n_rowparts + (tile % tiles_n) * 2 + half] =
+                make_float2(ln_s1[it], ln_s2[it]);
+          ln_s1[it] = ln_s2[it] = 0.f;
+        }
+      }
       if (LN && (tile % tiles_n) == tiles_n - 1) {
         // ---- fused LayerNorm of the 128 finished rows (modules/norm.py:15-18: unbiased std, eps added to std).
         // Row totals: over this lane's columns (registers), over the 8 lanes that share a row (shuffles), over the
@@ -609,30 +663,35 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false, bool LN = false>
+template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false, int LNM = LNM_NONE>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, int M, int N, int K,
               cudaStream_t stream, int split = 0) {
   constexpr size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 8 * 4096;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LNM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return CN_ERR_LAUNCH;
     configured = true;
   }
-  const int tiles = LN ? (M + BM - 1) / BM : ((M + BM - 1) / BM) * ((N + BN - 1) / BN);     // LN: whole row blocks per CTA
+  const int tiles = LNM == LNM_FUSED ? (M + BM - 1) / BM : ((M + BM - 1) / BM) * ((N + BN - 1) / BN);     // fused LN: whole row blocks per CTA
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LN><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
+  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LNM><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
 }  // namespace
 
 struct LnArgs { const float* a; const float* b; float eps; void* out; int64_t ld; };
+// LayerNorm folding: producer (part_out != NULL) or consumer (part_in != NULL)
+struct FoldArgs { float* part_out; const float* part_in; int n_parts; const float* c; float eps; int d; };
+
+static int gemm_tile_n(int64_t N, int64_t K, int split) { return (N > 128 && !(N <= 512 && K <= 512 && !split)) ? 256 : 128; }
 
 static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                          const float* residual, int64_t ldr, int64_t res_rows, float alpha, int act,
                          float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                         int split, int out_split, cn_stream_t stream_, const LnArgs* ln = nullptr) {
+                         int split, int out_split, cn_stream_t stream_, const LnArgs* ln = nullptr,
+                         const FoldArgs* fold = nullptr) {
   const int64_t kcols = split ? 2 * K : K, acols = split == 1 ? 2 * K : K;      // stored columns of W and A
   if (!A || !W || (!out_f32 && !out_bf16) || M < 0 || N < 0 || K <= 0 || lda < acols || ldw < kcols || ldc < N)
     return CN_ERR_BAD_ARG;
@@ -647,7 +706,13 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
   // 128x256 tiles unless the problem is the HBM-bound d x d projection shape (N, K <= 512): there the
   // epilogue streams more bytes than the mainloop computes, and 128x128 tiles fill the last wave of the
   // 148 persistent CTAs better (measured on [32000x512x512]: 38.8 -> 34.9 us)
-  int bn = (N > 128 && !(N <= 512 && K <= 512 && !split)) ? 256 : 128;
+  int bn = gemm_tile_n(N, K, split);
+  if (fold) {
+    // vector epilogue only; the producer writes fp32 rows (+ raw bf16 copy), the consumer has no residual
+    if (ln || split || out_split || (N & 3) || (ldc & 3) || (residual && (ldr & 3))) return CN_ERR_UNSUPPORTED;
+    if (fold->part_out && (act != CN_ACT_NONE || !out_f32)) return CN_ERR_BAD_ARG;
+    if (fold->part_in && (residual || !fold->c || fold->d < 2 || fold->n_parts < 1)) return CN_ERR_BAD_ARG;
+  }
   if (ln) {
     // fused LayerNorm: a CTA owns complete rows as at most two N tiles; vector epilogue only
     if (!ln->a || !ln->b || !ln->out || !out_f32 || out_bf16 || act != CN_ACT_NONE || ln->ld < N) return CN_ERR_BAD_ARG;
@@ -665,17 +730,40 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = out_split ? N : 0;
   ep.ln_a = ln ? ln->a : nullptr; ep.ln_b = ln ? ln->b : nullptr; ep.ln_eps = ln ? ln->eps : 0.f;
   ep.ln_out = ln ? (__nv_bfloat16*)ln->out : nullptr; ep.ld_ln = ln ? ln->ld : 0;
+  ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
+  if (fold && fold->part_out) {
+    ep.part = fold->part_out; ep.n_rowparts = 2 * (int)((N + bn - 1) / bn);
+    if (bn == 256) {
+      if (residual) return launch_tc<256, CN_ACT_NONE, true, false, false, false, LNM_PART>(ma, mw, ep, m, n, k, stream, split);
+      return launch_tc<256, CN_ACT_NONE, false, false, false, false, LNM_PART>(ma, mw, ep, m, n, k, stream, split);
+    }
+    if (residual) return launch_tc<128, CN_ACT_NONE, true, false, false, false, LNM_PART>(ma, mw, ep, m, n, k, stream, split);
+    return launch_tc<128, CN_ACT_NONE, false, false, false, false, LNM_PART>(ma, mw, ep, m, n, k, stream, split);
+  }
+  if (fold && fold->part_in) {
+    ep.part = const_cast<float*>(fold->part_in); ep.n_rowparts = fold->n_parts; ep.fold_c = fold->c; ep.fold_eps = fold->eps;
+    ep.fold_d = fold->d;
+#define CN_TC_FOLD(BN_)                                                                                                        \
+    do {                                                                                                                        \
+      if (act == CN_ACT_RELU) return launch_tc<BN_, CN_ACT_RELU, false, false, false, false, LNM_FOLD>(ma, mw, ep, m, n, k, stream, split);   \
+      if (act == CN_ACT_SWISH) return launch_tc<BN_, CN_ACT_SWISH, false, false, false, false, LNM_FOLD>(ma, mw, ep, m, n, k, stream, split); \
+      return launch_tc<BN_, CN_ACT_NONE, false, false, false, false, LNM_FOLD>(ma, mw, ep, m, n, k, stream, split);                           \
+    } while (0)
+    if (bn == 256) CN_TC_FOLD(256);
+    CN_TC_FOLD(128);
+#undef CN_TC_FOLD
+  }
   if (ln) {
     if (bn == 256) {
-      if (residual) return launch_tc<256, CN_ACT_NONE, true, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
-      return launch_tc<256, CN_ACT_NONE, false, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+      if (residual) return launch_tc<256, CN_ACT_NONE, true, false, false, false, LNM_FUSED>(ma, mw, ep, m, n, k, stream, split);
+      return launch_tc<256, CN_ACT_NONE, false, false, false, false, LNM_FUSED>(ma, mw, ep, m, n, k, stream, split);
     }
-    if (residual) return launch_tc<128, CN_ACT_NONE, true, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
-    return launch_tc<128, CN_ACT_NONE, false, false, false, false, true>(ma, mw, ep, m, n, k, stream, split);
+    if (residual) return launch_tc<128, CN_ACT_NONE, true, false, false, false, LNM_FUSED>(ma, mw, ep, m, n, k, stream, split);
+    return launch_tc<128, CN_ACT_NONE, false, false, false, false, LNM_FUSED>(ma, mw, ep, m, n, k, stream, split);
   }
 #define CN_TC_DISPATCH(BN_)                                                                                     \
   do {                                                                                                          \
@@ -708,6 +796,31 @@ extern "C" int cn_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_
   LnArgs ln{ln_a, ln_b, ln_eps, ln_out, ld_ln};
   return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, CN_ACT_NONE, out_f32, nullptr, ldc, M, N, K, 0, 0,
                         stream_, &ln);
+}
+
+extern "C" int64_t cn_gemm_rowpart_count(int64_t N, int64_t K) {
+  const int bn = gemm_tile_n(N, K, 0);
+  return 2 * ((N + bn - 1) / bn);
+}
+
+extern "C" int cn_gemm_bf16_rowpart(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                    const float* residual, int64_t ldr, int64_t res_rows, float alpha, float* out_f32,
+                                    void* out_bf16, int64_t ldc, float* part, int64_t M, int64_t N, int64_t K,
+                                    cn_stream_t stream_) {
+  if (!part) return CN_ERR_BAD_ARG;
+  FoldArgs f{part, nullptr, 0, nullptr, 0.f, 0};
+  return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, CN_ACT_NONE, out_f32, out_bf16, ldc, M, N, K, 0, 0,
+                        stream_, nullptr, &f);
+}
+
+extern "C" int cn_gemm_bf16_folded(const void* A_raw, int64_t lda, const void* W_folded, int64_t ldw, const float* bias_folded,
+                                   const float* colsum, const float* part, int64_t n_parts, int64_t ln_width, float ln_eps,
+                                   float alpha, int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N,
+                                   int64_t K, cn_stream_t stream_) {
+  if (!part || !colsum) return CN_ERR_BAD_ARG;
+  FoldArgs f{nullptr, part, (int)n_parts, colsum, ln_eps, (int)ln_width};
+  return gemm_bf16_impl(A_raw, lda, W_folded, ldw, bias_folded, nullptr, 0, 0, alpha, act, out_f32, out_bf16, ldc, M, N, K, 0, 0,
+                        stream_, nullptr, &f);
 }
 
 extern "C" int cn_gemm_bf16x3(const void* A, int64_t lda, int a_split, const void* W, int64_t ldw, const float* bias,
@@ -755,6 +868,7 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
   ep.bias = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = 1.f; ep.act = CN_ACT_NONE;
   ep.out_f32 = out_f32; ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ldc = ldc; ep.lo_off = 0;
   ep.ln_a = nullptr; ep.ln_b = nullptr; ep.ln_eps = 0.f; ep.ln_out = nullptr; ep.ld_ln = 0;
+  ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1092,6 +1206,7 @@ static int gemm_rowstats_impl(const void* A, int64_t lda, const void* W, int64_t
   ep.bias = bias; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = alpha; ep.act = CN_ACT_NONE;
   ep.out_f32 = nullptr; ep.out_bf16 = nullptr; ep.ldc = 0; ep.lo_off = 0;
   ep.ln_a = nullptr; ep.ln_b = nullptr; ep.ln_eps = 0.f; ep.ln_out = nullptr; ep.ld_ln = 0;
+  ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
   ep.st_max = pmax; ep.st_idx = pidx; ep.st_sum = psum; ep.st_max2 = top2 ? pmax2 : nullptr;
   ep.st_idx2 = top2 ? pidx2 : nullptr; ep.n_parts = parts;
   ep.st_target = target; ep.st_target_logit = target_logit;

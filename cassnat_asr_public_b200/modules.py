@@ -75,6 +75,9 @@ class LayerNorm(nn.Module):
         hit = getattr(x, "_cn_ln", None)
         if hit is not None and hit[0] is self and ops.get_precision() == "bf16":
             return hit[1]
+        hit = getattr(x, "_cn_fold", None)             # folded: the consumer GEMM applies this norm in its epilogue
+        if hit is not None and hit[0] is self and ops.get_precision() == "bf16" and ops.FOLD_LN:
+            return ops.FoldedLN(hit[1], hit[2], hit[3], self)
         return ops.layer_norm(x, self.a_2, self.b_2, self.eps, bf16=ops.is_bf16())
 
     def for_head(self, x):

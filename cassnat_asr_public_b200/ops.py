@@ -284,7 +284,10 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
     fp32 mode: FFMA kernel on f32 operands.  bf16 mode: x (f32 or bf16) and the weight go through the
     tcgen05 GEMM as bf16 with fp32 accumulation; out_bf16 returns a bf16 tensor (GEMM->GEMM chains).
     bf16x3 mode: three-pass split GEMM; out_split (with out_bf16) returns the hi half of a split operand for the
-    next GEMM.  With grad mode on and an input requiring grad the call is recorded for backward (grad.Linear)."""
+    next GEMM.  With grad mode on and an input requiring grad the call is recorded for backward (grad.Linear).
+    x may be a FoldedLN (fast mode): the LayerNorm it stands for is applied in this GEMM's epilogue."""
+    if isinstance(x, FoldedLN):
+        return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split, next_ln)
     if _needs_grad(x, weight, bias, residual):
         from . import grad
         assert out is None
@@ -292,6 +295,10 @@ def linear(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0,
     return linear_forward(x, weight, bias, residual, alpha, act, res_rows, out, out_bf16, out_split, next_ln)
 
 
+FOLD_LN = False      # opt-in: LayerNorm folded into its producer / consumer GEMMs (no LayerNorm kernel, see FoldedLN).
+#                      Measured on B200 (cfg3): the 22 LayerNorm launches (0.50 ms) disappear, but the extra bf16 copy +
+#                      partial sums in the producers' epilogues (+0.30 ms) and the rank-1 correction in the consumers'
+#                      (+0.25 ms) cost as much -- the GEMM epilogues are the contended resource of these shapes
 FUSE_LN_MAX_ROWS = 0      # (automatic use below this many rows: measured slower at cfg1 too, 0.967 vs 0.939 ms/step -> off)
 FUSE_LN = False      # opt-in: the LayerNorm that consumes a residual GEMM's output runs in that GEMM's epilogue
 #                      (cn_gemm_bf16_ln).  Measured on B200 at [32000x512x512]: 69 us fused vs 35 + 23 us for the GEMM and
@@ -299,17 +306,120 @@ FUSE_LN = False      # opt-in: the LayerNorm that consumes a residual GEMM's out
 #                      L2-hot rows costs more there than a separate bandwidth-bound kernel; kept for small batches
 
 
+class FoldedLN:
+    """What LayerNorm.for_gemm returns in fast mode when the GEMM that produced x already emitted the raw bf16 copy of
+    its rows and their partial sums (linear_bf16_rowpart): not a tensor but a promise -- the next ops.linear applies
+    the LayerNorm algebraically in its own epilogue (cn_gemm_bf16_folded), with the gain folded into its weight."""
+    __slots__ = ("x16", "part", "n_parts", "ln")
+    requires_grad = False
+    dtype = torch.bfloat16
+
+    def __init__(self, x16, part, n_parts, ln):
+        self.x16, self.part, self.n_parts, self.ln = x16, part, n_parts, ln
+
+    @property
+    def shape(self):
+        return self.x16.shape
+
+    @property
+    def device(self):
+        return self.x16.device
+
+    def size(self, i=None):
+        return self.x16.size() if i is None else self.x16.size(i)
+
+    def dim(self):
+        return self.x16.dim()
+
+
+_FOLDED = {}         # (weight id, ln id) -> (stamp, W' bf16, column sums f32, bias' f32)
+
+
+def folded_weight(weight, bias, ln):
+    """W' = bf16(W diag(a)), c = row sums of the ROUNDED W' (fp32), bias' = bias + W b: LN(x) W^T + bias =
+    rinv * (x W'^T - mean * c) + bias'.  Cached; rebuilt when the weight, the bias or the norm's parameters change."""
+    key = (id(weight), id(ln), None if bias is None else id(bias))
+    stamp = (weight.data_ptr(), weight._version, ln.a_2.data_ptr(), ln.a_2._version, ln.b_2._version,
+             None if bias is None else (bias.data_ptr(), bias._version))
+    hit = _FOLDED.get(key)
+    if hit is None or hit[0] != stamp:
+        global WEIGHT_EPOCH
+        WEIGHT_EPOCH += 1
+        with torch.no_grad():
+            w = weight.detach().float()
+            wf = cast_bf16((w * ln.a_2.detach().float()[None, :]).contiguous())
+            c = wf.float().sum(1).contiguous()
+            bf = torch.mv(w, ln.b_2.detach().float())
+            if bias is not None:
+                bf = bf + bias.detach().float()
+            hit = (stamp, wf, c, bf.contiguous(), weight, ln, bias)
+        _FOLDED[key] = hit
+    return hit[1], hit[2], hit[3]
+
+
+def linear_folded(f, weight, bias, alpha, act, out_bf16):
+    """act(LN(x) W^T + bias) * alpha with x given as a FoldedLN (raw bf16 rows + partial row sums)."""
+    x16 = f.x16
+    K = x16.shape[-1]
+    N = weight.shape[0]
+    wf, c, bf = folded_weight(weight, bias, f.ln)
+    x2 = x16.reshape(-1, K)
+    M = x2.shape[0]
+    lead = x16.shape[:-1]
+    o32 = None if out_bf16 else torch.empty(*lead, N, dtype=torch.float32, device=x16.device)
+    o16 = torch.empty(*lead, N, dtype=torch.bfloat16, device=x16.device) if out_bf16 else None
+    call("cn_gemm_bf16_folded", ptr(x2), x2.stride(0), ptr(wf), wf.stride(0), ptr(bf), ptr(c), ptr(f.part), int(f.n_parts), K,
+         float(f.ln.eps), float(alpha), ACT[act], ptr(o32), ptr(o16), N, M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (2.0 if out_bf16 else 4.0)),
+         tag=(f"cn_gemm_bf16[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else "cn_gemm_bf16"))
+    return o16 if out_bf16 else o32
+
+
+def linear_bf16_rowpart(x, weight_bf16, bias, residual, alpha, res_rows, ln):
+    """The residual GEMM as the producer of a folded LayerNorm: fp32 rows + their raw bf16 copy + per-row partial sums
+    (cn_gemm_bf16_rowpart); the pair rides on the fp32 tensor as `_cn_fold` where `ln.for_gemm` finds it."""
+    K = x.shape[-1]
+    N = weight_bf16.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    lead = x.shape[:-1]
+    dev = x.device
+    o32 = torch.empty(*lead, N, dtype=torch.float32, device=dev)
+    o16 = torch.empty(*lead, N, dtype=torch.bfloat16, device=dev)
+    n_parts = int(_lib.load().cn_gemm_rowpart_count(N, K))
+    part = torch.empty(M, n_parts, 2, dtype=torch.float32, device=dev)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1 or r2.stride(0) % 4 or r2.data_ptr() % 16:
+            r2 = r2.contiguous()
+    call("cn_gemm_bf16_rowpart", ptr(x2), x2.stride(0), ptr(weight_bf16), weight_bf16.stride(0), ptr(bias), ptr(r2),
+         r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ptr(o32), ptr(o16), N, ptr(part), M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (6.0 + (4.0 if r2 is not None else 0.0))),
+         tag=(f"cn_gemm_bf16[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else "cn_gemm_bf16"))
+    o32._cn_fold = (ln, o16, part, n_parts)
+    return o32
+
+
 def linear_forward(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows=0, out=None, out_bf16=False,
                    out_split=False, next_ln=None):
     """next_ln (fast mode): the LayerNorm module that will normalise this output next (the following sublayer's
     pre-norm).  Its bf16 result is produced by the same kernel and attached to the returned tensor, where
     LayerNorm.for_gemm finds it (cn_gemm_bf16_ln)."""
+    if isinstance(x, FoldedLN):
+        assert residual is None and out is None
+        return linear_folded(x, weight, bias, alpha, act, out_bf16)
     require_cuda(x, weight)
     if _PRECISION == "bf16x3" and x.shape[-1] % 64 == 0:
         return linear_x3(x, weight, bias, residual, alpha, act, res_rows, out_bf16, out_split)
     if _PRECISION != "fp32" and x.shape[-1] % 8 == 0:
         N = weight.shape[0]
         rows = x.numel() // x.shape[-1]
+        if (FOLD_LN and next_ln is not None and _PRECISION == "bf16" and not out_bf16 and act is None and N % 8 == 0 and
+                N == next_ln.a_2.numel()):
+            return linear_bf16_rowpart(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, res_rows, next_ln)
         if ((FUSE_LN or rows <= FUSE_LN_MAX_ROWS) and next_ln is not None and _PRECISION == "bf16" and not out_bf16 and
                 act is None and N <= 512 and N % 4 == 0 and N >= 8):
             return linear_bf16_ln(cast_bf16(x), bf16_weight(weight), bias, residual, alpha, res_rows, next_ln)

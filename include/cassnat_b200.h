@@ -233,6 +233,25 @@ int cn_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, cons
                     const float* ln_a, const float* ln_b, float ln_eps, void* ln_out, int64_t ld_ln,
                     int64_t M, int64_t N, int64_t K, cn_stream_t stream);
 
+/* LayerNorm folding (fast mode): the pre-norm LayerNorm between a residual GEMM and the GEMM that consumes it
+ * disappears as a kernel.  LN(x) W^T = rinv * (x (W diag(a))^T - mean * c) + (bias + W b), c_n = sum_k (W diag(a))_nk:
+ *   producer  cn_gemm_bf16_rowpart: the residual GEMM also writes the raw bf16 copy of its fp32 rows and per-row
+ *             partial sums (sum, sum of squares over each 128-column half): part f32 [M][n_parts][2],
+ *             n_parts = cn_gemm_rowpart_count(N, K);
+ *   consumer  cn_gemm_bf16_folded: A = the raw bf16 rows, W_folded = bf16(W diag(a)), colsum = c (of the ROUNDED
+ *             folded weight, so that a constant row cancels exactly), bias_folded = bias + W b; its epilogue
+ *             finalises mean / 1/(std_unbiased + eps) of its rows from the partial sums and applies the formula.
+ *   replaces: LayerNorm.forward between SublayerConnection and the next nn.Linear
+ *             src/models/modules/norm.py:15-18, modules/utils.py:25-32 */
+int64_t cn_gemm_rowpart_count(int64_t N, int64_t K);
+int cn_gemm_bf16_rowpart(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                         const float* residual, int64_t ldr, int64_t res_rows, float alpha, float* out_f32,
+                         void* out_bf16, int64_t ldc, float* part, int64_t M, int64_t N, int64_t K, cn_stream_t stream);
+int cn_gemm_bf16_folded(const void* A_raw, int64_t lda, const void* W_folded, int64_t ldw, const float* bias_folded,
+                        const float* colsum, const float* part, int64_t n_parts, int64_t ln_width, float ln_eps,
+                        float alpha, int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t M, int64_t N,
+                        int64_t K, cn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * bf16x3 ("split") arithmetic: fp32-grade products on the bf16 tensor cores.  A value v is carried as the pair
  * hi = bf16(v), lo = bf16(v - hi) (16 mantissa bits); a split operand matrix stores [hi | lo] along the contraction

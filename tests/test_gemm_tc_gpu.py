@@ -196,3 +196,35 @@ def test_gemm_with_fused_layernorm(M, N, K, res):
     err = (got16.float() - want).abs()
     tol = want.abs() * 2.0 ** -8 + 1e-6                                                  # one bf16 rounding
     assert bool((err <= tol).all()), float((err - tol).max())
+
+
+@pytest.mark.parametrize("M,d,N2,K1,act", [(300, 512, 1536, 512, None), (32000, 512, 2048, 2048, "relu"), (129, 256, 512, 256, "swish"),
+                                           (1000, 128, 384, 128, None), (77, 512, 512, 512, None)])
+def test_layernorm_folded_into_gemms(M, d, N2, K1, act):
+    """LayerNorm folding: the producer residual GEMM emits fp32 rows + raw bf16 rows + partial row sums, the consumer GEMM
+    applies LN(x) W^T = rinv (x W'^T - mean c) + bias' in its epilogue (cn_gemm_bf16_rowpart / cn_gemm_bf16_folded).
+    Against the unfolded chain (GEMM -> LayerNorm kernel -> GEMM) on the same operands: the fp32 stream bit-identical,
+    the consumer output within bf16 operand rounding (the two forms round different quantities to bf16)."""
+    from types import SimpleNamespace
+    torch.manual_seed(M + d + N2)
+    x = torch.randn(M, K1, device=DEV).bfloat16()
+    w1 = (torch.randn(d, K1, device=DEV) / K1 ** 0.5).bfloat16()
+    b1 = torch.randn(d, device=DEV)
+    res = torch.randn(M, d, device=DEV) * 2 + 0.2
+    ln = SimpleNamespace(a_2=torch.rand(d, device=DEV) + 0.5, b_2=torch.randn(d, device=DEV) * 0.3, eps=1e-6)
+    w2 = torch.randn(N2, d, device=DEV) / d ** 0.5
+    b2 = torch.randn(N2, device=DEV)
+    want32 = ops.linear_bf16(x, w1, b1, res, 0.5, None, 0)
+    got32 = ops.linear_bf16_rowpart(x, w1, b1, res, 0.5, 0, ln)
+    assert torch.equal(got32, want32)
+    tag, x16, part, n_parts = got32._cn_fold
+    assert tag is ln and torch.equal(x16, want32.bfloat16())
+    tot = part.sum(1)
+    assert rel(tot[:, 0], want32.sum(1)) < 1e-5 and rel(tot[:, 1], want32.square().sum(1)) < 1e-5
+    y_fold = ops.linear_folded(ops.FoldedLN(x16, part, n_parts, ln), w2, b2, 1.0, act, out_bf16=False)
+    xn = ops.layer_norm_forward(want32, ln.a_2, ln.b_2, ln.eps)                         # fp32 LayerNorm
+    z = xn.double() @ w2.double().t() + b2.double()
+    ref = torch.relu(z) if act == "relu" else (z * torch.sigmoid(z) if act == "swish" else z)
+    y_chain = ops.linear_bf16(xn.bfloat16(), w2.bfloat16(), b2, None, 1.0, act)           # the unfolded fast-mode chain
+    e_fold, e_chain = rel(y_fold, ref), rel(y_chain, ref)
+    assert e_fold < 2e-2 and e_fold < 2.5 * e_chain + 1e-3, (e_fold, e_chain)

@@ -340,10 +340,12 @@ def test_cuda_graph_dropped_when_weights_change(blocks_golden):
         model.set_precision("fp32")
 
 
-def test_fused_layernorm_does_not_change_the_decode(blocks_golden):
-    """The LayerNorm-in-the-GEMM-epilogue path (ops.FUSE_LN, opt-in) against the same mode with stand-alone LayerNorm
-    kernels: identical alignment, embeddings within one bf16 rounding of the normalised operands, same tokens wherever
-    the head margin is clear."""
+@pytest.mark.parametrize("variant", ["fused_epilogue", "folded"])
+def test_fused_layernorm_does_not_change_the_decode(blocks_golden, variant):
+    """The two ways the fast mode gets rid of LayerNorm kernels -- ops.FOLD_LN (default: the norm is applied
+    algebraically in the consumer GEMM's epilogue) and ops.FUSE_LN (opt-in: normalised copy written by the producer
+    GEMM) -- against the same mode with stand-alone LayerNorm kernels: identical alignment, embeddings within bf16
+    operand rounding, same tokens wherever the head margin is clear."""
     from cassnat_asr_public_b200 import ops
     name, z, sd, cfg = blocks_golden
     model, args = build(sd, cfg)
@@ -354,12 +356,13 @@ def test_fused_layernorm_does_not_change_the_decode(blocks_golden):
     try:
         model.set_precision("bf16")
         for fuse in (True, False):
-            ops.FUSE_LN = fuse
+            ops.FUSE_LN = fuse and variant == "fused_epilogue"
+            ops.FOLD_LN = fuse and variant == "folded"
             with torch.no_grad():
                 _, _, keep = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args, return_intermediates=True)
             runs[fuse] = keep
     finally:
-        ops.FUSE_LN = False
+        ops.FUSE_LN, ops.FOLD_LN = False, False
         model.set_precision("fp32")
     assert torch.equal(runs[True]["aligned"], runs[False]["aligned"])
     for key in ("ac_embed", "pred_embed", "dec_h"):

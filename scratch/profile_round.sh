@@ -2,7 +2,7 @@
 # Round profile capture: each ncu pass runs only after the same command exited 0 without ncu.
 # Usage (on the GPU box): bash scratch/profile_round.sh
 set -u
-ARGS="--steps 3 --warmup 3 --no-cpu-baseline --no-lattice --no-training --no-sampled"
+ARGS="--steps 3 --warmup 3 --no-cpu-baseline --no-lattice --no-training --no-sampled --no-parity --no-eager"
 timeout 300 python bench.py $ARGS > gpurun_out/prof_plain.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/prof_plain.log; exit 1; }
 echo "plain bench ok"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 400 --csv \

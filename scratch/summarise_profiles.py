@@ -65,11 +65,11 @@ def full_table(rep):
 if __name__ == "__main__":
     n, tot, lines = launch_table()
     ng, tr = gemm_traffic()
-    shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, "r01_bench_launches.csv"))
-    shutil.copy(os.path.join(G, "gemm_traffic.csv"), os.path.join(P, "r01_gemm_traffic.csv"))
+    shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, "r02_bench_launches.csv"))
+    shutil.copy(os.path.join(G, "gemm_traffic.csv"), os.path.join(P, "r02_gemm_traffic.csv"))
     json.dump({"cn_gemm_bf16": tr, "_note": f"average dram__bytes_read.sum + dram__bytes_write.sum per launch over {ng} consecutive "
                "gemm_bf16_tc_kernel launches of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lattice --no-training "
-               "--no-sampled`; ncu --metrics, --clock-control none (profiles/r01_gemm_traffic.csv)"},
+               "--no-sampled --no-parity --no-eager`; ncu --metrics, --clock-control none (profiles/r02_gemm_traffic.csv)"},
               open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
     out = {"launches": n, "total_us": tot, "launch_table": lines, "gemm": full_table("one_gemm_full"), "attn": full_table("one_attn_full"),
            "gemm_traffic": tr}

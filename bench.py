@@ -466,7 +466,7 @@ def parity_report(model, args, w, dev_in, precision):
         variants = [(precision, True, precision + " (decision-safe heads: K1/K9 as bf16x3)")]
         if precision == "bf16":
             variants += [("bf16", False, "bf16 with plain bf16 heads"),
-                         ("bf16x3", True, "bf16x3 (all GEMMs three-pass on tcgen05, fp32 attention)")]
+                         ("bf16x3", True, "bf16x3 (all GEMMs and the attention three-pass on tcgen05)")]
         for mode, safe, label in variants:
             hyp, got = run(mode, safe)
             same_al = got["aligned"] == ref["aligned"]

@@ -64,6 +64,8 @@ SIGNATURES = {
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "cn_attention_bf16x3": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64,
+                                   _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cn_conv_frontend_bf16": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "cn_decode_hints": (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cn_pack_mask_bits": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),

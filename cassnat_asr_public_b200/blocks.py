@@ -36,7 +36,7 @@ def _self_attention_block(x, sub, attn, mask, pos_embed=None, next_norm=None):
     norm = sub.norm
     y = norm.for_gemm(x)
     if pos_embed is None:
-        q, k, v = attn.project_qkv(y, out_bf16=ops.attn_bf16())   # bf16 -> tcgen05 attention
+        q, k, v = attn.project_qkv(y, **ops.attn_kw())            # bf16 (or split bf16) -> tcgen05 attention
         ctx = ops.attention(q, k, v, mask, attn.h, p_drop=_p(attn))
     else:
         from .modules import distinct_rel_rows
@@ -53,8 +53,8 @@ def _self_attention_block(x, sub, attn, mask, pos_embed=None, next_norm=None):
 
 def _src_attention_block(x, sub, attn, memory, mask, kv=None, next_norm=None):
     y = sub.norm.for_gemm(x)
-    q = attn.project_q(y, out_bf16=ops.attn_bf16())
-    k, v = kv if kv is not None else attn.project_kv(memory, out_bf16=ops.attn_bf16())
+    q = attn.project_q(y, **ops.attn_kw())
+    k, v = kv if kv is not None else attn.project_kv(memory, **ops.attn_kw())
     ctx = ops.attention(q, k, v, mask, attn.h, p_drop=_p(attn))
     return _residual(sub, x, lambda **kw: attn.output(ctx, **kw), next_norm=next_norm)
 
@@ -232,9 +232,10 @@ def _project_memory_all(dec, memory):
     attns = [layer.src_attn for layer in dec.layers]
     w = _cat_cached(dec, "kv_all_w", [t for a in attns for t in (a.linears[1].weight, a.linears[2].weight)])
     b = _cat_cached(dec, "kv_all_b", [t for a in attns for t in (a.linears[1].bias, a.linears[2].bias)])
-    kv = ops.linear(memory, w, b, out_bf16=ops.attn_bf16())                    # [B,T,2d*N]
+    kv = ops.linear(memory, w, b, **ops.attn_kw())                            # [B,T,2d*N]
     d = memory.size(-1)
-    return [(kv[..., 2 * i * d:(2 * i + 1) * d], kv[..., (2 * i + 1) * d:(2 * i + 2) * d]) for i in range(len(attns))]
+    return [(ops.split_cols(kv, 2 * i * d, (2 * i + 1) * d), ops.split_cols(kv, (2 * i + 1) * d, (2 * i + 2) * d))
+            for i in range(len(attns))]
 
 
 # ================================================================================= conformer family

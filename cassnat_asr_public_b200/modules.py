@@ -127,23 +127,24 @@ class MultiHeadedAttention(nn.Module):
         self.p_drop = dropout
 
     # -- pieces the fused decode plan reuses --------------------------------------------
-    def project_q(self, x, out_bf16=False):
-        return ops.linear(x, self.linears[0].weight, self.linears[0].bias, out_bf16=out_bf16)
+    def project_q(self, x, out_bf16=False, out_split=False):
+        q = ops.linear(x, self.linears[0].weight, self.linears[0].bias, out_bf16=out_bf16, out_split=out_split)
+        return ops.split_cols(q, 0, q.shape[-1]) if out_split else q
 
-    def project_kv(self, memory, out_bf16=False):
+    def project_kv(self, memory, out_bf16=False, out_split=False):
         """One GEMM for K and V: [B,T,2d]; returns the two strided views."""
         w = _cat_cached(self, "kv_w", [self.linears[1].weight, self.linears[2].weight])
         b = _cat_cached(self, "kv_b", [self.linears[1].bias, self.linears[2].bias])
-        kv = ops.linear(memory, w, b, out_bf16=out_bf16)
+        kv = ops.linear(memory, w, b, out_bf16=out_bf16, out_split=out_split)
         d = self.h * self.d_k
-        return kv[..., :d], kv[..., d:]
+        return ops.split_cols(kv, 0, d), ops.split_cols(kv, d, 2 * d)
 
-    def project_qkv(self, x, out_bf16=False):
+    def project_qkv(self, x, out_bf16=False, out_split=False):
         w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
         b = _cat_cached(self, "qkv_b", [l.bias for l in self.linears[:3]])
-        qkv = ops.linear(x, w, b, out_bf16=out_bf16)
+        qkv = ops.linear(x, w, b, out_bf16=out_bf16, out_split=out_split)
         d = self.h * self.d_k
-        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        return ops.split_cols(qkv, 0, d), ops.split_cols(qkv, d, 2 * d), ops.split_cols(qkv, 2 * d, 3 * d)
 
     def output(self, ctx, residual=None, scale=1.0, res_rows=0, next_ln=None):
         return ops.linear(ctx, self.linears[3].weight, self.linears[3].bias, residual=residual, alpha=scale,

@@ -219,9 +219,42 @@ X3_FP32_ATTENTION = True     # bf16x3 mode: Q/K/V stay fp32 and the attention ru
 #                              rounding is left anywhere on the path (the GEMMs are the 3-pass tensor-core ones)
 
 
+X3_SPLIT_ATTENTION = True    # ... unless the split-bf16 tcgen05 attention applies (key masks, d_k = 64, no relative term):
+#                              Q/K/V then stay (hi, lo) bf16 pairs and scores / context take three tensor-core passes each
+
+
 def attn_bf16():
-    """True when Q/K/V are produced in bf16 for the tcgen05 attention kernel."""
-    return _PRECISION == "bf16" or (_PRECISION == "bf16x3" and not X3_FP32_ATTENTION)
+    """True when Q/K/V are produced in plain bf16 for the tcgen05 attention kernel."""
+    return _PRECISION == "bf16" or (_PRECISION == "bf16x3" and not X3_FP32_ATTENTION and not attn_split())
+
+
+def attn_split():
+    """True when Q/K/V are produced as split (hi, lo) bf16 operands for cn_attention_bf16x3."""
+    return _PRECISION == "bf16x3" and X3_SPLIT_ATTENTION and not torch.is_grad_enabled()     # (forward-only kernel)
+
+
+def attn_kw():
+    """Keyword arguments of the Q/K/V projections for the attention kernel of the current mode."""
+    return dict(out_bf16=attn_bf16() or attn_split(), out_split=attn_split())
+
+
+def split_cols(t, lo, hi):
+    """Columns [lo, hi) of a projection output.  For the hi half of a split operand the slice carries its lo twin
+    as `_cn_lo` (same shape and pitches), which is how Q / K / V reach the split attention kernel."""
+    full = split_of(t)
+    out = t[..., lo:hi]
+    if full is not None:
+        n = t.shape[-1]
+        out._cn_lo = full[..., n + lo:n + hi]
+    return out
+
+
+def unsplit(t):
+    """fp32 value of a (hi, lo) pair (or of a plain tensor)."""
+    lo = getattr(t, "_cn_lo", None)
+    if lo is None and split_of(t) is not None:
+        lo = split_of(t)[..., t.shape[-1]:]
+    return t.float() + lo.float() if lo is not None else t.float()
 
 
 def split_of(x):
@@ -577,6 +610,12 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     dk = d // n_head
     for t in (q, k, v):
         assert t.stride(-1) == 1
+    if getattr(q, "_cn_lo", None) is not None:
+        key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
+        if rel is None and key_mask and dk == 64 and Tk <= 2048 and getattr(k, "_cn_lo", None) is not None and \
+                getattr(v, "_cn_lo", None) is not None and out is None:
+            return _attention_x3(q, k, v, mask, n_head)
+        q, k, v = unsplit(q), unsplit(k), unsplit(v)          # (relative term / per-row masks: fp32 kernel)
     if q.dtype == torch.bfloat16:
         key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
         if dk == 64 and Tk <= (2048 if key_mask else 512) and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
@@ -608,6 +647,8 @@ def segment_attention(q_rows, k, v, seg, ylens, src_mask, src_size, left, right,
     require_cuda(q_rows, k, v, seg)
     U, d = q_rows.shape
     B, T, _ = k.shape
+    if any(getattr(t, "_cn_lo", None) is not None for t in (q_rows, k, v)):
+        q_rows, k, v = unsplit(q_rows), unsplit(k), unsplit(v)
     if q_rows.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
             d // n_head == 64 and T <= 512 and out is None:
         return _segment_attention_bf16(q_rows, k, v, seg, ylens, src_mask, src_size, left, right, n_head, q_len)
@@ -885,6 +926,27 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, B, n_head, Tq, Tk, d // n_head,
          ptr(out), out.stride(1), out.stride(0), ptr(kv_len), ptr(q_len), ptr(order), stream(),
          work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
+    return out
+
+
+def _attention_x3(q, k, v, mask, n_head):
+    """Split-bf16 tcgen05 attention (precise mode): (hi, lo) bf16 Q/K/V -> context as the hi half of a split operand
+    (what the three-pass output projection reads; unsplit() gives the fp32 value)."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    full = torch.empty(B, Tq, 2 * d, dtype=torch.bfloat16, device=q.device)
+    out = _hi_view(full)
+    kv_len = getattr(mask, "_cn_kv_len", None) if mask is not None else None
+    q_len = getattr(mask, "_cn_q_len", None) if mask is not None else None
+    order = getattr(mask, "_cn_order", None) if mask is not None else None
+    m, mb, mi = _mask_strides(mask, B, Tq, Tk)
+    ql, kl, vl = q._cn_lo, k._cn_lo, v._cn_lo
+    for a, b_ in ((q, ql), (k, kl), (v, vl)):
+        assert a.stride() == b_.stride() and a.shape == b_.shape
+    call("cn_attention_bf16x3", ptr(q), ptr(ql), q.stride(1), q.stride(0), ptr(k), ptr(kl), k.stride(1), k.stride(0),
+         ptr(v), ptr(vl), v.stride(1), v.stride(0), ptr(m), mb, B, n_head, Tq, Tk, d // n_head, None, ptr(full), d,
+         full.stride(1), full.stride(0), ptr(kv_len), ptr(q_len), ptr(order), stream(),
+         work=dict(flops=4.0 * B * Tq * Tk * d, bytes=4.0 * B * d * (2 * Tq + 2 * Tk)))
     return out
 
 

@@ -314,6 +314,18 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           float* target_logit   /* f32 [M]: z[row, target[row]]; log-prob = target_logit - lse
                                                    (rescoring, src/models/cassnat.py:517: gather(lm_out, att_pred)) */,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+/* Attention in split-bf16 arithmetic (precise mode): Q/K/V as (hi, lo) bf16 pairs with common pitches, scores and
+ * context accumulated from three tcgen05 passes each (relative error ~2^-17).  Context out: fp32 `out`, or (out NULL)
+ * as (hi, lo) bf16 pairs at out16 / out16 + lo_off -- the operand of the three-pass output projection -- with the same
+ * pitches ldo / sbo (elements).  Key masks and the kv_len / q_len / order hints as cn_attention_bf16; d_k == 64,
+ * Tk <= 2048.
+ *   replaces (precise mode): attention()                       src/models/modules/attention.py:13-24 */
+int cn_attention_bf16x3(const void* Qhi, const void* Qlo, int64_t ldq, int64_t sbq, const void* Khi, const void* Klo,
+                        int64_t ldk, int64_t sbk, const void* Vhi, const void* Vlo, int64_t ldv, int64_t sbv,
+                        const uint8_t* mask, int64_t mb, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
+                        float* out, void* out16, int64_t lo_off, int64_t ldo, int64_t sbo, const int32_t* kv_len,
+                        const int32_t* q_len, const int32_t* order, cn_stream_t stream);
+
 /* The same head with split (bf16x3) operands A [M,2K], W [N,2K]: argmax / runner-up equal the fp32 result wherever
  * the fp32 top-2 margin exceeds ~1e-4 of the logit scale (decision-safe heads of the fast mode). */
 int cn_gemm_bf16x3_rowstats(const void* A_split, int64_t lda, const void* W_split, int64_t ldw, const float* bias,

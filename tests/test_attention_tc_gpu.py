@@ -169,3 +169,53 @@ def test_attention_tc_causal_hint():
     assert torch.equal(plain[valid], hinted[valid])
     want = ref_attention(q.float().cpu(), k.float().cpu(), v.float().cpu(), mask.cpu(), h)
     assert rel(plain.cpu()[valid.cpu()], want[valid.cpu()]) < 2e-2
+
+
+def _split(t):
+    hi = t.bfloat16()
+    lo = (t - hi.float()).bfloat16()
+    full = torch.cat([hi, lo], -1).to(DEV)
+    n = t.shape[-1]
+    out = full[..., :n]
+    out._cn_lo = full[..., n:]
+    return out
+
+
+@pytest.mark.parametrize("B,Tq,Tk,h", [(2, 128, 128, 1), (3, 100, 77, 2), (2, 390, 500, 8), (1, 7, 512, 4), (2, 257, 129, 2),
+                                       (2, 300, 875, 2), (1, 520, 2048, 1), (3, 40, 1300, 4)])
+def test_attention_split_bf16(B, Tq, Tk, h):
+    """cn_attention_bf16x3: (hi, lo) bf16 Q/K/V, three tensor-core passes for the scores and for the context, fp32 out.
+    Error vs fp64 on the fp32 inputs is that of the split (2^-17 per operand), far below plain bf16's 2^-9."""
+    d = 64 * h
+    torch.manual_seed(Tq * 7 + Tk)
+    q, k, v = (torch.randn(B, n, d) for n in (Tq, Tk, Tk))
+    lens = torch.randint(Tk // 2, Tk + 1, (B,))
+    key_mask = (torch.arange(Tk)[None] < lens[:, None]).unsqueeze(1)
+    for mask in (None, key_mask):
+        got = ops.attention(_split(q), _split(k), _split(v), mask.to(DEV) if mask is not None else None, h)
+        assert got.dtype == torch.bfloat16 and ops.split_of(got) is not None      # hi half of a split operand
+        got = ops.unsplit(got)
+        want = ref_attention(q, k, v, mask, h)
+        assert rel(got, want) < 5e-5, (None if mask is None else tuple(mask.shape), rel(got, want))
+
+
+def test_attention_split_bf16_hints_and_fallback():
+    """Length hints skip work without changing the needed rows; per-row masks fall back to the fp32 kernel."""
+    B, Tq, Tk, h = 4, 400, 700, 2
+    d = 64 * h
+    torch.manual_seed(5)
+    q, k, v = (torch.randn(B, n, d) for n in (Tq, Tk, Tk))
+    klen = torch.tensor([700, 130, 257, 1])
+    qlen = torch.tensor([400, 0, 129, 300])
+    mask = (torch.arange(Tk)[None] < klen[:, None]).unsqueeze(1).to(DEV)
+    plain = ops.unsplit(ops.attention(_split(q), _split(k), _split(v), mask, h))
+    ops.attach_length_hints(mask, kv_len=klen.to(DEV), q_len=qlen.to(DEV))
+    hinted = ops.unsplit(ops.attention(_split(q), _split(k), _split(v), mask, h))
+    for b in range(B):
+        n = int(qlen[b])
+        assert torch.equal(hinted[b, :n], plain[b, :n]), b
+        edge = min(-(-n // 128) * 128, Tq)
+        assert edge == Tq or float(hinted[b, edge:].abs().max()) == 0.0
+    full = (torch.rand(B, Tq, Tk) < 0.3)
+    got = ops.attention(_split(q), _split(k), _split(v), full.to(DEV), h)
+    assert rel(got, ref_attention(q, k, v, full, h)) < 1e-5

@@ -948,7 +948,11 @@ def alignment_lattice(dev, pk, B=256, T=1000, V=5000, U=200, iters=5):
     return {"workload": f"cfg2: B={B} T={T} V={V} U={U} planted posteriors ({4 * B * T * V / 1e9:.2f} GB f32)",
             "viterbi_ms": vit, "viterbi_utt_per_s": B / (vit / 1e3),
             "viterbi_lattice_GBps": lattice / (vit / 1e3) / 1e9, "viterbi_lattice_frac_of_hbm": lattice / (vit / 1e3) / 1e9 / pk["hbm"],
-            "viterbi_note": "emission gather touches one 64-B DRAM atom per (frame, label): see DESIGN.md §4",
+            "viterbi_gather_traffic_GBps": B * T * (U + 1) * 64.0 / (vit / 1e3) / 1e9,
+            "viterbi_gather_traffic_frac_of_hbm": B * T * (U + 1) * 64.0 / (vit / 1e3) / 1e9 / pk["hbm"],
+            "viterbi_note": "from [B,T,V] posteriors the kernel is bound by the emission gather: one 64-B DRAM atom per "
+                            "(frame, label) = B*T*(U+1)*64 bytes of real traffic (ncu: profiles/r02_summary.md); the "
+                            "lattice figure above divides SURVEY §8d's algorithmic bytes by the same time",
             "viterbi_compact_ms": vc, "viterbi_compact_lattice_GBps": lattice / (vc / 1e3) / 1e9,
             "viterbi_compact_lattice_frac_of_hbm": lattice / (vc / 1e3) / 1e9 / pk["hbm"],
             "gather_emissions_ms": ge, "compact_alignments_identical": same,

@@ -78,6 +78,9 @@ SIGNATURES = {
     "cn_act_bwd_colsum": (_int, [_vp, _i64, _vp, _i64, _int, _f32, _vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp]),
     "cn_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i64]),
     "cn_layernorm_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "cn_attention_bwd_small": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp,
+                                      _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _vp, _i64, _i64, _vp, _i64, _i64,
+                                      _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "cn_attn_softmax_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
     "cn_dropout": (_int, [_vp, _int, _vp, _int, _i64, _f32, _vp, _i64, _i64, _vp]),
     "cn_label_smoothing": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _f32, _f32, _vp, _vp, _i64, _vp, _i64, _vp]),

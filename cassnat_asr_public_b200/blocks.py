@@ -234,8 +234,8 @@ def _project_memory_all(dec, memory):
     b = _cat_cached(dec, "kv_all_b", [t for a in attns for t in (a.linears[1].bias, a.linears[2].bias)])
     kv = ops.linear(memory, w, b, **ops.attn_kw())                            # [B,T,2d*N]
     d = memory.size(-1)
-    return [(ops.split_cols(kv, 2 * i * d, (2 * i + 1) * d), ops.split_cols(kv, (2 * i + 1) * d, (2 * i + 2) * d))
-            for i in range(len(attns))]
+    parts = ops.split_cols_multi(kv, tuple(i * d for i in range(2 * len(attns) + 1)))
+    return [(parts[2 * i], parts[2 * i + 1]) for i in range(len(attns))]
 
 
 # ================================================================================= conformer family

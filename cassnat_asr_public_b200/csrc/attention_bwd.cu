@@ -1,0 +1,323 @@
+// Backward of masked multi-head attention for the decoder side of the training step (few query rows per utterance:
+// the label tokens), fused into ONE launch per attention: recompute the probabilities, dP = dO V^T, softmax
+// backward, dV = P~^T dO, dK = dS^T Q / sqrt(dk), dQ = dS K / sqrt(dk) -- the composition the reference's autograd
+// runs for attention() of src/models/modules/attention.py:13-24 (incl. dropout on the probabilities, :22-23).
+//
+// One CTA per (utterance, head), all Tq <= 128 query rows resident in shared memory (Q, dO, dQ accumulator), the
+// keys walked in tiles of 64 twice: pass 1 gives every row its softmax statistics, pass 2 recomputes the tile's
+// probabilities, forms dS with D_i = dO_i . O_i (= sum_j P_ij dP_ij, also under dropout) and produces the tile's
+// dK / dV rows and the dQ contribution.  FFMA on shared-memory tiles: at 41 x 250 per (utterance, head) the five
+// products are 6 MFLOP -- what the composed path paid for was 5 strided-GEMM launches, a softmax launch, the
+// dropout launches and the dtype copies around them per attention, 14 attentions per step.
+// Masking semantics = cn_attn_softmax_bwd (plain variant): masked keys weigh exactly 0 in a row that keeps any key;
+// a row without kept keys is uniform over all Tk keys and carries no score gradient.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KT = 64, DK = 64, PITCH = 65, TQ_MAX = 128, NTH = 256;
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+// the keep decision of cn_dropout (backward.cu) for element idx of dropout site `site`
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t threshold) {
+  uint32_t h = fmix32((uint32_t)idx * 0x9E3779B1u ^ (uint32_t)seed);
+  h = fmix32(h ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u + site * 0xC2B2AE3Du + (uint32_t)(seed >> 32)));
+  return h >= threshold;
+}
+
+struct BwdArgs {
+  const void *q, *k, *v, *o, *go;      // [B,T,h*64] views (row pitch ld*, batch pitch sb*, elements)
+  int64_t ldq, sbq, ldk, sbk, ldv, sbv, ldo, sbo, ldg, sbg;
+  void *dq, *dk, *dv;                  // gradients, same element type, own pitches
+  int64_t lddq, sbdq, lddk, sbdk, lddv, sbdv;
+  const uint8_t* mask; int64_t mb, mi;
+  int h, Tq, Tk;
+  float scale, inv_keep; uint32_t threshold, site; const int64_t* seed_dev; uint64_t seed;
+};
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return (float)*p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v) { *p = (T)v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// rows [r0, r0+nr) x 64 features of a [T, h*64] view -> smem tile (row pitch PITCH), zero beyond nvalid rows
+template <typename T>
+__device__ __forceinline__ void load_tile(float* dst, const T* src, int64_t ld, int nr, int nvalid) {
+  for (int i = threadIdx.x; i < nr * DK; i += NTH) {
+    const int r = i >> 6, d = i & 63;
+    dst[r * PITCH + d] = r < nvalid ? ldf(src + (int64_t)r * ld + d) : 0.f;
+  }
+}
+
+// C[i][j] = sum_d A[i][d] * Bm[j][d]   (i < 16*RA rows of A, 64 rows of Bm): thread (ty, tx) owns rows ty + 16a,
+// columns tx + 16c
+template <int RA>
+__device__ __forceinline__ void prod_nt(const float* A, const float* Bm, float (&acc)[RA][4], int ty, int tx) {
+#pragma unroll
+  for (int a = 0; a < RA; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < DK; ++d) {
+    float av[RA], bv[4];
+#pragma unroll
+    for (int a = 0; a < RA; ++a) av[a] = A[(ty + 16 * a) * PITCH + d];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bv[c] = Bm[(tx + 16 * c) * PITCH + d];
+#pragma unroll
+    for (int a = 0; a < RA; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+  }
+}
+
+template <typename T, int RA>          // RA = padded query rows / 16
+__global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
+  constexpr int TQP = 16 * RA;
+  extern __shared__ float sm[];
+  float* Qs = sm;                       // [TQP][PITCH]
+  float* Gs = Qs + TQP * PITCH;         // dO
+  float* dQs = Gs + TQP * PITCH;        // accumulator
+  float* Ks = dQs + TQP * PITCH;        // [KT][PITCH]
+  float* Vs = Ks + KT * PITCH;
+  float* Ps = Vs + KT * PITCH;          // [TQP][PITCH]  scores -> dropped probabilities of the tile
+  float* Ss = Ps + TQP * PITCH;         // [TQP][PITCH]  dP -> dS of the tile
+  __shared__ float row_m[TQ_MAX], row_l[TQ_MAX], row_D[TQ_MAX];
+  __shared__ int row_any[TQ_MAX];
+
+  const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ty = tid >> 4, tx = tid & 15;
+  const int Tq = p.Tq, Tk = p.Tk;
+  const T* q = (const T*)p.q + (int64_t)b * p.sbq + hh * DK;
+  const T* k = (const T*)p.k + (int64_t)b * p.sbk + hh * DK;
+  const T* v = (const T*)p.v + (int64_t)b * p.sbv + hh * DK;
+  const T* o = (const T*)p.o + (int64_t)b * p.sbo + hh * DK;
+  const T* go = (const T*)p.go + (int64_t)b * p.sbg + hh * DK;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
+  const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
+  const bool drop = p.threshold != 0;
+
+  load_tile(Qs, q, p.ldq, TQP, Tq);
+  load_tile(Gs, go, p.ldg, TQP, Tq);
+  for (int i = tid; i < TQP * PITCH; i += NTH) dQs[i] = 0.f;
+  for (int i = tid; i < TQ_MAX; i += NTH) { row_m[i] = -INFINITY; row_l[i] = 0.f; row_any[i] = 0; row_D[i] = 0.f; }
+  __syncthreads();
+  // D_i = dO_i . O_i
+  for (int i = warp; i < Tq; i += NTH / 32) {
+    float s = Gs[i * PITCH + lane] * ldf(o + (int64_t)i * p.ldo + lane) +
+              Gs[i * PITCH + lane + 32] * ldf(o + (int64_t)i * p.ldo + lane + 32);
+    s = cn_warp_sum(s);
+    if (lane == 0) row_D[i] = s;
+  }
+
+  const int n_tiles = (Tk + KT - 1) / KT;
+  // ---- pass 1: softmax statistics of every query row (running maximum / sum over the kept keys)
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
+    __syncthreads();
+    float acc[RA][4];
+    prod_nt<RA>(Qs, Ks, acc, ty, tx);
+#pragma unroll
+    for (int a = 0; a < RA; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Ps[(ty + 16 * a) * PITCH + tx + 16 * c] = acc[a][c] * p.scale;
+    __syncthreads();
+    for (int i = warp; i < Tq; i += NTH / 32) {
+      const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
+      float mx = -INFINITY;
+      int any = 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = lane + 32 * c;
+        if (j < nk && (!mr || mr[k0 + j])) { mx = fmaxf(mx, Ps[i * PITCH + j]); any = 1; }
+      }
+      mx = cn_warp_max(mx);
+      any = __any_sync(0xffffffffu, any);
+      if (!any) continue;
+      const float m_old = row_m[i], m_new = fmaxf(m_old, mx);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = lane + 32 * c;
+        if (j < nk && (!mr || mr[k0 + j])) s += expf(Ps[i * PITCH + j] - m_new);
+      }
+      s = cn_warp_sum(s);
+      if (lane == 0) {
+        row_l[i] = row_l[i] * (m_old == -INFINITY ? 0.f : expf(m_old - m_new)) + s;
+        row_m[i] = m_new;
+        row_any[i] = 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: per key tile dV, dK rows and the dQ contribution
+  const float inv_tk = 1.f / (float)Tk;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
+    load_tile(Vs, v + (int64_t)k0 * p.ldv, p.ldv, KT, nk);
+    __syncthreads();
+    {
+      float acc[RA][4];
+      prod_nt<RA>(Qs, Ks, acc, ty, tx);          // scores
+      float acg[RA][4];
+      prod_nt<RA>(Gs, Vs, acg, ty, tx);          // dP~ = dO V^T
+#pragma unroll
+      for (int a = 0; a < RA; ++a) {
+        const int i = ty + 16 * a;
+        const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
+        const bool row_ok = i < Tq;
+        const int any = row_ok ? row_any[i] : 0;
+        const float m = row_m[i], inv_l = any ? 1.f / row_l[i] : 0.f, D = row_D[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = tx + 16 * c;
+          float pr = 0.f, ds = 0.f;
+          if (row_ok && j < nk) {
+            const bool kept = !mr || mr[k0 + j];
+            float dp = acg[a][c];
+            float keepf = 1.f;
+            if (drop) {
+              const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
+              keepf = dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+            }
+            if (any) {
+              pr = kept ? expf(acc[a][c] * p.scale - m) * inv_l : 0.f;
+              ds = pr * (dp * keepf - D);
+            } else {
+              pr = inv_tk;                       // fully masked row: uniform, constant -> no score gradient
+            }
+            pr *= keepf;
+          }
+          Ps[i * PITCH + j] = pr;
+          Ss[i * PITCH + j] = ds * p.scale;
+        }
+      }
+    }
+    __syncthreads();
+    // dV[j][d] = sum_i P~[i][j] dO[i][d];  dK[j][d] = sum_i dS[i][j] Q[i][d]      (keys ty + 16c, features tx + 16e)
+    {
+      float av[4][4], ak[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) av[c][e] = ak[c][e] = 0.f;
+      for (int i = 0; i < Tq; ++i) {
+        float pv[4], sv[4], gv[4], qv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { pv[c] = Ps[i * PITCH + ty + 16 * c]; sv[c] = Ss[i * PITCH + ty + 16 * c]; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { gv[e] = Gs[i * PITCH + tx + 16 * e]; qv[e] = Qs[i * PITCH + tx + 16 * e]; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            av[c][e] = fmaf(pv[c], gv[e], av[c][e]);
+            ak[c][e] = fmaf(sv[c], qv[e], ak[c][e]);
+          }
+      }
+      T* dvp = (T*)p.dv + (int64_t)b * p.sbdv + hh * DK;
+      T* dkp = (T*)p.dk + (int64_t)b * p.sbdk + hh * DK;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = ty + 16 * c;
+        if (j >= nk) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          stf(dvp + (int64_t)(k0 + j) * p.lddv + tx + 16 * e, av[c][e]);
+          stf(dkp + (int64_t)(k0 + j) * p.lddk + tx + 16 * e, ak[c][e]);
+        }
+      }
+    }
+    // dQ[i][d] += sum_j dS[i][j] K[j][d]
+    {
+      float aq[RA][4];
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aq[a][e] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < KT; ++j) {
+        float sv[RA], kv[4];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) sv[a] = Ss[(ty + 16 * a) * PITCH + j];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) kv[e] = Ks[j * PITCH + tx + 16 * e];
+#pragma unroll
+        for (int a = 0; a < RA; ++a)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) aq[a][e] = fmaf(sv[a], kv[e], aq[a][e]);
+      }
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dQs[(ty + 16 * a) * PITCH + tx + 16 * e] += aq[a][e];      // (own elements only)
+    }
+  }
+  __syncthreads();
+  T* dqp = (T*)p.dq + (int64_t)b * p.sbdq + hh * DK;
+  for (int i = tid; i < Tq * DK; i += NTH) {
+    const int r = i >> 6, d = i & 63;
+    stf(dqp + (int64_t)r * p.lddq + d, dQs[r * PITCH + d]);
+  }
+}
+
+template <typename T, int RA>
+int launch_bwd(const BwdArgs& p, int64_t B, cudaStream_t st) {
+  constexpr int TQP = 16 * RA;
+  const size_t smem = (size_t)(5 * TQP + 2 * KT) * PITCH * sizeof(float);
+  if (cudaFuncSetAttribute(attn_bwd_small_kernel<T, RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  attn_bwd_small_kernel<T, RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+
+template <typename T>
+int dispatch_bwd(const BwdArgs& p, int64_t B, cudaStream_t st) {
+  const int ra = (p.Tq + 15) / 16;
+  switch (ra) {
+    case 1: return launch_bwd<T, 1>(p, B, st);
+    case 2: return launch_bwd<T, 2>(p, B, st);
+    case 3: return launch_bwd<T, 3>(p, B, st);
+    case 4: return launch_bwd<T, 4>(p, B, st);
+    case 5: return launch_bwd<T, 5>(p, B, st);
+    case 6: return launch_bwd<T, 6>(p, B, st);
+    case 7: return launch_bwd<T, 7>(p, B, st);
+    case 8: return launch_bwd<T, 8>(p, B, st);
+    default: return CN_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+extern "C" int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, const void* k, int64_t ldk, int64_t sbk,
+                                      const void* v, int64_t ldv, int64_t sbv, const void* o, int64_t ldo, int64_t sbo,
+                                      const void* go, int64_t ldg, int64_t sbg, int is_bf16, const uint8_t* mask, int64_t mb,
+                                      int64_t mi, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, float p_drop,
+                                      const int64_t* seed_dev, int64_t seed, int64_t site, void* dq, int64_t lddq, int64_t sbdq,
+                                      void* dk_out, int64_t lddk, int64_t sbdk, void* dv, int64_t lddv, int64_t sbdv,
+                                      cn_stream_t stream) {
+  if (!q || !k || !v || !o || !go || !dq || !dk_out || !dv || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
+  if (!(p_drop >= 0.f) || p_drop >= 1.f) return CN_ERR_BAD_ARG;
+  if (dk != DK || Tq > TQ_MAX || B * h > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  if (B == 0 || Tq == 0) return CN_OK;
+  BwdArgs p;
+  p.q = q; p.k = k; p.v = v; p.o = o; p.go = go;
+  p.ldq = ldq; p.sbq = sbq; p.ldk = ldk; p.sbk = sbk; p.ldv = ldv; p.sbv = sbv; p.ldo = ldo; p.sbo = sbo; p.ldg = ldg; p.sbg = sbg;
+  p.dq = dq; p.dk = dk_out; p.dv = dv;
+  p.lddq = lddq; p.sbdq = sbdq; p.lddk = lddk; p.sbdk = sbdk; p.lddv = lddv; p.sbdv = sbdv;
+  p.mask = mask; p.mb = mb; p.mi = mi;
+  p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
+  p.scale = 1.f / sqrtf((float)dk);
+  p.threshold = (uint32_t)((double)p_drop * 4294967296.0);
+  p.inv_keep = 1.f / (1.f - p_drop);
+  p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
+  return is_bf16 ? dispatch_bwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_bwd<float>(p, B, (cudaStream_t)stream);
+}

@@ -579,28 +579,20 @@ __global__ void __launch_bounds__(256) gather_emissions_kernel(const float* __re
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // a warp takes 4 of the block's 32 frames and keeps the loads of all of them in flight (32 per lane)
-  for (int u0 = 0; u0 <= U; u0 += 32 * 8) {
-    float v[4][8];
-    int col[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) col[k] = gcols[min(u0 + k * 32 + lane, U)];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = min(t0 + warp + 8 * i, T - 1);
-      const float* row = logp + (int64_t)b * sb + (int64_t)t * st;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[i][k] = u0 + k * 32 + lane <= U ? cn_ld_stream_f32(row + col[k]) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + warp + 8 * i;
-      if (t >= T) continue;
-      float* out = emis + ((int64_t)b * T + t) * (U + 1);
+  for (int f = warp; f < 32 && t0 + f < T; f += 8) {           // a warp per frame, 4 frames per warp
+    const float* row = logp + (int64_t)b * sb + (int64_t)(t0 + f) * st;
+    float* out = emis + ((int64_t)b * T + t0 + f) * (U + 1);
+    for (int u0 = 0; u0 <= U; u0 += 32 * 8) {
+      float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int u = u0 + k * 32 + lane;
-        if (u <= U) out[u] = v[i][k];
+        v[k] = u <= U ? cn_ld_stream_f32(row + gcols[u]) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = u0 + k * 32 + lane;
+        if (u <= U) out[u] = v[k];
       }
     }
   }

@@ -236,6 +236,34 @@ def _attn_probs_dropped(S, mask, B, h, Tq, Tk, zero_masked, p, site):
 
 
 # =============================================================================== attention
+class SplitCols(torch.autograd.Function):
+    """Column blocks of a fused projection output (q | k | v, or the K/V of every decoder layer) as views.  Backward
+    is ONE concatenation of the block gradients -- autograd's own slicing would materialise a zero-padded full-width
+    gradient per block and add them up (3 + 2 kernels per attention instead of 1)."""
+
+    @staticmethod
+    def forward(ctx, t, *bounds):
+        ctx.bounds = bounds
+        ctx.meta = (t.shape, t.dtype, t.device)
+        return tuple(t[..., lo:hi] for lo, hi in zip(bounds[:-1], bounds[1:]))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        shape, dtype, dev = ctx.meta
+        b = ctx.bounds
+        parts = []
+        if b[0] > 0:
+            parts.append(torch.zeros(*shape[:-1], b[0], dtype=dtype, device=dev))
+        for g, lo, hi in zip(gs, b[:-1], b[1:]):
+            parts.append(g.to(dtype) if g is not None else torch.zeros(*shape[:-1], hi - lo, dtype=dtype, device=dev))
+        if b[-1] < shape[-1]:
+            parts.append(torch.zeros(*shape[:-1], shape[-1] - b[-1], dtype=dtype, device=dev))
+        return (torch.cat(parts, -1),) + (None,) * len(b)
+
+
+FUSED_SMALL_BWD = True      # attention backward of up to 128 query rows as one launch (tests compare with the composed path)
+
+
 class Attention(torch.autograd.Function):
     """Masked multi-head attention (ops.attention, plain variant).  Backward recomputes the
     probabilities: S = QK^T/sqrt(dk), dP = dO V^T, softmax backward in place, then
@@ -263,17 +291,34 @@ class Attention(torch.autograd.Function):
                 out = ops.attention_forward(q, k, v, mask, n_head)
         ctx.n_head, ctx.p, ctx.site = n_head, p, site
         ctx.mask = mask
-        ctx.save_for_backward(q, k, v)
+        ctx.save_for_backward(q, k, v, out)
         return out
 
     @staticmethod
     def backward(ctx, go):
-        q, k, v = ctx.saved_tensors
+        q, k, v, out = ctx.saved_tensors
         h = ctx.n_head
         B, Tq, d = q.shape
         Tk = k.shape[1]
         dk = d // h
         dev = q.device
+        if FUSED_SMALL_BWD and Tq <= 128 and dk == 64 and q.dtype in (torch.float32, torch.bfloat16) and \
+                k.dtype == q.dtype and v.dtype == q.dtype and go.dtype == q.dtype and out.dtype == q.dtype:
+            # few query rows (the label-token side of training): one fused launch (cn_attention_bwd_small)
+            g = go if go.stride(-1) == 1 else go.contiguous()
+            for t in (q, k, v, out):
+                assert t.stride(-1) == 1
+            dq = torch.empty(B, Tq, d, dtype=q.dtype, device=dev)
+            dk_ = torch.empty(B, Tk, d, dtype=q.dtype, device=dev)
+            dv = torch.empty(B, Tk, d, dtype=q.dtype, device=dev)
+            m, mb, mi = ops._mask_strides(ctx.mask, B, Tq, Tk)
+            call("cn_attention_bwd_small", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                 v.stride(0), ptr(out), out.stride(1), out.stride(0), ptr(g), g.stride(1), g.stride(0),
+                 int(q.dtype == torch.bfloat16), ptr(m), mb, mi, B, h, Tq, Tk, dk, float(ctx.p), ptr(ops.DROPOUT_SEED_DEV),
+                 int(ops.DROPOUT_SEED), int(ctx.site), ptr(dq), dq.stride(1), dq.stride(0), ptr(dk_), dk_.stride(1),
+                 dk_.stride(0), ptr(dv), dv.stride(1), dv.stride(0), stream(),
+                 work=dict(flops=12.0 * B * Tq * Tk * d))
+            return dq, dk_, dv, None, None, None, None
         f = lambda t: t if t.dtype == torch.float32 else t.float()
         qf, kf, vf, gf = f(q), f(k), f(v), f(go)
         if gf.stride(-1) != 1:

@@ -137,14 +137,14 @@ class MultiHeadedAttention(nn.Module):
         b = _cat_cached(self, "kv_b", [self.linears[1].bias, self.linears[2].bias])
         kv = ops.linear(memory, w, b, out_bf16=out_bf16, out_split=out_split)
         d = self.h * self.d_k
-        return ops.split_cols(kv, 0, d), ops.split_cols(kv, d, 2 * d)
+        return ops.split_cols_multi(kv, (0, d, 2 * d))
 
     def project_qkv(self, x, out_bf16=False, out_split=False):
         w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
         b = _cat_cached(self, "qkv_b", [l.bias for l in self.linears[:3]])
         qkv = ops.linear(x, w, b, out_bf16=out_bf16, out_split=out_split)
         d = self.h * self.d_k
-        return ops.split_cols(qkv, 0, d), ops.split_cols(qkv, d, 2 * d), ops.split_cols(qkv, 2 * d, 3 * d)
+        return ops.split_cols_multi(qkv, (0, d, 2 * d, 3 * d))
 
     def output(self, ctx, residual=None, scale=1.0, res_rows=0, next_ln=None):
         return ops.linear(ctx, self.linears[3].weight, self.linears[3].bias, residual=residual, alpha=scale,

@@ -249,6 +249,15 @@ def split_cols(t, lo, hi):
     return out
 
 
+def split_cols_multi(t, bounds):
+    """Consecutive column blocks t[..., bounds[i]:bounds[i+1]] of a fused projection output (see split_cols).  In
+    training the blocks come from one autograd node whose backward is a single concatenation (grad.SplitCols)."""
+    if torch.is_grad_enabled() and t.requires_grad and split_of(t) is None:
+        from . import grad
+        return grad.SplitCols.apply(t, *bounds)
+    return tuple(split_cols(t, lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:]))
+
+
 def unsplit(t):
     """fp32 value of a (hi, lo) pair (or of a plain tensor)."""
     lo = getattr(t, "_cn_lo", None)

@@ -436,6 +436,21 @@ int cn_layernorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t lddy,
 int cn_attn_softmax_bwd(float* S, float* dP, const uint8_t* mask, int64_t mb, int64_t mi, int64_t B, int64_t h,
                         int64_t Tq, int64_t Tk, int zero_masked, cn_stream_t stream);
 
+/* Attention backward for few query rows (Tq <= 128, d_k == 64: the label-token side of the training step), ONE launch:
+ * recomputes the probabilities of attention() (masking as cn_attn_softmax_bwd, plain variant; dropout on the
+ * probabilities regenerated from (seed, site) exactly as cn_dropout applied it to the [B,h,Tq,Tk] probabilities in
+ * the forward), and writes dq / dk / dv.  q, k, v, o (the forward's context), go (its gradient) and the three
+ * gradients share one element type (is_bf16 ? bf16 : f32); all are [B,T,h*64] views with row / batch pitches in
+ * elements.  mask u8 [B,1|Tq,Tk] or NULL (mb / mi as cn_attention_f32).
+ *   replaces (training): autograd through attention()           src/models/modules/attention.py:13-24 */
+int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, const void* k, int64_t ldk, int64_t sbk,
+                           const void* v, int64_t ldv, int64_t sbv, const void* o, int64_t ldo, int64_t sbo,
+                           const void* go, int64_t ldg, int64_t sbg, int is_bf16, const uint8_t* mask, int64_t mb,
+                           int64_t mi, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, float p_drop,
+                           const int64_t* seed_dev, int64_t seed, int64_t site, void* dq, int64_t lddq, int64_t sbdq,
+                           void* dk_out, int64_t lddk, int64_t sbdk, void* dv, int64_t lddv, int64_t sbdv,
+                           cn_stream_t stream);
+
 /* Dropout (training): out[i] = keep(i) ? x[i] / (1 - p) : 0 with keep a counter-based hash of (seed, site, i):
  * stateless, so the backward pass regenerates the mask from the same (seed, site) instead of storing it.
  *   replaces: nn.Dropout                 src/models/modules/utils.py:21,32; attention.py:22-23,140-141;

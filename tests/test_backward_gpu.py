@@ -97,9 +97,11 @@ def ref_attention(q, k, v, mask, h):
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("bf16", 3e-2)])
 @pytest.mark.parametrize("B,h,Tq,Tk,dk,kind", [(2, 2, 5, 9, 64, "key"), (3, 4, 33, 33, 64, "full"), (2, 8, 70, 130, 64, "key"),
-                                               (2, 8, 64, 64, 64, "none"), (2, 2, 41, 250, 64, "full")])
+                                               (2, 8, 64, 64, 64, "none"), (2, 2, 41, 250, 64, "full"),
+                                               (2, 2, 128, 200, 64, "full"), (2, 2, 150, 90, 64, "key")])
 def test_attention_backward(precision, tol, B, h, Tq, Tk, dk, kind):
-    """Includes fully masked rows (uniform probabilities, no score gradient) in the 'full' case."""
+    """Includes fully masked rows (uniform probabilities, no score gradient) in the 'full' case.  Up to 128 query rows
+    the backward is the fused single launch (cn_attention_bwd_small), beyond that the composed strided-GEMM path."""
     ops.set_precision(precision)
     d = h * dk
     dt = torch.bfloat16 if precision == "bf16" and dk == 64 else torch.float32
@@ -127,6 +129,35 @@ def test_attention_backward(precision, tol, B, h, Tq, Tk, dk, kind):
     assert rel(out.float(), ref) < tol
     ref.backward(go)
     assert rel(got, qkv.grad) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_attention_backward_fused_equals_composed(dt):
+    """The fused small-Tq backward against the composed path (strided GEMMs + cn_attn_softmax_bwd) on the same
+    inputs, with dropout on the probabilities: same masks by construction (seed, site)."""
+    from cassnat_asr_public_b200 import grad
+    ops.set_precision("fp32" if dt == torch.float32 else "bf16")
+    B, h, Tq, Tk = 3, 4, 41, 250
+    d = 64 * h
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    mask = torch.rand(B, Tq, Tk, device=DEV, generator=gen) > 0.3
+    mask[:, 7] = False
+    go = torch.randn(B, Tq, d, device=DEV, generator=gen).to(dt)
+    res = {}
+    for fused in (True, False):
+        grad.FUSED_SMALL_BWD = fused
+        try:
+            q, k, v = (torch.randn(B, n, d, device=DEV, generator=torch.Generator(device=DEV).manual_seed(s)).to(dt).requires_grad_(True)
+                       for n, s in ((Tq, 1), (Tk, 2), (Tk, 3)))
+            ops.dropout_begin_step(seed=77)
+            out = grad.Attention.apply(q, k, v, mask, h, 0.1, 3)
+            out.backward(go)
+            res[fused] = (out.detach().float(), q.grad.float(), k.grad.float(), v.grad.float())
+        finally:
+            grad.FUSED_SMALL_BWD = True
+    tol = 2e-5 if dt == torch.float32 else 2e-2
+    for a, b_, nm in zip(res[True], res[False], ("out", "dq", "dk", "dv")):
+        assert rel(a, b_) < tol, (nm, rel(a, b_))
 
 
 def ref_rel_attention(q, k, v, P, u, vb, mask, h, m):

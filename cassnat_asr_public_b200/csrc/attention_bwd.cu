@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int KT = 64, DK = 64, PITCH = 65, TQ_MAX = 128, NTH = 256;
+constexpr int KT = 64, DK = 64, PITCH = 68, TQ_MAX = 128, NTH = 256;      // PITCH: 16-byte rows, conflict-free float4 reads
 
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -52,25 +52,32 @@ __device__ __forceinline__ void load_tile(float* dst, const T* src, int64_t ld, 
   }
 }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
 // C[i][j] = sum_d A[i][d] * Bm[j][d]   (i < 16*RA rows of A, 64 rows of Bm): thread (ty, tx) owns rows ty + 16a,
-// columns tx + 16c
+// columns tx + 16c; the contraction is read four features at a time (RA + 4 vector loads per 16 RA FMAs)
 template <int RA>
 __device__ __forceinline__ void prod_nt(const float* A, const float* Bm, float (&acc)[RA][4], int ty, int tx) {
 #pragma unroll
   for (int a = 0; a < RA; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-#pragma unroll 4
-  for (int d = 0; d < DK; ++d) {
-    float av[RA], bv[4];
+#pragma unroll 2
+  for (int d = 0; d < DK; d += 4) {
+    float4 av[RA], bv[4];
 #pragma unroll
-    for (int a = 0; a < RA; ++a) av[a] = A[(ty + 16 * a) * PITCH + d];
+    for (int a = 0; a < RA; ++a) av[a] = ld4(A + (ty + 16 * a) * PITCH + d);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) bv[c] = Bm[(tx + 16 * c) * PITCH + d];
+    for (int c = 0; c < 4; ++c) bv[c] = ld4(Bm + (tx + 16 * c) * PITCH + d);
 #pragma unroll
     for (int a = 0; a < RA; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+      for (int c = 0; c < 4; ++c) {
+        acc[a][c] = fmaf(av[a].x, bv[c].x, acc[a][c]);
+        acc[a][c] = fmaf(av[a].y, bv[c].y, acc[a][c]);
+        acc[a][c] = fmaf(av[a].z, bv[c].z, acc[a][c]);
+        acc[a][c] = fmaf(av[a].w, bv[c].w, acc[a][c]);
+      }
   }
 }
 
@@ -202,19 +209,19 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
       }
     }
     __syncthreads();
-    // dV[j][d] = sum_i P~[i][j] dO[i][d];  dK[j][d] = sum_i dS[i][j] Q[i][d]      (keys ty + 16c, features tx + 16e)
+    // dV[j][d] = sum_i P~[i][j] dO[i][d];  dK[j][d] = sum_i dS[i][j] Q[i][d]      (keys 4ty..4ty+3, features 4tx..4tx+3)
     {
       float av[4][4], ak[4][4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int e = 0; e < 4; ++e) av[c][e] = ak[c][e] = 0.f;
+#pragma unroll 2
       for (int i = 0; i < Tq; ++i) {
-        float pv[4], sv[4], gv[4], qv[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { pv[c] = Ps[i * PITCH + ty + 16 * c]; sv[c] = Ss[i * PITCH + ty + 16 * c]; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { gv[e] = Gs[i * PITCH + tx + 16 * e]; qv[e] = Qs[i * PITCH + tx + 16 * e]; }
+        const float4 p4 = ld4(Ps + i * PITCH + 4 * ty), s4 = ld4(Ss + i * PITCH + 4 * ty);
+        const float4 g4 = ld4(Gs + i * PITCH + 4 * tx), q4 = ld4(Qs + i * PITCH + 4 * tx);
+        const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -227,38 +234,45 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
       T* dkp = (T*)p.dk + (int64_t)b * p.sbdk + hh * DK;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int j = ty + 16 * c;
+        const int j = 4 * ty + c;
         if (j >= nk) continue;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          stf(dvp + (int64_t)(k0 + j) * p.lddv + tx + 16 * e, av[c][e]);
-          stf(dkp + (int64_t)(k0 + j) * p.lddk + tx + 16 * e, ak[c][e]);
+          stf(dvp + (int64_t)(k0 + j) * p.lddv + 4 * tx + e, av[c][e]);
+          stf(dkp + (int64_t)(k0 + j) * p.lddk + 4 * tx + e, ak[c][e]);
         }
       }
     }
-    // dQ[i][d] += sum_j dS[i][j] K[j][d]
+    // dQ[i][d] += sum_j dS[i][j] K[j][d]      (rows ty + 16a, features 4tx..4tx+3; four keys per step)
     {
       float aq[RA][4];
 #pragma unroll
       for (int a = 0; a < RA; ++a)
 #pragma unroll
         for (int e = 0; e < 4; ++e) aq[a][e] = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < KT; ++j) {
-        float sv[RA], kv[4];
+#pragma unroll 2
+      for (int j = 0; j < KT; j += 4) {
+        float4 sv[RA], kv[4];
 #pragma unroll
-        for (int a = 0; a < RA; ++a) sv[a] = Ss[(ty + 16 * a) * PITCH + j];
+        for (int a = 0; a < RA; ++a) sv[a] = ld4(Ss + (ty + 16 * a) * PITCH + j);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) kv[e] = Ks[j * PITCH + tx + 16 * e];
+        for (int jj = 0; jj < 4; ++jj) kv[jj] = ld4(Ks + (j + jj) * PITCH + 4 * tx);
 #pragma unroll
-        for (int a = 0; a < RA; ++a)
+        for (int a = 0; a < RA; ++a) {
+          const float s_[4] = {sv[a].x, sv[a].y, sv[a].z, sv[a].w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) aq[a][e] = fmaf(sv[a], kv[e], aq[a][e]);
+          for (int jj = 0; jj < 4; ++jj) {
+            aq[a][0] = fmaf(s_[jj], kv[jj].x, aq[a][0]);
+            aq[a][1] = fmaf(s_[jj], kv[jj].y, aq[a][1]);
+            aq[a][2] = fmaf(s_[jj], kv[jj].z, aq[a][2]);
+            aq[a][3] = fmaf(s_[jj], kv[jj].w, aq[a][3]);
+          }
+        }
       }
 #pragma unroll
       for (int a = 0; a < RA; ++a)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dQs[(ty + 16 * a) * PITCH + tx + 16 * e] += aq[a][e];      // (own elements only)
+        for (int e = 0; e < 4; ++e) dQs[(ty + 16 * a) * PITCH + 4 * tx + e] += aq[a][e];      // (own elements only)
     }
   }
   __syncthreads();
@@ -266,6 +280,169 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
   for (int i = tid; i < Tq * DK; i += NTH) {
     const int r = i >> 6, d = i & 63;
     stf(dqp + (int64_t)r * p.lddq + d, dQs[r * PITCH + d]);
+  }
+}
+
+// ---------------------------------------------------------------- forward with dropout on the probabilities
+// The training forward of the same attentions (attention.py:22-23: p_attn = dropout(softmax(scores))): one launch,
+// online softmax over the key tiles, the keep mask regenerated from (seed, site, element index) -- the index being
+// that of the [B,h,Tq,Tk] probability tensor, so that the backward above sees the same mask.
+struct FwdArgs {
+  const void *q, *k, *v; void* out;
+  int64_t ldq, sbq, ldk, sbk, ldv, sbv, ldo, sbo;
+  const uint8_t* mask; int64_t mb, mi;
+  int h, Tq, Tk;
+  float scale, inv_keep; uint32_t threshold, site; const int64_t* seed_dev; uint64_t seed;
+};
+
+template <typename T, int RA>
+__global__ void __launch_bounds__(NTH) attn_fwd_small_kernel(FwdArgs p) {
+  constexpr int TQP = 16 * RA;
+  extern __shared__ float sm[];
+  float* Qs = sm;                       // [TQP][PITCH]
+  float* Ks = Qs + TQP * PITCH;         // [KT][PITCH]
+  float* Vs = Ks + KT * PITCH;
+  float* Ps = Vs + KT * PITCH;          // [TQP][PITCH]
+  __shared__ int row_any[TQ_MAX];
+
+  const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ty = tid >> 4, tx = tid & 15;
+  const int Tq = p.Tq, Tk = p.Tk;
+  const T* q = (const T*)p.q + (int64_t)b * p.sbq + hh * DK;
+  const T* k = (const T*)p.k + (int64_t)b * p.sbk + hh * DK;
+  const T* v = (const T*)p.v + (int64_t)b * p.sbv + hh * DK;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
+  const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
+  const bool drop = p.threshold != 0;
+
+  load_tile(Qs, q, p.ldq, TQP, Tq);
+  // rows without any kept key are uniform over all Tk keys (masked_fill(finfo.min) + softmax): found up front
+  for (int i = warp; i < TQP; i += NTH / 32) {
+    int any = 0;
+    if (i < Tq) {
+      if (!mk) any = 1;
+      else {
+        const uint8_t* mr = mk + (int64_t)i * p.mi;
+        for (int j = lane; j < Tk; j += 32) any |= mr[j] != 0;
+      }
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) row_any[i] = any;
+  }
+  float o[RA][4], m_run[RA], l_run[RA];
+#pragma unroll
+  for (int a = 0; a < RA; ++a) {
+    m_run[a] = -INFINITY;
+    l_run[a] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[a][e] = 0.f;
+  }
+  const float inv_tk = 1.f / (float)Tk;
+  const int n_tiles = (Tk + KT - 1) / KT;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
+    load_tile(Vs, v + (int64_t)k0 * p.ldv, p.ldv, KT, nk);
+    __syncthreads();
+    float acc[RA][4];
+    prod_nt<RA>(Qs, Ks, acc, ty, tx);
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+      const int i = ty + 16 * a;
+      const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
+      const bool row_ok = i < Tq;
+      const int any = row_any[i];
+      bool kept[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tx + 16 * c;
+        kept[c] = row_ok && j < nk && (!mr || mr[k0 + j]);
+        acc[a][c] *= p.scale;
+        if (kept[c]) mx = fmaxf(mx, acc[a][c]);
+      }
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));      // the 16 tx lanes of a row
+      const float m_new = fmaxf(m_run[a], mx);
+      const float corr = (m_run[a] == -INFINITY) ? 0.f : expf(m_run[a] - m_new);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tx + 16 * c;
+        float pr = kept[c] ? expf(acc[a][c] - m_new) : 0.f;
+        sum += pr;
+        if (!any) pr = (row_ok && j < nk) ? inv_tk : 0.f;
+        if (drop && pr != 0.f) {
+          const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
+          pr *= dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+        }
+        Ps[i * PITCH + j] = pr;
+      }
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      if (mx > -INFINITY) {
+        l_run[a] = l_run[a] * corr + sum;
+        m_run[a] = m_new;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[a][e] *= corr;
+      }
+    }
+    __syncthreads();
+    // O[i][d] += sum_j P~[i][j] V[j][d]      (rows ty + 16a, features 4tx..4tx+3; four keys per step)
+#pragma unroll 2
+    for (int j = 0; j < KT; j += 4) {
+      float4 pv[RA], vv[4];
+#pragma unroll
+      for (int a = 0; a < RA; ++a) pv[a] = ld4(Ps + (ty + 16 * a) * PITCH + j);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) vv[jj] = ld4(Vs + (j + jj) * PITCH + 4 * tx);
+#pragma unroll
+      for (int a = 0; a < RA; ++a) {
+        const float p_[4] = {pv[a].x, pv[a].y, pv[a].z, pv[a].w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          o[a][0] = fmaf(p_[jj], vv[jj].x, o[a][0]);
+          o[a][1] = fmaf(p_[jj], vv[jj].y, o[a][1]);
+          o[a][2] = fmaf(p_[jj], vv[jj].z, o[a][2]);
+          o[a][3] = fmaf(p_[jj], vv[jj].w, o[a][3]);
+        }
+      }
+    }
+  }
+  T* op = (T*)p.out + (int64_t)b * p.sbo + hh * DK;
+#pragma unroll
+  for (int a = 0; a < RA; ++a) {
+    const int i = ty + 16 * a;
+    if (i >= Tq) continue;
+    const float inv = row_any[i] ? 1.f / l_run[a] : 1.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) stf(op + (int64_t)i * p.ldo + 4 * tx + e, o[a][e] * inv);
+  }
+}
+
+template <typename T, int RA>
+int launch_fwd(const FwdArgs& p, int64_t B, cudaStream_t st) {
+  constexpr int TQP = 16 * RA;
+  const size_t smem = (size_t)(2 * TQP + 2 * KT) * PITCH * sizeof(float);
+  if (cudaFuncSetAttribute(attn_fwd_small_kernel<T, RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  attn_fwd_small_kernel<T, RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+
+template <typename T>
+int dispatch_fwd(const FwdArgs& p, int64_t B, cudaStream_t st) {
+  switch ((p.Tq + 15) / 16) {
+    case 1: return launch_fwd<T, 1>(p, B, st);
+    case 2: return launch_fwd<T, 2>(p, B, st);
+    case 3: return launch_fwd<T, 3>(p, B, st);
+    case 4: return launch_fwd<T, 4>(p, B, st);
+    case 5: return launch_fwd<T, 5>(p, B, st);
+    case 6: return launch_fwd<T, 6>(p, B, st);
+    case 7: return launch_fwd<T, 7>(p, B, st);
+    case 8: return launch_fwd<T, 8>(p, B, st);
+    default: return CN_ERR_UNSUPPORTED;
   }
 }
 
@@ -320,4 +497,25 @@ extern "C" int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, c
   p.inv_keep = 1.f / (1.f - p_drop);
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
   return is_bf16 ? dispatch_bwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_bwd<float>(p, B, (cudaStream_t)stream);
+}
+
+extern "C" int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, const void* k, int64_t ldk, int64_t sbk,
+                                      const void* v, int64_t ldv, int64_t sbv, int is_bf16, const uint8_t* mask, int64_t mb,
+                                      int64_t mi, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, float p_drop,
+                                      const int64_t* seed_dev, int64_t seed, int64_t site, void* out, int64_t ldo, int64_t sbo,
+                                      cn_stream_t stream) {
+  if (!q || !k || !v || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
+  if (!(p_drop >= 0.f) || p_drop >= 1.f) return CN_ERR_BAD_ARG;
+  if (dk != DK || Tq > TQ_MAX || B * h > 0x7fffffff) return CN_ERR_UNSUPPORTED;
+  if (B == 0 || Tq == 0) return CN_OK;
+  FwdArgs p;
+  p.q = q; p.k = k; p.v = v; p.out = out;
+  p.ldq = ldq; p.sbq = sbq; p.ldk = ldk; p.sbk = sbk; p.ldv = ldv; p.sbv = sbv; p.ldo = ldo; p.sbo = sbo;
+  p.mask = mask; p.mb = mb; p.mi = mi;
+  p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
+  p.scale = 1.f / sqrtf((float)dk);
+  p.threshold = (uint32_t)((double)p_drop * 4294967296.0);
+  p.inv_keep = 1.f / (1.f - p_drop);
+  p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
+  return is_bf16 ? dispatch_fwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_fwd<float>(p, B, (cudaStream_t)stream);
 }

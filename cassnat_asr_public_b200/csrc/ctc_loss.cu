@@ -5,9 +5,12 @@
 //             l' of 2L+1 states, per-utterance nll / max(L,1), mean over the batch, inf -> 0)
 // Three launches:
 //   1. gather   E[b,t,i] = logp[b,t,l_i]            (i = 0 is blank)       fully parallel
-//   2. alpha-beta: one warp per utterance, lattice states strided over lanes (SPL per lane),
-//      alpha in registers / neighbours by shuffle, alpha_t spilled to the workspace, beta fused
-//      on the way back so that the workspace ends up holding alpha_t(s) + beta_t(s)
+//   2. alpha-beta: two warps per utterance running CONCURRENTLY -- warp 0 the forward variable from frame 0 up,
+//      warp 1 the backward variable from the last frame down -- lattice states strided over lanes (SPL per lane),
+//      values in registers / neighbours by shuffle, the rows written to the workspace.  The recursion runs in the
+//      log2 domain: the three-way log-sum-exp of a state is max + lg2(ex2 + ex2 + ex2) on the MUFU unit (rows are
+//      stored in nats); rows are renormalised (max state = 0, the removed scale accumulated in double) every 8 frames
+//      instead of every frame; the emissions of the next 16 frames arrive by cp.async while the current 16 are used
 //   3. gradient w.r.t. the LOGITS, one CTA per frame: softmax - occupancy, written once:
 //      d loss / d z[b,t,c] = scale_b * (exp(logp[b,t,c]) - sum_{s: l'_s = c} exp(ab_t(s) + nll_b - logp[b,t,c]))
 #include "common.cuh"
@@ -37,24 +40,45 @@ __global__ void __launch_bounds__(256) ctc_gather_kernel(const float* __restrict
 struct AbArgs {
   const float* E; const int64_t* targets; int64_t tgt_stride;
   const int64_t* in_len; const int64_t* tgt_len;
-  int T, L; float* ab; float* nll;
-  double* off_a;      // [B,T] running log-scale of the normalised alpha rows
-  float* off;         // [B,T] off_a[t] + off_b[t] + nll: what turns (alpha^ + beta^) into a log-occupancy
+  int T, L; float* ab; float* bb; float* nll;
+  double* off_a;      // [B,T] log-scale (nats) removed from the stored alpha rows
+  double* off_b;      // [B,T] the same for the beta rows
+  double* nll_d;      // [B]
 };
 
-// one warp per utterance; lane owns states [lane*SPL, lane*SPL + SPL); SPL even -> odd j = label state
+constexpr int kCtcChunk = 16;        // frames per staged emission chunk
+constexpr int kCtcNorm = 8;          // frames between renormalisations
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// log2(2^a + 2^b + 2^c); -inf operands contribute nothing, all -inf gives -inf
+__device__ __forceinline__ float lse2_3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  const float ms = (m == -INFINITY) ? 0.f : m;
+  return ms + fast_lg2(fast_ex2(a - ms) + fast_ex2(b - ms) + fast_ex2(c - ms));
+}
+__device__ __forceinline__ float lse2_2(float a, float b) {
+  const float m = fmaxf(a, b);
+  const float ms = (m == -INFINITY) ? 0.f : m;
+  return ms + fast_lg2(fast_ex2(a - ms) + fast_ex2(b - ms));
+}
+
+// CTA = 2 warps per utterance: warp 0 alpha (frames up), warp 1 beta (frames down); lane owns states
+// [lane*SPL, lane*SPL + SPL); SPL even -> odd j = label state
 template <int SPL>
-__global__ void __launch_bounds__(32) ctc_alpha_beta_kernel(AbArgs p) {
-  const int b = blockIdx.x, lane = threadIdx.x;
-  const int L = p.L, T = p.T;
+__global__ void __launch_bounds__(64) ctc_alpha_beta_kernel(AbArgs p) {
+  extern __shared__ float esm[];                          // [2 warps][2 buffers][kCtcChunk][L+1] staged emissions
+  __shared__ float fin[32 * SPL];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, T = p.T, L1 = L + 1;
   int Tb = (int)p.in_len[b];
   Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
   int Lb = (int)p.tgt_len[b];
   Lb = Lb < 0 ? 0 : (Lb > L ? L : Lb);
   const int Sb = 2 * Lb + 1;                              // states of this utterance
   const int S = 32 * SPL;                                 // padded row length in the workspace
-  const float* Eb = p.E + (int64_t)b * T * (L + 1);
-  float* abb = p.ab + (int64_t)b * T * S;
+  const float* Eb = p.E + (int64_t)b * T * L1;
   const int64_t* tg = p.targets + (int64_t)b * p.tgt_stride;
   // skip transitions: into odd state s from s-2 iff labels differ (forward); out of s into s+2 (backward)
   uint32_t skip_in = 0, skip_out = 0, live = 0;
@@ -69,13 +93,30 @@ __global__ void __launch_bounds__(32) ctc_alpha_beta_kernel(AbArgs p) {
     }
   }
   if (Tb == 0) {
-    if (lane == 0) p.nll[b] = (Lb == 0) ? 0.f : INFINITY;
+    if (threadIdx.x == 0) { p.nll[b] = (Lb == 0) ? 0.f : INFINITY; p.nll_d[b] = (Lb == 0) ? 0.0 : (double)INFINITY; }
     return;
   }
-  auto emission = [&](int t, int j) -> float {
-    const int s = lane * SPL + j;
-    if (s >= Sb) return -INFINITY;
-    return Eb[(int64_t)t * (L + 1) + ((j & 1) ? ((s + 1) >> 1) : 0)];
+  // ---- emission staging: chunk c = frames [c*16, c*16+16), both warps walk their own sequence of chunks
+  const int n_chunks = (Tb + kCtcChunk - 1) / kCtcChunk;
+  float* ering = esm + warp * 2 * kCtcChunk * L1;
+  auto stage = [&](int c, int buf) {                      // asynchronous copy of chunk c (contiguous rows of E)
+    if (c >= 0 && c < n_chunks) {
+      const int t0 = c * kCtcChunk, n = (min(kCtcChunk, Tb - t0)) * L1;
+      const float* src = Eb + (int64_t)t0 * L1;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ering + buf * kCtcChunk * L1);
+      for (int i = lane; i < n; i += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)i), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // emissions of frame t (log2 units) for this lane's states, out of the staged chunk
+  auto emissions = [&](const float* row, float& eb, float (&el)[SPL / 2]) {
+    eb = row[0] * kLog2e;
+#pragma unroll
+    for (int j = 0; j < SPL / 2; ++j) {
+      const int s = lane * SPL + 2 * j + 1;
+      el[j] = s < Sb ? row[(s + 1) >> 1] * kLog2e : -INFINITY;
+    }
   };
   // Rows are kept NORMALISED (max state = 0) and the removed log-scale is accumulated in double:
   // raw alpha reaches ~ -8 nats/frame, where fp32 has only ~1e-4 of absolute resolution.
@@ -91,90 +132,120 @@ __global__ void __launch_bounds__(32) ctc_alpha_beta_kernel(AbArgs p) {
     }
     return 0.f;
   };
-  double* offa = p.off_a + (int64_t)b * T;
-  float* offo = p.off + (int64_t)b * T;
-  float a[SPL];
-  double ca = 0.0;
-  // ---- forward
+  float x[SPL];                                           // alpha (warp 0) / beta (warp 1), log2 units
+  double cx = 0.0;                                        // removed scale, log2 units
+  if (warp == 0) {
+    // =========================== forward
+    float* rows = p.ab + (int64_t)b * T * S;
+    double* offs = p.off_a + (int64_t)b * T;
+    stage(0, 0);
+    stage(1, 1);
+    for (int c = 0; c < n_chunks; ++c) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const float* e = ering + (c & 1) * kCtcChunk * L1;
+      const int t0 = c * kCtcChunk, nf = min(kCtcChunk, Tb - t0);
+      for (int f = 0; f < nf; ++f) {
+        const int t = t0 + f;
+        float eb, el[SPL / 2];
+        emissions(e + f * L1, eb, el);
+        if (t == 0) {
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const int s = lane * SPL + j;
-    a[j] = (s < 2 && s < Sb) ? emission(0, j) : -INFINITY;
-  }
-  ca += (double)normalise(a);
-  if (lane == 0) offa[0] = ca;
+          for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            x[j] = (s < 2 && s < Sb) ? ((j & 1) ? el[j >> 1] : eb) : -INFINITY;
+          }
+        } else {
+          float up1 = __shfl_up_sync(0xffffffffu, x[SPL - 1], 1), up2 = __shfl_up_sync(0xffffffffu, x[SPL - 2], 1);
+          if (lane == 0) { up1 = -INFINITY; up2 = -INFINITY; }
+          float nx[SPL];
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) abb[lane * SPL + j] = a[j];
-  for (int t = 1; t < Tb; ++t) {
-    float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1), up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
-    if (lane == 0) { up1 = -INFINITY; up2 = -INFINITY; }
-    float na[SPL];
+          for (int j = 0; j < SPL; ++j) {
+            const float c1 = (j >= 1) ? x[j - 1] : up1;
+            float v;
+            if (j & 1) {
+              const float c2 = ((skip_in >> j) & 1u) ? ((j >= 2) ? x[j - 2] : up1) : -INFINITY;
+              v = lse2_3(x[j], c1, c2);
+            } else {
+              v = lse2_2(x[j], c1);
+            }
+            nx[j] = ((live >> j) & 1u) ? v + ((j & 1) ? el[j >> 1] : eb) : -INFINITY;
+          }
 #pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-      const float c1 = (j >= 1) ? a[j - 1] : up1;
-      const float c2 = ((skip_in >> j) & 1u) ? ((j >= 2) ? a[j - 2] : (j == 1 ? up1 : up2)) : -INFINITY;
-      float v = log_add(log_add(a[j], c1), c2);
-      na[j] = ((live >> j) & 1u) ? v + emission(t, j) : -INFINITY;
+          for (int j = 0; j < SPL; ++j) x[j] = nx[j];
+        }
+        if (t % kCtcNorm == 0 || t == Tb - 1) cx += (double)normalise(x);
+        if (lane == 0) offs[t] = cx * (double)kLn2;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) rows[(int64_t)t * S + lane * SPL + j] = x[j] * kLn2;
+      }
+      __syncwarp();
+      stage(c + 2, c & 1);
     }
-    ca += (double)normalise(na);
-    if (lane == 0) offa[t] = ca;
+    // ---- nll = -log( alpha_{Tb-1}(Sb-1) + alpha_{Tb-1}(Sb-2) )
 #pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-      a[j] = na[j];
-      abb[(int64_t)t * S + lane * SPL + j] = a[j];
+    for (int j = 0; j < SPL; ++j) fin[lane * SPL + j] = x[j];
+    __syncwarp();
+    const float l1 = fin[Sb - 1], l2 = (Sb >= 2) ? fin[Sb - 2] : -INFINITY;
+    const double nll_d = -((double)lse2_2(l1, l2) + cx) * (double)kLn2;
+    if (lane == 0) { p.nll[b] = (float)nll_d; p.nll_d[b] = nll_d; }
+  } else {
+    // =========================== backward
+    float* rows = p.bb + (int64_t)b * T * S;
+    double* offs = p.off_b + (int64_t)b * T;
+    stage(n_chunks - 1, (n_chunks - 1) & 1);
+    stage(n_chunks - 2, (n_chunks - 2) & 1);
+    for (int c = n_chunks - 1; c >= 0; --c) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const float* e = ering + (c & 1) * kCtcChunk * L1;
+      const int t0 = c * kCtcChunk, nf = min(kCtcChunk, Tb - t0);
+      for (int f = nf - 1; f >= 0; --f) {
+        const int t = t0 + f;
+        float eb, el[SPL / 2];
+        emissions(e + f * L1, eb, el);
+        if (t == Tb - 1) {
+#pragma unroll
+          for (int j = 0; j < SPL; ++j) {
+            const int s = lane * SPL + j;
+            x[j] = (s < Sb && s >= Sb - 2) ? ((j & 1) ? el[j >> 1] : eb) : -INFINITY;
+          }
+        } else {
+          float dn1 = __shfl_down_sync(0xffffffffu, x[0], 1), dn2 = __shfl_down_sync(0xffffffffu, x[1], 1);
+          if (lane == 31) { dn1 = -INFINITY; dn2 = -INFINITY; }
+          float nx[SPL];
+#pragma unroll
+          for (int j = 0; j < SPL; ++j) {
+            const float c1 = (j + 1 < SPL) ? x[j + 1] : dn1;
+            float v;
+            if (j & 1) {
+              const float c2 = ((skip_out >> j) & 1u) ? ((j + 2 < SPL) ? x[j + 2] : dn2) : -INFINITY;
+              v = lse2_3(x[j], c1, c2);
+            } else {
+              v = lse2_2(x[j], c1);
+            }
+            nx[j] = ((live >> j) & 1u) ? v + ((j & 1) ? el[j >> 1] : eb) : -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < SPL; ++j) x[j] = nx[j];
+        }
+        if (t % kCtcNorm == 0 || t == Tb - 1) cx += (double)normalise(x);
+        if (lane == 0) offs[t] = cx * (double)kLn2;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) rows[(int64_t)t * S + lane * SPL + j] = x[j] * kLn2;
+      }
+      __syncwarp();
+      stage(c - 2, c & 1);
     }
   }
-  // ---- nll = -log( alpha_{Tb-1}(Sb-1) + alpha_{Tb-1}(Sb-2) )
-  __shared__ float fin[32 * SPL];
-#pragma unroll
-  for (int j = 0; j < SPL; ++j) fin[lane * SPL + j] = a[j];
-  __syncwarp();
-  const float l1 = fin[Sb - 1], l2 = (Sb >= 2) ? fin[Sb - 2] : -INFINITY;
-  const double nll_d = -((double)log_add(l1, l2) + ca);
-  if (lane == 0) p.nll[b] = (float)nll_d;
-  // ---- backward, fused with ab = alpha + beta (overwrites the stored alpha)
-  float be[SPL];
-  double cb = 0.0;
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const int s = lane * SPL + j;
-    be[j] = (s < Sb && s >= Sb - 2) ? emission(Tb - 1, j) : -INFINITY;
-  }
-  cb += (double)normalise(be);
-  if (lane == 0) offo[Tb - 1] = (float)(offa[Tb - 1] + cb + nll_d);
-#pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    float* slot = abb + (int64_t)(Tb - 1) * S + lane * SPL + j;
-    *slot = *slot + be[j];
-  }
-  for (int t = Tb - 2; t >= 0; --t) {
-    float dn1 = __shfl_down_sync(0xffffffffu, be[0], 1), dn2 = __shfl_down_sync(0xffffffffu, be[1], 1);
-    if (lane == 31) { dn1 = -INFINITY; dn2 = -INFINITY; }
-    float nb[SPL];
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-      const float c1 = (j + 1 < SPL) ? be[j + 1] : dn1;
-      const float c2 = ((skip_out >> j) & 1u) ? ((j + 2 < SPL) ? be[j + 2] : (j + 2 == SPL ? dn1 : dn2)) : -INFINITY;
-      float v = log_add(log_add(be[j], c1), c2);
-      nb[j] = ((live >> j) & 1u) ? v + emission(t, j) : -INFINITY;
-    }
-    cb += (double)normalise(nb);
-    if (lane == 0) offo[t] = (float)(offa[t] + cb + nll_d);
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-      be[j] = nb[j];
-      float* slot = abb + (int64_t)t * S + lane * SPL + j;
-      *slot = *slot + be[j];
-    }
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 struct GradArgs {
   const float* logp; int64_t sb, st;
   const int64_t* targets; int64_t tgt_stride;
   const int64_t* in_len; const int64_t* tgt_len;
-  const float* ab; const float* nll; const float* off;
+  const float* ab; const float* bb; const float* nll; const double* off_a; const double* off_b; const double* nll_d;
   int T, L, V, S, B; int64_t blank; float grad_out;
   float* grad; int64_t gsb, gst;
 };
@@ -195,12 +266,14 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(GradArgs p) {
   if (dead) return;
   __syncthreads();
   const int64_t* tg = p.targets + (int64_t)b * p.tgt_stride;
-  const float* abt = p.ab + ((int64_t)b * p.T + t) * p.S;
-  const float shift = p.off[(int64_t)b * p.T + t];       // log-scale of this frame's rows + nll
+  const float* abt = p.ab + ((int64_t)b * p.T + t) * p.S;      // alpha_t rows; beta_t rows at the same offset of bb
+  const float* bbt = p.bb + ((int64_t)b * p.T + t) * p.S;
+  // log-scale of this frame's rows + nll
+  const float shift = (float)(p.off_a[(int64_t)b * p.T + t] + p.off_b[(int64_t)b * p.T + t] + p.nll_d[b]);
   // blank column: all even states, warp-tree reduction in a fixed order (deterministic)
   if (threadIdx.x < 32) {
     float acc = -INFINITY;
-    for (int i = threadIdx.x; i <= Lb; i += 32) acc = log_add(acc, abt[2 * i]);
+    for (int i = threadIdx.x; i <= Lb; i += 32) acc = log_add(acc, abt[2 * i] + bbt[2 * i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc = log_add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
     if (threadIdx.x == 0) {
@@ -215,9 +288,9 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(GradArgs p) {
     for (int k = 0; k < i; ++k)
       if (tg[k] == c) { leader = false; break; }
     if (!leader || c < 0 || c >= p.V || c == p.blank) continue;
-    float acc = abt[2 * i + 1];
+    float acc = abt[2 * i + 1] + bbt[2 * i + 1];
     for (int k = i + 1; k < Lb; ++k)
-      if (tg[k] == c) acc = log_add(acc, abt[2 * k + 1]);
+      if (tg[k] == c) acc = log_add(acc, abt[2 * k + 1] + bbt[2 * k + 1]);
     g[c] = scale * (expf(row[c]) - expf(acc + shift - row[c]));
   }
 }
@@ -247,7 +320,11 @@ int spl_for(int64_t L) {
 
 template <int SPL>
 int launch_ab(const AbArgs& p, int64_t B, cudaStream_t s) {
-  ctc_alpha_beta_kernel<SPL><<<(unsigned)B, 32, 0, s>>>(p);
+  const size_t smem = (size_t)2 * 2 * kCtcChunk * (p.L + 1) * sizeof(float);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(ctc_alpha_beta_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  ctc_alpha_beta_kernel<SPL><<<(unsigned)B, 64, smem, s>>>(p);
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 
@@ -256,7 +333,7 @@ int launch_ab(const AbArgs& p, int64_t B, cudaStream_t s) {
 extern "C" int64_t cn_ctc_loss_workspace_bytes(int64_t B, int64_t T, int64_t L) {
   if (B < 0 || T < 0 || L < 0 || L > 511) return -1;
   const int64_t S = 32 * (int64_t)spl_for(L);
-  return (B * T * (L + 1) + B * T * S + B * T) * 4 + B * T * 8 + 512;
+  return (B * T * (L + 1) + 2 * B * T * S) * 4 + (2 * B * T + B) * 8 + 512;
 }
 
 extern "C" int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, int64_t sb, int64_t st,
@@ -273,14 +350,16 @@ extern "C" int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, i
   const int S = 32 * spl;
   float* E = (float*)workspace;
   float* ab = E + B * T * (L + 1);
-  float* off = ab + B * T * S;
-  double* off_a = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(off + B * T) + 255) & ~uintptr_t(255));
+  float* bb = ab + B * T * S;
+  double* off_a = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(bb + B * T * S) + 255) & ~uintptr_t(255));
+  double* off_b = off_a + B * T;
+  double* nll_dbl = off_b + B * T;
   ctc_gather_kernel<<<dim3((unsigned)T, (unsigned)B), 256, 0, stream>>>(logp, sb, st, targets, tgt_stride, (int)T, (int)L,
                                                                          (int)V, blank, E);
   CN_CHECK_LAUNCH();
   AbArgs p;
   p.E = E; p.targets = targets; p.tgt_stride = tgt_stride; p.in_len = input_lengths; p.tgt_len = target_lengths;
-  p.T = (int)T; p.L = (int)L; p.ab = ab; p.nll = nll; p.off_a = off_a; p.off = off;
+  p.T = (int)T; p.L = (int)L; p.ab = ab; p.bb = bb; p.nll = nll; p.off_a = off_a; p.off_b = off_b; p.nll_d = nll_dbl;
   int rc;
   switch (spl) {
     case 2: rc = launch_ab<2>(p, B, stream); break;
@@ -303,7 +382,7 @@ extern "C" int cn_ctc_loss(const float* logp, int64_t B, int64_t T, int64_t V, i
   if (grad_logits) {
     GradArgs g;
     g.logp = logp; g.sb = sb; g.st = st; g.targets = targets; g.tgt_stride = tgt_stride; g.in_len = input_lengths;
-    g.tgt_len = target_lengths; g.ab = ab; g.nll = nll; g.off = off; g.T = (int)T; g.L = (int)L; g.V = (int)V; g.S = S; g.B = (int)B;
+    g.tgt_len = target_lengths; g.ab = ab; g.bb = bb; g.nll = nll; g.off_a = off_a; g.off_b = off_b; g.nll_d = nll_dbl; g.T = (int)T; g.L = (int)L; g.V = (int)V; g.S = S; g.B = (int)B;
     g.blank = blank; g.grad_out = grad_out; g.grad = grad_logits; g.gsb = gsb; g.gst = gst;
     ctc_grad_kernel<<<dim3((unsigned)T, (unsigned)B), 256, 0, stream>>>(g);
     CN_CHECK_LAUNCH();

@@ -272,7 +272,20 @@ class Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, n_head, p=0.0, site=0):
         with torch.no_grad():
-            if p > 0.0:
+            if p > 0.0 and FUSED_SMALL_BWD and q.shape[1] <= 128 and q.shape[-1] // n_head == 64 and \
+                    q.dtype in (torch.float32, torch.bfloat16) and k.dtype == q.dtype and v.dtype == q.dtype:
+                # few query rows: dropout on the probabilities inside one fused launch (cn_attention_fwd_small)
+                B, Tq, d = q.shape
+                Tk = k.shape[1]
+                for t in (q, k, v):
+                    assert t.stride(-1) == 1
+                out = torch.empty(B, Tq, d, dtype=q.dtype, device=q.device)
+                m, mb, mi = ops._mask_strides(mask, B, Tq, Tk)
+                call("cn_attention_fwd_small", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v),
+                     v.stride(1), v.stride(0), int(q.dtype == torch.bfloat16), ptr(m), mb, mi, B, n_head, Tq, Tk, 64, float(p),
+                     ptr(ops.DROPOUT_SEED_DEV), int(ops.DROPOUT_SEED), int(site), ptr(out), out.stride(1), out.stride(0),
+                     stream(), work=dict(flops=4.0 * B * Tq * Tk * d))
+            elif p > 0.0:
                 # dropout on the probabilities (attention.py:22-23): materialised scores, P, dropout, P V
                 B, Tq, d = q.shape
                 Tk, dk = k.shape[1], d // n_head

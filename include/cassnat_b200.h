@@ -451,6 +451,15 @@ int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, const void* 
                            void* dk_out, int64_t lddk, int64_t sbdk, void* dv, int64_t lddv, int64_t sbdv,
                            cn_stream_t stream);
 
+/* The forward of the same attentions with dropout on the probabilities (attention.py:22-23), one launch: online
+ * softmax over the key tiles, the keep mask a function of (seed, site, index into the [B,h,Tq,Tk] probabilities) --
+ * the mask cn_attention_bwd_small regenerates.  Tq <= 128, d_k == 64; element type as above. */
+int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, const void* k, int64_t ldk, int64_t sbk,
+                           const void* v, int64_t ldv, int64_t sbv, int is_bf16, const uint8_t* mask, int64_t mb,
+                           int64_t mi, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk, float p_drop,
+                           const int64_t* seed_dev, int64_t seed, int64_t site, void* out, int64_t ldo, int64_t sbo,
+                           cn_stream_t stream);
+
 /* Dropout (training): out[i] = keep(i) ? x[i] / (1 - p) : 0 with keep a counter-based hash of (seed, site, i):
  * stateless, so the backward pass regenerates the mask from the same (seed, site) instead of storing it.
  *   replaces: nn.Dropout                 src/models/modules/utils.py:21,32; attention.py:22-23,140-141;

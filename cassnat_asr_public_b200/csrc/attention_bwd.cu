@@ -34,7 +34,7 @@ struct BwdArgs {
   void *dq, *dk, *dv;                  // gradients, same element type, own pitches
   int64_t lddq, sbdq, lddk, sbdk, lddv, sbdv;
   const uint8_t* mask; int64_t mb, mi;
-  int h, Tq, Tk;
+  int h, Tq, Tk; bool vec;
   float scale, inv_keep; uint32_t threshold, site; const int64_t* seed_dev; uint64_t seed;
 };
 
@@ -43,12 +43,46 @@ template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloa
 template <typename T> __device__ __forceinline__ void stf(T* p, float v) { *p = (T)v; }
 template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-// rows [r0, r0+nr) x 64 features of a [T, h*64] view -> smem tile (row pitch PITCH), zero beyond nvalid rows
-template <typename T>
-__device__ __forceinline__ void load_tile(float* dst, const T* src, int64_t ld, int nr, int nvalid) {
-  for (int i = threadIdx.x; i < nr * DK; i += NTH) {
-    const int r = i >> 6, d = i & 63;
-    dst[r * PITCH + d] = r < nvalid ? ldf(src + (int64_t)r * ld + d) : 0.f;
+__device__ __forceinline__ void unpack8(const uint4& raw, const __nv_bfloat16*, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+}
+// NR rows x 64 features of a [T, h*64] view -> smem tile (row pitch PITCH), zero beyond nvalid rows.  vec: rows are
+// 16-byte aligned -> 16-byte loads, all of a thread's loads issued before the first is used (a scalar loop pays the
+// L2 latency once per element: 14 tile loads x 16 elements per thread made the kernel latency-bound)
+template <int NR, typename T>
+__device__ __forceinline__ void load_tile(float* dst, const T* src, int64_t ld, int nvalid, bool vec) {
+  constexpr int EPV = 16 / (int)sizeof(T);        // elements per 16-byte vector
+  constexpr int VPR = DK / EPV;                   // vectors per row
+  constexpr int NIT = (NR * VPR + NTH - 1) / NTH;
+  if (vec) {
+    uint4 raw[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * NTH, r = i / VPR, c = i % VPR;
+      raw[it] = (i < NR * VPR && r < nvalid) ? *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c * EPV)
+                                             : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * NTH, r = i / VPR, c = i % VPR;
+      if (i >= NR * VPR) continue;
+      float* d = dst + r * PITCH + c * EPV;
+      if (sizeof(T) == 2) {
+        float f[8];
+        unpack8(raw[it], (const __nv_bfloat16*)nullptr, f);
+        *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        *reinterpret_cast<uint4*>(d) = raw[it];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < NR * DK; i += NTH) {
+      const int r = i >> 6, d = i & 63;
+      dst[r * PITCH + d] = r < nvalid ? ldf(src + (int64_t)r * ld + d) : 0.f;
+    }
   }
 }
 
@@ -107,8 +141,8 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
   const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
   const bool drop = p.threshold != 0;
 
-  load_tile(Qs, q, p.ldq, TQP, Tq);
-  load_tile(Gs, go, p.ldg, TQP, Tq);
+  load_tile<TQP>(Qs, q, p.ldq, Tq, p.vec);
+  load_tile<TQP>(Gs, go, p.ldg, Tq, p.vec);
   for (int i = tid; i < TQP * PITCH; i += NTH) dQs[i] = 0.f;
   for (int i = tid; i < TQ_MAX; i += NTH) { row_m[i] = -INFINITY; row_l[i] = 0.f; row_any[i] = 0; row_D[i] = 0.f; }
   __syncthreads();
@@ -125,7 +159,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = t * KT, nk = min(KT, Tk - k0);
     __syncthreads();
-    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
+    load_tile<KT>(Ks, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
     __syncthreads();
     float acc[RA][4];
     prod_nt<RA>(Qs, Ks, acc, ty, tx);
@@ -168,8 +202,8 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_kernel(BwdArgs p) {
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = t * KT, nk = min(KT, Tk - k0);
     __syncthreads();
-    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
-    load_tile(Vs, v + (int64_t)k0 * p.ldv, p.ldv, KT, nk);
+    load_tile<KT>(Ks, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    load_tile<KT>(Vs, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
     __syncthreads();
     {
       float acc[RA][4];
@@ -291,7 +325,7 @@ struct FwdArgs {
   const void *q, *k, *v; void* out;
   int64_t ldq, sbq, ldk, sbk, ldv, sbv, ldo, sbo;
   const uint8_t* mask; int64_t mb, mi;
-  int h, Tq, Tk;
+  int h, Tq, Tk; bool vec;
   float scale, inv_keep; uint32_t threshold, site; const int64_t* seed_dev; uint64_t seed;
 };
 
@@ -315,7 +349,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_kernel(FwdArgs p) {
   const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
   const bool drop = p.threshold != 0;
 
-  load_tile(Qs, q, p.ldq, TQP, Tq);
+  load_tile<TQP>(Qs, q, p.ldq, Tq, p.vec);
   // rows without any kept key are uniform over all Tk keys (masked_fill(finfo.min) + softmax): found up front
   for (int i = warp; i < TQP; i += NTH / 32) {
     int any = 0;
@@ -342,8 +376,8 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_kernel(FwdArgs p) {
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = t * KT, nk = min(KT, Tk - k0);
     __syncthreads();
-    load_tile(Ks, k + (int64_t)k0 * p.ldk, p.ldk, KT, nk);
-    load_tile(Vs, v + (int64_t)k0 * p.ldv, p.ldv, KT, nk);
+    load_tile<KT>(Ks, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    load_tile<KT>(Vs, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
     __syncthreads();
     float acc[RA][4];
     prod_nt<RA>(Qs, Ks, acc, ty, tx);
@@ -495,6 +529,12 @@ extern "C" int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, c
   p.scale = 1.f / sqrtf((float)dk);
   p.threshold = (uint32_t)((double)p_drop * 4294967296.0);
   p.inv_keep = 1.f / (1.f - p_drop);
+  {
+    const int64_t es = is_bf16 ? 2 : 4;
+    const uintptr_t ptrs = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)go;
+    const int64_t pit = (ldq | sbq | ldk | sbk | ldv | sbv | ldg | sbg) * es;
+    p.vec = !(ptrs & 15) && !(pit & 15);
+  }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
   return is_bf16 ? dispatch_bwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_bwd<float>(p, B, (cudaStream_t)stream);
 }
@@ -516,6 +556,12 @@ extern "C" int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, c
   p.scale = 1.f / sqrtf((float)dk);
   p.threshold = (uint32_t)((double)p_drop * 4294967296.0);
   p.inv_keep = 1.f / (1.f - p_drop);
+  {
+    const int64_t es = is_bf16 ? 2 : 4;
+    const uintptr_t ptrs = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v;
+    const int64_t pit = (ldq | sbq | ldk | sbk | ldv | sbv) * es;
+    p.vec = !(ptrs & 15) && !(pit & 15);
+  }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
   return is_bf16 ? dispatch_fwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_fwd<float>(p, B, (cudaStream_t)stream);
 }

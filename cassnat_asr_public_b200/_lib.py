@@ -75,6 +75,7 @@ SIGNATURES = {
     "cn_gemm_f32_strided": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                    _i64, _i64, _i64, _i64, _i64, _f32, _f32, _vp]),
     "cn_colsum_workspace_bytes": (_i64, [_i64, _i64]),
+    "cn_act_bwd_colsum_bf16": (_int, [_vp, _int, _i64, _vp, _int, _i64, _int, _f32, _vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp]),
     "cn_act_bwd_colsum": (_int, [_vp, _i64, _vp, _i64, _int, _f32, _vp, _i64, _i64, _i64, _vp, _int, _vp, _i64, _vp]),
     "cn_layernorm_bwd_workspace_bytes": (_i64, [_i64, _i64]),
     "cn_layernorm_bwd": (_int, [_vp, _i64, _vp, _i64, _vp, _f32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
@@ -136,7 +137,7 @@ LAUNCHES = {"cn_row_stats": 1, "cn_bestpath_collapse": 1, "cn_bestpath_from_logp
             "cn_align_to_mask": 1, "cn_expand_trigger_mask": 1, "cn_tgt_length_mask": 1, "cn_gemm_f32": 1,
             "cn_layernorm": 1, "cn_attention_f32": 1, "cn_segment_attention_f32": 3,
             "cn_glu_dwconv_groupnorm_act": 3, "cn_gemm_bf16_rowstats": 2, "cn_gemm_bf16x3_rowstats": 2, "cn_rel_attention_bf16": 2,
-            "cn_act_bwd_colsum": 2, "cn_layernorm_bwd": 3, "cn_label_smoothing": 3, "cn_ctc_loss": 4,
+            "cn_act_bwd_colsum": 2, "cn_act_bwd_colsum_bf16": 2, "cn_layernorm_bwd": 3, "cn_label_smoothing": 3, "cn_ctc_loss": 4,
             "cn_glu_dwconv_groupnorm_act_bwd": 7, "cn_conv_frontend_bf16": 2}
 launch_count = 0          # running total of our kernel launches (bench.py reads and resets it)
 _profile = None           # list of (name, start_event, end_event, work) while profiling

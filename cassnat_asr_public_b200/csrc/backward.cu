@@ -111,6 +111,34 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __rest
   if (partial) partial[(int64_t)blockIdx.y * N + c] = s;
 }
 
+// The same with mixed element types: dy and saved may be bf16 (gradients / activations of bf16 GEMM outputs), dpre is
+// written in bf16 -- the operand both backward GEMMs read -- so that the tensor-core backward of a linear layer needs
+// no dtype copies around this kernel.
+template <typename TD, typename TS>
+__global__ void __launch_bounds__(256) act_bwd_colsum16_kernel(const TD* __restrict__ dy, int64_t lddy,
+                                                               const TS* __restrict__ saved, int64_t lds, int act,
+                                                               float alpha, __nv_bfloat16* __restrict__ dpre, int64_t ldp,
+                                                               int64_t M, int64_t N, float* __restrict__ partial) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+  const int64_t r1 = (r0 + CS_ROWS < M) ? r0 + CS_ROWS : M;
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    float v = alpha * (float)dy[r * lddy + c];
+    if (act == CN_ACT_RELU) {
+      v = (float)saved[r * lds + c] > 0.f ? v : 0.f;
+    } else if (act == CN_ACT_SWISH) {
+      const float z = (float)saved[r * lds + c];
+      const float sg = 1.f / (1.f + expf(-z));
+      v *= sg * (1.f + z * (1.f - sg));
+    }
+    if (dpre) dpre[r * ldp + c] = __float2bfloat16(v);
+    s += v;
+  }
+  if (partial) partial[(int64_t)blockIdx.y * N + c] = s;
+}
+
 // ===================================================================== LayerNorm backward
 constexpr int LN_ROWS = 32;
 
@@ -447,6 +475,35 @@ extern "C" int cn_act_bwd_colsum(const float* dy, int64_t lddy, const float* sav
   CN_CHECK_LAUNCH();
   if (colsum) {
     colsum_reduce_kernel<<<(unsigned)((N + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, nblk, N, colsum, accumulate);
+    CN_CHECK_LAUNCH();
+  }
+  return CN_OK;
+}
+
+extern "C" int cn_act_bwd_colsum_bf16(const void* dy, int dy_is_bf16, int64_t lddy, const void* saved, int saved_is_bf16,
+                                      int64_t lds, int act, float alpha, void* dpre_bf16, int64_t ldp, int64_t M, int64_t N,
+                                      float* colsum, int accumulate, void* workspace, int64_t workspace_bytes,
+                                      cn_stream_t stream) {
+  if (!dy || M < 0 || N < 0 || (act != CN_ACT_NONE && !saved) || (!dpre_bf16 && !colsum)) return CN_ERR_BAD_ARG;
+  if (M == 0 || N == 0) return CN_OK;
+  const int64_t nblk = (M + CS_ROWS - 1) / CS_ROWS;
+  if (nblk > 65535) return CN_ERR_UNSUPPORTED;
+  if (colsum && (!workspace || workspace_bytes < cn_colsum_workspace_bytes(M, N))) return CN_ERR_WORKSPACE;
+  float* partial = colsum ? (float*)workspace : nullptr;
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)nblk);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* dp = (__nv_bfloat16*)dpre_bf16;
+  if (dy_is_bf16 && saved_is_bf16)
+    act_bwd_colsum16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)saved, lds, act, alpha, dp, ldp, M, N, partial);
+  else if (dy_is_bf16)
+    act_bwd_colsum16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, lddy, (const float*)saved, lds, act, alpha, dp, ldp, M, N, partial);
+  else if (saved_is_bf16)
+    act_bwd_colsum16_kernel<<<grid, 256, 0, st>>>((const float*)dy, lddy, (const __nv_bfloat16*)saved, lds, act, alpha, dp, ldp, M, N, partial);
+  else
+    act_bwd_colsum16_kernel<<<grid, 256, 0, st>>>((const float*)dy, lddy, (const float*)saved, lds, act, alpha, dp, ldp, M, N, partial);
+  CN_CHECK_LAUNCH();
+  if (colsum) {
+    colsum_reduce_kernel<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(partial, nblk, N, colsum, accumulate);
     CN_CHECK_LAUNCH();
   }
   return CN_OK;

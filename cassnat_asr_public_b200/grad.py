@@ -95,6 +95,28 @@ def gemm_bf16_mn(A, a_mn, W, M, N, K, out_dtype):
 
 
 # =============================================================================== linear
+def act_bwd_colsum_bf16(dy, saved, act, alpha, want_colsum):
+    """-> (dpre bf16 [M,N], colsum or None) of cn_act_bwd_colsum_bf16 on 2-D dy / saved in f32 or bf16 (no dtype copies)."""
+    M, N = dy.shape
+    dpre = torch.empty(M, N, dtype=torch.bfloat16, device=dy.device)
+    col = torch.empty(N, dtype=torch.float32, device=dy.device) if want_colsum else None
+    ws_bytes = _lib.load().cn_colsum_workspace_bytes(M, N) if want_colsum else 0
+    ws = _ws(ws_bytes, dy.device)
+    call("cn_act_bwd_colsum_bf16", ptr(dy), int(dy.dtype == torch.bfloat16), dy.stride(0), ptr(saved),
+         int(saved is not None and saved.dtype == torch.bfloat16), saved.stride(0) if saved is not None else 0, _ACT[act],
+         float(alpha), ptr(dpre), N, M, N, ptr(col), 0, ptr(ws), ws_bytes, stream(),
+         work=dict(bytes=float(M * N) * (dy.element_size() + 2 + (saved.element_size() if saved is not None else 0))))
+    return dpre, col
+
+
+def _rows_2d(t, cols):
+    """2-D view [-1, cols] with unit column stride in f32 or bf16 (other types -> f32)."""
+    t = t.reshape(-1, cols)
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.float()
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
 class Linear(torch.autograd.Function):
     """residual + alpha * act(x W^T + b)  (ops.linear); dX = dpre W, dW = dpre^T X, db = colsum(dpre),
     dpre = alpha * dY * act'."""
@@ -133,7 +155,8 @@ class Linear(torch.autograd.Function):
         x, weight, y_act = ctx.saved_tensors
         N, K = weight.shape
         needs = ctx.needs_input_grad
-        gy2 = _f32_2d(gy, N)
+        fused16 = ctx.tc and N % 8 == 0 and USE_MN_GEMM       # tensor-core backward: dY goes to the GEMMs as bf16
+        gy2 = _rows_2d(gy, N) if fused16 else _f32_2d(gy, N)
         M = gy2.shape[0]
         dev = gy2.device
         g_res = None
@@ -141,19 +164,29 @@ class Linear(torch.autograd.Function):
             g_res = gy if gy.dtype == torch.float32 else gy.float()
             if ctx.res_rows:
                 g_res = g_res.reshape(-1, ctx.res_rows, N).sum(0)
-        saved = _f32_2d(y_act, N) if y_act is not None else None
         want_dpre = ctx.act is not None or ctx.alpha != 1.0
         want_db = ctx.has_bias and needs[2]
-        if want_dpre or want_db:
-            dpre, db = act_bwd_colsum(gy2, saved, ctx.act, ctx.alpha, want_dpre, want_db)
-            if dpre is None:
-                dpre = gy2
+        d16 = None
+        if fused16:
+            saved = _rows_2d(y_act, N) if y_act is not None else None
+            if want_dpre or want_db or gy2.dtype != torch.bfloat16:
+                d16, db = act_bwd_colsum_bf16(gy2, saved, ctx.act, ctx.alpha, want_db)      # one pass: act', bf16, colsum
+            else:
+                d16, db = gy2, None
+                if d16.stride(0) % 8 or d16.data_ptr() % 16:
+                    d16 = d16.contiguous()
+            dpre = None
         else:
-            dpre, db = gy2, None
+            saved = _f32_2d(y_act, N) if y_act is not None else None
+            if want_dpre or want_db:
+                dpre, db = act_bwd_colsum(gy2, saved, ctx.act, ctx.alpha, want_dpre, want_db)
+                if dpre is None:
+                    dpre = gy2
+            else:
+                dpre, db = gy2, None
         x2 = x.reshape(-1, K)
         dx = dw = None
-        if ctx.tc and N % 8 == 0 and USE_MN_GEMM:
-            d16 = ops.cast_bf16(dpre)                                              # [M,N], read in place by both GEMMs
+        if fused16:
             if needs[0]:
                 dx = gemm_bf16_mn(d16, False, ctx.wb, M, K, N, ctx.x_dtype)        # dY [M,N] x W [N,K] (contraction-major)
             if needs[1]:

@@ -421,6 +421,12 @@ int cn_act_bwd_colsum(const float* dy, int64_t lddy, const float* saved, int64_t
                       float* dpre, int64_t ldp, int64_t M, int64_t N, float* colsum, int accumulate,
                       void* workspace, int64_t workspace_bytes, cn_stream_t stream);
 
+/* The same for the tensor-core backward of a linear layer: dy / saved in f32 or bf16 (flags), dpre written in bf16
+ * (the operand of the dX and dW GEMMs); dpre_bf16 or colsum may be NULL. */
+int cn_act_bwd_colsum_bf16(const void* dy, int dy_is_bf16, int64_t lddy, const void* saved, int saved_is_bf16, int64_t lds,
+                           int act, float alpha, void* dpre_bf16, int64_t ldp, int64_t M, int64_t N, float* colsum,
+                           int accumulate, void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+
 /* Backward of y = a*(x-mean)/(std_unbiased+eps)+b: dx [rows,d], da [d], db [d].
  *   replaces: autograd of LayerNorm.forward          src/models/modules/norm.py:15-18 */
 int64_t cn_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d);

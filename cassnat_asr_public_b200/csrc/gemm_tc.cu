@@ -707,6 +707,12 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
   // epilogue streams more bytes than the mainloop computes, and 128x128 tiles fill the last wave of the
   // 148 persistent CTAs better (measured on [32000x512x512]: 38.8 -> 34.9 us)
   int bn = gemm_tile_n(N, K, split);
+  if (!fold && !ln) {
+    // few rows (the small model, the label-token side of training): narrower tiles until the persistent grid has a
+    // tile for every SM -- at [4000 x 256 x 2048] a 128x256 tiling keeps 32 of 148 SMs busy
+    const int64_t mblocks = (M + BM - 1) / BM;
+    while (bn > 64 && mblocks * ((N + bn - 1) / bn) < sm_count()) bn /= 2;
+  }
   if (fold) {
     // vector epilogue only; the producer writes fp32 rows (+ raw bf16 copy), the consumer has no residual
     if (ln || split || out_split || (N & 3) || (ldc & 3) || (residual && (ldr & 3))) return CN_ERR_UNSUPPORTED;
@@ -777,6 +783,7 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
     return launch_tc<BN_, CN_ACT_NONE, false>(ma, mw, ep, m, n, k, stream, split);                             \
   } while (0)
   if (bn == 256) CN_TC_DISPATCH(256);
+  if (bn == 64) CN_TC_DISPATCH(64);
   CN_TC_DISPATCH(128);
 #undef CN_TC_DISPATCH
 }
@@ -860,7 +867,11 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
     return CN_ERR_UNSUPPORTED;
   if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x7fffff00) return CN_ERR_UNSUPPORTED;
   if (M == 0 || N == 0) return CN_OK;
-  const int bn = N > 128 ? 256 : 128;
+  int bn = N > 128 ? 256 : 128;
+  {
+    const int64_t mblocks = (M + BM - 1) / BM;              // (few output rows: narrower tiles, see gemm_bf16_impl)
+    while (bn > 64 && mblocks * ((N + bn - 1) / bn) < sm_count()) bn /= 2;
+  }
   CUtensorMap ma, mw;
   const bool ok_a = a_mn ? make_map_mn(&ma, A, K, M, lda) : make_map(&ma, A, M, K, lda, BM);
   if (!ok_a || !make_map_mn(&mw, W, K, N, ldw)) return CN_ERR_DEVICE;
@@ -875,9 +886,11 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
   const int m = (int)M, n = (int)N, k = (int)K;
   if (a_mn) {
     if (bn == 256) return launch_tc<256, CN_ACT_NONE, false, false, true, true>(ma, mw, ep, m, n, k, stream);
+    if (bn == 64) return launch_tc<64, CN_ACT_NONE, false, false, true, true>(ma, mw, ep, m, n, k, stream);
     return launch_tc<128, CN_ACT_NONE, false, false, true, true>(ma, mw, ep, m, n, k, stream);
   }
   if (bn == 256) return launch_tc<256, CN_ACT_NONE, false, false, false, true>(ma, mw, ep, m, n, k, stream);
+  if (bn == 64) return launch_tc<64, CN_ACT_NONE, false, false, false, true>(ma, mw, ep, m, n, k, stream);
   return launch_tc<128, CN_ACT_NONE, false, false, false, true>(ma, mw, ep, m, n, k, stream);
 }
 

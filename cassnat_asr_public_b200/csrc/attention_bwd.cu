@@ -480,6 +480,435 @@ int dispatch_fwd(const FwdArgs& p, int64_t B, cudaStream_t st) {
   }
 }
 
+// ================================================================ bf16: the same two kernels on mma.sync
+// For bf16 operands the five products run on the tensor cores (mma.sync.m16n8k16, fp32 accumulate; tcgen05's
+// 128-row tiles do not fit 41-row problems): Q, dO, K, V stay bf16 in shared memory (row pitch 72 elements:
+// conflict-free ldmatrix), P~ and dS are rounded to bf16 for the second-level products exactly as the forward
+// attention kernel rounds P.  Warp w owns the w-th 8-column slice of every product.
+constexpr int PB = 72;               // bf16 row pitch (144 B)
+constexpr int PF = 68;               // f32 scratch row pitch
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// fragment addresses (bytes, shared space) for lane l
+__device__ __forceinline__ uint32_t a_rowmajor(uint32_t base, int m0, int k0, int l) {          // X[m][k]
+  return base + 2u * (uint32_t)((m0 + (l & 15)) * PB + k0 + ((l >> 4) << 3));
+}
+__device__ __forceinline__ uint32_t a_transposed(uint32_t base, int m0, int k0, int l) {        // X[k][m], use .trans
+  return base + 2u * (uint32_t)((k0 + (l & 7) + ((l >> 4) << 3)) * PB + m0 + (((l >> 3) & 1) << 3));
+}
+__device__ __forceinline__ uint32_t b_nk(uint32_t base, int n0, int k0, int l) {                // X[n][k]
+  return base + 2u * (uint32_t)((n0 + (l & 7)) * PB + k0 + (((l >> 3) & 1) << 3));
+}
+__device__ __forceinline__ uint32_t b_kn(uint32_t base, int n0, int k0, int l) {                // X[k][n], use .trans
+  return base + 2u * (uint32_t)((k0 + (l & 15)) * PB + n0);
+}
+
+// NR rows x 64 bf16 of a [T, h*64] view -> smem (pitch PB), zero beyond nvalid rows; 16-byte copies
+template <int NR>
+__device__ __forceinline__ void load_tile_b(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nvalid, bool vec) {
+  constexpr int NIT = (NR * 8 + NTH - 1) / NTH;
+  if (vec) {
+    uint4 raw[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * NTH, r = i >> 3, c = i & 7;
+      raw[it] = (i < NR * 8 && r < nvalid) ? *reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * NTH, r = i >> 3, c = i & 7;
+      if (i < NR * 8) *reinterpret_cast<uint4*>(dst + r * PB + c * 8) = raw[it];
+    }
+  } else {
+    for (int i = threadIdx.x; i < NR * DK; i += NTH) {
+      const int r = i >> 6, d = i & 63;
+      dst[r * PB + d] = r < nvalid ? src[(int64_t)r * ld + d] : __float2bfloat16(0.f);
+    }
+  }
+}
+
+// scores of one key tile: acc[a] = fragment (rows 16a + g, +8; columns 8*warp + 2t, +1) of X Y^T, X [TQP][64], Y [64][64]
+template <int RA>
+__device__ __forceinline__ void mma_nt(uint32_t X, uint32_t Y, float (&acc)[RA][4], int warp, int lane) {
+  uint32_t bf[4][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x2(bf[ks], b_nk(Y, 8 * warp, 16 * ks, lane));
+#pragma unroll
+  for (int a = 0; a < RA; ++a) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[a][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[4];
+      ldsm_x4(af, a_rowmajor(X, 16 * a, 16 * ks, lane));
+      mma16816(acc[a], af, bf[ks]);
+    }
+  }
+}
+
+// row statistics of the staged f32 score tile (pass 1 of both kernels)
+__device__ __forceinline__ void row_stats_update(const float* Sf, const uint8_t* mk, int64_t mi, int Tq, int k0, int nk,
+                                                 float* row_m, float* row_l, int* row_any, int warp, int lane) {
+  for (int i = warp; i < Tq; i += NTH / 32) {
+    const uint8_t* mr = mk ? mk + (int64_t)i * mi : nullptr;
+    float mx = -INFINITY;
+    int any = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = lane + 32 * c;
+      if (j < nk && (!mr || mr[k0 + j])) { mx = fmaxf(mx, Sf[i * PF + j]); any = 1; }
+    }
+    mx = cn_warp_max(mx);
+    any = __any_sync(0xffffffffu, any);
+    if (!any) continue;
+    const float m_old = row_m[i], m_new = fmaxf(m_old, mx);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = lane + 32 * c;
+      if (j < nk && (!mr || mr[k0 + j])) s += expf(Sf[i * PF + j] - m_new);
+    }
+    s = cn_warp_sum(s);
+    if (lane == 0) {
+      row_l[i] = row_l[i] * (m_old == -INFINITY ? 0.f : expf(m_old - m_new)) + s;
+      row_m[i] = m_new;
+      row_any[i] = 1;
+    }
+  }
+}
+
+template <int RA>
+__global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
+  constexpr int TQP = 16 * RA;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(smraw);      // [TQP][PB]
+  __nv_bfloat16* Gb = Qb + TQP * PB;                                 // dO
+  __nv_bfloat16* Kb = Gb + TQP * PB;                                 // [KT][PB]
+  __nv_bfloat16* Vb = Kb + KT * PB;
+  __nv_bfloat16* Pb = Vb + KT * PB;                                  // [TQP][PB] dropped probabilities of the tile
+  __nv_bfloat16* Sb = Pb + TQP * PB;                                 // [TQP][PB] dS * scale
+  float* Sf = reinterpret_cast<float*>(Sb + TQP * PB);               // [TQP][PF] scores of pass 1
+  __shared__ float row_m[TQ_MAX], row_l[TQ_MAX], row_D[TQ_MAX];
+  __shared__ int row_any[TQ_MAX];
+  typedef __nv_bfloat16 T;
+
+  const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int Tq = p.Tq, Tk = p.Tk;
+  const T* q = (const T*)p.q + (int64_t)b * p.sbq + hh * DK;
+  const T* k = (const T*)p.k + (int64_t)b * p.sbk + hh * DK;
+  const T* v = (const T*)p.v + (int64_t)b * p.sbv + hh * DK;
+  const T* o = (const T*)p.o + (int64_t)b * p.sbo + hh * DK;
+  const T* go = (const T*)p.go + (int64_t)b * p.sbg + hh * DK;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
+  const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
+  const bool drop = p.threshold != 0;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(Qb), sG = (uint32_t)__cvta_generic_to_shared(Gb),
+                 sK = (uint32_t)__cvta_generic_to_shared(Kb), sV = (uint32_t)__cvta_generic_to_shared(Vb),
+                 sP = (uint32_t)__cvta_generic_to_shared(Pb), sS = (uint32_t)__cvta_generic_to_shared(Sb);
+
+  load_tile_b<TQP>(Qb, q, p.ldq, Tq, p.vec);
+  load_tile_b<TQP>(Gb, go, p.ldg, Tq, p.vec);
+  for (int i = tid; i < TQ_MAX; i += NTH) { row_m[i] = -INFINITY; row_l[i] = 0.f; row_any[i] = 0; row_D[i] = 0.f; }
+  __syncthreads();
+  for (int i = warp; i < Tq; i += NTH / 32) {           // D_i = dO_i . O_i
+    float s = __bfloat162float(Gb[i * PB + lane]) * __bfloat162float(o[(int64_t)i * p.ldo + lane]) +
+              __bfloat162float(Gb[i * PB + lane + 32]) * __bfloat162float(o[(int64_t)i * p.ldo + lane + 32]);
+    s = cn_warp_sum(s);
+    if (lane == 0) row_D[i] = s;
+  }
+  const int n_tiles = (Tk + KT - 1) / KT;
+  // ---- pass 1: softmax statistics
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    __syncthreads();
+    float acc[RA][4];
+    mma_nt<RA>(sQ, sK, acc, warp, lane);
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+      Sf[(16 * a + g) * PF + 8 * warp + 2 * t4] = acc[a][0] * p.scale;
+      Sf[(16 * a + g) * PF + 8 * warp + 2 * t4 + 1] = acc[a][1] * p.scale;
+      Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4] = acc[a][2] * p.scale;
+      Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4 + 1] = acc[a][3] * p.scale;
+    }
+    __syncthreads();
+    row_stats_update(Sf, mk, p.mi, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+  }
+  __syncthreads();
+  // ---- pass 2
+  float dq[RA][4];
+#pragma unroll
+  for (int a = 0; a < RA; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq[a][e] = 0.f;
+  const float inv_tk = 1.f / (float)Tk;
+  T* dvp = (T*)p.dv + (int64_t)b * p.sbdv + hh * DK;
+  T* dkp = (T*)p.dk + (int64_t)b * p.sbdk + hh * DK;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    load_tile_b<KT>(Vb, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
+    __syncthreads();
+    {
+      float acc[RA][4], acg[RA][4];
+      mma_nt<RA>(sQ, sK, acc, warp, lane);        // scores
+      mma_nt<RA>(sG, sV, acg, warp, lane);        // dP~ = dO V^T
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {           // the fragment's two rows
+          const int i = 16 * a + g + 8 * hr;
+          const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
+          const bool row_ok = i < Tq;
+          const int any = row_ok ? row_any[i] : 0;
+          const float m = row_m[i], inv_l = any ? 1.f / row_l[i] : 0.f, D = row_D[i];
+          float pr2[2], ds2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 8 * warp + 2 * t4 + e;
+            float pr = 0.f, ds = 0.f;
+            if (row_ok && j < nk) {
+              const bool kept = !mr || mr[k0 + j];
+              float keepf = 1.f;
+              if (drop) {
+                const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
+                keepf = dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+              }
+              if (any) {
+                pr = kept ? expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f;
+                ds = pr * (acg[a][2 * hr + e] * keepf - D);
+              } else {
+                pr = inv_tk;
+              }
+              pr *= keepf;
+            }
+            pr2[e] = pr;
+            ds2[e] = ds * p.scale;
+          }
+          *reinterpret_cast<__nv_bfloat162*>(Pb + i * PB + 8 * warp + 2 * t4) = __floats2bfloat162_rn(pr2[0], pr2[1]);
+          *reinterpret_cast<__nv_bfloat162*>(Sb + i * PB + 8 * warp + 2 * t4) = __floats2bfloat162_rn(ds2[0], ds2[1]);
+        }
+    }
+    __syncthreads();
+    // dV = P~^T dO, dK = dS^T Q: [64 keys x 64 features], contraction over the query rows; warp w: features 8w..8w+7
+    {
+      uint32_t bg[RA][2], bq[RA][2];
+#pragma unroll
+      for (int ks = 0; ks < RA; ++ks) {
+        ldsm_x2_t(bg[ks], b_kn(sG, 8 * warp, 16 * ks, lane));
+        ldsm_x2_t(bq[ks], b_kn(sQ, 8 * warp, 16 * ks, lane));
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        float cv[4] = {0.f, 0.f, 0.f, 0.f}, ck[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < RA; ++ks) {
+          uint32_t ap[4], as[4];
+          ldsm_x4_t(ap, a_transposed(sP, 16 * mt, 16 * ks, lane));
+          ldsm_x4_t(as, a_transposed(sS, 16 * mt, 16 * ks, lane));
+          mma16816(cv, ap, bg[ks]);
+          mma16816(ck, as, bq[ks]);
+        }
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int j = 16 * mt + g + 8 * hr;
+          if (j < nk) {
+            *reinterpret_cast<__nv_bfloat162*>(dvp + (int64_t)(k0 + j) * p.lddv + 8 * warp + 2 * t4) = __floats2bfloat162_rn(cv[2 * hr], cv[2 * hr + 1]);
+            *reinterpret_cast<__nv_bfloat162*>(dkp + (int64_t)(k0 + j) * p.lddk + 8 * warp + 2 * t4) = __floats2bfloat162_rn(ck[2 * hr], ck[2 * hr + 1]);
+          }
+        }
+      }
+    }
+    // dQ += dS K: [TQP x 64 features], contraction over the 64 keys
+    {
+      uint32_t bk[4][2];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm_x2_t(bk[ks], b_kn(sK, 8 * warp, 16 * ks, lane));
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t as[4];
+          ldsm_x4(as, a_rowmajor(sS, 16 * a, 16 * ks, lane));
+          mma16816(dq[a], as, bk[ks]);
+        }
+    }
+  }
+  T* dqp = (T*)p.dq + (int64_t)b * p.sbdq + hh * DK;
+#pragma unroll
+  for (int a = 0; a < RA; ++a)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int i = 16 * a + g + 8 * hr;
+      if (i < Tq)
+        *reinterpret_cast<__nv_bfloat162*>(dqp + (int64_t)i * p.lddq + 8 * warp + 2 * t4) = __floats2bfloat162_rn(dq[a][2 * hr], dq[a][2 * hr + 1]);
+    }
+}
+
+template <int RA>
+__global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
+  constexpr int TQP = 16 * RA;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(smraw);      // [TQP][PB]
+  __nv_bfloat16* Kb = Qb + TQP * PB;                                 // [KT][PB]
+  __nv_bfloat16* Vb = Kb + KT * PB;
+  __nv_bfloat16* Pb = Vb + KT * PB;                                  // [TQP][PB]
+  float* Sf = reinterpret_cast<float*>(Pb + TQP * PB);               // [TQP][PF]
+  __shared__ float row_m[TQ_MAX], row_l[TQ_MAX];
+  __shared__ int row_any[TQ_MAX];
+  typedef __nv_bfloat16 T;
+
+  const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int Tq = p.Tq, Tk = p.Tk;
+  const T* q = (const T*)p.q + (int64_t)b * p.sbq + hh * DK;
+  const T* k = (const T*)p.k + (int64_t)b * p.sbk + hh * DK;
+  const T* v = (const T*)p.v + (int64_t)b * p.sbv + hh * DK;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
+  const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
+  const bool drop = p.threshold != 0;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(Qb), sK = (uint32_t)__cvta_generic_to_shared(Kb),
+                 sV = (uint32_t)__cvta_generic_to_shared(Vb), sP = (uint32_t)__cvta_generic_to_shared(Pb);
+  load_tile_b<TQP>(Qb, q, p.ldq, Tq, p.vec);
+  for (int i = tid; i < TQ_MAX; i += NTH) { row_m[i] = -INFINITY; row_l[i] = 0.f; row_any[i] = 0; }
+  const int n_tiles = (Tk + KT - 1) / KT;
+  for (int t = 0; t < n_tiles; ++t) {              // pass 1: row statistics
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    __syncthreads();
+    float acc[RA][4];
+    mma_nt<RA>(sQ, sK, acc, warp, lane);
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+      Sf[(16 * a + g) * PF + 8 * warp + 2 * t4] = acc[a][0] * p.scale;
+      Sf[(16 * a + g) * PF + 8 * warp + 2 * t4 + 1] = acc[a][1] * p.scale;
+      Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4] = acc[a][2] * p.scale;
+      Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4 + 1] = acc[a][3] * p.scale;
+    }
+    __syncthreads();
+    row_stats_update(Sf, mk, p.mi, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+  }
+  __syncthreads();
+  float oacc[RA][4];
+#pragma unroll
+  for (int a = 0; a < RA; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[a][e] = 0.f;
+  const float inv_tk = 1.f / (float)Tk;
+  for (int t = 0; t < n_tiles; ++t) {              // pass 2: P~ and O += P~ V
+    const int k0 = t * KT, nk = min(KT, Tk - k0);
+    __syncthreads();
+    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
+    load_tile_b<KT>(Vb, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
+    __syncthreads();
+    {
+      float acc[RA][4];
+      mma_nt<RA>(sQ, sK, acc, warp, lane);
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+          const int i = 16 * a + g + 8 * hr;
+          const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
+          const bool row_ok = i < Tq;
+          const int any = row_ok ? row_any[i] : 0;
+          const float m = row_m[i], inv_l = any ? 1.f / row_l[i] : 0.f;
+          float pr2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 8 * warp + 2 * t4 + e;
+            float pr = 0.f;
+            if (row_ok && j < nk) {
+              const bool kept = !mr || mr[k0 + j];
+              pr = any ? (kept ? expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f) : inv_tk;
+              if (drop && pr != 0.f) {
+                const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
+                pr *= dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+              }
+            }
+            pr2[e] = pr;
+          }
+          *reinterpret_cast<__nv_bfloat162*>(Pb + i * PB + 8 * warp + 2 * t4) = __floats2bfloat162_rn(pr2[0], pr2[1]);
+        }
+    }
+    __syncthreads();
+    {
+      uint32_t bv[4][2];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm_x2_t(bv[ks], b_kn(sV, 8 * warp, 16 * ks, lane));
+#pragma unroll
+      for (int a = 0; a < RA; ++a)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t ap[4];
+          ldsm_x4(ap, a_rowmajor(sP, 16 * a, 16 * ks, lane));
+          mma16816(oacc[a], ap, bv[ks]);
+        }
+    }
+  }
+  T* op = (T*)p.out + (int64_t)b * p.sbo + hh * DK;
+#pragma unroll
+  for (int a = 0; a < RA; ++a)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int i = 16 * a + g + 8 * hr;
+      if (i < Tq)
+        *reinterpret_cast<__nv_bfloat162*>(op + (int64_t)i * p.ldo + 8 * warp + 2 * t4) = __floats2bfloat162_rn(oacc[a][2 * hr], oacc[a][2 * hr + 1]);
+    }
+}
+
+template <int RA>
+int launch_bwd_mma(const BwdArgs& p, int64_t B, cudaStream_t st) {
+  constexpr int TQP = 16 * RA;
+  const size_t smem = (size_t)(4 * TQP + 2 * KT) * PB * 2 + (size_t)TQP * PF * 4;
+  if (cudaFuncSetAttribute(attn_bwd_small_mma_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  attn_bwd_small_mma_kernel<RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+template <int RA>
+int launch_fwd_mma(const FwdArgs& p, int64_t B, cudaStream_t st) {
+  constexpr int TQP = 16 * RA;
+  const size_t smem = (size_t)(2 * TQP + 2 * KT) * PB * 2 + (size_t)TQP * PF * 4;
+  if (cudaFuncSetAttribute(attn_fwd_small_mma_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  attn_fwd_small_mma_kernel<RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+#define CN_RA_SWITCH(FN, P, B_, ST)                \
+  switch ((P.Tq + 15) / 16) {                      \
+    case 1: return FN<1>(P, B_, ST);               \
+    case 2: return FN<2>(P, B_, ST);               \
+    case 3: return FN<3>(P, B_, ST);               \
+    case 4: return FN<4>(P, B_, ST);               \
+    case 5: return FN<5>(P, B_, ST);               \
+    case 6: return FN<6>(P, B_, ST);               \
+    case 7: return FN<7>(P, B_, ST);               \
+    case 8: return FN<8>(P, B_, ST);               \
+    default: return CN_ERR_UNSUPPORTED;            \
+  }
+int dispatch_bwd_mma(const BwdArgs& p, int64_t B, cudaStream_t st) { CN_RA_SWITCH(launch_bwd_mma, p, B, st) }
+int dispatch_fwd_mma(const FwdArgs& p, int64_t B, cudaStream_t st) { CN_RA_SWITCH(launch_fwd_mma, p, B, st) }
+
 template <typename T, int RA>
 int launch_bwd(const BwdArgs& p, int64_t B, cudaStream_t st) {
   constexpr int TQP = 16 * RA;
@@ -536,6 +965,9 @@ extern "C" int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, c
     p.vec = !(ptrs & 15) && !(pit & 15);
   }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
+  // bf16: tensor-core kernel when the outputs allow paired stores; f32: FFMA kernel
+  if (is_bf16 && !((lddq | sbdq | lddk | sbdk | lddv | sbdv) & 1) && !(((uintptr_t)dq | (uintptr_t)dk_out | (uintptr_t)dv) & 3))
+    return dispatch_bwd_mma(p, B, (cudaStream_t)stream);
   return is_bf16 ? dispatch_bwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_bwd<float>(p, B, (cudaStream_t)stream);
 }
 
@@ -563,5 +995,6 @@ extern "C" int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, c
     p.vec = !(ptrs & 15) && !(pit & 15);
   }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
+  if (is_bf16 && !((ldo | sbo) & 1) && !((uintptr_t)out & 3)) return dispatch_fwd_mma(p, B, (cudaStream_t)stream);
   return is_bf16 ? dispatch_fwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_fwd<float>(p, B, (cudaStream_t)stream);
 }

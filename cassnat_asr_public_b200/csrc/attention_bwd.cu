@@ -542,6 +542,27 @@ __device__ __forceinline__ void load_tile_b(__nv_bfloat16* dst, const __nv_bfloa
   }
 }
 
+// the same as an asynchronous copy (cp.async, one commit group per call): the next key tile is fetched while the
+// current one is being used.  Rows beyond nvalid are zero-filled with ordinary stores.
+template <int NR>
+__device__ __forceinline__ void load_tile_b_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t ld, int nvalid, bool vec) {
+  if (vec) {
+    for (int i = threadIdx.x; i < NR * 8; i += NTH) {
+      const int r = i >> 3, c = i & 7;
+      __nv_bfloat16* d = dst + r * PB + c * 8;
+      if (r < nvalid) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)),
+                     "l"(src + (int64_t)r * ld + c * 8) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  } else {
+    load_tile_b<NR>(dst, src, ld, nvalid, false);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // scores of one key tile: acc[a] = fragment (rows 16a + g, +8; columns 8*warp + 2t, +1) of X Y^T, X [TQP][64], Y [64][64]
 template <int RA>
 __device__ __forceinline__ void mma_nt(uint32_t X, uint32_t Y, float (&acc)[RA][4], int warp, int lane) {
@@ -561,17 +582,52 @@ __device__ __forceinline__ void mma_nt(uint32_t X, uint32_t Y, float (&acc)[RA][
   }
 }
 
-// row statistics of the staged f32 score tile (pass 1 of both kernels)
-__device__ __forceinline__ void row_stats_update(const float* Sf, const uint8_t* mk, int64_t mi, int Tq, int k0, int nk,
-                                                 float* row_m, float* row_l, int* row_any, int warp, int lane) {
+// cn_dropout's keep decision for an element index below 2^32 (the high word contributes a per-launch constant c2)
+__device__ __forceinline__ float keep_factor32(uint32_t seed_lo, uint32_t c2, uint32_t idx, uint32_t threshold, float inv_keep) {
+  uint32_t h = fmix32(idx * 0x9E3779B1u ^ seed_lo);
+  h = fmix32(h ^ c2);
+  return h >= threshold ? inv_keep : 0.f;
+}
+
+constexpr int MW = 64;               // mask words per row (Tk <= 2048)
+// keep-mask of the whole problem as bits in shared memory, built once: reading mask bytes from global memory inside
+// the per-tile loops costs an L2 round trip per row and tile (measured: 3 us per key tile, 10x the arithmetic)
+__device__ __forceinline__ void build_mask_bits(uint32_t* Mw, const uint8_t* mk, int64_t mi, int Tq, int Tk, int warp, int lane) {
+  const int n_rows = mk ? (mi ? Tq : 1) : 0, n_words = (Tk + 31) / 32;
+  for (int i = warp; i < n_rows; i += NTH / 32) {
+    const uint8_t* mr = mk + (int64_t)i * mi;
+    for (int w0 = 0; w0 < n_words; w0 += 8) {
+      uint8_t byte[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = (w0 + u) * 32 + lane;
+        byte[u] = j < Tk ? mr[j] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, byte[u] != 0);
+        if (lane == 0 && w0 + u < n_words) Mw[i * MW + w0 + u] = bits;
+      }
+    }
+  }
+}
+__device__ __forceinline__ bool mask_kept(const uint32_t* Mw, bool has_mask, bool per_row, int i, int key) {
+  return !has_mask || ((Mw[(per_row ? i : 0) * MW + (key >> 5)] >> (key & 31)) & 1u);
+}
+
+// row statistics of the staged f32 score tile (pass 1 of both kernels), mask from the shared-memory bits
+__device__ __forceinline__ void row_stats_update_bits(const float* Sf, const uint32_t* Mw, bool has_mask, bool per_row, int Tq,
+                                                      int k0, int nk, float* row_m, float* row_l, int* row_any, int warp,
+                                                      int lane) {
   for (int i = warp; i < Tq; i += NTH / 32) {
-    const uint8_t* mr = mk ? mk + (int64_t)i * mi : nullptr;
     float mx = -INFINITY;
     int any = 0;
+    bool kept[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int j = lane + 32 * c;
-      if (j < nk && (!mr || mr[k0 + j])) { mx = fmaxf(mx, Sf[i * PF + j]); any = 1; }
+      kept[c] = j < nk && mask_kept(Mw, has_mask, per_row, i, k0 + j);
+      if (kept[c]) { mx = fmaxf(mx, Sf[i * PF + j]); any = 1; }
     }
     mx = cn_warp_max(mx);
     any = __any_sync(0xffffffffu, any);
@@ -579,13 +635,11 @@ __device__ __forceinline__ void row_stats_update(const float* Sf, const uint8_t*
     const float m_old = row_m[i], m_new = fmaxf(m_old, mx);
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int j = lane + 32 * c;
-      if (j < nk && (!mr || mr[k0 + j])) s += expf(Sf[i * PF + j] - m_new);
-    }
+    for (int c = 0; c < 2; ++c)
+      if (kept[c]) s += __expf(Sf[i * PF + lane + 32 * c] - m_new);
     s = cn_warp_sum(s);
     if (lane == 0) {
-      row_l[i] = row_l[i] * (m_old == -INFINITY ? 0.f : expf(m_old - m_new)) + s;
+      row_l[i] = row_l[i] * (m_old == -INFINITY ? 0.f : __expf(m_old - m_new)) + s;
       row_m[i] = m_new;
       row_any[i] = 1;
     }
@@ -598,13 +652,14 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(smraw);      // [TQP][PB]
   __nv_bfloat16* Gb = Qb + TQP * PB;                                 // dO
-  __nv_bfloat16* Kb = Gb + TQP * PB;                                 // [KT][PB]
-  __nv_bfloat16* Vb = Kb + KT * PB;
-  __nv_bfloat16* Pb = Vb + KT * PB;                                  // [TQP][PB] dropped probabilities of the tile
+  __nv_bfloat16* Kb = Gb + TQP * PB;                                 // [2][KT][PB]  (double-buffered key tiles)
+  __nv_bfloat16* Vb = Kb + 2 * KT * PB;                              // [2][KT][PB]
+  __nv_bfloat16* Pb = Vb + 2 * KT * PB;                              // [TQP][PB] dropped probabilities of the tile
   __nv_bfloat16* Sb = Pb + TQP * PB;                                 // [TQP][PB] dS * scale
   float* Sf = reinterpret_cast<float*>(Sb + TQP * PB);               // [TQP][PF] scores of pass 1
   __shared__ float row_m[TQ_MAX], row_l[TQ_MAX], row_D[TQ_MAX];
   __shared__ int row_any[TQ_MAX];
+  uint32_t* Mw = reinterpret_cast<uint32_t*>(Sf + TQP * PF);        // [TQP][MW] keep-mask bits
   typedef __nv_bfloat16 T;
 
   const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
@@ -618,8 +673,12 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
   const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
   const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
   const bool drop = p.threshold != 0;
+  const bool has_mask = mk != nullptr, per_row = p.mi != 0;
+  const uint32_t seed_lo = (uint32_t)seed, c2 = p.site * 0xC2B2AE3Du + (uint32_t)(seed >> 32);
+  const bool idx32 = (uint64_t)gridDim.x * (uint64_t)Tq * (uint64_t)Tk < 0xffffffffull;
+  build_mask_bits(Mw, mk, p.mi, Tq, Tk, warp, lane);
   const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(Qb), sG = (uint32_t)__cvta_generic_to_shared(Gb),
-                 sK = (uint32_t)__cvta_generic_to_shared(Kb), sV = (uint32_t)__cvta_generic_to_shared(Vb),
+                 sK0 = (uint32_t)__cvta_generic_to_shared(Kb), sV0 = (uint32_t)__cvta_generic_to_shared(Vb),
                  sP = (uint32_t)__cvta_generic_to_shared(Pb), sS = (uint32_t)__cvta_generic_to_shared(Sb);
 
   load_tile_b<TQP>(Qb, q, p.ldq, Tq, p.vec);
@@ -633,12 +692,22 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
     if (lane == 0) row_D[i] = s;
   }
   const int n_tiles = (Tk + KT - 1) / KT;
+  auto fetch_k = [&](int t) {
+    if (t < n_tiles) load_tile_b_async<KT>(Kb + (t & 1) * KT * PB, k + (int64_t)t * KT * p.ldk, p.ldk, min(KT, Tk - t * KT), p.vec);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto fetch_v = [&](int t) {
+    if (t < n_tiles) load_tile_b_async<KT>(Vb + (t & 1) * KT * PB, v + (int64_t)t * KT * p.ldv, p.ldv, min(KT, Tk - t * KT), p.vec);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   // ---- pass 1: softmax statistics
+  fetch_k(0);
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = t * KT, nk = min(KT, Tk - k0);
+    fetch_k(t + 1);                                  // (its buffer was last read two tiles ago, behind a barrier)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
-    __syncthreads();
+    const uint32_t sK = sK0 + (uint32_t)((t & 1) * KT * PB * 2);
     float acc[RA][4];
     mma_nt<RA>(sQ, sK, acc, warp, lane);
 #pragma unroll
@@ -649,9 +718,9 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
       Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4 + 1] = acc[a][3] * p.scale;
     }
     __syncthreads();
-    row_stats_update(Sf, mk, p.mi, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+    row_stats_update_bits(Sf, Mw, has_mask, per_row, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+    __syncthreads();
   }
-  __syncthreads();
   // ---- pass 2
   float dq[RA][4];
 #pragma unroll
@@ -661,12 +730,15 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
   const float inv_tk = 1.f / (float)Tk;
   T* dvp = (T*)p.dv + (int64_t)b * p.sbdv + hh * DK;
   T* dkp = (T*)p.dk + (int64_t)b * p.sbdk + hh * DK;
+  fetch_k(0);
+  fetch_v(0);
   for (int t = 0; t < n_tiles; ++t) {
     const int k0 = t * KT, nk = min(KT, Tk - k0);
+    fetch_k(t + 1);
+    fetch_v(t + 1);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
-    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
-    load_tile_b<KT>(Vb, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
-    __syncthreads();
+    const uint32_t sK = sK0 + (uint32_t)((t & 1) * KT * PB * 2), sV = sV0 + (uint32_t)((t & 1) * KT * PB * 2);
     {
       float acc[RA][4], acg[RA][4];
       mma_nt<RA>(sQ, sK, acc, warp, lane);        // scores
@@ -676,8 +748,9 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {           // the fragment's two rows
           const int i = 16 * a + g + 8 * hr;
-          const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
           const bool row_ok = i < Tq;
+          const uint64_t rowbase = ((uint64_t)(b * p.h + hh) * Tq + i) * Tk + (uint64_t)(k0 + 8 * warp + 2 * t4);
+          const uint32_t mword = has_mask ? Mw[(per_row ? i : 0) * MW + ((k0 + 8 * warp) >> 5)] >> ((k0 + 8 * warp + 2 * t4) & 31) : 3u;
           const int any = row_ok ? row_any[i] : 0;
           const float m = row_m[i], inv_l = any ? 1.f / row_l[i] : 0.f, D = row_D[i];
           float pr2[2], ds2[2];
@@ -686,14 +759,14 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
             const int j = 8 * warp + 2 * t4 + e;
             float pr = 0.f, ds = 0.f;
             if (row_ok && j < nk) {
-              const bool kept = !mr || mr[k0 + j];
+              const bool kept = (mword >> e) & 1u;
               float keepf = 1.f;
               if (drop) {
-                const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
-                keepf = dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+                keepf = idx32 ? keep_factor32(seed_lo, c2, (uint32_t)rowbase + e, p.threshold, p.inv_keep)
+                              : (dropout_keep(seed, p.site, rowbase + e, p.threshold) ? p.inv_keep : 0.f);
               }
               if (any) {
-                pr = kept ? expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f;
+                pr = kept ? __expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f;
                 ds = pr * (acg[a][2 * hr + e] * keepf - D);
               } else {
                 pr = inv_tk;
@@ -751,6 +824,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_small_mma_kernel(BwdArgs p) {
           mma16816(dq[a], as, bk[ks]);
         }
     }
+    __syncthreads();
   }
   T* dqp = (T*)p.dq + (int64_t)b * p.sbdq + hh * DK;
 #pragma unroll
@@ -768,12 +842,13 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
   constexpr int TQP = 16 * RA;
   extern __shared__ __align__(16) unsigned char smraw[];
   __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(smraw);      // [TQP][PB]
-  __nv_bfloat16* Kb = Qb + TQP * PB;                                 // [KT][PB]
-  __nv_bfloat16* Vb = Kb + KT * PB;
-  __nv_bfloat16* Pb = Vb + KT * PB;                                  // [TQP][PB]
+  __nv_bfloat16* Kb = Qb + TQP * PB;                                 // [2][KT][PB]
+  __nv_bfloat16* Vb = Kb + 2 * KT * PB;                              // [2][KT][PB]
+  __nv_bfloat16* Pb = Vb + 2 * KT * PB;                              // [TQP][PB]
   float* Sf = reinterpret_cast<float*>(Pb + TQP * PB);               // [TQP][PF]
   __shared__ float row_m[TQ_MAX], row_l[TQ_MAX];
   __shared__ int row_any[TQ_MAX];
+  uint32_t* Mw = reinterpret_cast<uint32_t*>(Sf + TQP * PF);        // [TQP][MW] keep-mask bits
   typedef __nv_bfloat16 T;
 
   const int b = blockIdx.x / p.h, hh = blockIdx.x % p.h;
@@ -785,16 +860,30 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
   const uint8_t* mk = p.mask ? p.mask + (int64_t)b * p.mb : nullptr;
   const uint64_t seed = p.seed_dev ? (uint64_t)p.seed_dev[0] : p.seed;
   const bool drop = p.threshold != 0;
-  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(Qb), sK = (uint32_t)__cvta_generic_to_shared(Kb),
-                 sV = (uint32_t)__cvta_generic_to_shared(Vb), sP = (uint32_t)__cvta_generic_to_shared(Pb);
+  const bool has_mask = mk != nullptr, per_row = p.mi != 0;
+  const uint32_t seed_lo = (uint32_t)seed, c2 = p.site * 0xC2B2AE3Du + (uint32_t)(seed >> 32);
+  const bool idx32 = (uint64_t)gridDim.x * (uint64_t)Tq * (uint64_t)Tk < 0xffffffffull;
+  build_mask_bits(Mw, mk, p.mi, Tq, Tk, warp, lane);
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(Qb), sK0 = (uint32_t)__cvta_generic_to_shared(Kb),
+                 sV0 = (uint32_t)__cvta_generic_to_shared(Vb), sP = (uint32_t)__cvta_generic_to_shared(Pb);
   load_tile_b<TQP>(Qb, q, p.ldq, Tq, p.vec);
   for (int i = tid; i < TQ_MAX; i += NTH) { row_m[i] = -INFINITY; row_l[i] = 0.f; row_any[i] = 0; }
   const int n_tiles = (Tk + KT - 1) / KT;
+  auto fetch_k = [&](int t) {
+    if (t < n_tiles) load_tile_b_async<KT>(Kb + (t & 1) * KT * PB, k + (int64_t)t * KT * p.ldk, p.ldk, min(KT, Tk - t * KT), p.vec);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto fetch_v = [&](int t) {
+    if (t < n_tiles) load_tile_b_async<KT>(Vb + (t & 1) * KT * PB, v + (int64_t)t * KT * p.ldv, p.ldv, min(KT, Tk - t * KT), p.vec);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch_k(0);
   for (int t = 0; t < n_tiles; ++t) {              // pass 1: row statistics
     const int k0 = t * KT, nk = min(KT, Tk - k0);
+    fetch_k(t + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
-    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
-    __syncthreads();
+    const uint32_t sK = sK0 + (uint32_t)((t & 1) * KT * PB * 2);
     float acc[RA][4];
     mma_nt<RA>(sQ, sK, acc, warp, lane);
 #pragma unroll
@@ -805,21 +894,24 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
       Sf[(16 * a + g + 8) * PF + 8 * warp + 2 * t4 + 1] = acc[a][3] * p.scale;
     }
     __syncthreads();
-    row_stats_update(Sf, mk, p.mi, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+    row_stats_update_bits(Sf, Mw, has_mask, per_row, Tq, k0, nk, row_m, row_l, row_any, warp, lane);
+    __syncthreads();
   }
-  __syncthreads();
   float oacc[RA][4];
 #pragma unroll
   for (int a = 0; a < RA; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) oacc[a][e] = 0.f;
   const float inv_tk = 1.f / (float)Tk;
+  fetch_k(0);
+  fetch_v(0);
   for (int t = 0; t < n_tiles; ++t) {              // pass 2: P~ and O += P~ V
     const int k0 = t * KT, nk = min(KT, Tk - k0);
+    fetch_k(t + 1);
+    fetch_v(t + 1);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncthreads();
-    load_tile_b<KT>(Kb, k + (int64_t)k0 * p.ldk, p.ldk, nk, p.vec);
-    load_tile_b<KT>(Vb, v + (int64_t)k0 * p.ldv, p.ldv, nk, p.vec);
-    __syncthreads();
+    const uint32_t sK = sK0 + (uint32_t)((t & 1) * KT * PB * 2), sV = sV0 + (uint32_t)((t & 1) * KT * PB * 2);
     {
       float acc[RA][4];
       mma_nt<RA>(sQ, sK, acc, warp, lane);
@@ -828,8 +920,9 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
 #pragma unroll
         for (int hr = 0; hr < 2; ++hr) {
           const int i = 16 * a + g + 8 * hr;
-          const uint8_t* mr = mk ? mk + (int64_t)i * p.mi : nullptr;
           const bool row_ok = i < Tq;
+          const uint64_t rowbase = ((uint64_t)(b * p.h + hh) * Tq + i) * Tk + (uint64_t)(k0 + 8 * warp + 2 * t4);
+          const uint32_t mword = has_mask ? Mw[(per_row ? i : 0) * MW + ((k0 + 8 * warp) >> 5)] >> ((k0 + 8 * warp + 2 * t4) & 31) : 3u;
           const int any = row_ok ? row_any[i] : 0;
           const float m = row_m[i], inv_l = any ? 1.f / row_l[i] : 0.f;
           float pr2[2];
@@ -838,11 +931,11 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
             const int j = 8 * warp + 2 * t4 + e;
             float pr = 0.f;
             if (row_ok && j < nk) {
-              const bool kept = !mr || mr[k0 + j];
-              pr = any ? (kept ? expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f) : inv_tk;
+              const bool kept = (mword >> e) & 1u;
+              pr = any ? (kept ? __expf(acc[a][2 * hr + e] * p.scale - m) * inv_l : 0.f) : inv_tk;
               if (drop && pr != 0.f) {
-                const uint64_t idx = (((uint64_t)(b * p.h + hh) * Tq + i) * Tk) + (uint64_t)(k0 + j);
-                pr *= dropout_keep(seed, p.site, idx, p.threshold) ? p.inv_keep : 0.f;
+                pr *= idx32 ? keep_factor32(seed_lo, c2, (uint32_t)rowbase + e, p.threshold, p.inv_keep)
+                            : (dropout_keep(seed, p.site, rowbase + e, p.threshold) ? p.inv_keep : 0.f);
               }
             }
             pr2[e] = pr;
@@ -864,6 +957,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
           mma16816(oacc[a], ap, bv[ks]);
         }
     }
+    __syncthreads();
   }
   T* op = (T*)p.out + (int64_t)b * p.sbo + hh * DK;
 #pragma unroll
@@ -879,7 +973,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_small_mma_kernel(FwdArgs p) {
 template <int RA>
 int launch_bwd_mma(const BwdArgs& p, int64_t B, cudaStream_t st) {
   constexpr int TQP = 16 * RA;
-  const size_t smem = (size_t)(4 * TQP + 2 * KT) * PB * 2 + (size_t)TQP * PF * 4;
+  const size_t smem = (size_t)(4 * TQP + 4 * KT) * PB * 2 + (size_t)TQP * PF * 4 + (size_t)TQP * MW * 4;
   if (cudaFuncSetAttribute(attn_bwd_small_mma_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return CN_ERR_LAUNCH;
   attn_bwd_small_mma_kernel<RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
@@ -888,7 +982,7 @@ int launch_bwd_mma(const BwdArgs& p, int64_t B, cudaStream_t st) {
 template <int RA>
 int launch_fwd_mma(const FwdArgs& p, int64_t B, cudaStream_t st) {
   constexpr int TQP = 16 * RA;
-  const size_t smem = (size_t)(2 * TQP + 2 * KT) * PB * 2 + (size_t)TQP * PF * 4;
+  const size_t smem = (size_t)(2 * TQP + 4 * KT) * PB * 2 + (size_t)TQP * PF * 4 + (size_t)TQP * MW * 4;
   if (cudaFuncSetAttribute(attn_fwd_small_mma_kernel<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return CN_ERR_LAUNCH;
   attn_fwd_small_mma_kernel<RA><<<(unsigned)(B * p.h), NTH, smem, st>>>(p);
@@ -966,7 +1060,7 @@ extern "C" int cn_attention_bwd_small(const void* q, int64_t ldq, int64_t sbq, c
   }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
   // bf16: tensor-core kernel when the outputs allow paired stores; f32: FFMA kernel
-  if (is_bf16 && !((lddq | sbdq | lddk | sbdk | lddv | sbdv) & 1) && !(((uintptr_t)dq | (uintptr_t)dk_out | (uintptr_t)dv) & 3))
+  if (is_bf16 && Tk <= 32 * MW && !((lddq | sbdq | lddk | sbdk | lddv | sbdv) & 1) && !(((uintptr_t)dq | (uintptr_t)dk_out | (uintptr_t)dv) & 3))
     return dispatch_bwd_mma(p, B, (cudaStream_t)stream);
   return is_bf16 ? dispatch_bwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_bwd<float>(p, B, (cudaStream_t)stream);
 }
@@ -995,6 +1089,6 @@ extern "C" int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, c
     p.vec = !(ptrs & 15) && !(pit & 15);
   }
   p.site = (uint32_t)site; p.seed_dev = seed_dev; p.seed = (uint64_t)seed;
-  if (is_bf16 && !((ldo | sbo) & 1) && !((uintptr_t)out & 3)) return dispatch_fwd_mma(p, B, (cudaStream_t)stream);
+  if (is_bf16 && Tk <= 32 * MW && !((ldo | sbo) & 1) && !((uintptr_t)out & 3)) return dispatch_fwd_mma(p, B, (cudaStream_t)stream);
   return is_bf16 ? dispatch_fwd<__nv_bfloat16>(p, B, (cudaStream_t)stream) : dispatch_fwd<float>(p, B, (cudaStream_t)stream);
 }

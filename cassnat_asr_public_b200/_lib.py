@@ -64,6 +64,7 @@ SIGNATURES = {
                            _vp, _i64, _i64, _vp, _i64, _vp]),
     "cn_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "cn_gemm_bf16_ce_grad": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_attention_bf16x3": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64,
                                    _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cn_conv_frontend_bf16": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -603,7 +603,16 @@ class CassNAT(nn.Module):
             dec_h, inter_tap = self.decoder(dec_in, mem, mem_mask, dec_mask, mixce, args.interce_layer)
         else:
             dec_h = self.decoder(dec_in, mem, mem_mask, dec_mask)
-        if taped:
+        if taped and getattr(args, "fused_ce", False) and ops.is_bf16() and not ops.is_x3():
+            # opt-in: head + label-smoothing loss without the [B,U,V] logits / log-probs; the
+            # call then returns att_out = None and leaves the argmax ids in self.last_att_pred (token accuracy)
+            proj = self.att_generator.proj
+            hd = self.att_generator.norm(dec_h) if self.att_generator.add_norm else dec_h
+            att_loss, self.last_att_pred = grad.LinearCE.apply(hd.reshape(-1, hd.size(-1)), proj.weight, proj.bias,
+                                                               tgt_label.reshape(-1), args.padding_idx, args.label_smooth)
+            self.last_att_pred = self.last_att_pred.view(tgt_label.shape)
+            att_out = None
+        elif taped:
             z = self.att_generator.logits(dec_h)                                        # :226 + :248
             att_out, att_loss = grad.LabelSmoothingFromLogits.apply(z.reshape(-1, z.size(-1)), tgt_label.reshape(-1),
                                                                     args.padding_idx, args.label_smooth)

@@ -145,6 +145,10 @@ struct Epilogue {
   // STATS mode: per-(row, column-part) partial row statistics instead of (or besides) the matrix
   float* st_max; int32_t* st_idx; float* st_sum; float* st_max2; int32_t* st_idx2; int n_parts;
   const int32_t* st_target; float* st_target_logit;    // optional: the logit of one given column per row
+  // CE mode (LNM_CE, fused linear + label-smoothed cross entropy, backward): the tile's logits z = A W^T + bias are
+  // turned into the loss gradient  dz = rowscale_m * (exp(z - lse_m) - w),  w = conf at column target_m, eps elsewhere
+  // (src/utils/loss.py:21-35: KLDiv against the smoothed one-hot), and only dz (bf16) is written
+  const float* ce_lse; const int32_t* ce_target; const float* ce_rowscale; float ce_conf, ce_eps;
 };
 
 template <int ACT>
@@ -154,7 +158,7 @@ __device__ __forceinline__ float act_fn(float v) {
   return v;
 }
 
-constexpr int LNM_NONE = 0, LNM_FUSED = 1, LNM_PART = 2, LNM_FOLD = 3;
+constexpr int LNM_NONE = 0, LNM_FUSED = 1, LNM_PART = 2, LNM_FOLD = 3, LNM_CE = 4;
 
 template <int BN, int ACT, bool RES, bool STATS, bool A_MN = false, bool B_MN = false, int LNM = LNM_NONE>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -391,6 +395,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       };
       float4 res_cur[8], res_next[8];
       if (RES) load_res(half * (BN / 2), res_cur);
+      float f_lse[8], f_rs[8];                                  // LNM_CE: log-sum-exp / gradient scale of this lane's 8 rows
+      int f_tgt[8];
+      if (LNM == LNM_CE) {
+        const int myrow = m0 + quarter * 32 + lane;
+        const float lse = myrow < M ? __ldg(ep.ce_lse + myrow) : 0.f, rs = myrow < M ? __ldg(ep.ce_rowscale + myrow) : 0.f;
+        const int tg = myrow < M ? __ldg(ep.ce_target + myrow) : -1;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          f_lse[it] = __shfl_sync(0xffffffffu, lse, it * 4 + rr);
+          f_rs[it] = __shfl_sync(0xffffffffu, rs, it * 4 + rr);
+          f_tgt[it] = __shfl_sync(0xffffffffu, tg, it * 4 + rr);
+        }
+      }
       float f_mean[8], f_rinv[8];                               // LNM_FOLD: LayerNorm statistics of this lane's 8 rows
       if (LNM == LNM_FOLD) {
         // lane l finalises row (quarter*32 + l) from the producer's partial sums, then the 8 rows a lane stores
@@ -457,6 +474,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
           x[it][1] = act_fn<ACT>(x[it][1] + bz.y) * ep.alpha;
           x[it][2] = act_fn<ACT>(x[it][2] + bz.z) * ep.alpha;
           x[it][3] = act_fn<ACT>(x[it][3] + bz.w) * ep.alpha;
+        }
+        if (LNM == LNM_CE) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              x[it][q] = f_rs[it] * (__expf(x[it][q] - f_lse[it]) - (gcol + q == f_tgt[it] ? ep.ce_conf : ep.ce_eps));
         }
         if (vec_ok && gcol + 3 < N) {
           if (RES) {
@@ -739,6 +763,7 @@ static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw
   ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
+  ep.ce_lse = nullptr; ep.ce_target = nullptr; ep.ce_rowscale = nullptr; ep.ce_conf = 0.f; ep.ce_eps = 0.f;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
   if (fold && fold->part_out) {
@@ -794,6 +819,32 @@ extern "C" int cn_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                             cn_stream_t stream_) {
   return gemm_bf16_impl(A, lda, W, ldw, bias, residual, ldr, res_rows, alpha, act, out_f32, out_bf16, ldc, M, N, K, 0, 0,
                         stream_);
+}
+
+// Backward half of the fused linear + label-smoothed cross entropy: recompute the logits tile by
+// tile and write ONLY their loss gradient, in bf16 -- the operand of the dX / dW GEMMs.  The forward half is
+// cn_gemm_bf16_rowstats (log-sum-exp and target logit per row, no logits written) plus the row sums of the logits,
+// which are a matrix-vector product with the column sums of W.
+extern "C" int cn_gemm_bf16_ce_grad(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* lse,
+                                    const int32_t* target, const float* rowscale, float conf, float eps, void* dz_bf16,
+                                    int64_t ldc, int64_t M, int64_t N, int64_t K, cn_stream_t stream_) {
+  if (!A || !W || !lse || !target || !rowscale || !dz_bf16 || M < 0 || N < 0 || K <= 0 || lda < K || ldw < K || ldc < N)
+    return CN_ERR_BAD_ARG;
+  if ((lda & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return CN_ERR_UNSUPPORTED;
+  if (M > 0x7fffff00 || N > 0x7fffff00 || K > 0x3fffff00) return CN_ERR_UNSUPPORTED;
+  if (M == 0 || N == 0) return CN_OK;
+  CUtensorMap ma, mw;
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mw, W, N, K, ldw, 256)) return CN_ERR_DEVICE;
+  Epilogue ep;
+  ep.bias = bias; ep.residual = nullptr; ep.ldr = 0; ep.res_rows = 0; ep.alpha = 1.f; ep.act = CN_ACT_NONE;
+  ep.out_f32 = nullptr; ep.out_bf16 = (__nv_bfloat16*)dz_bf16; ep.ldc = ldc; ep.lo_off = 0;
+  ep.ln_a = nullptr; ep.ln_b = nullptr; ep.ln_eps = 0.f; ep.ln_out = nullptr; ep.ld_ln = 0;
+  ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
+  ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
+  ep.st_target = nullptr; ep.st_target_logit = nullptr;
+  ep.ce_lse = lse; ep.ce_target = target; ep.ce_rowscale = rowscale; ep.ce_conf = conf; ep.ce_eps = eps;
+  return launch_tc<256, CN_ACT_NONE, false, false, false, false, LNM_CE>(ma, mw, ep, (int)M, (int)N, (int)K, (cudaStream_t)stream_, 0);
 }
 
 extern "C" int cn_gemm_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
@@ -882,6 +933,7 @@ extern "C" int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void*
   ep.part = nullptr; ep.n_rowparts = 0; ep.fold_c = nullptr; ep.fold_eps = 0.f; ep.fold_d = 0;
   ep.st_max = nullptr; ep.st_idx = nullptr; ep.st_sum = nullptr; ep.st_max2 = nullptr; ep.st_idx2 = nullptr; ep.n_parts = 0;
   ep.st_target = nullptr; ep.st_target_logit = nullptr;
+  ep.ce_lse = nullptr; ep.ce_target = nullptr; ep.ce_rowscale = nullptr; ep.ce_conf = 0.f; ep.ce_eps = 0.f;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int m = (int)M, n = (int)N, k = (int)K;
   if (a_mn) {

@@ -7,6 +7,8 @@ backward, label smoothing) plus, in the bf16 mode, the tcgen05 GEMM on transpose
 `ops.linear / layer_norm / attention / cast_bf16` dispatch here when grad mode is on and an input
 requires grad; PyTorch autograd only provides the tape (slicing, concatenation of the fused QKV
 weights, residual adds)."""
+import math
+
 import torch
 
 from . import _lib
@@ -95,10 +97,11 @@ def gemm_bf16_mn(A, a_mn, W, M, N, K, out_dtype):
 
 
 # =============================================================================== linear
-def act_bwd_colsum_bf16(dy, saved, act, alpha, want_colsum):
-    """-> (dpre bf16 [M,N], colsum or None) of cn_act_bwd_colsum_bf16 on 2-D dy / saved in f32 or bf16 (no dtype copies)."""
+def act_bwd_colsum_bf16(dy, saved, act, alpha, want_colsum, want_dpre=True):
+    """-> (dpre bf16 [M,N] or None, colsum or None) of cn_act_bwd_colsum_bf16 on 2-D dy / saved in f32 or bf16 (no dtype
+    copies)."""
     M, N = dy.shape
-    dpre = torch.empty(M, N, dtype=torch.bfloat16, device=dy.device)
+    dpre = torch.empty(M, N, dtype=torch.bfloat16, device=dy.device) if want_dpre else None
     col = torch.empty(N, dtype=torch.float32, device=dy.device) if want_colsum else None
     ws_bytes = _lib.load().cn_colsum_workspace_bytes(M, N) if want_colsum else 0
     ws = _ws(ws_bytes, dy.device)
@@ -269,6 +272,59 @@ def _attn_probs_dropped(S, mask, B, h, Tq, Tk, zero_masked, p, site):
 
 
 # =============================================================================== attention
+class LinearCE(torch.autograd.Function):
+    """Fused output head + label-smoothing loss (src/models/cassnat.py:226,248 with
+    src/utils/loss.py:21-35): loss = sum over non-pad rows of KL(smoothed one-hot || softmax(x W^T + b)) / #tokens,
+    without the [rows, V] logits / log-probs / gradient tensors of the unfused path.  Forward: the tcgen05 GEMM's
+    row-statistics epilogue gives log-sum-exp, target logit and argmax per row; the row sum of the logits, which the
+    smoothing term needs, is x . colsum(W) + sum(b).  Backward: the logits are recomputed tile by tile and leave the
+    GEMM as dz in bf16 (cn_gemm_bf16_ce_grad), feeding the dX / dW tensor-core GEMMs.  Returns (loss, argmax ids)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, padding_idx, smoothing):
+        with torch.no_grad():
+            K, V = x.shape[-1], weight.shape[0]
+            xs = ops.cast_bf16(x.detach()).reshape(-1, K)
+            if xs.stride(-1) != 1 or xs.stride(0) % 8 or xs.data_ptr() % 16:
+                xs = xs.contiguous()
+            wb = ops.bf16_weight(weight)
+            tgt = target.reshape(-1)
+            st = ops.head_rowstats(xs, weight, bias, target=tgt, safe=False)
+            keep = tgt != padding_idx
+            tokens = keep.sum().clamp(min=1).float()
+            wsum = wb.float().sum(0)                                              # [K]: column sums of the rounded weight
+            sumz = xs.float() @ wsum + (bias.float().sum() if bias is not None else 0.0)
+            conf, eps = 1.0 - smoothing, smoothing / (V - 1)
+            const = (conf * math.log(conf) if conf > 0 else 0.0) + ((V - 1) * eps * math.log(eps) if eps > 0 else 0.0)
+            lp_t = st["target_logit"] - st["lse"]
+            per_tok = const - conf * lp_t - eps * ((sumz - V * st["lse"]) - lp_t)
+            loss = per_tok.masked_fill(~keep, 0).sum() / tokens
+        ctx.save_for_backward(xs, weight, bias, st["lse"], tgt.to(torch.int32), (keep.float() / tokens))
+        ctx.wb, ctx.conf, ctx.eps, ctx.x_shape, ctx.x_dtype = wb, float(conf), float(eps), x.shape, x.dtype
+        ctx.mark_non_differentiable(st["top1"])
+        return loss, st["top1"].to(torch.int64)
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_ids):
+        xs, weight, bias, lse, tgt, rowscale = ctx.saved_tensors
+        V, K = weight.shape
+        R = xs.shape[0]
+        rs = (rowscale * g_loss).contiguous()
+        dz = torch.empty(R, V, dtype=torch.bfloat16, device=xs.device)
+        call("cn_gemm_bf16_ce_grad", ptr(xs), xs.stride(0), ptr(ctx.wb), ctx.wb.stride(0), ptr(bias), ptr(lse), ptr(tgt), ptr(rs),
+             ctx.conf, ctx.eps, ptr(dz), V, R, V, K, stream(),
+             work=dict(flops=2.0 * R * V * K, bytes=2.0 * (R * K + V * K + R * V)))
+        needs = ctx.needs_input_grad
+        dx = dw = db = None
+        if needs[0]:
+            dx = gemm_bf16_mn(dz, False, ctx.wb, R, K, V, ctx.x_dtype).reshape(ctx.x_shape)
+        if needs[1]:
+            dw = gemm_bf16_mn(dz, True, xs, V, K, R, torch.float32)
+        if bias is not None and needs[2]:
+            _, db = act_bwd_colsum_bf16(dz, None, None, 1.0, True, want_dpre=False)
+        return dx, dw, db, None, None, None
+
+
 class SplitCols(torch.autograd.Function):
     """Column blocks of a fused projection output (q | k | v, or the K/V of every decoder layer) as views.  Backward
     is ONE concatenation of the block gradients -- autograd's own slicing would materialise a zero-padded full-width

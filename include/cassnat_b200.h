@@ -314,6 +314,16 @@ int cn_gemm_bf16_rowstats(const void* A, int64_t lda, const void* W, int64_t ldw
                           float* target_logit   /* f32 [M]: z[row, target[row]]; log-prob = target_logit - lse
                                                    (rescoring, src/models/cassnat.py:517: gather(lm_out, att_pred)) */,
                           void* workspace, int64_t workspace_bytes, cn_stream_t stream);
+/* Fused linear + label-smoothed cross entropy, backward half: recomputes z = A W^T + bias tile
+ * by tile and writes only dz = rowscale[m] * (exp(z - lse[m]) - w), w = conf at column target[m] and eps elsewhere,
+ * in bf16 (the operand of the dX / dW GEMMs).  The forward half is cn_gemm_bf16_rowstats (lse, target logit, argmax;
+ * no logits) plus the row sums of the logits = A . colsum(W) + sum(bias).  No fp32 [rows, V] tensor exists in either
+ * direction.
+ *   replaces: Generator + LabelSmoothing + their autograd      src/models/cassnat.py:226,248, src/utils/loss.py:21-35 */
+int cn_gemm_bf16_ce_grad(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* lse,
+                         const int32_t* target, const float* rowscale, float conf, float eps, void* dz_bf16, int64_t ldc,
+                         int64_t M, int64_t N, int64_t K, cn_stream_t stream);
+
 /* Attention in split-bf16 arithmetic (precise mode): Q/K/V as (hi, lo) bf16 pairs with common pitches, scores and
  * context accumulated from three tcgen05 passes each (relative error ~2^-17).  Context out: fp32 `out`, or (out NULL)
  * as (hi, lo) bf16 pairs at out16 / out16 + lo_off -- the operand of the three-pass output projection -- with the same

@@ -373,3 +373,81 @@ def test_training_call_intermediate_losses_and_unimask(fam, case):
     with torch.no_grad():
         out = model(src, mask, size, labels, sizes, args)
     assert abs(float(out[2]) - float(want[0])) < 1e-4 * max(1.0, abs(float(want[0])))
+
+
+def test_fused_linear_cross_entropy():
+    """grad.LinearCE (head + label-smoothing loss without logits) against the unfused pair
+    ops.linear -> LabelSmoothingFromLogits on the same bf16 GEMM arithmetic, and against torch in fp64."""
+    from cassnat_asr_public_b200 import grad
+    ops.set_precision("bf16")
+    R, K, V, pad, ls = 700, 256, 1000, 0, 0.1
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    x0 = torch.randn(R, K, device=DEV, generator=gen)
+    w0 = torch.randn(V, K, device=DEV, generator=gen) * 0.05
+    b0 = torch.randn(V, device=DEV, generator=gen) * 0.1
+    tgt = torch.randint(1, V, (R,), device=DEV, generator=gen)
+    tgt[::7] = pad
+    res = {}
+    for name in ("fused", "plain"):
+        x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+        if name == "fused":
+            loss, ids = grad.LinearCE.apply(x, w, b, tgt, pad, ls)
+        else:
+            z = ops.linear(x, w, b)
+            _, loss = grad.LabelSmoothingFromLogits.apply(z, tgt, pad, ls)
+            ids = z.argmax(-1)
+        (loss * 3.0).backward()
+        res[name] = (loss.detach(), x.grad, w.grad, b.grad, ids)
+    assert abs(float(res["fused"][0]) - float(res["plain"][0])) < 2e-5 * abs(float(res["plain"][0]))
+    for a, b_, nm in zip(res["fused"][1:4], res["plain"][1:4], ("dx", "dw", "db")):
+        assert rel(a, b_) < 1.5e-2, (nm, rel(a, b_))                 # dz is rounded to bf16 before the two GEMMs
+    assert (res["fused"][4] == res["plain"][4]).float().mean() > 0.995
+    # torch fp64 on the bf16-rounded operands
+    xd, wd, bd = x0.bfloat16().double().requires_grad_(True), w0.bfloat16().double().requires_grad_(True), b0.double().requires_grad_(True)
+    logp = torch.log_softmax(xd @ wd.T + bd, -1)
+    keep = tgt != pad
+    true = torch.full_like(logp, ls / (V - 1)).scatter_(1, tgt.unsqueeze(1), 1.0 - ls)
+    want = (torch.nn.functional.kl_div(logp, true, reduction="none").sum(1) * keep).sum() / keep.sum()
+    (want * 3.0).backward()
+    assert abs(float(res["fused"][0]) - float(want)) < 1e-4 * abs(float(want))
+    assert rel(res["fused"][1], xd.grad) < 1.5e-2 and rel(res["fused"][2], wd.grad) < 1.5e-2 and rel(res["fused"][3], bd.grad) < 1.5e-2
+
+
+def test_training_call_with_fused_cross_entropy():
+    """args.fused_ce (opt-in): the training call without [B,U,V] log-probs returns the same loss and parameter
+    gradients as the default path (bf16 GEMM arithmetic in both), att_out is None, argmax ids in last_att_pred."""
+    import bench
+    from cassnat_asr_public_b200.cassnat import make_model
+    w = dict(d_model=128, n_head=2, d_ff=256, N_enc=2, N_mix_dec=2)
+    args = bench.model_args(w, vocab_size=64, dropout=0.0, precision="bf16")
+    torch.manual_seed(4)
+    model = make_model(16, args).to(DEV).train()
+    model.set_precision("bf16")
+    model.zero_dropout()
+    B, Tin = 3, 64
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    src = torch.randn(B, Tin, 16, device=DEV, generator=gen)
+    mask = torch.ones(B, 1, Tin, dtype=torch.bool, device=DEV)
+    labels = torch.randint(4, 64, (B, 7), device=DEV, generator=gen)
+    labels[:, -1] = 2
+    sizes = torch.full((B,), 6, dtype=torch.int64, device=DEV)
+    ratio = torch.ones(B, device=DEV)
+    res = {}
+    for fused in (False, True):
+        args.fused_ce = fused
+        model.zero_grad(set_to_none=True)
+        out = model(src, mask, ratio, labels, sizes, args)
+        out[2].backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        res[fused] = (float(out[2]), float(out[4]), grads, out[1])
+    args.fused_ce = False
+    ops.set_precision("fp32")
+    assert res[True][3] is None and res[False][3] is not None
+    assert abs(res[True][1] - res[False][1]) < 1e-4 * abs(res[False][1])
+    assert abs(res[True][0] - res[False][0]) < 1e-4 * abs(res[False][0])
+    assert res[True][2].keys() == res[False][2].keys()
+    for n, g in res[False][2].items():
+        assert rel(res[True][2][n], g) < 3e-2, n
+    pred = model.last_att_pred
+    assert pred.shape == labels.shape and pred.dtype == torch.int64
+    assert (pred == res[False][3].argmax(-1)).float().mean() > 0.9

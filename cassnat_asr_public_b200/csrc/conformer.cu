@@ -131,6 +131,107 @@ __global__ void __launch_bounds__(CC) glu_dwconv2_kernel(const TIn* __restrict__
   }
 }
 
+// pass 1, wide variant: time tiles of 128 rows (a 31-tap kernel's halo is then 23 % instead of the 94 % of a 32-row
+// tile), 128 channels per CTA, one channel per thread in the convolution with the KSZ taps in registers and eight
+// outputs per register tile (KSZ + 7 shared-memory reads for 8 KSZ FMAs; the generic kernels re-read every tap weight
+// and every input per FMA).  Measured on the encoder's conv module (k = 31, [64 x 500 x 512]): 664 -> see DESIGN.
+constexpr int CW = 128, TO = 8, WTH = 256;             // channels per CTA, outputs per register tile, threads
+template <int KSZ> struct WideTile { static constexpr int TLW = KSZ >= 15 ? 128 : 64; };      // rows per CTA
+template <typename TIn, int KSZ>
+__global__ void __launch_bounds__(WTH) glu_dwconv_wide_kernel(const TIn* __restrict__ y, int64_t ldy, int64_t sby,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              int L, int C, float* __restrict__ z, double* __restrict__ partial) {
+  extern __shared__ float g[];                      // [TLW + KSZ - 1][CW]
+  constexpr int TLW = WideTile<KSZ>::TLW, ROWS = TLW + KSZ - 1, PAD = (KSZ - 1) / 2;
+  const int b = blockIdx.y, l0 = blockIdx.x * TLW, c0 = blockIdx.z * CW;
+  // ---- GLU of the tile (+ halo): pairs of adjacent channels, eight rows in flight per thread
+  for (int i0 = threadIdx.x; i0 < ROWS * (CW / 2); i0 += WTH * 8) {
+    float2 a[8], gt[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * WTH, r = i / (CW / 2), c = c0 + 2 * (i % (CW / 2)), l = l0 - PAD + r;
+      const bool ok = i < ROWS * (CW / 2) && c < C && l >= 0 && l < L;
+      const TIn* row = y + (int64_t)b * sby + (int64_t)(ok ? l : 0) * ldy;
+      a[k] = ok ? ld2_as_f32(row + c) : make_float2(0.f, 0.f);
+      gt[k] = ok ? ld2_as_f32(row + C + c) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * WTH;
+      if (i < ROWS * (CW / 2)) {
+        const int r = i / (CW / 2), cp = 2 * (i % (CW / 2));
+        *reinterpret_cast<float2*>(g + r * CW + cp) =
+            make_float2(a[k].x * (1.f / (1.f + __expf(-gt[k].x))), a[k].y * (1.f / (1.f + __expf(-gt[k].y))));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- depthwise convolution along time: thread = (channel, half of the tile's rows)
+  const int ch = threadIdx.x % CW, half = threadIdx.x / CW, c = c0 + ch;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    float wr[KSZ];
+#pragma unroll
+    for (int k = 0; k < KSZ; ++k) wr[k] = w[c * KSZ + k];
+    const float bz = bias ? bias[c] : 0.f;
+    const int nout = min(TLW, L - l0);
+    for (int i0 = half * (TLW / 2); i0 < min(nout, (half + 1) * (TLW / 2)); i0 += TO) {
+      float in[TO + KSZ - 1];
+#pragma unroll
+      for (int k = 0; k < TO + KSZ - 1; ++k) in[k] = g[(i0 + k) * CW + ch];
+#pragma unroll
+      for (int o = 0; o < TO; ++o) {
+        float acc = bz;
+#pragma unroll
+        for (int k = 0; k < KSZ; ++k) acc = fmaf(wr[k], in[o + k], acc);
+        if (i0 + o < nout) {
+          z[((int64_t)b * L + (l0 + i0 + o)) * C + c] = acc;
+          s1 += acc;
+          s2 = fmaf(acc, acc, s2);
+        }
+      }
+    }
+  }
+  __shared__ double red[2][WTH / 32];
+  double d1 = s1, d2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d1; red[1][threadIdx.x >> 5] = d2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t1 = 0, t2 = 0;
+    for (int i = 0; i < WTH / 32; ++i) { t1 += red[0][i]; t2 += red[1][i]; }
+    const int64_t blk = ((int64_t)b * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z;
+    partial[blk * 2 + 0] = t1;
+    partial[blk * 2 + 1] = t2;
+  }
+}
+template <typename TIn, int KSZ>
+int launch_wide(const TIn* y, int64_t ldy, int64_t sby, const float* w, const float* bias, int L, int C, int64_t B, float* z,
+                double* partial, cudaStream_t stream) {
+  constexpr int TLW = WideTile<KSZ>::TLW;
+  constexpr int smem = (TLW + KSZ - 1) * CW * (int)sizeof(float);
+  if (cudaFuncSetAttribute(glu_dwconv_wide_kernel<TIn, KSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return CN_ERR_LAUNCH;
+  dim3 grid((unsigned)((L + TLW - 1) / TLW), (unsigned)B, (unsigned)((C + CW - 1) / CW));
+  glu_dwconv_wide_kernel<TIn, KSZ><<<grid, WTH, smem, stream>>>(y, ldy, sby, w, bias, L, C, z, partial);
+  return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
+}
+template <typename TIn>
+int dispatch_wide(int ksz, const TIn* y, int64_t ldy, int64_t sby, const float* w, const float* bias, int L, int C, int64_t B,
+                  float* z, double* partial, cudaStream_t stream) {
+  switch (ksz) {
+    case 3: return launch_wide<TIn, 3>(y, ldy, sby, w, bias, L, C, B, z, partial, stream);
+    case 7: return launch_wide<TIn, 7>(y, ldy, sby, w, bias, L, C, B, z, partial, stream);
+    case 15: return launch_wide<TIn, 15>(y, ldy, sby, w, bias, L, C, B, z, partial, stream);
+    case 31: return launch_wide<TIn, 31>(y, ldy, sby, w, bias, L, C, B, z, partial, stream);
+    default: return CN_ERR_UNSUPPORTED;
+  }
+}
+
 // pass 1b: per-utterance mean / rstd from the double partials (one warp per utterance); keeps the fp64 divide and
 // square root out of the elementwise pass
 __global__ void __launch_bounds__(32) gn_finalize_kernel(const double* __restrict__ partial, int nblk, int L, int C, float eps,
@@ -416,7 +517,18 @@ extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t
   if (!set_smem_limits()) return CN_ERR_LAUNCH;
   const bool pair = (C & 1) == 0 && (ldy & 1) == 0 && (sby & 1) == 0 && ksz <= 31 &&
                     (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
-  if (pair && y_is_bf16)
+  // wide variant (128-row time tiles, taps in registers): its (time tile, channel block) partial sums must fit the
+  // workspace, which is sized for one partial per 32 rows
+  const int tlw = ksz >= 15 ? 128 : 64;
+  const int nblk_w = (int)((L + tlw - 1) / tlw) * (int)((C + CW - 1) / CW);
+  const bool wide = pair && (ksz == 3 || ksz == 7 || ksz == 15 || ksz == 31) && nblk_w <= nblk;
+  if (wide) {
+    const int rc = y_is_bf16 ? dispatch_wide((int)ksz, (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, B, out,
+                                             (double*)workspace, stream)
+                             : dispatch_wide((int)ksz, (const float*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, B, out,
+                                             (double*)workspace, stream);
+    if (rc != CN_OK) return rc;
+  } else if (pair && y_is_bf16)
     glu_dwconv2_kernel<__nv_bfloat16><<<dim3(nblk, (unsigned)B), CC, 2 * smem, stream>>>(
         (const __nv_bfloat16*)y, ldy, sby, dw_weight, dw_bias, (int)L, (int)C, (int)ksz, out, (double*)workspace);
   else if (pair)
@@ -431,7 +543,7 @@ extern "C" int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t
   CN_CHECK_LAUNCH();
   if (L * C > 0x7fffffff) return CN_ERR_UNSUPPORTED;
   float* stats = reinterpret_cast<float*>((char*)workspace + (int64_t)B * nblk * 2 * sizeof(double));
-  gn_finalize_kernel<<<(unsigned)B, 32, 0, stream>>>((const double*)workspace, nblk, (int)L, (int)C, eps, stats);
+  gn_finalize_kernel<<<(unsigned)B, 32, 0, stream>>>((const double*)workspace, wide ? nblk_w : nblk, (int)L, (int)C, eps, stats);
   CN_CHECK_LAUNCH();
   const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 &&
                    (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0;

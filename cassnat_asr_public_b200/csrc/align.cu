@@ -253,28 +253,30 @@ __device__ __forceinline__ bool mask_final(const MaskCtx& c, int u, int t, int l
 
 __device__ void block_segment_scan(const int64_t* __restrict__ aligned_row, int T, int64_t blank, int* seg,
                                    int* warp_tot) {
-  // inclusive prefix count of non-blank entries; T is processed in blockDim-sized slabs
-  int carry = 0;
+  // inclusive prefix count of non-blank entries: a thread owns VT consecutive frames (one pass over its frames for the
+  // local count, one block-wide scan of the 256 partial counts, one pass to write)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int t0 = 0; t0 < T; t0 += blockDim.x) {
-    const int t = t0 + threadIdx.x;
-    int v = (t < T && aligned_row[t] != blank) ? 1 : 0;
-    int inc = v;
+  const int VT = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int t0 = threadIdx.x * VT, t1 = min(t0 + VT, T);
+  int cnt = 0;
+  for (int t = t0; t < t1; ++t) cnt += aligned_row[t] != blank ? 1 : 0;
+  int inc = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int n = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += n;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    int slab = 0;
-    for (int w = 0; w < nwarp; ++w) slab += warp_tot[w];
-    if (t < T) seg[t] = carry + before + inc;
-    carry += slab;
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
   }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_tot[w];
+  int run = before + inc - cnt;                       // exclusive prefix of this thread's first frame
+  for (int t = t0; t < t1; ++t) {
+    run += aligned_row[t] != blank ? 1 : 0;
+    seg[t] = run;
+  }
+  (void)nwarp;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) align_to_mask_kernel(
@@ -302,7 +304,56 @@ __global__ void __launch_bounds__(256) align_to_mask_kernel(
   const int u0 = blockIdx.y * rows_per_cta;
   const int u1 = min(u0 + rows_per_cta, n_rows);
   uint8_t* out = mask_out + ((int64_t)b * n_rows) * T;
-  if ((T & 3) == 0) {
+  if ((T & 7) == 0 && (reinterpret_cast<uintptr_t>(mask_out) & 7) == 0) {
+    // Word-wise synthesis: seg is non-decreasing, so row u's frames are one range [lo, hi] (two binary searches);
+    // a lane builds the 32-frame word of the row from range masks, the source-mask word, the eos cell and the
+    // dilation carries of the neighbouring words, then expands the bits to bytes (8-byte stores).  The
+    // per-element predicate version below spent ~15 instructions per output byte.
+    uint32_t* srcw = reinterpret_cast<uint32_t*>(seg + T);              // [ceil(T/32)] source-mask bits
+    const int n_words = (T + 31) >> 5;
+    for (int t0 = 0; t0 < n_words * 32; t0 += blockDim.x) {
+      const int t = t0 + threadIdx.x;
+      const uint32_t w = __ballot_sync(0xffffffffu, t < T && c.src[t] != 0);
+      if ((threadIdx.x & 31) == 0 && (t >> 5) < n_words) srcw[t >> 5] = w;
+    }
+    __syncthreads();
+    auto lower_bound = [&](int val) {                 // first t with seg[t] >= val
+      int lo = 0, hi = T;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] < val) lo = mid + 1; else hi = mid; }
+      return lo;
+    };
+    int* first = reinterpret_cast<int*>(srcw + n_words);               // [rows + 1]: first frame of every row of the CTA
+    for (int i = threadIdx.x; i <= u1 - u0; i += blockDim.x) first[i] = lower_bound(u0 + i);      // (searches in parallel)
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int u = u0 + warp; u < u1; u += nwarp) {
+      const int lo = first[u - u0], hi = first[u - u0 + 1] - 1;
+      const bool eos_row = u == c.ylens && c.fix_t >= 0 && c.fix_t < T;
+      auto base = [&](int w) -> uint32_t {            // align_to_mask's own value for frames [32w, 32w+32)
+        if (w < 0 || w >= n_words) return 0u;
+        const int a = max(lo - w * 32, 0), e = min(hi - w * 32, 31);
+        uint32_t m = 0;
+        if (a <= e) m = (e == 31 ? 0xffffffffu : ((1u << (e + 1)) - 1u)) & ~((1u << a) - 1u);
+        m &= srcw[w];
+        if (eos_row && (c.fix_t >> 5) == w) m |= 1u << (c.fix_t & 31);
+        return m;
+      };
+      // a lane owns 8 frames (consecutive lanes write consecutive 8-byte pieces: 256 contiguous bytes per warp store);
+      // the four lanes of a word recompute it
+      for (int o8 = lane; o8 < (T >> 3); o8 += 32) {
+        const int w = o8 >> 2, q = o8 & 3;
+        const uint32_t b0 = base(w);
+        uint32_t m = b0;
+        if (right) m |= (b0 << 1) | (base(w - 1) >> 31);
+        if (left) m |= (b0 >> 1) | (base(w + 1) << 31);
+        if (and_src) m &= srcw[w];
+        const uint32_t bits8 = m >> (8 * q);
+        const uint32_t lo4 = ((bits8 & 0xFu) * 0x00204081u) & 0x01010101u;          // 4 bits -> 4 bytes
+        const uint32_t hi4 = (((bits8 >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint2*>(out + (int64_t)u * T + o8 * 8) = make_uint2(lo4, hi4);
+      }
+    }
+  } else if ((T & 3) == 0) {
     const int T4 = T >> 2;
     for (int idx = threadIdx.x; idx < (u1 - u0) * T4; idx += blockDim.x) {
       const int u = u0 + idx / T4, t = (idx % T4) << 2;
@@ -476,7 +527,7 @@ extern "C" int cn_align_to_mask(const int64_t* aligned, const int64_t* ylens, co
   chunks = (n_rows + rows_per_cta - 1) / rows_per_cta;
   if (!mask_out) chunks = 1;
   dim3 grid((unsigned)B, (unsigned)chunks);
-  align_to_mask_kernel<<<grid, 256, (size_t)T * sizeof(int), stream>>>(
+  align_to_mask_kernel<<<grid, 256, (size_t)T * sizeof(int) + (size_t)((T + 31) / 32) * sizeof(uint32_t) + (size_t)(rows_per_cta + 1) * sizeof(int), stream>>>(
       aligned, ylens, src_mask, src_size, (int)T, n_rows, blank, left != 0, right != 0, and_src_mask != 0,
       rows_per_cta, mask_out, ylen_out, seg_out);
   CN_CHECK_LAUNCH();

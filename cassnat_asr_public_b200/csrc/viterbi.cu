@@ -61,10 +61,13 @@ __device__ __forceinline__ float pick(float x, float y, uint32_t m) {           
 //   up1/2  : alpha of the two states below the lane's first one (previous frame)
 //   eb, el : blank / label emissions of the frame for this lane
 //   skm    : per label state (odd j) all-ones when the skip s-2 -> s is allowed, else zero
-//   SECOND : frames of a sampled alignment take the runner-up predecessor (cassnat.py:321-326)
+//   MODE   : 0 = utterance without masked frames: blank states take the two-way maximum (their forbidden skip holds
+//            LOGZERO, which can only win once alpha itself has dropped below LOGZERO, i.e. after a masked frame);
+//            1 = the full three-way comparison; 2 = frames of a sampled alignment, which take the runner-up
+//            predecessor (cassnat.py:321-326)
 // Returns the lane's 2-bit back-pointers (state j at bits 2j).  alpha = max over the predecessors: fmaxf equals the
 // reference's sequence of strict '>' selects up to the sign of a zero, which no comparison can see.
-template <int SPL, bool SECOND>
+template <int SPL, int MODE>
 __device__ __forceinline__ uint32_t vit_frame(float (&a)[SPL], const uint32_t (&skm)[SPL / 2], float up1, float up2, float eb,
                                               const float (&el)[SPL / 2], bool first_lane) {
   float na[SPL];
@@ -74,15 +77,16 @@ __device__ __forceinline__ uint32_t vit_frame(float (&a)[SPL], const uint32_t (&
     const float c0 = a[j];
     const float c1 = (j >= 1) ? a[j - 1] : up1;
     float best;
+    constexpr bool SECOND = MODE == 2;
     if (!SECOND) {
       const float m01 = fmaxf(c0, c1);
       const uint32_t adv = c1 > c0 ? 1u : 0u;
-      if (!(j & 1)) {
-        // blank state: stay or advance (the skip never applies)
+      if (!(j & 1) && MODE == 0) {
+        // blank state: stay or advance (the forbidden skip cannot win)
         best = m01;
         bits |= adv << (2 * j);
       } else {
-        const float c2 = keep_or_logzero((j >= 2) ? a[j - 2] : up1, skm[j >> 1]);
+        const float c2 = (j & 1) ? keep_or_logzero((j >= 2) ? a[j - 2] : up1, skm[j >> 1]) : CN_LOGZERO;
         best = fmaxf(m01, c2);
         bits |= (c2 > m01 ? 2u : adv) << (2 * j);
       }
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
             for (int j = 0; j < SPL / 2; ++j) el[j] = lds_f32(e_lab + 4u * (uint32_t)(f * SW + j));
           }
         };
-        if (nf == kFrames && second_mask == 0) {
+        if (nf == kFrames && second_mask == 0 && !any_masked) {
           // the common case, fully unrolled: compile-time slots, no branches, every select on an invariant condition
           // done with masks.  Small lattices per lane: the chunk's emissions and seam values are read up front, so
           // that the recursion itself never waits behind the fill warps' traffic in the load/store unit.
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
             }
             i1 = keep_or_logzero(i1, has_in_m);
             const float up1 = pick(__shfl_up_sync(0xffffffffu, a[SPL - 1], 1), i1, lane0_m);
-            const uint32_t bits = vit_frame<SPL, false>(a, skm, up1, 0.f, eb, el, g == 0);
+            const uint32_t bits = vit_frame<SPL, 0>(a, skm, up1, 0.f, eb, el, g == 0);
             if (seam_wr) sts_f32x2(s_out + 8u * (uint32_t)f, a[SPL - 1], a[SPL - 2]);
             acc |= bits << ((f % FPW) * BITS);
             if (f % FPW == FPW - 1) {
@@ -384,8 +388,8 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(VitArgs p) {
             float up1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
             float up2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
             if (lane == 0) { up1 = in1; up2 = in2; }
-            const uint32_t bits = ((second_mask >> f) & 1u) ? vit_frame<SPL, true>(a, skm, up1, up2, eb, el, g == 0)
-                                                            : vit_frame<SPL, false>(a, skm, up1, up2, eb, el, g == 0);
+            const uint32_t bits = ((second_mask >> f) & 1u) ? vit_frame<SPL, 2>(a, skm, up1, up2, eb, el, g == 0)
+                                                            : vit_frame<SPL, 1>(a, skm, up1, up2, eb, el, g == 0);
             if (seam_wr) sts_f32x2(s_out + 8u * (uint32_t)f, a[SPL - 1], a[SPL - 2]);
             acc |= bits << ((f % FPW) * BITS);
             if (f % FPW == FPW - 1 || t0 + f == xb - 1) {

@@ -97,7 +97,8 @@ def planted(seed, B, T, V, U, peak=8.0, ragged=True):
 
 
 @pytest.mark.parametrize("B,T,V,U,peak", [(6, 200, 300, 40, 8.0), (4, 333, 97, 100, 2.0), (3, 150, 5000, 7, 0.0),
-                                          (2, 520, 64, 255, 4.0), (2, 700, 50, 300, 3.0), (5, 64, 40, 1, 1.0)])
+                                          (2, 520, 64, 255, 4.0), (2, 700, 50, 300, 3.0), (5, 64, 40, 1, 1.0),
+                                          (2, 1000, 40, 450, 3.0), (3, 257, 80, 31, 2.0), (3, 300, 80, 63, 2.0)])
 def test_random_vs_oracle(B, T, V, U, peak):
     lp, mask, xl, ys, yls = planted(B * 1000 + T, B, T, V, U, peak)
     a, yl, ym = ops.best_path_align(cu(lp), cu(mask), cu(xl), 0)
@@ -192,3 +193,25 @@ def test_decode_hints_kernel():
         for key, got in ((((kv + 127) // 128) * qt, h["order_tgt"]), (((last + 127) // 128) * qt, h["order_src"])):
             want = torch.argsort(key, descending=True, stable=True)
             assert torch.equal(got.cpu().long(), want)
+
+
+@pytest.mark.parametrize("U", [5, 40, 120, 200])
+def test_viterbi_with_masked_frames_inside_the_utterance(U):
+    """Frames masked out INSIDE the valid length.  The reference's prefix masks never produce them, and its own result
+    is then ill-defined (every alpha drops below LOGZERO, so the forbidden / out-of-lattice candidates, which hold
+    LOGZERO, win and the back-pointers of states 0 and 1 index state -1): what is pinned here is that the kernel stays
+    memory-safe and deterministic, and that the posterior path and the compact path (cp.async ring + patching of the
+    masked rows) agree bit for bit."""
+    B, T, V = 4, 2 * U + 150, 60
+    lp, mask, xl, ys, yls = planted(77 + U, B, T, V, U, 3.0)
+    rng = np.random.default_rng(U)
+    mask = mask.copy()
+    for b in range(B):
+        holes = rng.choice(np.arange(1, int(xl[b]) - 1), size=7, replace=False)
+        mask[b, 0, holes] = False
+    va, _, _ = ops.viterbi_align(cu(lp), cu(mask), cu(xl), cu(ys), cu(yls), 0)
+    vb, _, _ = ops.viterbi_align(cu(lp), cu(mask), cu(xl), cu(ys), cu(yls), 0)
+    ca, _, _ = ops.viterbi_align_compact(ops.gather_emissions(cu(lp), cu(ys), 0), V, cu(mask), cu(xl), cu(ys), cu(yls), 0)
+    assert torch.equal(va, vb) and torch.equal(va, ca)
+    labels = set(np.unique(ys).tolist()) | {0}
+    assert set(np.unique(va.cpu().numpy()).tolist()) <= labels

@@ -350,7 +350,8 @@ class SplitCols(torch.autograd.Function):
         return (torch.cat(parts, -1),) + (None,) * len(b)
 
 
-FUSED_SMALL_BWD = True      # attention backward of up to 128 query rows as one launch (tests compare with the composed path)
+FUSED_SMALL_ATTENTION = True      # attention of up to 128 query rows: backward (and the forward with dropout on the
+#                                   probabilities) as one launch each; tests compare with the composed path
 
 
 class Attention(torch.autograd.Function):
@@ -361,7 +362,7 @@ class Attention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, mask, n_head, p=0.0, site=0):
         with torch.no_grad():
-            if p > 0.0 and FUSED_SMALL_BWD and q.shape[1] <= 128 and q.shape[-1] // n_head == 64 and \
+            if p > 0.0 and FUSED_SMALL_ATTENTION and q.shape[1] <= 128 and q.shape[-1] // n_head == 64 and \
                     q.dtype in (torch.float32, torch.bfloat16) and k.dtype == q.dtype and v.dtype == q.dtype:
                 # few query rows: dropout on the probabilities inside one fused launch (cn_attention_fwd_small)
                 B, Tq, d = q.shape
@@ -404,7 +405,7 @@ class Attention(torch.autograd.Function):
         Tk = k.shape[1]
         dk = d // h
         dev = q.device
-        if FUSED_SMALL_BWD and Tq <= 128 and dk == 64 and q.dtype in (torch.float32, torch.bfloat16) and \
+        if FUSED_SMALL_ATTENTION and Tq <= 128 and dk == 64 and q.dtype in (torch.float32, torch.bfloat16) and \
                 k.dtype == q.dtype and v.dtype == q.dtype and go.dtype == q.dtype and out.dtype == q.dtype:
             # few query rows (the label-token side of training): one fused launch (cn_attention_bwd_small)
             g = go if go.stride(-1) == 1 else go.contiguous()

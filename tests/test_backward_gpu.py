@@ -145,7 +145,7 @@ def test_attention_backward_fused_equals_composed(dt):
     go = torch.randn(B, Tq, d, device=DEV, generator=gen).to(dt)
     res = {}
     for fused in (True, False):
-        grad.FUSED_SMALL_BWD = fused
+        grad.FUSED_SMALL_ATTENTION = fused
         try:
             q, k, v = (torch.randn(B, n, d, device=DEV, generator=torch.Generator(device=DEV).manual_seed(s)).to(dt).requires_grad_(True)
                        for n, s in ((Tq, 1), (Tk, 2), (Tk, 3)))
@@ -154,7 +154,7 @@ def test_attention_backward_fused_equals_composed(dt):
             out.backward(go)
             res[fused] = (out.detach().float(), q.grad.float(), k.grad.float(), v.grad.float())
         finally:
-            grad.FUSED_SMALL_BWD = True
+            grad.FUSED_SMALL_ATTENTION = True
     tol = 2e-5 if dt == torch.float32 else 2e-2
     for a, b_, nm in zip(res[True], res[False], ("out", "dq", "dk", "dv")):
         assert rel(a, b_) < tol, (nm, rel(a, b_))

@@ -260,11 +260,15 @@ class OverlappedFlatGradients(FlatGradients):
         for i, (lo, hi) in enumerate(self.bounds):
             if self._work[i] is None:
                 self._launch(i)
+        inv = 1.0 / self.world
         for i, (lo, hi) in enumerate(self.bounds):
             self._work[i].wait()
             if self.comm is not None:
-                self.flat[lo:hi].copy_(self.comm[lo:hi])
-        self.flat.div_(self.world)
+                # cast back and average in one pass (the product is formed in the comm dtype: exact for power-of-two
+                # world sizes, otherwise one more rounding of the size the bf16 exchange already has)
+                torch.mul(self.comm[lo:hi], inv, out=self.flat[lo:hi])
+            else:
+                self.flat[lo:hi].mul_(inv)
 
     all_reduce = finish
 

@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // Fast path: the row lives in registers (NV float4 per lane), 128-bit loads and stores.
-template <int NV>
+// RCP (bf16-only output of the fast mode): one reciprocal per row instead of a division per element -- the sixteen
+// IEEE divisions of a 512-wide row made the kernel issue-bound (ncu: 67 % issue slots busy at 39 % of the DRAM
+// peak); the parity paths (fp32 output, split bf16x3 output) keep the reference's x / (std + eps) element by element.
+template <int NV, bool RCP>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int64_t ldx,
                                                             const float* __restrict__ a, const float* __restrict__ b,
                                                             float eps, float* __restrict__ of32,
@@ -179,13 +182,19 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q); q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
   }
   const float denom = sqrtf(cn_warp_sum(q) / (float)(D - 1)) + eps;
+  const float rinv = 1.f / denom;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(a + c)), be = __ldg(reinterpret_cast<const float4*>(b + c));
     float4 y;
-    y.x = ga.x * v[i].x / denom + be.x; y.y = ga.y * v[i].y / denom + be.y;
-    y.z = ga.z * v[i].z / denom + be.z; y.w = ga.w * v[i].w / denom + be.w;
+    if (RCP) {
+      y.x = fmaf(ga.x * v[i].x, rinv, be.x); y.y = fmaf(ga.y * v[i].y, rinv, be.y);
+      y.z = fmaf(ga.z * v[i].z, rinv, be.z); y.w = fmaf(ga.w * v[i].w, rinv, be.w);
+    } else {
+      y.x = ga.x * v[i].x / denom + be.x; y.y = ga.y * v[i].y / denom + be.y;
+      y.z = ga.z * v[i].z / denom + be.z; y.w = ga.w * v[i].w / denom + be.w;
+    }
     if (of32) *reinterpret_cast<float4*>(of32 + r * ldo + c) = y;
     if (obf) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
@@ -216,11 +225,18 @@ static int layernorm_impl(const float* x, int64_t rows, int64_t d, int64_t ldx, 
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                          reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && (ldob & 3) == 0 && (lo_off & 3) == 0;
-  if (aligned && d == 128) layernorm_vec_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
-  else if (aligned && d == 256) layernorm_vec_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
-  else if (aligned && d == 512) layernorm_vec_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
-  else if (aligned && d == 1024) layernorm_vec_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+  const bool rcp = !out_f32 && lo_off == 0;          // fast mode's plain bf16 copy only
+#define CN_LN_VEC(NV_)                                                                                                  \
+  do {                                                                                                                  \
+    if (rcp) layernorm_vec_kernel<NV_, true><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);  \
+    else layernorm_vec_kernel<NV_, false><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);    \
+  } while (0)
+  if (aligned && d == 128) CN_LN_VEC(1);
+  else if (aligned && d == 256) CN_LN_VEC(2);
+  else if (aligned && d == 512) CN_LN_VEC(4);
+  else if (aligned && d == 1024) CN_LN_VEC(8);
   else layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, rows, (int)d, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);
+#undef CN_LN_VEC
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

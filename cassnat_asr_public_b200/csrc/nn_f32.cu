@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // Fast path: the row lives in registers (NV float4 per lane), 128-bit loads and stores.
-// RCP (bf16-only output of the fast mode): one reciprocal per row instead of a division per element -- the sixteen
+// RCP (bf16 / split-bf16 output of the tensor-core modes): one reciprocal per row instead of a division per element -- the sixteen
 // IEEE divisions of a 512-wide row made the kernel issue-bound (ncu: 67 % issue slots busy at 39 % of the DRAM
-// peak); the parity paths (fp32 output, split bf16x3 output) keep the reference's x / (std + eps) element by element.
+// peak); the fp32-output path (parity mode) keeps the reference's x / (std + eps) element by element.
 template <int NV, bool RCP>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t rows, int64_t ldx,
                                                             const float* __restrict__ a, const float* __restrict__ b,
@@ -225,7 +225,8 @@ static int layernorm_impl(const float* x, int64_t rows, int64_t d, int64_t ldx, 
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                          reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && (ldob & 3) == 0 && (lo_off & 3) == 0;
-  const bool rcp = !out_f32 && lo_off == 0;          // fast mode's plain bf16 copy only
+  const bool rcp = !out_f32;                         // tensor-core modes (bf16 copy, or the split bf16x3 operand whose
+                                                     // own resolution is 2^-17); fp32 output keeps the exact form
 #define CN_LN_VEC(NV_)                                                                                                  \
   do {                                                                                                                  \
     if (rcp) layernorm_vec_kernel<NV_, true><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);  \

@@ -58,6 +58,9 @@ SIGNATURES = {
     "cn_rel_attention_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "cn_rel_attention_bf16": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                      _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "cn_rel_attention_bf16_table": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
+                                           _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64,
+                                           _vp, _vp]),
     "cn_rescore_select": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,

@@ -41,13 +41,18 @@ def _self_attention_block(x, sub, attn, mask, pos_embed=None, next_norm=None):
     else:
         from .modules import distinct_rel_rows
         table, m = distinct_rel_rows(pos_embed, x.size(1))
-        fast = ops.attn_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= 64
-        rel_pos = ops.linear(table, attn.linear_pos.weight)
-        if torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad):
-            q, k, v = attn.project_qkv(y, out_bf16=fast)           # training: raw q, grad.RelAttention adds u
+        fast = ops.attn_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= ops.REL_TC_MAX
+        if fast and not (torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad)) and _p(attn) == 0:
+            # fast: q + pos_bias_u in bf16, and the relative term's table out of the same GEMM
+            q, k, v, tab = attn.project_qkv_rel(y, table, m)
+            ctx = ops.attention(q, k, v, mask, attn.h, (None, attn.pos_bias_u, attn.pos_bias_v, m, tab))
         else:
-            q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
-        ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m), p_drop=_p(attn))
+            rel_pos = ops.linear(table, attn.linear_pos.weight)
+            if torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad):
+                q, k, v = attn.project_qkv(y, out_bf16=fast)           # training: raw q, grad.RelAttention adds u
+            else:
+                q, k, v = attn.project_qkv_rel(y) if fast else attn.project_qkv(y)     # fast: q + pos_bias_u, bf16
+            ctx = ops.attention(q, k, v, mask, attn.h, (rel_pos, attn.pos_bias_u, attn.pos_bias_v, m), p_drop=_p(attn))
     return _residual(sub, x, lambda **kw: attn.output(ctx, **kw), next_norm=next_norm)
 
 

@@ -16,6 +16,7 @@
 //   * a dedicated TMA warp runs ahead through the schedule (next Q tiles, next item's K/V as soon
 //     as the last MMA that reads a slot has retired).
 // Replaces (fast mode) attention() of src/models/modules/attention.py:13-24.
+#include <cstdlib>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -141,13 +142,17 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major)
          ((uint32_t)(m >> 4) << 24);
 }
 
+struct RelTable { const void* data; int bf16; int64_t ld, sb, hs; };      // see AttnTcArgs::reltab
+
 struct AttnTcArgs {
   const uint8_t* mask; int64_t mb;          // key mask u8 [B,Tk] (row pitch mb), shared by all query rows
   const uint32_t* mask_bits;                // or: per-row mask, bit-packed [B,Tq,16 words] (bit t of word t/32 = keep)
   int q_bcast;                              // Q is [1,Tq,d], shared by every utterance (extractor queries)
   int B, h, Tq, Tk;
   __nv_bfloat16* out; int64_t ldo, sbo;
-  const float* relbias; int max_rel;         // REL: [B,h,Tq,2m+1] = (q_i + v_h) . P[r,h]  (pre-kernel)
+  // REL: table of (q_i + v_h) . P[r,h] for the 2m+1 clamped offsets, f32 or bf16, element (b, i, head, r) at
+  // reltab[b*rel_sb + i*rel_ld + head*rel_hs + r]; rel_slab = floats of shared memory per softmax group for it
+  const void* reltab; int rel_bf16; int64_t rel_ld, rel_sb, rel_hs; int max_rel; int rel_slab;
   // optional per-utterance hints (key masks only): keys >= kv_len[b] are all masked (their tiles are
   // skipped: exactly zero weight), query rows >= q_len[b] are not needed by the caller (zero-filled)
   const int32_t* kv_len; const int32_t* q_len;
@@ -374,9 +379,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       // at most RESCALE_LOG2, so P stays below 2^8 and O / l_run need no per-tile correction.
       float m_run = -INFINITY, l_run = 0.f;
       // relative-position term (modules/attention.py:104-143): score += (q_i+v).P[clamp(j-i,-m,m)+m]
+      // Each thread copies its own row's 2m+1 entries into its group's slab of shared memory, SKEWED: entry r of
+      // local row il goes to [(il + r) * nrel + r], i.e. to [(j - j_first) * nrel + r] for the key j = i - m + r it
+      // applies to -- the lanes of a warp (consecutive query rows) gathering the band entries of ONE key then read
+      // consecutive words.  The loads fly while the first score tile is being computed.
       const int nrel = 2 * p.max_rel + 1;
-      const float* rb = REL ? p.relbias + (((int64_t)b * p.h + hh) * p.Tq + (qi < p.Tq ? qi : p.Tq - 1)) * nrel : nullptr;
-      const float rel_left = REL ? rb[0] : 0.f, rel_right = REL ? rb[nrel - 1] : 0.f;
+      const int qic = qi < p.Tq ? qi : p.Tq - 1;
+      float* slab = reinterpret_cast<float*>(smem + OFF_BAR + 1024) + g * p.rel_slab;
+      float rel_left = 0.f, rel_right = 0.f;
+      if (REL) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");       // the previous item's gathers are done
+        const int64_t src = (int64_t)b * p.rel_sb + (int64_t)qic * p.rel_ld + (int64_t)hh * p.rel_hs;
+        float* dst = slab + row * nrel;
+        if (p.rel_bf16) {
+          const __nv_bfloat16* t16 = reinterpret_cast<const __nv_bfloat16*>(p.reltab) + src;
+#pragma unroll 4
+          for (int r = 0; r < nrel; ++r) {
+            const float v = __bfloat162float(t16[r]);
+            dst[r * (nrel + 1)] = v;
+            if (r == 0) rel_left = v;
+            rel_right = v;
+          }
+        } else {
+          const float* t32 = reinterpret_cast<const float*>(p.reltab) + src;
+#pragma unroll 4
+          for (int r = 0; r < nrel; ++r) {
+            const float v = __ldg(t32 + r);
+            dst[r * (nrel + 1)] = v;
+            if (r == 0) rel_left = v;
+            rel_right = v;
+          }
+        }
+      }
+      const int i_lo = min(qt * QT + (warp & 3) * 32, p.Tq - 1), i_hi = min(qt * QT + (warp & 3) * 32 + 31, p.Tq - 1);   // this warp's rows
       bool any_keep = false;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(bar(B_SFULL + g), s_cnt & 1);
@@ -384,6 +419,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
         fence_after();
         const int k0 = j * KT;
         const uint32_t s_addr = tm_s(g) + lane_addr;
+        if (REL && j == 0) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // every row of the slab is written
+        if (REL) {
+          // Band pre-pass: the 32-key chunks in which some row of this warp is within +-max_rel of a key get the
+          // gathered term added IN TENSOR MEMORY (load, add, store back) -- a chunk's TMEM column is a run-time
+          // address, so ONE copy of the gather code serves all chunks (unrolled into the register-resident score
+          // row below it quadrupled the loop body and the kernel became instruction-fetch bound).
+#pragma unroll 1
+          for (int c = 0; c < KT; c += 32) {
+            if (k0 + c + 31 - i_lo <= -p.max_rel || k0 + c - i_hi >= p.max_rel || k0 + c >= p.Tk) continue;
+            float sb[32];
+            tmem_ld32(s_addr + c, sb);
+            const int r0 = k0 + c - qic + p.max_rel;                        // table column of the chunk's first key
+            const int lr0 = k0 + c + p.max_rel - qt * QT;                   // slab row of the chunk's first key
+            float bv[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int rc = min(max(r0 + q, 0), nrel - 1);
+              bv[q] = slab[min(max(lr0 + q, 0), QT + 2 * p.max_rel - 1) * nrel + rc];   // (clamped entries are not used)
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int r = r0 + q;
+              sb[q] += r < 0 ? rel_left : (r >= nrel ? rel_right : bv[q]);
+            }
+            tmem_st32(s_addr + c, reinterpret_cast<uint32_t*>(sb));
+            tmem_wait_st();
+          }
+        }
         float t[KT];                                               // this thread's score row of the tile
 #pragma unroll
         for (int c = 0; c < KT; c += 32) tmem_ld32(s_addr + c, t + c);
@@ -406,18 +470,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
           off[ci] = 0.f;
           if (REL) {
             // away from the diagonal every key of the chunk clamps to the same table entry (ONE offset, folded into
-            // the exponent for free); only chunks that straddle the +-max_rel band gather per element
-            const int d_lo = k0 + c - qi;                                   // j - i of the chunk's first key
-            if (__all_sync(0xffffffffu, d_lo + 31 <= -p.max_rel)) off[ci] = rel_left;
-            else if (__all_sync(0xffffffffu, d_lo >= p.max_rel)) off[ci] = rel_right;
-            else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) {
-                int r = d_lo + q;
-                r = r < -p.max_rel ? -p.max_rel : (r > p.max_rel ? p.max_rel : r);
-                tc[q] += __ldg(rb + r + p.max_rel);
-              }
-            }
+            // the exponent for free); chunks that straddle the +-max_rel band got their terms in the pre-pass above
+            if (k0 + c + 31 - i_lo <= -p.max_rel) off[ci] = rel_left;
+            else if (k0 + c - i_hi >= p.max_rel) off[ci] = rel_right;
             any_keep = any_keep || ((keep & valid) != 0u);
           }
           if (BITS && uniform_row) {
@@ -613,7 +668,7 @@ __global__ void __launch_bounds__(128) rel_bias_kernel(const __nv_bfloat16* __re
 static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
                                const uint32_t* mask_bits, int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
-                               void* out, int64_t ldo, int64_t sbo, const float* relbias, int max_rel,
+                               void* out, int64_t ldo, int64_t sbo, const RelTable* rel, int max_rel,
                                const int32_t* kv_len, const int32_t* q_len, const int32_t* order, int causal,
                                cn_stream_t stream_) {
   if (!Q || !K || !V || !out || B < 0 || h <= 0 || Tq < 0 || Tk <= 0) return CN_ERR_BAD_ARG;
@@ -635,11 +690,21 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   AttnTcArgs p;
   p.mask = mask_bits ? nullptr : mask; p.mb = mb; p.mask_bits = mask_bits; p.q_bcast = q_bcast ? 1 : 0;
   p.B = (int)B; p.h = (int)h; p.Tq = (int)Tq; p.Tk = (int)Tk;
-  p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.relbias = relbias; p.max_rel = max_rel;
+  p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.sbo = sbo; p.max_rel = max_rel;
+  p.reltab = nullptr; p.rel_bf16 = 0; p.rel_ld = p.rel_sb = p.rel_hs = 0; p.rel_slab = 0;
+  size_t smem_bytes = SMEM_BYTES;
+  const bool relbias = rel != nullptr;
+  if (relbias) {
+    const int64_t slab = (int64_t)(QT + 2 * max_rel) * (2 * max_rel + 1);      // floats per softmax group
+    if (SMEM_BYTES + 2 * slab * 4 > 227 * 1024) return CN_ERR_UNSUPPORTED;      // max_rel <= 22
+    p.reltab = rel->data; p.rel_bf16 = rel->bf16; p.rel_ld = rel->ld; p.rel_sb = rel->sb; p.rel_hs = rel->hs;
+    p.rel_slab = (int)slab;
+    smem_bytes += 2 * slab * 4;
+  }
   p.kv_len = (mask || mask_bits) ? kv_len : nullptr; p.q_len = q_len; p.order = order; p.causal = causal;
   static bool configured = false;
   if (!configured) {
-    const int sm = (int)SMEM_BYTES;
+    const int sm = 227 * 1024;
     const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
     if (cudaFuncSetAttribute(attention_tc_kernel<false, false, false>, at, sm) != cudaSuccess ||
         cudaFuncSetAttribute(attention_tc_kernel<false, false, true>, at, sm) != cudaSuccess ||
@@ -657,8 +722,8 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   if (relbias && mask_bits) return CN_ERR_UNSUPPORTED;
   const bool ring = Tk > MAX_TILES * KT;
   cudaStream_t st = (cudaStream_t)stream_;
-  if (relbias && ring) attention_tc_kernel<true, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
-  else if (relbias) attention_tc_kernel<true, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  if (relbias && ring) attention_tc_kernel<true, false, true><<<grid, NTHREADS, smem_bytes, st>>>(mq, mk, mv, p);
+  else if (relbias) attention_tc_kernel<true, false, false><<<grid, NTHREADS, smem_bytes, st>>>(mq, mk, mv, p);
   else if (mask_bits) attention_tc_kernel<false, true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   else if (ring) attention_tc_kernel<false, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
   else attention_tc_kernel<false, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
@@ -695,7 +760,7 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
                                      void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
                                      const int32_t* kv_len, cn_stream_t stream_) {
   if (!rel_pos || !rel_bias_u || !rel_bias_v || !workspace || max_rel < 0 || !Q) return CN_ERR_BAD_ARG;
-  if (h > 8 || max_rel > 64 || dk != DK) return CN_ERR_UNSUPPORTED;
+  if (h > 8 || max_rel > 22 || dk != DK) return CN_ERR_UNSUPPORTED;
   if (workspace_bytes < cn_rel_attention_workspace_bytes(B, h, Tq, max_rel)) return CN_ERR_WORKSPACE;
   if (B == 0 || Tq == 0) return CN_OK;
   float* relbias = (float*)workspace;
@@ -704,6 +769,21 @@ extern "C" int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, co
                     (cudaStream_t)stream_>>>((const __nv_bfloat16*)Q, ldq, sbq, rel_pos, rel_bias_u, rel_bias_v, (int)B, (int)h,
                                              (int)Tq, nrel, relbias);
   CN_CHECK_LAUNCH();
+  const RelTable rel = {relbias, 0, nrel, h * Tq * nrel, Tq * nrel};            // [B,h,Tq,2m+1] f32
   return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
-                             relbias, (int)max_rel, kv_len, nullptr, nullptr, 0, stream_);
+                             &rel, (int)max_rel, kv_len, nullptr, nullptr, 0, stream_);
+}
+
+extern "C" int cn_rel_attention_bf16_table(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                                           const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb,
+                                           int64_t mi, const void* table, int table_is_bf16, int64_t table_ld,
+                                           int64_t table_sb, int64_t table_hs, int64_t max_rel, int64_t B, int64_t h,
+                                           int64_t Tq, int64_t Tk, int64_t dk, void* out, int64_t ldo, int64_t sbo,
+                                           const int32_t* kv_len, cn_stream_t stream_) {
+  if (!table || max_rel < 0 || !Q) return CN_ERR_BAD_ARG;
+  if (h > 8 || max_rel > 22 || dk != DK) return CN_ERR_UNSUPPORTED;
+  if (B == 0 || Tq == 0) return CN_OK;
+  const RelTable rel = {table, table_is_bf16 ? 1 : 0, table_ld, table_sb, table_hs};
+  return attention_bf16_impl(Q, ldq, sbq, K, ldk, sbk, V, ldv, sbv, mask, mb, mi, nullptr, B, h, Tq, Tk, dk, out, ldo, sbo,
+                             &rel, (int)max_rel, kv_len, nullptr, nullptr, 0, stream_);
 }

@@ -154,7 +154,7 @@ struct Epilogue {
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
   if (ACT == CN_ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == CN_ACT_SWISH) return v / (1.f + __expf(-v));
+  if (ACT == CN_ACT_SWISH) return __fdividef(v, 1.f + __expf(-v));      // (IEEE division: ~10 more instructions per element)
   return v;
 }
 

@@ -181,15 +181,45 @@ class RelMultiHeadedAttention(nn.Module):
     project_qkv = MultiHeadedAttention.project_qkv
     output = MultiHeadedAttention.output
 
-    def project_qkv_rel(self, x):
+    def project_qkv_rel(self, x, table=None, m=0):
         """Fused QKV projection for the tcgen05 relative attention: bf16 out, pos_bias_u folded into
-        the query bias so that the kernel's Q operand is q + u."""
-        w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
-        bq_u = _cat_cached(self, "q_bias_u", [self.linears[0].bias, self.pos_bias_u.reshape(-1)])
+        the query bias so that the kernel's Q operand is q + u.
+
+        With `table` ([2m+1, d] distinct rows of the clamped relative-position embedding) the projection also
+        emits the relative term's table (q_i + v_h) . P[r,h] (attention.py:115-117 before the shift) as
+        h*(2m+1) extra output columns: P = linear_pos(table) and linear_q are both linear in x, so
+        (x Wq_h^T + bq_h + v_h) . P[r,h] = x . (Wq_h^T P[r,h]) + (bq_h + v_h) . P[r,h] -- a folded weight, built once
+        per weight version.  Returns (q, k, v, table_view [B,L,h*(2m+1)] bf16)."""
         d = self.h * self.d_k
-        b = _cat_cached(self, "qkv_b_rel", [bq_u[:d] + bq_u[d:], self.linears[1].bias, self.linears[2].bias])
+        if table is None:
+            w = _cat_cached(self, "qkv_w", [l.weight for l in self.linears[:3]])
+            bq_u = _cat_cached(self, "q_bias_u", [self.linears[0].bias, self.pos_bias_u.reshape(-1)])
+            b = _cat_cached(self, "qkv_b_rel", [bq_u[:d] + bq_u[d:], self.linears[1].bias, self.linears[2].bias])
+            qkv = ops.linear(x, w, b, out_bf16=True)
+            return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        params = [l.weight for l in self.linears[:3]] + [l.bias for l in self.linears[:3]] + \
+                 [self.pos_bias_u, self.pos_bias_v, self.linear_pos.weight, table]
+        stamp = tuple((t.data_ptr(), t._version, t.device) for t in params) + (int(m),)
+        cache = self.__dict__.setdefault("_cn_cache", {})
+        hit = cache.get("qkv_rel_table")
+        if hit is None or hit[0] != stamp:
+            with torch.no_grad():
+                nrel = 2 * int(m) + 1
+                wq, bq = self.linears[0].weight.detach().float(), self.linears[0].bias.detach().float()
+                P = torch.matmul(table.detach().float(), self.linear_pos.weight.detach().float().t())     # [nrel, d]
+                P = P.view(nrel, self.h, self.d_k)
+                w_rel = torch.einsum("rhk,hkd->hrd", P, wq.view(self.h, self.d_k, -1)).reshape(self.h * nrel, -1)
+                b_rel = torch.einsum("rhk,hk->hr", P, bq.view(self.h, self.d_k) + self.pos_bias_v.detach().float()).reshape(-1)
+                pad = (-self.h * nrel) % 8                 # keep the fused buffer's row pitch a multiple of 16 bytes
+                w = torch.cat([l.weight.detach().float() for l in self.linears[:3]] +
+                              [w_rel, w_rel.new_zeros(pad, w_rel.size(1))], 0).contiguous()
+                b = torch.cat([bq + self.pos_bias_u.detach().float().reshape(-1), self.linears[1].bias.detach().float(),
+                               self.linears[2].bias.detach().float(), b_rel, b_rel.new_zeros(pad)], 0).contiguous()
+            hit = (stamp, w, b, nrel)
+            cache["qkv_rel_table"] = hit
+        _, w, b, nrel = hit
         qkv = ops.linear(x, w, b, out_bf16=True)
-        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        return qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:3 * d], qkv[..., 3 * d:3 * d + self.h * nrel]
 
     def forward(self, query, key, value, mask=None, pos_embed=None):
         """pos_embed: [2L-1, d] rows of the clamped relative-position table (what

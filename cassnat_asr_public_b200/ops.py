@@ -596,6 +596,9 @@ def dropout(x, p, training=True):
     return dropout_forward(x, p, site)
 
 
+REL_TC_MAX = 22           # largest max_rel of the tcgen05 relative attention (table rows staged in shared memory)
+
+
 def attention(q, k, v, mask, n_head, rel=None, out=None, p_drop=0.0):
     """Masked multi-head attention on projected q [B,Tq,d], k/v [B,Tk,d] (views with a row stride
     are fine, e.g. slices of a fused QKV buffer).  mask: [B,1,Tk] or [B,Tq,Tk], 0 = masked.
@@ -628,10 +631,10 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     if q.dtype == torch.bfloat16:
         key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1
         if dk == 64 and Tk <= (2048 if key_mask else 512) and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and \
-                (rel is None or (n_head <= 8 and rel[3] <= 64 and key_mask)):
+                (rel is None or (n_head <= 8 and rel[3] <= REL_TC_MAX and key_mask)):
             return _attention_bf16(q, k, v, mask, n_head, rel)      # rel: q must already hold q + pos_bias_u
         if rel is not None and key_mask:
-            raise RuntimeError("bf16 relative attention outside the tcgen05 kernel's range (Tk<=512, h<=8, m<=64)")
+            raise RuntimeError("bf16 relative attention outside the tcgen05 kernel's range (h<=8, m<=22)")
         q, k, v = q.float(), k.float(), v.float()        # (rel + per-row mask: fp32 kernel, q without pos_bias_u)
     if out is None:
         out = torch.empty(B, Tq, d, dtype=torch.float32, device=q.device)
@@ -639,7 +642,7 @@ def attention_forward(q, k, v, mask, n_head, rel=None, out=None):
     rp = ru = rv = None
     mr = 0
     if rel is not None:
-        rp, ru, rv, mr = rel
+        rp, ru, rv, mr = rel[:4]
         rp, ru, rv = rp.contiguous(), ru.contiguous(), rv.contiguous()
     call("cn_attention_f32", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
          ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(rp), ptr(ru), ptr(rv), int(mr),
@@ -920,8 +923,17 @@ def _attention_bf16(q, k, v, mask, n_head, rel=None):
              out.stride(0), None, None, int(bool(getattr(mask, "_cn_causal", False)) and Tq == Tk), stream(),
              work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
         return out
+    if rel is not None and len(rel) > 4 and rel[4] is not None:
+        tab, mr = rel[4], rel[3]                      # [B,Tq,h*(2m+1)] view of the fused projection's extra columns
+        assert tab.dtype in (torch.bfloat16, torch.float32) and tab.stride(2) == 1
+        call("cn_rel_attention_bf16_table", ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0),
+             ptr(v), v.stride(1), v.stride(0), ptr(m), mb, mi, ptr(tab), int(tab.dtype == torch.bfloat16), tab.stride(1),
+             tab.stride(0), 2 * int(mr) + 1, int(mr), B, n_head, Tq, Tk, d // n_head, ptr(out), out.stride(1),
+             out.stride(0), ptr(kv_len), stream(),
+             work=dict(flops=4.0 * B * Tq * Tk * d, bytes=2.0 * B * d * (2 * Tq + 2 * Tk)))
+        return out
     if rel is not None:
-        rp, ru, rv, mr = rel
+        rp, ru, rv, mr = rel[:4]
         ws_bytes = _lib.load().cn_rel_attention_workspace_bytes(B, n_head, Tq, int(mr))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
         rp, ru, rv = rp.float().contiguous(), ru.contiguous(), rv.contiguous()

@@ -390,7 +390,8 @@ int cn_attention_bf16_bits(const void* Q, int64_t ldq, int64_t sbq, const void* 
  * [2m+1, h*64] = linear_pos(embedding rows); rel_bias_u / rel_bias_v f32 [h,64].  A pre-kernel
  * tabulates (q_i + v_h).P[r,h] into the workspace; the attention kernel adds
  * table[clamp(j-i,-m,m)+m] to the scores and re-zeroes fully masked rows (attention.py:138).
- * h <= 8, max_rel <= 64.  workspace: cn_rel_attention_workspace_bytes(B,h,Tq,max_rel). */
+ * h <= 8, max_rel <= 22 (the table rows of a query tile are staged in shared memory).
+ * workspace: cn_rel_attention_workspace_bytes(B,h,Tq,max_rel). */
 int64_t cn_rel_attention_workspace_bytes(int64_t B, int64_t h, int64_t Tq, int64_t max_rel);
 int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
                           const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
@@ -398,6 +399,16 @@ int cn_rel_attention_bf16(const void* Q, int64_t ldq, int64_t sbq, const void* K
                           int64_t B, int64_t h, int64_t Tq, int64_t Tk, int64_t dk,
                           void* out, int64_t ldo, int64_t sbo, void* workspace, int64_t workspace_bytes,
                           const int32_t* kv_len, cn_stream_t stream);
+/* Same attention on a table the caller already has: element (b, i, head, r) = (q_i + v_head).P[r,head] at
+ * table[b*table_sb + i*table_ld + head*table_hs + r], f32 or bf16 (table_is_bf16).  The host side folds
+ * linear_q, linear_pos and pos_bias_v into h*(2m+1) extra output columns of the fused QKV projection
+ * (modules.RelMultiHeadedAttention.project_qkv_rel), so the table costs no launch of its own. */
+int cn_rel_attention_bf16_table(const void* Q, int64_t ldq, int64_t sbq, const void* K, int64_t ldk, int64_t sbk,
+                                const void* V, int64_t ldv, int64_t sbv, const uint8_t* mask, int64_t mb, int64_t mi,
+                                const void* table, int table_is_bf16, int64_t table_ld, int64_t table_sb,
+                                int64_t table_hs, int64_t max_rel, int64_t B, int64_t h, int64_t Tq, int64_t Tk,
+                                int64_t dk, void* out, int64_t ldo, int64_t sbo, const int32_t* kv_len,
+                                cn_stream_t stream);
 
 /* K11  sampled-alignment rescoring: per sample the mean ranker log-probability of the predicted ids
  * over the valid tokens (exact zeros do not count), then the first arg-max over the S samples.

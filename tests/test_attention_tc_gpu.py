@@ -54,9 +54,11 @@ def test_attention_tc_on_fused_buffers():
     assert rel(got.float(), want) < 2e-2
 
 
-@pytest.mark.parametrize("B,U,h,m", [(2, 90, 2, 8), (3, 300, 4, 20), (2, 500, 8, 8)])
-def test_rel_attention_tc(B, U, h, m):
-    """tcgen05 relative-position attention vs the oracle's rel_mha core on bf16-rounded q/k/v."""
+@pytest.mark.parametrize("table", ["pre-kernel", "f32", "bf16"])
+@pytest.mark.parametrize("B,U,h,m", [(2, 90, 2, 8), (3, 300, 4, 20), (2, 500, 8, 8), (2, 130, 2, 22), (1, 5, 1, 4)])
+def test_rel_attention_tc(B, U, h, m, table):
+    """tcgen05 relative-position attention vs the oracle's rel_mha core on bf16-rounded q/k/v; the relative term's
+    table either from the pre-kernel or handed in (what the fused projection's extra columns hold), f32 or bf16."""
     d = 64 * h
     torch.manual_seed(U + m)
     q, k, v = (torch.randn(B, U, d).bfloat16() for _ in range(3))
@@ -77,8 +79,14 @@ def test_rel_attention_tc(B, U, h, m):
     want = (torch.softmax(s, -1).masked_fill(mm, 0.0) @ vh).transpose(1, 2).reshape(B, U, d)
     # kernel: Q operand = q + u (what project_qkv_rel produces)
     q_u = (q.float().view(B, U, h, 64) + u_b[None, None]).reshape(B, U, d).bfloat16()
-    got = ops.attention(q_u.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV), h,
-                        (relp.to(DEV), u_b.to(DEV), v_b.to(DEV), m))
+    rel_args = (relp.to(DEV), u_b.to(DEV), v_b.to(DEV), m)
+    if table != "pre-kernel":
+        # (q + v).P for the bf16-rounded q, laid out [B,U,h*(2m+1)] inside a wider buffer (row pitch != width)
+        tab = qp.float().permute(0, 2, 1, 3).reshape(B, U, h * (2 * m + 1))
+        wide = torch.zeros(B, U, h * (2 * m + 1) + 24, dtype=torch.bfloat16 if table == "bf16" else torch.float32)
+        wide[..., 8:8 + tab.size(-1)] = tab
+        rel_args = (None, u_b.to(DEV), v_b.to(DEV), m, wide.to(DEV)[..., 8:8 + tab.size(-1)])
+    got = ops.attention(q_u.to(DEV), k.to(DEV), v.to(DEV), mask.to(DEV), h, rel_args)
     assert got.dtype == torch.bfloat16
     # (q+u) is rounded to bf16 once more than in the reference: tolerance 3e-2 of the output's max
     assert rel(got.float(), want) < 3e-2

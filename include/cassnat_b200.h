@@ -201,7 +201,9 @@ int64_t cn_segment_attention_workspace_bytes(int64_t B, int64_t U, int64_t d /* 
  * GroupNorm(1,C) over the whole padded [C,L] slab of each utterance -> activation.
  *   replaces: F.glu / depthwise_conv / GroupNorm / Swish      src/models/modules/conformer_related.py:33-38
  * y f32 or bf16 [B,L,2C] (row stride ldy, batch stride sby) = pointwise_conv1 output; dw_weight [C,ksz];
- * out f32 [B,L,C] contiguous.  workspace: cn_conv_module_workspace_bytes(B,L). */
+ * out f32 [B,L,C] contiguous; out_bf16 (optional) receives the result as bf16 -- with bf16 y and kernel sizes
+ * 3/7 the convolution is then evaluated twice from y (statistics, then normalise-and-store) instead of being
+ * written to `out`, whose contents are unspecified in that case.  workspace: cn_conv_module_workspace_bytes(B,L). */
 int64_t cn_conv_module_workspace_bytes(int64_t B, int64_t L);
 int cn_glu_dwconv_groupnorm_act(const void* y, int y_is_bf16, int64_t ldy, int64_t sby, const float* dw_weight,
                                 const float* dw_bias, const float* gamma, const float* beta, float eps, int act,

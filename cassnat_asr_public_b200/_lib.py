@@ -61,6 +61,7 @@ SIGNATURES = {
     "cn_rel_attention_bf16_table": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64,
                                            _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64,
                                            _vp, _vp]),
+    "cn_set_sm_limit": (_int, [_int]),
     "cn_rescore_select": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "cn_ctc_loss_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "cn_ctc_loss": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _f32, _vp, _vp,

@@ -676,6 +676,7 @@ bool make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_sm_limit = 0;          // cn_set_sm_limit: CTAs of the persistent GEMMs (0 = one per SM)
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -684,7 +685,7 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 template <int BN, int ACT, bool RES, bool STATS = false, bool A_MN = false, bool B_MN = false, int LNM = LNM_NONE>
@@ -1355,4 +1356,10 @@ extern "C" int cn_cast_bf16(const float* x, void* y, int64_t n, cn_stream_t stre
   cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, (__nv_bfloat16*)y, n / 4);
   CN_CHECK_LAUNCH();
   return CN_OK;
+}
+
+extern "C" int cn_set_sm_limit(int n_ctas) {
+  const int before = g_sm_limit;
+  g_sm_limit = n_ctas > 0 ? n_ctas : 0;
+  return before;
 }

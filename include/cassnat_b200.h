@@ -544,6 +544,12 @@ int cn_gemm_bf16_mn(const void* A, int64_t lda, int a_mn, const void* W, int64_t
 int cn_transpose_bf16(const void* in, int in_is_bf16, int64_t ldi, int64_t R, int64_t C, void* out, int64_t ldo,
                       cn_stream_t stream);
 
+/* Data-parallel training: caps the CTA count of the persistent tensor-core GEMMs (0 = one per SM, the default) so
+ * that a collective running on another stream (the bucketed gradient all_reduce of tasks/base_task.py:82-83's DDP)
+ * finds free SMs while backward is still running.  Returns the previous value.  Takes effect at the next launch
+ * (a captured CUDA graph keeps the grid it was captured with). */
+int cn_set_sm_limit(int n_ctas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,7 +169,7 @@ class CassNAT(nn.Module):
         return self.encoder(x, src_mask), src_mask
 
     def decode_from_encoder(self, enc_h, src_mask, src_size, vocab, args, lm_model=None, labels=None,
-                            label_sizes=None, return_intermediates=False):
+                            label_sizes=None, return_intermediates=False, features=None):
         """Everything CassNAT.beam_decode does after the encoder (cassnat.py:433-637).
         src_size is the length RATIO tensor the reference takes (frames = (ratio*T).long(), :436)."""
         beam = args.lm_weight > 0 or args.beam_width != 1        # cassnat.py:600-636: per-position top-k (+ token-level LM)
@@ -229,7 +229,8 @@ class CassNAT(nn.Module):
             keep.update(aligned=aligned, seg=seg, ylen=ylen, ymax=ymax,
                         ac_embed=first(ac_embed), pred_embed=first(pred_embed), dec_h=dec_h, ids=ids, logp=logp)
         if S > 1:
-            ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax)
+            ids, logp, ylen, ymax, best = self._rescore(ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax,
+                                                        vocab=vocab, features=features)
             keep["best_sample"] = best
         if beam:
             out = self._assemble_beam(self.att_generator(dec_h).float(), ylen, ymax, args, lm_model, sos)
@@ -470,16 +471,31 @@ class CassNAT(nn.Module):
              int(blank), int(S if S > 1 else 0), float(threshold), 1, ptr(aligned), ptr(ylen), ptr(ymax), stream())
         return aligned, ylen, int(ymax.item())          # the one host sync the API needs (cassnat.py:387)
 
-    def _rescore(self, ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax):
-        """cassnat.py:499-561 with rank_model in {'lm','at_baseline'-style callable}: the ranker is a
-        stock PyTorch module supplied by the caller; K11 = gather/mean/argmax."""
-        if args.rank_model != "lm":
+    def _rescore(self, ids, logp, ylen, tgt_mask, lm_model, args, sos, B, S, ymax, vocab=None, features=None):
+        """cassnat.py:499-561: the S sampled hypotheses of an utterance are ranked by `lm_model`, the caller's stock
+        module, and the best one is kept.  rank_model 'lm' (a language model on the predicted ids,
+        :510-512), 'at_baseline' (an autoregressive ASR model re-encoding the utterance's features and scoring the
+        ids with its decoder, :513-519; `features` = the (src, x_mask) beam_decode was called with) or 'n-gram'
+        (`lm_model.score(sentence)` on the detokenised text, host side like the reference, :525-536).
+        K11 = gather / mean / first arg-max."""
+        if args.rank_model == "n-gram":
+            return self._rescore_ngram(ids, logp, ylen, tgt_mask, lm_model, vocab, B, S)
+        if args.rank_model not in ("lm", "at_baseline"):
             raise NotImplementedError(f"rank_model={args.rank_model!r}")
+        if args.rank_model == "at_baseline" and features is None:
+            raise ValueError("rank_model='at_baseline' re-encodes the features: call beam_decode, or pass features=(src, x_mask)")
         ids64 = ids.long()
         lm_in = torch.cat([torch.full((B * S, 1), sos, dtype=torch.long, device=ids.device), ids64[:, :-1]], 1)
         causal = torch.tril(torch.ones(ymax, ymax, dtype=torch.uint8, device=ids.device)).unsqueeze(0)
         lm_mask = tgt_mask & causal
-        if hasattr(lm_model, "score_tokens") and S <= 32:
+        if args.rank_model == "at_baseline":
+            src, x_mask = features
+            x, at_mask = lm_model.src_embed(src, x_mask)                                   # :515-519
+            at_h = lm_model.encoder(x, at_mask)
+            at_h = at_h.unsqueeze(1).repeat(1, S, 1, 1).reshape(-1, at_h.size(1), at_h.size(2))
+            at_mask = at_mask.unsqueeze(1).repeat(1, S, 1, 1).reshape(-1, at_mask.size(1), at_mask.size(2))
+            lm_out = lm_model.forward_decoder(at_h, lm_in, at_mask, lm_mask.to(at_mask.dtype))
+        elif hasattr(lm_model, "score_tokens") and S <= 32:
             # this package's LM mirror: log p(id) per position straight from the fused head epilogue (fast mode),
             # the [B*S,U,V] tensor is never materialised; K11 then runs on the [B*S,U] scores (V = 1, id 0)
             sc = lm_model.score_tokens(lm_in, lm_mask, ids, causal=True).float().contiguous()
@@ -515,12 +531,30 @@ class CassNAT(nn.Module):
         ylen = ylen.reshape(B, S).gather(1, best).squeeze(1)
         return ids, logp, ylen, int(ylen.max().item()), best.squeeze(1)
 
+    def _rescore_ngram(self, ids, logp, ylen, tgt_mask, lm_model, vocab, B, S):
+        """cassnat.py:525-536: every sampled hypothesis is detokenised on the host (eos pieces dropped, sentencepiece
+        word marks turned into blanks) and scored by the caller's n-gram model; score / length, first maximum."""
+        tgt_len = tgt_mask.reshape(B * S, -1).sum(-1).cpu()
+        ids_h = ids.cpu().tolist()
+        prob_sum = torch.zeros(B * S)
+        for i in range(B * S):
+            n = int(tgt_len[i])
+            pieces = [vocab.index2word[t] for t in ids_h[i][:n] if t != 2]
+            prob_sum[i] = lm_model.score("".join(pieces).replace("\u2581", " ").strip()) / tgt_len[i]
+        best = prob_sum.reshape(B, S).max(-1, keepdim=True)[1].to(ids.device)                # [B,1]
+        pick = lambda x: x.reshape(B, S, -1).gather(1, best.unsqueeze(-1).expand(B, 1, x.shape[-1])).squeeze(1)
+        ids = pick(ids.masked_fill(tgt_mask.squeeze(1) == 0, 0))
+        logp = pick(logp.masked_fill(tgt_mask.squeeze(1) == 0, 0.0))
+        ylen = ylen.reshape(B, S).gather(1, best).squeeze(1)
+        return ids, logp, ylen, int(ylen.max().item()), best.squeeze(1)
+
     def beam_decode(self, src, x_mask, src_size, vocab, args, lm_model=None, ctc_top_seqs=None, labels=None,
                     label_sizes=None):
         """cassnat.py:420-637 -> (batch_top_seqs, args)."""
         with torch.no_grad():
             enc_h, src_mask = self.encode(src, x_mask)
-            return self.decode_from_encoder(enc_h, src_mask, src_size, vocab, args, lm_model, labels, label_sizes)
+            return self.decode_from_encoder(enc_h, src_mask, src_size, vocab, args, lm_model, labels, label_sizes,
+                                            features=(src, x_mask))
 
     def forward(self, src, src_mask, src_size, tgt_label, label_sizes, args):
         """cassnat.py:136-257 -> (ctc_out, att_out, loss, ctc_loss, att_loss).  With grad mode on and

@@ -119,6 +119,28 @@ def test_sampled_decode_with_ranker(blocks_golden):
     assert [o[0]["hyp"] for o in out] == hyps_of(z, "sampled")
 
 
+@pytest.mark.parametrize("kind", ["n-gram", "at_baseline"])
+def test_sampled_decode_other_rankers(kind):
+    """rank_model 'n-gram' / 'at_baseline' (cassnat.py:513-536): the hypotheses the UNMODIFIED reference produced with
+    the stand-in rankers of tests/golden/ranker_standins.py (tests/golden/make_golden_rankers.py), same CPU-generator
+    draw for the sampled alignments."""
+    import os, sys
+    from conftest import load_blocks
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from ranker_standins import TinyAT, TinyNgram, index2word
+    z, sd, cfg = load_blocks("trf")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankers.npz"))
+    model, args = build(sd, cfg, sample_num=3, threshold=0.9, rank_model=kind)
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    vocab = SimpleNamespace(word2index=VOCAB.word2index, index2word=index2word(cfg.vocab_size))
+    ranker = TinyNgram() if kind == "n-gram" else TinyAT(src.size(-1), cfg.vocab_size).to(DEV)
+    torch.manual_seed(555)
+    out, _ = model.beam_decode(src, mask, size, vocab, args, lm_model=ranker)
+    tag = kind.replace("-", "")
+    assert [o[0]["hyp"] for o in out] == hyps_of(g, tag)
+    assert np.allclose([o[0]["score"] for o in out], g[tag + "::score"], rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("mode", ["bf16", "bf16x3"])
 def test_bf16_tensor_core_mode(blocks_golden, mode):
     """Fast mode (bf16 operands on tcgen05, fp32 accumulation) and the precise tensor-core mode (bf16x3 GEMMs).

@@ -117,6 +117,21 @@ def make_model(input_size, args):
     return model
 
 
+class PendingHypotheses:
+    """Handle returned by decode_from_encoder(..., defer=True): the batch's device work is queued; result() waits for
+    its read-back and assembles the reference's `batch_top_seqs` (once)."""
+
+    def __init__(self, assemble, done):
+        self._assemble, self._done, self._out = assemble, done, None
+
+    def result(self):
+        if self._assemble is not None:
+            if self._done is not None:
+                self._done.synchronize()
+            self._out, self._assemble = self._assemble(), None
+        return self._out
+
+
 class CassNAT(nn.Module):
     def __init__(self, src_embed, encoder, acembed_extractor, embed_mapper, decoder, ctc_gen, att_gen, pe,
                  interctc_gen, interce_gen, args):
@@ -169,7 +184,7 @@ class CassNAT(nn.Module):
         return self.encoder(x, src_mask), src_mask
 
     def decode_from_encoder(self, enc_h, src_mask, src_size, vocab, args, lm_model=None, labels=None,
-                            label_sizes=None, return_intermediates=False, features=None):
+                            label_sizes=None, return_intermediates=False, features=None, defer=False):
         """Everything CassNAT.beam_decode does after the encoder (cassnat.py:433-637).
         src_size is the length RATIO tensor the reference takes (frames = (ratio*T).long(), :436)."""
         beam = args.lm_weight > 0 or args.beam_width != 1        # cassnat.py:600-636: per-position top-k (+ token-level LM)
@@ -234,15 +249,31 @@ class CassNAT(nn.Module):
             keep["best_sample"] = best
         if beam:
             out = self._assemble_beam(self.att_generator(dec_h).float(), ylen, ymax, args, lm_model, sos)
+            if defer:
+                return PendingHypotheses(lambda: out, None), args
             return (out, args, keep) if return_intermediates else (out, args)
         # ---- hypothesis assembly (cassnat.py:574-637 for beam_width 1): one D2H copy
         # one device->host transfer: [ids | logp bits | ylen] packed into a pinned int32 buffer
         U_ = ids.shape[1]
         packed = torch.cat([ids.reshape(B, U_).to(torch.int32), logp.reshape(B, U_).view(torch.int32),
                             ylen.reshape(B, 1).to(torch.int32)], 1)
-        host = self._pinned(packed.shape)
+        host = self._pinned(packed.shape, slot=self._next_slot() if defer else 0)
         host.copy_(packed, non_blocking=True)
+        if defer:
+            # serving loops: the device work of this batch is queued, the hypotheses are assembled when the caller
+            # asks for them -- typically after queueing the next batch, so that the host-side assembly overlaps it
+            done = torch.cuda.Event()
+            done.record()
+            return PendingHypotheses(lambda: self._assemble_greedy(host, U_, B, ymax, sos, args, dev), done), args
         torch.cuda.current_stream().synchronize()
+        out = self._assemble_greedy(host, U_, B, ymax, sos, args, dev)
+        if return_intermediates:
+            return out, args, keep
+        return out, args
+
+    @staticmethod
+    def _assemble_greedy(host, U_, B, ymax, sos, args, dev):
+        """cassnat.py:574-637 for beam_width 1 on the packed [ids | logp bits | ylen] rows read back from the device."""
         arr = host.numpy()
         ids_h, ylen_h = arr[:, :U_], arr[:, 2 * U_].tolist()
         # sequential float64 running sum == the reference's `seq['score'] + token_score` chain
@@ -255,9 +286,11 @@ class CassNAT(nn.Module):
             n = min(int(ylen_h[b]) + 1, ymax)          # the reference keeps i <= ylen[b] (one past eos)
             out.append([{"ys": ys0, "score": float(csum[b, n - 1]) if n else 0.0,
                          "hyp": [sos] + ids_h[b, :n].tolist()}])
-        if return_intermediates:
-            return out, args, keep
-        return out, args
+        return out
+
+    def _next_slot(self):
+        self.__dict__["_pin_slot"] = 1 + (self.__dict__.get("_pin_slot", 0) % 2)       # slots 1, 2 (0: synchronous calls)
+        return self.__dict__["_pin_slot"]
 
     def _assemble_beam(self, att_out, ylen, ymax, args, lm_model, sos):
         """cassnat.py:574-637 for beam_width > 1 and / or lm_weight > 0: every kept hypothesis is extended by the
@@ -443,13 +476,15 @@ class CassNAT(nn.Module):
                                                    if not n.startswith(("src_embed.", "encoder.", "ctc_generator."))]
         return hash(tuple([p._version for p in ps] + [p.data_ptr() for p in ps]))
 
-    def _pinned(self, shape):
-        """Reusable pinned int32 staging buffer for the hypothesis read-back."""
-        buf = self.__dict__.get("_pin_buf")
+    def _pinned(self, shape, slot=0):
+        """Reusable pinned int32 staging buffer for the hypothesis read-back (deferred calls alternate between two
+        buffers of their own: at most two batches are in flight)."""
+        bufs = self.__dict__.setdefault("_pin_bufs", {})
+        buf = bufs.get(slot)
         n = int(shape[0]) * int(shape[1])
         if buf is None or buf.numel() < n:
             buf = torch.empty(max(n, 1 << 16), dtype=torch.int32, pin_memory=True)
-            self.__dict__["_pin_buf"] = buf
+            bufs[slot] = buf
         return buf[:n].view(*shape)
 
     def _collapse(self, st, mask2, B, T, S, blank, threshold):

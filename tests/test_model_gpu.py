@@ -119,6 +119,29 @@ def test_sampled_decode_with_ranker(blocks_golden):
     assert [o[0]["hyp"] for o in out] == hyps_of(z, "sampled")
 
 
+def test_deferred_hypotheses(blocks_golden):
+    """decode_from_encoder(defer=True): the handle's result() equals the synchronous call's return value, also with
+    two batches in flight (each keeps its own read-back buffer) and with CUDA graphs on."""
+    name, z, sd, cfg = blocks_golden
+    model, args = build(sd, cfg)
+    src, mask, size = (torch.from_numpy(z[k]).to(DEV) for k in ("src", "src_mask", "src_size"))
+    with torch.no_grad():
+        enc_h, m2 = model.encode(src, mask)
+        enc_b, m2_b, size_b = enc_h[[1, 0, 3]].contiguous(), m2[[1, 0, 3]].contiguous(), size[[1, 0, 3]].contiguous()
+        for graphs in (False, True):
+            model.use_cuda_graphs = graphs
+            want_a, _ = model.decode_from_encoder(enc_h, m2, size, VOCAB, args)
+            want_b, _ = model.decode_from_encoder(enc_b, m2_b, size_b, VOCAB, args)
+            pa, _ = model.decode_from_encoder(enc_h, m2, size, VOCAB, args, defer=True)
+            pb, _ = model.decode_from_encoder(enc_b, m2_b, size_b, VOCAB, args, defer=True)
+            for pend, want in ((pa, want_a), (pb, want_b)):
+                got = pend.result()
+                assert got is pend.result()
+                assert [o[0]["hyp"] for o in got] == [o[0]["hyp"] for o in want]
+                assert [o[0]["score"] for o in got] == [o[0]["score"] for o in want]
+    model.use_cuda_graphs = False
+
+
 @pytest.mark.parametrize("kind", ["n-gram", "at_baseline"])
 def test_sampled_decode_other_rankers(kind):
     """rank_model 'n-gram' / 'at_baseline' (cassnat.py:513-536): the hypotheses the UNMODIFIED reference produced with

@@ -198,10 +198,26 @@ class CassNAT(nn.Module):
         mask2 = src_mask.reshape(B, T)
         frames = (src_size.to(dev) * T).long()                                       # :436 / :471
         keep = {}
+        graphable = (self.use_cuda_graphs and args.use_trigger and S == 1 and not args.use_unimask and not beam and
+                     not args.src_trigger and not getattr(args, "save_embedding", False) and not return_intermediates)
+        # host work the graph replay needs but that does not depend on the token count is done here, while the device
+        # is still busy with whatever was queued before this call (the replay itself has to wait for `ymax`)
+        stamp = self._weight_stamp() if graphable else None
         if ops.is_bf16():
             # one bf16 copy feeds the CTC head and every K/V projection; with decision-safe heads (or in bf16x3 mode)
-            # it is the hi half of a split operand whose lo half the CTC head also reads
-            enc_h = ops.cast_bf16(enc_h, split=ops.SAFE_HEADS or ops.is_x3())
+            # it is the hi half of a split operand whose lo half the CTC head also reads.  With graphs on it is written
+            # straight into the buffer the captured graph reads (no 65 MB copy into a static input per call).
+            split = ops.SAFE_HEADS or ops.is_x3()
+            buf = None
+            if graphable and enc_h.dtype == torch.float32 and d % 4 == 0:
+                bufs = self.__dict__.setdefault("_enc_static", {})
+                shape = (B, T, 2 * d if split else d)
+                buf = bufs.get(shape)
+                if buf is None:
+                    if len(bufs) >= self._GRAPH_CACHE_SIZE:
+                        bufs.pop(next(iter(bufs)))
+                    buf = bufs[shape] = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+            enc_h = ops.cast_bf16(enc_h, split=split, out=buf)
 
         # ---- K1 + K2: CTC head -> per-frame argmax/top-2 -> collapsed, shifted alignment
         if args.use_trigger and args.decode_type == "oracle_att":
@@ -231,10 +247,8 @@ class CassNAT(nn.Module):
         # ---- K4..K9: segments -> extractor -> SAD -> MAD -> head (optionally replayed as a CUDA graph)
         if beam and S > 1:
             raise NotImplementedError("beam_width > 1 / lm_weight > 0 together with sampled alignments")
-        graphable = (self.use_cuda_graphs and args.use_trigger and S == 1 and not args.use_unimask and not beam and
-                     not args.src_trigger and not getattr(args, "save_embedding", False) and not return_intermediates)
         if graphable:
-            ids, logp, ylen, ymax = self._stage_b_graphed(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
+            ids, logp, ylen, ymax = self._stage_b_graphed(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank, stamp)
             ac_embed = pred_embed = dec_h = seg = None
         else:
             ids, logp, ylen, ymax, ac_embed, pred_embed, dec_h, seg, tgt_mask = self._stage_b(
@@ -415,7 +429,7 @@ class CassNAT(nn.Module):
     graph_bucket = 0                 # opt-in: token-axis bucket size for graph reuse across batches (0 = exact length)
     _GRAPH_CACHE_SIZE = 4
 
-    def _stage_b_graphed(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank):
+    def _stage_b_graphed(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank, stamp=None):
         """Same as _stage_b, captured once per (batch, frames, tokens, precision) shape and replayed:
         ~150 kernel launches become one graph launch.  The first call of a shape runs eagerly (it also
         warms the weight caches) and captures for the following calls."""
@@ -432,7 +446,8 @@ class CassNAT(nn.Module):
             ymax = padded - 1
         # A captured graph holds raw pointers to derived weight copies (bf16 casts, fused QKV / KV concatenations):
         # every graph is dropped when any parameter was updated, replaced or moved since it was captured.
-        stamp = self._weight_stamp()
+        if stamp is None:
+            stamp = self._weight_stamp()
         cache = self.__dict__.setdefault("_graphs", {})
         if self.__dict__.get("_graphs_stamp") != stamp:
             cache.clear()
@@ -445,7 +460,9 @@ class CassNAT(nn.Module):
         live = (enc_full if enc_full is not None else enc_h, src_mask, frames, aligned, ylen)
         if hit is None:
             out = self._stage_b(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
-            statics = [t.clone() for t in live]
+            # (the encoder operand usually IS a persistent buffer already, see decode_from_encoder: captured in place)
+            persistent = any(live[0] is b for b in self.__dict__.get("_enc_static", {}).values())
+            statics = [t if (i == 0 and persistent) else t.clone() for i, t in enumerate(live)]
             s_enc = ops._hi_view(statics[0]) if enc_full is not None else statics[0]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -461,7 +478,8 @@ class CassNAT(nn.Module):
             return fix(out[:4])
         graph, statics, res, n_kernels = hit
         for dst, src in zip(statics, live):
-            dst.copy_(src, non_blocking=True)
+            if dst is not src:
+                dst.copy_(src, non_blocking=True)
         graph.replay()
         from . import _lib
         _lib.launch_count += n_kernels

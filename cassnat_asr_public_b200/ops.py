@@ -706,7 +706,7 @@ def glu_dwconv_groupnorm_act_forward(y, dw_weight, dw_bias, gamma, beta, eps, ac
 
 
 # ----------------------------------------------------------------------------- bf16 tensor-core path
-def cast_bf16_split(x, tag=True):
+def cast_bf16_split(x, tag=True, out=None):
     """f32 [.., K] -> split bf16 operand [.., 2K] = [hi | lo] (see cn_gemm_bf16x3).  Returns the hi half (a strided
     [.., K] view, usable wherever a plain bf16 tensor is) tagged with the full tensor; tag=False returns the full one."""
     require_cuda(x)
@@ -714,7 +714,8 @@ def cast_bf16_split(x, tag=True):
     x2 = x.reshape(-1, K)
     if x2.stride(-1) != 1 or x2.stride(0) % 4 or x2.data_ptr() % 16 or x2.dtype != torch.float32:
         x2 = x2.float().contiguous()
-    full = torch.empty(*x.shape[:-1], 2 * K, dtype=torch.bfloat16, device=x.device)
+    full = out if out is not None else torch.empty(*x.shape[:-1], 2 * K, dtype=torch.bfloat16, device=x.device)
+    assert full.shape == (*x.shape[:-1], 2 * K) and full.dtype == torch.bfloat16 and full.is_contiguous()
     call("cn_cast_bf16_split", ptr(x2), x2.stride(0), ptr(full), 2 * K, x2.shape[0], K, stream(),
          work=dict(bytes=8.0 * x2.shape[0] * K))
     return _hi_view(full) if tag else full
@@ -760,19 +761,21 @@ def linear_x3(x, weight, bias=None, residual=None, alpha=1.0, act=None, res_rows
     return _hi_view(o16) if split_out else o16
 
 
-def cast_bf16(x, split=False):
+def cast_bf16(x, split=False, out=None):
     """f32 -> bf16 copy (operands of the tensor-core GEMMs that arrive in fp32).  split=True also produces the lo
-    half (the returned tensor is the hi half of a split operand, see cast_bf16_split)."""
+    half (the returned tensor is the hi half of a split operand, see cast_bf16_split).  out: a caller-owned buffer of
+    the result's full shape ([.., 2K] for a split operand) -- used when it can be written directly."""
     require_cuda(x)
     if x.dtype == torch.bfloat16:
         return x
     if split and not _needs_grad(x) and x.shape[-1] % 4 == 0:
-        return cast_bf16_split(x)
+        return cast_bf16_split(x, out=out)
     if _needs_grad(x):
         from . import grad
         return grad.CastBf16.apply(x)
     xc = x.contiguous()
-    out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
+    if out is None or out.shape != xc.shape or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        out = torch.empty(xc.shape, dtype=torch.bfloat16, device=x.device)
     n = xc.numel()
     if n % 4 == 0:
         call("cn_cast_bf16", ptr(xc), ptr(out), n, stream(), work=dict(bytes=6.0 * n))

@@ -122,7 +122,10 @@ def run_reference(a, w):
     torch.manual_seed(1234)
     model = make_model(80, args)                    # parameter container only (never runs on this arm)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
-    sample = a.ref_sample                           # per step; sized so that --steps 50 ends within a minute
+    # utterances per step: the workload's full per-GPU batch when the whole run then stays within ~2.5 minutes of CPU
+    # work (about 14 utt/s on 16 cores), else a bounded sample of it
+    full = a.batch or w["batch"]
+    sample = a.ref_sample or max(8, min(full, int(150 * 14 / (a.steps + max(a.warmup, 1))) // 8 * 8))
     enc_h, mask, ratio, lens = synth_encoder_output(w, sample, 1234)
     frames = (ratio * enc_h.size(1)).long()
     cfg = SimpleNamespace(**vars(args))
@@ -339,6 +342,16 @@ def run_ours(a, w):
     roof["peak_source"] = pk["source"]
     roof["avg_launch_ms"] = d["ms"] / d["calls"]
     roof["share_of_step"] = d["ms"] / sum(v["ms"] for v in prof.values())
+    # the whole step: algorithmic flops over the step time, and the time-weighted roofline fraction of its kernels
+    # (each kernel against whichever of the two bounds it is closer to)
+    k_ms = sum(v["ms"] for v in prof.values())
+    step_ms = total_ms / a.steps
+    fr = lambda v: max(v["flops"] / (v["ms"] / 1e3) / 1e12 / pk["tensor"] if v["flops"] else 0.0,
+                       v["bytes"] / (v["ms"] / 1e3) / 1e9 / pk["hbm"] if v["bytes"] else 0.0)
+    roof["whole_step"] = {"algorithmic_tflop": sum(v["flops"] for v in prof.values()) / 1e12,
+                          "frac_tensor": sum(v["flops"] for v in prof.values()) / (step_ms / 1e3) / 1e12 / pk["tensor"],
+                          "kernel_time_weighted_frac": sum(v["ms"] * fr(v) for v in prof.values()) / k_ms,
+                          "kernel_ms": k_ms, "step_ms": step_ms}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and a.workload == "cfg3" and a.precision == "bf16" and B == w["batch"]:
         roof["traffic"] = json.load(open(tpath)).get(name)      # ncu capture of exactly this workload (profiles/)
@@ -361,9 +374,14 @@ def run_ours(a, w):
                     "ms_per_step": e2e_s / a.steps * 1e3, "h2d_alone_ms": h2d_alone_s * 1e3,
                     "h2d_alone_GBps": h2d / h2d_alone_s / 1e9},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            # per kernel: algorithmic flops and operand + result bytes over its CUDA-event time, each against the
+            # measured peak -- a kernel is at its roofline when EITHER fraction is near 1 (the d x d projections with
+            # their fp32 residual stream are bound by HBM, not by the tensor pipe)
             "kernels": {k: {"ms_per_step": round(v["ms"], 4), "calls_per_step": v["calls"],
-                            **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1)} if v["flops"] else
-                               {"GBps": round(v["bytes"] / v["ms"] / 1e6, 1)})}
+                            **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1),
+                                "frac_tensor": round(v["flops"] / v["ms"] / 1e9 / pk["tensor"], 3)} if v["flops"] else {}),
+                            **({"GBps": round(v["bytes"] / v["ms"] / 1e6, 1),
+                                "frac_hbm": round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)} if v["bytes"] else {})}
                         for k, v in sorted(prof_shapes.items(), key=lambda kv: -kv[1]["ms"])}}
     if per_rank is not None:
         line["ms_per_step_by_rank"] = per_rank
@@ -1054,7 +1072,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--precision", default=os.environ.get("CASSNAT_PRECISION", "bf16"), choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--cpu-sample", type=int, default=192, help="utterances of the cpu_baseline leg (~10-20 s of CPU work)")
-    ap.add_argument("--ref-sample", type=int, default=16, help="utterances per step of the --impl reference arm")
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="utterances per step of the --impl reference arm (0: the full batch if the run stays within minutes)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the per-GPU batch is fixed; strong: the workload's batch is split over the GPUs")
     ap.add_argument("--no-parity", action="store_true", help="skip the fast-mode vs parity-mode agreement report")

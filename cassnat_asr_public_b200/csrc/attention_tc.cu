@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  cn_pdl_wait();                 // (prologue above overlapped the predecessor's tail)
+  cn_pdl_launch();
   // TMEM columns: S_A 0..127 | S_B 128..255 | O_A 256..319 | O_B 320..383 | P_A 384..447 | P_B 448..511 (bf16 pairs)
   auto tm_s = [&](int g) { return tmem + g * 128; };
   auto tm_o = [&](int g) { return tmem + 256 + g * 64; };
@@ -722,11 +724,11 @@ static int attention_bf16_impl(const void* Q, int64_t ldq, int64_t sbq, const vo
   if (relbias && mask_bits) return CN_ERR_UNSUPPORTED;
   const bool ring = Tk > MAX_TILES * KT;
   cudaStream_t st = (cudaStream_t)stream_;
-  if (relbias && ring) attention_tc_kernel<true, false, true><<<grid, NTHREADS, smem_bytes, st>>>(mq, mk, mv, p);
-  else if (relbias) attention_tc_kernel<true, false, false><<<grid, NTHREADS, smem_bytes, st>>>(mq, mk, mv, p);
-  else if (mask_bits) attention_tc_kernel<false, true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
-  else if (ring) attention_tc_kernel<false, false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
-  else attention_tc_kernel<false, false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mq, mk, mv, p);
+  if (relbias && ring) cn_launch_pdl(attention_tc_kernel<true, false, true>, dim3(grid), dim3(NTHREADS), smem_bytes, st, mq, mk, mv, p);
+  else if (relbias) cn_launch_pdl(attention_tc_kernel<true, false, false>, dim3(grid), dim3(NTHREADS), smem_bytes, st, mq, mk, mv, p);
+  else if (mask_bits) cn_launch_pdl(attention_tc_kernel<false, true, false>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, mq, mk, mv, p);
+  else if (ring) cn_launch_pdl(attention_tc_kernel<false, false, true>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, mq, mk, mv, p);
+  else cn_launch_pdl(attention_tc_kernel<false, false, false>, dim3(grid), dim3(NTHREADS), SMEM_BYTES, st, mq, mk, mv, p);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

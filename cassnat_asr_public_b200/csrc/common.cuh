@@ -22,6 +22,36 @@
 
 static inline int cn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch: a kernel launched through cn_launch_pdl may be scheduled while its predecessor in
+// the stream is still running -- its CTAs take the SMs the predecessor's tail leaves idle, run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) and then block in cn_pdl_wait() until the predecessor has
+// completed and its writes are visible.  EVERY global-memory access of such a kernel comes after cn_pdl_wait();
+// cn_pdl_launch() right after it lets the successor do the same (look-ahead of one kernel).  Without the launch
+// attribute both instructions are no-ops.  OFF by default (CN_PDL=1 in the environment turns the attribute on): measured
+// on the cfg3 decode step, replayed as a CUDA graph, it costs 0.2 ms of 5.3 (5.48-5.53 vs 5.26-5.36 ms/step, two A/B
+// pairs on one B200) -- the step's kernels are persistent one-CTA-per-SM grids that cannot co-reside with their
+// successor anyway, and the programmatic edges make the graph's kernel-to-kernel hand-over slower, not faster.
+#include <stdlib.h>
+#include <utility>
+__device__ __forceinline__ void cn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cn_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static inline bool cn_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CN_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = cn_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ float cn_ld_stream_f32(const float* p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));

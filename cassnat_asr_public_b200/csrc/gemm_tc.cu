@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  cn_pdl_wait();                 // (prologue above overlapped the predecessor's tail)
+  cn_pdl_launch();
   // (setmaxnreg re-balancing between the single-lane roles and the epilogue warps was tried: ptxas then spills in
   // every instantiation, with or without role-pure warpgroups; the epilogue stays inside the common 168 registers)
 
@@ -700,7 +702,9 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const Epilogue& ep, 
   }
   const int tiles = LNM == LNM_FUSED ? (M + BM - 1) / BM : ((M + BM - 1) / BM) * ((N + BN - 1) / BN);     // fused LN: whole row blocks per CTA
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LNM><<<grid, THREADS, smem, stream>>>(ma, mw, ep, M, N, K, split);
+  if (cn_launch_pdl(gemm_bf16_tc_kernel<BN, ACT, RES, STATS, A_MN, B_MN, LNM>, dim3(grid), dim3(THREADS), smem, stream, ma, mw, ep, M, N, K,
+                    split) != cudaSuccess)
+    return CN_ERR_LAUNCH;
   return cudaGetLastError() == cudaSuccess ? CN_OK : CN_ERR_LAUNCH;
 }
 

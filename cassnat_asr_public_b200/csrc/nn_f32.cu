@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= rows) return;
+  cn_pdl_wait();
+  if (r >= rows) return;        // (an exiting CTA counts as having released its dependents)
   const float4* row = reinterpret_cast<const float4*>(x + r * ldx);
   float4 v[NV];
 #pragma unroll
@@ -229,8 +230,8 @@ static int layernorm_impl(const float* x, int64_t rows, int64_t d, int64_t ldx, 
                                                      // own resolution is 2^-17); fp32 output keeps the exact form
 #define CN_LN_VEC(NV_)                                                                                                  \
   do {                                                                                                                  \
-    if (rcp) layernorm_vec_kernel<NV_, true><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);  \
-    else layernorm_vec_kernel<NV_, false><<<(unsigned)blocks, 256, 0, stream>>>(x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);    \
+    if (rcp) cn_launch_pdl(layernorm_vec_kernel<NV_, true>, dim3((unsigned)blocks), dim3(256), 0, stream, x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);  \
+    else cn_launch_pdl(layernorm_vec_kernel<NV_, false>, dim3((unsigned)blocks), dim3(256), 0, stream, x, rows, ldx, a, b, eps, out_f32, obf, ldo, ldob, lo_off);    \
   } while (0)
   if (aligned && d == 128) CN_LN_VEC(1);
   else if (aligned && d == 256) CN_LN_VEC(2);

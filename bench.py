@@ -344,13 +344,13 @@ def run_ours(a, w):
     roof["share_of_step"] = d["ms"] / sum(v["ms"] for v in prof.values())
     # the whole step: algorithmic flops over the step time, and the time-weighted roofline fraction of its kernels
     # (each kernel against whichever of the two bounds it is closer to)
-    k_ms = sum(v["ms"] for v in prof.values())
+    k_ms = sum(v["ms"] for v in prof.values()) / 2              # (the profile covers two eager steps)
     step_ms = total_ms / a.steps
     fr = lambda v: max(v["flops"] / (v["ms"] / 1e3) / 1e12 / pk["tensor"] if v["flops"] else 0.0,
                        v["bytes"] / (v["ms"] / 1e3) / 1e9 / pk["hbm"] if v["bytes"] else 0.0)
-    roof["whole_step"] = {"algorithmic_tflop": sum(v["flops"] for v in prof.values()) / 1e12,
-                          "frac_tensor": sum(v["flops"] for v in prof.values()) / (step_ms / 1e3) / 1e12 / pk["tensor"],
-                          "kernel_time_weighted_frac": sum(v["ms"] * fr(v) for v in prof.values()) / k_ms,
+    roof["whole_step"] = {"algorithmic_tflop": sum(v["flops"] for v in prof.values()) / 2 / 1e12,
+                          "frac_tensor": sum(v["flops"] for v in prof.values()) / 2 / (step_ms / 1e3) / 1e12 / pk["tensor"],
+                          "kernel_time_weighted_frac": sum(v["ms"] * fr(v) for v in prof.values()) / 2 / k_ms,
                           "kernel_ms": k_ms, "step_ms": step_ms}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and a.workload == "cfg3" and a.precision == "bf16" and B == w["batch"]:

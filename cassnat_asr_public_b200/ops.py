@@ -807,7 +807,10 @@ def linear_bf16(x, weight_bf16, bias=None, residual=None, alpha=1.0, act=None, r
             r2 = r2.contiguous()
     call("cn_gemm_bf16", ptr(x2), x2.stride(0), ptr(weight_bf16), weight_bf16.stride(0), ptr(bias), ptr(r2),
          r2.stride(0) if r2 is not None else 0, int(res_rows), float(alpha), ACT[act], ptr(o32), ptr(o16), N,
-         M, N, K, stream(), work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * (4.0 if o32 is not None else 2.0)),
+         M, N, K, stream(),
+         work=dict(flops=2.0 * M * N * K, bytes=2.0 * (M * K + N * K) + M * N * ((4.0 if o32 is not None else 0.0) +
+                                                                              (2.0 if o16 is not None else 0.0) +
+                                                                              (4.0 if r2 is not None else 0.0))),
          tag=(f"cn_gemm_bf16[{M}x{N}x{K}]" if _lib.PROFILE_SHAPES else None))
     if o32 is not None and o16 is not None:
         return o32, o16

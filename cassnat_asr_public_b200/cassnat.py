@@ -187,6 +187,8 @@ class CassNAT(nn.Module):
                             label_sizes=None, return_intermediates=False, features=None, defer=False):
         """Everything CassNAT.beam_decode does after the encoder (cassnat.py:433-637).
         src_size is the length RATIO tensor the reference takes (frames = (ratio*T).long(), :436)."""
+        if defer and return_intermediates:
+            raise ValueError("defer=True returns a handle to the hypotheses only; intermediates need the synchronous call")
         beam = args.lm_weight > 0 or args.beam_width != 1        # cassnat.py:600-636: per-position top-k (+ token-level LM)
         hitrate = bool(getattr(args, "test_hitrate", False)) and args.use_trigger
         if hitrate and enc_h.size(0) != 1:

@@ -41,9 +41,9 @@ def _self_attention_block(x, sub, attn, mask, pos_embed=None, next_norm=None):
     else:
         from .modules import distinct_rel_rows
         table, m = distinct_rel_rows(pos_embed, x.size(1))
-        fast = ops.attn_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= ops.REL_TC_MAX
-        key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1        # (per-row masks: the fp32 kernel, below)
-        if fast and key_mask and not (torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad)) and _p(attn) == 0:
+        key_mask = mask is None or mask.dim() == 2 or mask.shape[1] == 1        # (per-row masks: the fp32 kernel)
+        fast = ops.attn_bf16() and x.size(1) <= 2048 and attn.h <= 8 and m <= ops.REL_TC_MAX and key_mask
+        if fast and not (torch.is_grad_enabled() and (y.requires_grad or attn.pos_bias_u.requires_grad)) and _p(attn) == 0:
             # fast: q + pos_bias_u in bf16, and the relative term's table out of the same GEMM
             q, k, v, tab = attn.project_qkv_rel(y, table, m)
             ctx = ops.attention(q, k, v, mask, attn.h, (None, attn.pos_bias_u, attn.pos_bias_v, m, tab))

@@ -91,6 +91,7 @@ SIGNATURES = {
                                       _i64, _f32, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "cn_attn_softmax_bwd": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
     "cn_dropout": (_int, [_vp, _int, _vp, _int, _i64, _f32, _vp, _i64, _i64, _vp]),
+    "cn_dropout_add": (_int, [_vp, _int, _vp, _vp, _i64, _f32, _f32, _vp, _i64, _i64, _vp]),
     "cn_label_smoothing": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _f32, _f32, _vp, _vp, _i64, _vp, _i64, _vp]),
     "cn_gemm_bf16_mn": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     "cn_transpose_bf16": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _vp]),

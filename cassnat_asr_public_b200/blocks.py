@@ -26,7 +26,7 @@ def _residual(sub, x, branch, scale=1.0, next_norm=None, **kw):
     the next LayerNorm) is fused into the branch's last GEMM; with dropout the branch output is dropped first."""
     p = _p(sub)
     if p > 0:
-        return x + scale * ops.dropout(branch(residual=None, scale=1.0, **kw), p)
+        return ops.dropout_add(branch(residual=None, scale=1.0, **kw), x, p, scale)     # one launch (was dropout, mul, add)
     return branch(residual=x, scale=scale, next_ln=next_norm, **kw)
 
 

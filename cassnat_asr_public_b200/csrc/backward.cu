@@ -257,10 +257,11 @@ __device__ __forceinline__ bool cn_dropout_keep(uint64_t seed, uint32_t site, ui
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) dropout_kernel(const TI* __restrict__ x, TO* __restrict__ out, int64_t n, uint32_t threshold,
                                                       float inv_keep, const int64_t* __restrict__ seed_dev, uint64_t seed,
-                                                      uint32_t site) {
+                                                      uint32_t site, const float* __restrict__ res = nullptr) {
   const uint64_t sd = seed_dev ? (uint64_t)seed_dev[0] : seed;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = cn_dropout_keep(sd, site, (uint64_t)i, threshold) ? (float)x[i] * inv_keep : 0.f;
+    float v = cn_dropout_keep(sd, site, (uint64_t)i, threshold) ? (float)x[i] * inv_keep : 0.f;
+    if (res) v += res[i];                                   // residual + scale * dropout(branch) in one pass
     out[i] = (TO)v;
   }
 }
@@ -527,9 +528,7 @@ extern "C" int cn_layernorm_bwd(const float* x, int64_t ldx, const float* dy, in
     layernorm_bwd_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, a, eps, rows, (int)d, dx, lddx, pa, pb);
     CN_CHECK_LAUNCH();
   }
-  colsum_reduce_kernel<<<(unsigned)((d + 31) / 32), 256, 0, (cudaStream_t)stream>>>(pa, nblk, d, da, 0);
-  CN_CHECK_LAUNCH();
-  colsum_reduce_kernel<<<(unsigned)((d + 31) / 32), 256, 0, (cudaStream_t)stream>>>(pb, nblk, d, db, 0);
+  colsum_reduce_kernel<<<dim3((unsigned)((d + 31) / 32), 2), 256, 0, (cudaStream_t)stream>>>(pa, nblk, d, da, 0, pb, db);   // both sums, one launch
   CN_CHECK_LAUNCH();
   return CN_OK;
 }
@@ -552,6 +551,23 @@ extern "C" int cn_dropout(const void* x, int x_is_bf16, void* out, int out_is_bf
     dropout_kernel<<<g, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
   else
     dropout_kernel<<<g, 256, 0, st>>>((const float*)x, (float*)out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site);
+  CN_CHECK_LAUNCH();
+  return CN_OK;
+}
+
+extern "C" int cn_dropout_add(const void* x, int x_is_bf16, const float* residual, float* out, int64_t n, float p, float scale,
+                              const int64_t* seed_dev, int64_t seed, int64_t site, cn_stream_t stream) {
+  if (!x || !out || n < 0 || !(p >= 0.f) || p >= 1.f) return CN_ERR_BAD_ARG;
+  if (n == 0) return CN_OK;
+  const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
+  const float inv_keep = scale / (1.f - p);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_is_bf16)
+    dropout_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site, residual);
+  else
+    dropout_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)x, out, n, thr, inv_keep, seed_dev, (uint64_t)seed, (uint32_t)site, residual);
   CN_CHECK_LAUNCH();
   return CN_OK;
 }

@@ -87,8 +87,12 @@ __device__ __forceinline__ bool cn_better(float va, int ia, float vb, int ib) {
 }
 
 // out[c] = sum_blk partial[blk][c] in block order; 32 columns x 8 row groups per CTA.
+// blockIdx.y selects one of up to two (partial, out) pairs that share nblk and N (LayerNorm backward: dgamma and dbeta).
 static __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, int64_t nblk, int64_t N,
-                                                            float* __restrict__ out, int accumulate) {
+                                                            float* __restrict__ out, int accumulate,
+                                                            const float* __restrict__ partial2 = nullptr,
+                                                            float* __restrict__ out2 = nullptr) {
+  if (blockIdx.y == 1) { partial = partial2; out = out2; }
   __shared__ float sh[8][33];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + cx;

@@ -263,6 +263,23 @@ class Dropout(torch.autograd.Function):
         return ops.dropout_forward(gy, ctx.p, ctx.site), None, None
 
 
+class DropoutAdd(torch.autograd.Function):
+    """y = residual + scale * x * mask / (1 - p) in one pass; backward: d x = scale * mask / (1 - p) * g (mask regenerated
+    from (seed, site)), d residual = g."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, scale, site):
+        ctx.p, ctx.scale, ctx.site, ctx.x_dtype = p, scale, site, x.dtype
+        return ops.dropout_add_forward(x, residual, p, scale, site)
+
+    @staticmethod
+    def backward(ctx, gy):
+        gx = ops.dropout_add_forward(gy, None, ctx.p, ctx.scale, ctx.site) if ctx.needs_input_grad[0] else None
+        if gx is not None and ctx.x_dtype != torch.float32:
+            gx = gx.to(ctx.x_dtype)
+        return gx, (gy if ctx.needs_input_grad[1] else None), None, None, None
+
+
 def _attn_probs_dropped(S, mask, B, h, Tq, Tk, zero_masked, p, site):
     """In place on the scaled scores S [B,h,Tq,Tk]: softmax with the reference's masking, then dropout."""
     m, mb, mi = ops._mask_strides(mask, B, Tq, Tk)

@@ -112,7 +112,9 @@ class SublayerConnection(nn.Module):
 
     def forward(self, x, sublayer, scale=1.0, has_cache=False):
         residual = x[:, -1:, :] if has_cache else x
-        y = ops.dropout(sublayer(self.norm(x)), _p(self))                   # utils.py:32
+        y = sublayer(self.norm(x))
+        if _p(self) > 0:
+            return ops.dropout_add(y, residual, _p(self), scale)            # utils.py:32 in one launch
         return residual + scale * y
 
 

@@ -580,6 +580,33 @@ def dropout_forward(x, p, site, inplace=False):
     return out
 
 
+def dropout_add_forward(x, residual, p, scale, site):
+    """residual + scale * dropout(x) (residual None: scale * dropout(x)) in one launch, f32 out; the mask of `site`."""
+    require_cuda(x)
+    xc = x if x.is_contiguous() else x.contiguous()
+    if xc.dtype not in (torch.float32, torch.bfloat16):
+        xc = xc.float()
+    rc = None
+    if residual is not None:
+        rc = residual if (residual.is_contiguous() and residual.dtype == torch.float32) else residual.float().contiguous()
+        assert rc.shape == xc.shape
+    out = torch.empty(xc.shape, dtype=torch.float32, device=xc.device)
+    call("cn_dropout_add", ptr(xc), int(xc.dtype == torch.bfloat16), ptr(rc), ptr(out), xc.numel(), float(p), float(scale),
+         ptr(DROPOUT_SEED_DEV), int(DROPOUT_SEED), int(site), stream(),
+         work=dict(bytes=float(xc.numel()) * (xc.element_size() + 4 + (4 if rc is not None else 0))))
+    return out
+
+
+def dropout_add(x, residual, p, scale=1.0):
+    """residual + scale * nn.Dropout(p)(x) of SublayerConnection (modules/utils.py:32), training mode, one launch (and
+    one in backward: the branch gradient is scale * mask * g, the residual's is g itself)."""
+    site = _next_site()
+    if _needs_grad(x, residual):
+        from . import grad
+        return grad.DropoutAdd.apply(x, residual, float(p), float(scale), site)
+    return dropout_add_forward(x, residual, p, scale, site)
+
+
 def dropout_mask(shape, p, site, device):
     """The multiplicative mask (0 or 1/(1-p)) the kernels use for `site` under the current seed (tests)."""
     return dropout_forward(torch.ones(shape, dtype=torch.float32, device=device), p, site)

@@ -498,6 +498,11 @@ int cn_attention_fwd_small(const void* q, int64_t ldq, int64_t sbq, const void* 
  * call site of a step. */
 int cn_dropout(const void* x, int x_is_bf16, void* out, int out_is_bf16, int64_t n, float p, const int64_t* seed_dev,
                int64_t seed, int64_t site, cn_stream_t stream);
+/* residual + scale * dropout(x) in one pass (SublayerConnection, src/models/modules/utils.py:32); residual f32 [n] or NULL
+ * (then: scale * dropout(x), the branch gradient of the same expression), out f32 [n]; same mask as cn_dropout for the
+ * same (seed, site). */
+int cn_dropout_add(const void* x, int x_is_bf16, const float* residual, float* out, int64_t n, float p, float scale,
+                   const int64_t* seed_dev, int64_t seed, int64_t site, cn_stream_t stream);
 
 /* Label-smoothing KL loss over log-softmax rows and its gradient at the logits:
  *   loss = sum_{rows with target != pad} KL(w || p) / #such rows,  w = (1-s) one-hot + s/(V-1) elsewhere

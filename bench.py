@@ -261,32 +261,42 @@ def run_ours(a, w):
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     # ---- end to end: pinned host buffers in, hypotheses (python lists) out, copies inside the clock
     # (double-buffered: the copy of step i+1 runs on a side stream while step i computes)
+    # two preallocated device batches (no allocation inside the loop).  Copying only the frames an utterance has (one copy
+    # per utterance, 19 % fewer bytes) was measured and is slower on one GPU: 5.90 vs 5.48-5.54 ms/step
+    # (scratch/e2e_diag.py) -- 64 small copies per step cost more than the padding they skip.
     copy_stream = torch.cuda.Stream(device=dev)
+    stage_bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    reader_done = [None, None]               # the step that last read a staging batch has been queued up to this event
+    h2d = sum(t.numel() * t.element_size() for t in host)
 
-    def stage():
+    def stage(k):
+        bufs = stage_bufs[k % 2]
         with torch.cuda.stream(copy_stream):
-            bufs = [t.to(dev, non_blocking=True) for t in host]
+            if reader_done[k % 2] is not None:
+                copy_stream.wait_event(reader_done[k % 2])
+            for d_, s_ in zip(bufs, host):
+                d_.copy_(s_, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return bufs, ev
 
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(4):                       # (copy alone, for the record: what the host link of this box delivers)
-        stage()[1].synchronize()
+    for j in range(4):                       # (copy alone, for the record: what the host link of this box delivers)
+        stage(j)[1].synchronize()
     h2d_alone_s = (time.perf_counter() - t0) / 4
     sync_all()
     t0 = time.perf_counter()
-    nxt = stage()
+    nxt = stage(0)
     pend = None
     for i in range(a.steps):
         staged, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
-        for t in staged:
-            t.record_stream(torch.cuda.current_stream())
         if i + 1 < a.steps:
-            nxt = stage()
+            nxt = stage(i + 1)
         queued = step_async(staged)
+        reader_done[i % 2] = torch.cuda.Event()
+        reader_done[i % 2].record()
         if pend is not None:
             hyps = collect(pend)
         pend = queued
@@ -355,7 +365,6 @@ def run_ours(a, w):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and a.workload == "cfg3" and a.precision == "bf16" and B == w["batch"]:
         roof["traffic"] = json.load(open(tpath)).get(name)      # ncu capture of exactly this workload (profiles/)
-    h2d = sum(t.numel() * t.element_size() for t in host)
     ymax = max(len(h) - 1 for h in hyps[:B])
     d2h = B * ymax * (4 + 8) + B * 8 + 4          # ids i32 + logp f64 + ylen i64 + the ymax scalar
     line = {"metric": "utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": a.steps,

@@ -18,6 +18,7 @@ enc_h, mask, ratio, _ = bench.synth_encoder_output(w, 64, 1234)
 host = [t.pin_memory() for t in (enc_h, mask, ratio)]
 res = [t.to(dev) for t in host]
 N = 40
+n_valid = mask.reshape(64, -1).sum(1).tolist()
 copy_stream = torch.cuda.Stream(device=dev)
 
 
@@ -28,9 +29,13 @@ def run(kind):
         with torch.cuda.stream(copy_stream):
             if kind == "fresh":
                 b = [t.to(dev, non_blocking=True) for t in host]
+            elif kind == "ragged":
+                b = bufs2[i % 2]
+                for u in range(64):
+                    b[0][u, :n_valid[u]].copy_(host[0][u, :n_valid[u]], non_blocking=True)
+                b[1].copy_(host[1], non_blocking=True); b[2].copy_(host[2], non_blocking=True)
             else:
                 b = bufs2[i % 2]
-                copy_stream.wait_stream(torch.cuda.current_stream()) if False else None
                 for d, s in zip(b, host):
                     d.copy_(s, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(copy_stream)
@@ -52,7 +57,7 @@ def run(kind):
                     for t in inp:
                         t.record_stream(torch.cuda.current_stream())
                 if i + 1 < N:
-                    if kind == "prealloc":          # the buffer about to be overwritten was read by step i-1's stage A: done
+                    if kind in ("prealloc", "ragged"):          # the buffer about to be overwritten was read by step i-1's stage A: done
                         copy_stream.wait_stream(torch.cuda.current_stream())
                     nxt = stage(i + 1)
             q, _ = model.decode_from_encoder(*inp, bench.VOCAB, args, defer=True)
@@ -61,8 +66,15 @@ def run(kind):
             pend = q
         pend.result()
         torch.cuda.synchronize()
-        return (time.perf_counter() - t0) / N * 1e3
+        t_all = (time.perf_counter() - t0) / N * 1e3
+        t0 = time.perf_counter()
+        if kind != "resident":
+            for i in range(10):
+                stage(i)
+        t_host = (time.perf_counter() - t0) / 10 * 1e3
+        torch.cuda.synchronize()
+        return t_all, t_host
 
 
-for kind in ("resident", "fresh", "prealloc", "resident", "fresh", "prealloc"):
-    print(kind, "%.3f ms/step" % run(kind), flush=True)
+for kind in ("resident", "fresh", "prealloc", "ragged", "prealloc", "ragged"):
+    print(kind, "%.3f ms/step, stage() host time %.3f ms" % run(kind), flush=True)

@@ -227,3 +227,36 @@ def test_attention_split_bf16_hints_and_fallback():
     full = (torch.rand(B, Tq, Tk) < 0.3)
     got = ops.attention(_split(q), _split(k), _split(v), full.to(DEV), h)
     assert rel(got, ref_attention(q, k, v, full, h)) < 1e-5
+
+
+@pytest.mark.parametrize("h,m,L", [(2, 8, 90), (4, 20, 150), (8, 3, 40)])
+def test_rel_table_from_fused_projection(h, m, L):
+    """modules.RelMultiHeadedAttention.project_qkv_rel(x, table, m): q (+ pos_bias_u), k, v and the relative term's
+    table (q + pos_bias_v) . linear_pos(table)[r] come out of ONE GEMM whose weight folds linear_q, linear_pos and the
+    biases -- checked against the unfused fp64 arithmetic of modules/attention.py:104-117 (bf16 operands: 2e-2 of the
+    output scale), also after a weight update (the folded weight is rebuilt)."""
+    from cassnat_asr_public_b200 import modules
+    d = 64 * h
+    torch.manual_seed(h + m)
+    attn = modules.RelMultiHeadedAttention(h, d, dropout=0.0).to(DEV).eval()
+    table = torch.randn(2 * m + 1, d, device=DEV)
+    x = torch.randn(2, L, d, device=DEV)
+    ops.set_precision("bf16")
+    try:
+        for _ in range(2):
+            with torch.no_grad():
+                q, k, v, tab = attn.project_qkv_rel(x, table, m)
+            xd = x.double()
+            lin = lambda i: xd @ attn.linears[i].weight.double().t() + attn.linears[i].bias.double()
+            qd = lin(0).view(2, L, h, 64)
+            P = (table.double() @ attn.linear_pos.weight.double().t()).view(2 * m + 1, h, 64)
+            want_tab = torch.einsum("blhk,rhk->blhr", qd + attn.pos_bias_v.double(), P).reshape(2, L, h * (2 * m + 1))
+            want_q = (qd + attn.pos_bias_u.double()).reshape(2, L, d)
+            for got, want in ((tab, want_tab), (q, want_q), (k, lin(1)), (v, lin(2))):
+                assert got.dtype == torch.bfloat16 and got.shape == want.shape
+                assert rel(got.float(), want) < 2e-2
+            with torch.no_grad():                      # an optimizer step: the cached folded weight must follow
+                attn.linears[0].weight.mul_(1.5)
+                attn.pos_bias_v.add_(0.25)
+    finally:
+        ops.set_precision("fp32")

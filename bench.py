@@ -381,7 +381,10 @@ def run_ours(a, w):
             "rtf": (total_ms / 1e3 / a.steps) / (B * w["audio_s"]),
             "e2e": {"value": units / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "h2d_alone_ms": h2d_alone_s * 1e3,
-                    "h2d_alone_GBps": h2d / h2d_alone_s / 1e9},
+                    "h2d_alone_GBps": h2d / h2d_alone_s / 1e9,
+                    # the copy of batch i+1 overlaps batch i: when the host link needs longer for one batch than the device
+                    # does, the end-to-end number measures the link of this box, not the path
+                    "bound": "host link" if h2d_alone_s * 1e3 > total_ms / a.steps else "device"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             # per kernel: algorithmic flops and operand + result bytes over its CUDA-event time, each against the
             # measured peak -- a kernel is at its roofline when EITHER fraction is near 1 (the d x d projections with

@@ -55,7 +55,8 @@ def test_attention_tc_on_fused_buffers():
 
 
 @pytest.mark.parametrize("table", ["pre-kernel", "f32", "bf16"])
-@pytest.mark.parametrize("B,U,h,m", [(2, 90, 2, 8), (3, 300, 4, 20), (2, 500, 8, 8), (2, 130, 2, 22), (1, 5, 1, 4)])
+@pytest.mark.parametrize("B,U,h,m", [(2, 90, 2, 8), (3, 300, 4, 20), (2, 500, 8, 8), (2, 130, 2, 22), (1, 5, 1, 4),
+                                     (2, 700, 2, 8), (1, 1100, 1, 20)])       # (> 512 keys: K/V tiles stream through the ring)
 def test_rel_attention_tc(B, U, h, m, table):
     """tcgen05 relative-position attention vs the oracle's rel_mha core on bf16-rounded q/k/v; the relative term's
     table either from the pre-kernel or handed in (what the fused projection's extra columns hold), f32 or bf16."""

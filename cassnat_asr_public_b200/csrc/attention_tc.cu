@@ -434,18 +434,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
             tmem_ld32(s_addr + c, sb);
             const int r0 = k0 + c - qic + p.max_rel;                        // table column of the chunk's first key
             const int lr0 = k0 + c + p.max_rel - qt * QT;                   // slab row of the chunk's first key
+            // key q of the chunk uses table column r0 + q of slab row lr0 + q: one stride of nrel + 1 words per key;
+            // columns outside [0, nrel) are the clamped ends (this row's first / last entry, already in registers)
+            const float* band = slab + lr0 * nrel + r0;
             float bv[32];
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              const int rc = min(max(r0 + q, 0), nrel - 1);
-              bv[q] = slab[min(max(lr0 + q, 0), QT + 2 * p.max_rel - 1) * nrel + rc];   // (clamped entries are not used)
+              const bool inside = (unsigned)(r0 + q) < (unsigned)nrel;
+              bv[q] = inside ? band[q * (nrel + 1)] : (r0 + q < 0 ? rel_left : rel_right);
             }
             tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const int r = r0 + q;
-              sb[q] += r < 0 ? rel_left : (r >= nrel ? rel_right : bv[q]);
-            }
+            for (int q = 0; q < 32; ++q) sb[q] += bv[q];
             tmem_st32(s_addr + c, reinterpret_cast<uint32_t*>(sb));
             tmem_wait_st();
           }

@@ -358,7 +358,7 @@ def beam_assemble(att_out, ylen, ymax, cfg, lm_model=None, sos=1):
     return [[s["hyp"] for s in t] for t in tops], [[s["score"] for s in t] for t in tops]
 
 
-def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, lm_model=None):
+def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, lm_model=None, vocab=None, features=None):
     """Post-encoder part of CassNAT.beam_decode (cassnat.py:433-637), greedy pick.
     src_size_frames: int64 [B] == (ratio * T).long() of :436.
     select: host-drawn bits for sampled alignments (cfg.sample_num > 1).
@@ -379,16 +379,33 @@ def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, 
     out = dict(ctc_out=ctc_out, aligned=aligned, trigger=trig, ylen=ylen1, ymax=ymax1,
                ac_embed=ac, pred_embed=pred, dec_h=dec_h, att_out=att_out)
     ylen_t = torch.from_numpy(ylen1)
-    if S > 1:                                                     # :499-561, rank_model == 'lm'
+    if S > 1:                                                     # :499-561
         seql, dim = att_out.shape[1:]
         att_pred = att_out.argmax(-1)
-        lm_in = torch.cat([torch.full((att_out.size(0), 1), 1, dtype=torch.long), att_pred[:, :-1]], 1)
-        causal = torch.tril(torch.ones(ymax1, ymax1, dtype=torch.uint8)).unsqueeze(0)
-        lm_mask = tgt_mask & causal.type_as(tgt_mask)
-        lm_out = lm_model(lm_in, lm_mask)
-        sc = torch.gather(lm_out, -1, att_pred.unsqueeze(-1)).squeeze(-1)
-        sc = sc.reshape(-1, S, seql).masked_fill(tgt_mask.reshape(-1, S, seql) == 0, 0)
-        mean = sc.sum(-1) / (sc != 0).sum(-1).float()
+        kind = getattr(cfg, "rank_model", "lm")
+        if kind == "n-gram":                                      # :525-536: text of every sample scored on the host
+            tgt_len = tgt_mask.sum(-1)
+            mean = torch.zeros(att_pred.size(0))
+            for i in range(att_pred.size(0)):
+                pieces = [vocab.index2word[int(t)] for t in att_pred[i, :int(tgt_len[i])] if int(t) != 2]
+                mean[i] = lm_model.score("".join(pieces).replace("\u2581", " ").strip()) / tgt_len[i]
+            mean = mean.reshape(-1, S)
+        else:
+            lm_in = torch.cat([torch.full((att_out.size(0), 1), 1, dtype=torch.long), att_pred[:, :-1]], 1)
+            causal = torch.tril(torch.ones(ymax1, ymax1, dtype=torch.uint8)).unsqueeze(0)
+            lm_mask = tgt_mask & causal.type_as(tgt_mask)
+            if kind == "at_baseline":                             # :513-519: the AT model re-encodes the features
+                src, x_mask = features
+                x, at_mask = lm_model.src_embed(src, x_mask)
+                at_h = lm_model.encoder(x, at_mask)
+                at_h = at_h.unsqueeze(1).repeat(1, S, 1, 1).reshape(-1, at_h.size(1), at_h.size(2))
+                at_mask = at_mask.unsqueeze(1).repeat(1, S, 1, 1).reshape(-1, at_mask.size(1), at_mask.size(2))
+                lm_out = lm_model.forward_decoder(at_h, lm_in, at_mask, lm_mask)
+            else:
+                lm_out = lm_model(lm_in, lm_mask)
+            sc = torch.gather(lm_out, -1, att_pred.unsqueeze(-1)).squeeze(-1)
+            sc = sc.reshape(-1, S, seql).masked_fill(tgt_mask.reshape(-1, S, seql) == 0, 0)
+            mean = sc.sum(-1) / (sc != 0).sum(-1).float()
         best = mean.max(-1, keepdim=True)[1]
         att_out = att_out.reshape(-1, S, seql, dim).masked_fill(
             tgt_mask.reshape(-1, S, 1, seql).transpose(2, 3) == 0, 0)
@@ -403,11 +420,11 @@ def decode_from_encoder(enc_h, src_mask, src_size_frames, sd, cfg, select=None, 
     return out
 
 
-def beam_decode(src, src_mask, src_size, sd, cfg, select=None, lm_model=None):
+def beam_decode(src, src_mask, src_size, sd, cfg, select=None, lm_model=None, vocab=None):
     """Whole CassNAT.beam_decode (cassnat.py:420-637): encoder + the conditioned path."""
     enc_h, mask = encode(src, src_mask, sd, cfg)
     frames = (src_size * enc_h.size(1)).long()                   # :436
-    out = decode_from_encoder(enc_h, mask, frames, sd, cfg, select, lm_model)
+    out = decode_from_encoder(enc_h, mask, frames, sd, cfg, select, lm_model, vocab, (src, src_mask))
     out["enc_h"] = enc_h
     return out
 

@@ -4,6 +4,7 @@ import os
 from types import SimpleNamespace
 
 import numpy as np
+import pytest
 import torch
 
 import oracle.align_np as A
@@ -174,3 +175,37 @@ def test_beam_assembly_port():
         flat = [t for beams in o["beam_hyps"] for h in beams for t in h]
         assert flat == g[case + "::hyp_flat"].tolist(), case
         assert np.allclose(np.asarray(sum(o["beam_scores"], [])), g[case + "::score"], rtol=1e-5, atol=1e-5), case
+
+
+@pytest.mark.parametrize("kind", ["n-gram", "at_baseline"])
+def test_other_rankers_port(kind):
+    """rank_model 'n-gram' / 'at_baseline' of the oracle against the hypotheses the unmodified reference produced with
+    the same stand-in rankers (tests/golden/rankers.npz, made by tests/golden/make_golden_rankers.py)."""
+    import os
+    import sys
+    from types import SimpleNamespace
+
+    import numpy as np
+    import torch
+
+    import oracle.nat_torch as O
+    from conftest import load_blocks
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from ranker_standins import TinyAT, TinyNgram, index2word
+    z, sd, cfg = load_blocks("trf")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rankers.npz"))
+    cfg = SimpleNamespace(**{**vars(cfg), "sample_num": 3, "threshold": 0.9, "rank_model": kind})
+    src, mask, size = (torch.from_numpy(z[k]) for k in ("src", "src_mask", "src_size"))
+    ranker = TinyNgram() if kind == "n-gram" else TinyAT(src.size(-1), cfg.vocab_size)
+    vocab = SimpleNamespace(index2word=index2word(cfg.vocab_size))
+    select = z["sampled::select"]                       # the reference's CPU-generator draw under manual_seed(555)
+    with torch.no_grad():
+        o = O.beam_decode(src, mask, size, sd, cfg, select, ranker, vocab)
+    tag = kind.replace("-", "")
+    flat, lens = g[tag + "::hyp_flat"], g[tag + "::hyp_len"]
+    want, at = [], 0
+    for n in lens:
+        want.append(flat[at:at + n].tolist())
+        at += n
+    assert o["hyps"] == want
+    assert np.allclose(o["scores"], g[tag + "::score"], rtol=1e-4, atol=1e-4)

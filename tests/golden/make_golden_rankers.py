@@ -11,6 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from _ref_harness import VOCAB, load_reference, make_args  # noqa: E402
 from ranker_standins import TinyAT, TinyNgram, index2word  # noqa: E402
 
@@ -40,6 +41,13 @@ def main():
         with torch.no_grad():
             res, _ = model.beam_decode(src, src_mask, src_size, vocab, a, lm_model=ranker)
         hyps = [r_[0]["hyp"] for r_ in res]
+        # the oracle port must agree before anything is saved (same draw of the sampling bits)
+        import oracle.nat_torch as O
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        with torch.no_grad():
+            o = O.beam_decode(src, src_mask, src_size, sd, SimpleNamespace(**vars(a)), z["sampled::select"],
+                              TinyNgram() if kind == "n-gram" else ranker, vocab)
+        assert o["hyps"] == hyps, (kind, o["hyps"], hyps)
         tag = kind.replace("-", "") + "::"
         out[tag + "hyp_flat"] = np.asarray([t for h in hyps for t in h], dtype=np.int64)
         out[tag + "hyp_len"] = np.asarray([len(h) for h in hyps], dtype=np.int64)

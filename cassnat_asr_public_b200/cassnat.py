@@ -434,7 +434,8 @@ class CassNAT(nn.Module):
     def _stage_b_graphed(self, enc_h, src_mask, frames, aligned, ylen, ymax, args, blank, stamp=None):
         """Same as _stage_b, captured once per (batch, frames, tokens, precision) shape and replayed:
         ~150 kernel launches become one graph launch.  The first call of a shape runs eagerly (it also
-        warms the weight caches) and captures for the following calls."""
+        warms the weight caches); the `graph_capture_after`-th call of the same shape (default: the second) runs
+        eagerly once more and captures, later calls replay."""
         # The graph is specialised on the token-axis length.  With `model.graph_bucket = n` (> 1, transformer family:
         # token rows are independent of the padded length) the length is rounded up to a multiple of n — extra rows are
         # masked and never read — so that batches with similar lengths share one graph; the conformer family
@@ -462,6 +463,14 @@ class CassNAT(nn.Module):
         live = (enc_full if enc_full is not None else enc_h, src_mask, frames, aligned, ylen)
         if hit is None:
             out = self._stage_b(enc_h, src_mask, frames, aligned, ylen, ymax, args, blank)
+            # A capture costs a synchronisation and a second pass over the stage: only shapes that come back are worth
+            # it (with real, variable-length batches most (frames, tokens) shapes are seen once).
+            seen = self.__dict__.setdefault("_graph_seen", {})
+            if len(seen) > 256:
+                seen.clear()
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] < int(getattr(self, "graph_capture_after", 2)):
+                return fix(out[:4])
             # (the encoder operand usually IS a persistent buffer already, see decode_from_encoder: captured in place)
             persistent = any(live[0] is b for b in self.__dict__.get("_enc_static", {}).values())
             statics = [t if (i == 0 and persistent) else t.clone() for i, t in enumerate(live)]

@@ -232,10 +232,10 @@ def test_cuda_graph_replay_matches_eager(blocks_golden):
     want = hyps_of(z, "greedy")
     with torch.no_grad():
         model.use_cuda_graphs = True
-        for it in range(3):                                   # eager+capture, replay, replay
+        for it in range(3):                                   # eager, eager + capture (the shape came back), replay
             out, _ = model.decode_from_encoder(enc_h, src_mask, size, VOCAB, args)
             assert [o[0]["hyp"] for o in out] == want, it
-        assert len(model._graphs) == 1
+            assert len(model._graphs) == (0 if it == 0 else 1)
         # different content, same shapes: compare with an eager run of the same input
         g = torch.Generator(device=DEV).manual_seed(7)
         enc2 = enc_h + 0.05 * torch.randn(enc_h.shape, device=DEV, generator=g)
